@@ -1,0 +1,503 @@
+// capdec_b200 — persistent warp-specialised TF32 GEMM on tcgen05 (sm_100a).
+//
+//   C[M,N] = act( sum_k A(m,k) * B(n,k) + bias[n] )
+//
+// Replaces nn.Linear (train.py:113-118,124-126,144-147,241), HF Conv1D (HF:pytorch_utils.py:97-123),
+// the tied lm_head (HF:modeling_gpt2.py:703-706) and every dgrad / wgrad product autograd derives from them
+// (train.py:351).  One kernel serves all operand orientations:
+//   K-major  operand: TMA box {32 fp32 (=128 B, one swizzle row), rows} with SWIZZLE_128B,
+//                     UMMA descriptor SWIZZLE_128B, SBO = 1024 B, k-step = +32 B inside the swizzle atom;
+//   MN-major operand: TMA boxes {32 fp32 along M/N, 32 rows of K} with SWIZZLE_128B_ATOM_32B (the only layout
+//                     tcgen05 accepts for 32-bit MN-major data), UMMA descriptor SWIZZLE_128B_BASE32B,
+//                     LBO = 4096 B (next 32-wide M/N slab), SBO = 512 B (next 4 k-rows), k-step = +1024 B.
+// Pipeline: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (tcgen05.ld -> bias/activation -> swizzled smem -> TMA store / TMA reduce-add).
+// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the mainloop of tile i+1.
+// 3xTF32 ("parity") mode runs three K passes (hi*hi, lo*hi, hi*lo) into the same TMEM accumulator.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/capdec_b200.h"
+#include "common.cuh"
+
+namespace capdec {
+
+// ---------------------------------------------------------------------------------------------------------------
+// library-wide helpers (defined once here)
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return CAPDEC_OK;
+  set_last_error("%s: %s", what, cudaGetErrorString(e));
+  return CAPDEC_ERR_CUDA;
+}
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;  // fp32 elements per k-block = 128 bytes = one swizzle row
+constexpr int kUmmaK = 8;    // tf32
+constexpr int kThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr int kABytes = kBlockM * kBlockK * 4;  // 16 KB
+constexpr int kStagingBytes = 128 * 128;        // 128 rows x 32 fp32
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = 256;  // columns per accumulator stage
+constexpr int kSmemLimit = 227 * 1024;
+
+struct __align__(64) GemmDev {
+  CUtensorMap tmA[2];  // [0] = hi (or the operand itself), [1] = lo residual (3xTF32)
+  CUtensorMap tmB[2];
+  CUtensorMap tmC;
+  CUtensorMap tmAux;
+  const float* bias;
+  int M, N, K;
+  int block_n, stages;
+  int m_tiles, n_tiles, splits, kb_per_split, kb_total;
+  int nseg;
+  int act, has_aux, accumulate;
+  int a_mn, b_mn;
+  uint32_t idesc;
+  uint32_t adesc_hi, bdesc_hi;      // upper 32 bits of the smem descriptors (SBO, version, layout)
+  uint32_t adesc_lo16, bdesc_lo16;  // LBO field (bits 16..29 of the low word), pre-shifted
+  uint32_t a_kstep, b_kstep;        // start-address increment per UMMA_K step, in 16-byte units
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case 1: return gelu_new_fwd(x);
+    case 2: return tanhf(x);
+    case 3: return fmaxf(x, 0.0f);
+    default: return x;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_constant__ GemmDev p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve-up (all tile buffers 1024-byte aligned for the 128B swizzle patterns)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.block_n * kBlockK * 4;
+  const int stage_bytes = kABytes + b_bytes;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + p.stages * kABytes;
+  uint8_t* sStage = smem + p.stages * stage_bytes;  // 2 x 16 KB epilogue staging
+  float* sBias = reinterpret_cast<float*>(sStage + 2 * kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 256);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.tmA[0]);
+    prefetch_tensormap(&p.tmB[0]);
+    prefetch_tensormap(&p.tmC);
+    if (p.nseg > 1) {
+      prefetch_tensormap(&p.tmA[1]);
+      prefetch_tensormap(&p.tmB[1]);
+    }
+    if (p.has_aux) prefetch_tensormap(&p.tmAux);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], kEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        const int m_blk = (tile / p.n_tiles) % p.m_tiles;
+        const int split = tile / (p.n_tiles * p.m_tiles);
+        const int m0 = m_blk * kBlockM, n0 = n_blk * p.block_n;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          const CUtensorMap* mapA = (seg == 1) ? &p.tmA[1] : &p.tmA[0];
+          const CUtensorMap* mapB = (seg == 2) ? &p.tmB[1] : &p.tmB[0];
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+            const int k0 = kb * kBlockK;
+            uint8_t* a_dst = sA + stage * kABytes;
+            uint8_t* b_dst = sB + stage * b_bytes;
+            if (!p.a_mn) {
+              tma_load_2d(a_dst, mapA, &full_bar[stage], k0, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < kBlockM / 32; ++i)
+                tma_load_2d(a_dst + i * 4096, mapA, &full_bar[stage], m0 + 32 * i, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(b_dst, mapB, &full_bar[stage], k0, n0);
+            } else {
+              for (int i = 0; i < p.block_n / 32; ++i)
+                tma_load_2d(b_dst + i * 4096, mapB, &full_bar[stage], n0 + 32 * i, k0);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== MMA issuer (one thread) ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+        uint32_t accumulate = 0;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase, 3);
+            tc_fence_after();
+            const uint32_t a_start = smem_u32(sA + stage * kABytes) >> 4;
+            const uint32_t b_start = smem_u32(sB + stage * b_bytes) >> 4;
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t adesc = ((uint64_t)p.adesc_hi << 32) |
+                                     (uint64_t)(p.adesc_lo16 | ((a_start + k * p.a_kstep) & 0x3FFFu));
+              const uint64_t bdesc = ((uint64_t)p.bdesc_hi << 32) |
+                                     (uint64_t)(p.bdesc_lo16 | ((b_start + k * p.b_kstep) & 0x3FFFu));
+              umma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ============================== epilogue (4 warps = 128 TMEM lanes) ==============================
+    const int q = warp & 3;                   // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;            // row of the 128-row tile owned by this thread
+    const int epi_tid = threadIdx.x - 4 * 32;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles;
+      const int m_blk = (tile / p.n_tiles) % p.m_tiles;
+      const int split = tile / (p.n_tiles * p.m_tiles);
+      const int m0 = m_blk * kBlockM, n0 = n_blk * p.block_n;
+      const bool use_bias = (p.bias != nullptr) && (split == 0);
+      if (use_bias) {
+        for (int i = epi_tid; i < p.block_n; i += kEpiThreads) sBias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase, 4);
+      tc_fence_after();
+      named_bar_sync(1, kEpiThreads);  // bias tile visible
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols);
+      const int n_chunks = min(p.block_n, p.N - n0 + 31) / 32;  // skip chunks fully past N
+      for (int c = 0; c < n_chunks; ++c) {
+        float v[32];
+        tmem_ld32(t_row + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (c == n_chunks - 1) {
+          // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (use_bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += sBias[c * 32 + j];
+        }
+        // staging buffer(s): without aux double-buffer on c; with aux buffer 0 = activated, 1 = pre-activation
+        uint8_t* buf0 = sStage + (p.has_aux ? 0 : (c & 1)) * kStagingBytes;
+        uint8_t* buf1 = sStage + kStagingBytes;
+        if (epi_tid == 0) {
+          if (p.has_aux) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+        }
+        named_bar_sync(1, kEpiThreads);
+        if (p.has_aux) {
+          float4* d1 = reinterpret_cast<float4*>(buf1 + row * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d1[j ^ (row & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (p.act != 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+        }
+        {
+          float4* d0 = reinterpret_cast<float4*>(buf0 + row * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d0[j ^ (row & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, kEpiThreads);
+        if (epi_tid == 0) {
+          if (p.accumulate) tma_reduce_add_2d(&p.tmC, buf0, n0 + c * 32, m0);
+          else tma_store_2d(&p.tmC, buf0, n0 + c * 32, m0);
+          if (p.has_aux) tma_store_2d(&p.tmAux, buf1, n0 + c * 32, m0);
+          tma_store_commit();
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (epi_tid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// 2-D fp32 tensor map: dim0 = contiguous extent, dim1 = rows with pitch `pitch_elems`.
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t pitch_elems,
+                    uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return CAPDEC_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {pitch_elems * 4};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): ptr=%p dims=(%llu,%llu) pitch=%llu box=(%u,%u) swz=%d", (int)r,
+                   ptr, (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)pitch_elems, box0,
+                   box1, (int)swz);
+    return CAPDEC_ERR_CUDA;
+  }
+  return CAPDEC_OK;
+}
+
+// bring-up overrides for the MN-major encoding (see capdec_gemm_debug_mn_encoding)
+static int g_mn_layout = -1, g_mn_lbo = -1, g_mn_sbo = -1, g_mn_swz = -1;
+
+struct OperandEnc {
+  uint32_t desc_hi, desc_lo16, kstep;
+  CUtensorMapSwizzle swz;
+};
+static OperandEnc operand_encoding(bool mn_major) {
+  OperandEnc e;
+  uint32_t layout, lbo, sbo;
+  if (!mn_major) {
+    layout = 2;  // SWIZZLE_128B
+    lbo = 16;    // unused for swizzled K-major
+    sbo = 1024;  // 8 rows x 128 B
+    e.kstep = (kUmmaK * 4) >> 4;
+    e.swz = CU_TENSOR_MAP_SWIZZLE_128B;
+  } else {
+    layout = g_mn_layout >= 0 ? (uint32_t)g_mn_layout : 1;  // SWIZZLE_128B_BASE32B
+    lbo = g_mn_lbo >= 0 ? (uint32_t)g_mn_lbo : 4096;        // next 32-wide MN slab (32 k-rows x 128 B)
+    sbo = g_mn_sbo >= 0 ? (uint32_t)g_mn_sbo : 512;         // next group of 4 k-rows
+    e.kstep = (kUmmaK * 128) >> 4;                          // 8 k-rows x 128 B
+    e.swz = g_mn_swz >= 0 ? (CUtensorMapSwizzle)g_mn_swz : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  }
+  e.desc_lo16 = ((lbo >> 4) & 0x3FFFu) << 16;
+  e.desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) /* version = 1 (sm_100) */ | (layout << 29);
+  return e;
+}
+
+static void choose_tiling(int M, int N, int kb_total, int accumulate, int& block_n, int& splits) {
+  const int nsm = num_sms();
+  const int m_tiles = (M + kBlockM - 1) / kBlockM;
+  auto cost = [&](int bn, int s) {
+    const long tiles = (long)m_tiles * ((N + bn - 1) / bn) * s;
+    const long waves = (tiles + nsm - 1) / nsm;
+    const double kb = (double)((kb_total + s - 1) / s);
+    // per-tile time ~ k-blocks x (MMA cycles ~ bn, but small tiles are L2-feed bound) + epilogue
+    const double per_kb = (bn >= 256) ? 1.0 : (bn == 128 ? 0.62 : 0.40);
+    const double epi = (bn / 256.0) * 5.0;
+    return waves * (kb * per_kb + epi + 1.5);
+  };
+  int best_bn = block_n, best_s = splits;
+  double best = 1e30;
+  const int bns[3] = {256, 128, 64};
+  for (int bi = 0; bi < 3; ++bi) {
+    const int bn = bns[bi];
+    if (block_n > 0 && bn != block_n) continue;
+    const int smax = (splits > 0) ? splits : (accumulate ? 32 : 1);
+    for (int s = (splits > 0 ? splits : 1); s <= smax; ++s) {
+      if (s > 1 && kb_total / s < 4) break;
+      const double c = cost(bn, s);
+      if (c < best * 0.999) { best = c; best_bn = bn; best_s = s; }
+    }
+  }
+  block_n = best_bn > 0 ? best_bn : 128;
+  splits = best_s > 0 ? best_s : 1;
+}
+
+}  // namespace capdec
+
+using namespace capdec;
+
+extern "C" const char* capdec_last_error(void) { return g_err; }
+extern "C" int capdec_version(void) { return 100; }
+extern "C" int64_t capdec_launch_count(void) { return g_launches.load(); }
+
+extern "C" void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, int sbo_bytes, int tma_swizzle) {
+  g_mn_layout = layout_type;
+  g_mn_lbo = lbo_bytes;
+  g_mn_sbo = sbo_bytes;
+  g_mn_swz = tma_swizzle;
+}
+
+extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
+                                float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
+                                int accumulate, int precision, const float* a_lo, const float* b_lo, int block_n,
+                                int split_k, capdec_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CAPDEC_REQUIRE(A && B && C, "gemm: null operand");
+  CAPDEC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  CAPDEC_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0, "gemm: leading dims must be multiples of 4 (16 B TMA pitch): lda=%lld ldb=%lld ldc=%lld", (long long)lda, (long long)ldb, (long long)ldc);
+  CAPDEC_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0, "gemm: operands must be 16-byte aligned");
+  CAPDEC_REQUIRE(lda >= (a_major ? M : K) && ldb >= (b_major ? N : K) && ldc >= N, "gemm: leading dim smaller than extent");
+  CAPDEC_REQUIRE(precision == 0 || (a_lo && b_lo), "gemm: 3xTF32 needs a_lo and b_lo");
+  CAPDEC_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 256, "gemm: block_n must be 0/64/128/256");
+  CAPDEC_REQUIRE(act >= 0 && act <= 3, "gemm: bad act %d", act);
+  CAPDEC_REQUIRE(!aux || ((uintptr_t)aux % 16) == 0, "gemm: aux must be 16-byte aligned");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm_tf32_kernel)");
+    attr_set = true;
+  }
+
+  GemmDev p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.kb_total = (K + kBlockK - 1) / kBlockK;
+  int bn = block_n, splits = split_k;
+  if (!accumulate) splits = 1;
+  choose_tiling(M, N, p.kb_total, accumulate, bn, splits);
+  CAPDEC_REQUIRE(splits == 1 || (accumulate && act == 0 && !aux), "gemm: split-K needs accumulate=1, act=0, no aux");
+  p.block_n = bn;
+  p.splits = splits;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // drop empty splits
+  p.m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.n_tiles = (N + bn - 1) / bn;
+  p.nseg = precision ? 3 : 1;
+  p.act = act;
+  p.has_aux = aux ? 1 : 0;
+  p.accumulate = accumulate ? 1 : 0;
+  p.a_mn = a_major ? 1 : 0;
+  p.b_mn = b_major ? 1 : 0;
+  p.bias = bias;
+
+  const int b_bytes = bn * kBlockK * 4;
+  const int fixed = 2 * kStagingBytes + 256 * 4 + (2 * kMaxStages + 4) * 8 + 16 + 1024 /* alignment slack */;
+  int stages = (kSmemLimit - fixed) / (kABytes + b_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
+  const int smem_bytes = stages * (kABytes + b_bytes) + fixed;
+
+  const OperandEnc ea = operand_encoding(a_major != 0), eb = operand_encoding(b_major != 0);
+  p.adesc_hi = ea.desc_hi; p.adesc_lo16 = ea.desc_lo16; p.a_kstep = ea.kstep;
+  p.bdesc_hi = eb.desc_hi; p.bdesc_lo16 = eb.desc_lo16; p.b_kstep = eb.kstep;
+  // instruction descriptor: D=F32 (bits 4-5 = 1), A/B = TF32 (2) at bits 7-9 / 10-12, majors at 15/16,
+  // N>>3 at bits 17-22, M>>4 at bits 24-28
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_major ? 1 : 0) << 15) |
+            ((uint32_t)(b_major ? 1 : 0) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+
+  int rc;
+  for (int s = 0; s < p.nseg && s < 2; ++s) {
+    const float* a = s ? a_lo : A;
+    const float* b = s ? b_lo : B;
+    if (!a_major) rc = make_map(&p.tmA[s], a, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBlockK, kBlockM, ea.swz);
+    else rc = make_map(&p.tmA[s], a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, kBlockK, ea.swz);
+    if (rc) return rc;
+    if (!b_major) rc = make_map(&p.tmB[s], b, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBlockK, (uint32_t)bn, eb.swz);
+    else rc = make_map(&p.tmB[s], b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, kBlockK, eb.swz);
+    if (rc) return rc;
+  }
+  rc = make_map(&p.tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  if (aux) {
+    rc = make_map(&p.tmAux, aux, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  gemm_tf32_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  g_launches.fetch_add(1);
+  CAPDEC_LAUNCH_CHECK("gemm_tf32_kernel");
+  return CAPDEC_OK;
+}

@@ -1,0 +1,149 @@
+/*
+ * capdec_b200 — C ABI of the B200-native (sm_100a) CapDec training-step hot path.
+ *
+ * The reference (DavidHuji/CapDec) has no FFI: its hot path is Python calling torch / HuggingFace modules
+ * (train.py:345-354).  This header is the seam we introduce beneath the reference's Python class surface
+ * (SURVEY.md §8b): one entry point per fused op, plain device pointers + sizes + a cudaStream_t, no torch
+ * types.  Each declaration cites the reference code it replaces (file:line into DavidHuji/CapDec, `HF:` =
+ * transformers' modeling_gpt2.py / pytorch_utils.py / activations.py as called from train.py:259).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator); callee never allocates;
+ *   - launches are asynchronous on `stream` (pass torch.cuda.current_stream()); CUDA-graph capturable;
+ *   - return 0 on success, <0 on error; capdec_last_error() returns a thread-local message; nothing throws;
+ *   - all tensors fp32 row-major unless noted; token ids are int64 (as torch.int64 in train.py:57).
+ */
+#ifndef CAPDEC_B200_H_
+#define CAPDEC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* capdec_stream_t; /* cudaStream_t */
+
+const char* capdec_last_error(void);
+int capdec_version(void);
+/* number of kernels launched by this library since load (the bench's `gpu_launches` evidence) */
+int64_t capdec_launch_count(void);
+
+/* ---- GEMM: C[M,N] = act( A[M,K] . B[N,K]^T + bias[N] )  on tcgen05 (TF32 in, FP32 accumulate in TMEM) -----------
+ * Replaces every dense contraction on the path: nn.Linear (train.py:113-118, :124-126, :144-147, :241),
+ * HF Conv1D addmm (HF:pytorch_utils.py:97-123, used by c_attn/c_proj/c_fc HF:modeling_gpt2.py:106-107,232-233),
+ * lm_head (HF:modeling_gpt2.py:703-706) and all their autograd dgrad/wgrad products (train.py:351).
+ *   a_major / b_major: 0 = K-major  (A stored [M,K] / B stored [N,K], K contiguous, leading dim = row pitch)
+ *                      1 = MN-major (A stored [K,M] / B stored [K,N], M resp. N contiguous)
+ *   precision: 0 = 1xTF32 (perf mode), 1 = 3xTF32 split (fp32-grade, needs a_lo/b_lo = x - tf32_trunc(x),
+ *              produced by capdec_split_tf32)
+ *   act: 0 none, 1 gelu_new (HF:activations.py:59-66), 2 tanh (train.py:106 MLP act), 3 relu (train.py:121)
+ *   aux: optional second output receiving the PRE-activation (needed by backward); ld = ldc
+ *   accumulate: C += result (TMA reduce-add in L2); required for split_k > 1 (wgrad over M = B*T)
+ *   block_n / split_k: 0 = auto
+ */
+int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb, float* C,
+                     int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux, int accumulate,
+                     int precision, const float* a_lo, const float* b_lo, int block_n, int split_k,
+                     capdec_stream_t stream);
+
+/* debug/bring-up override of the UMMA shared-memory descriptor encoding for MN-major operands
+ * (layout_type, LBO bytes, SBO bytes, TMA swizzle enum); pass -1 to keep the default. Not used in production. */
+void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, int sbo_bytes, int tma_swizzle);
+
+/* fp32 CUDA-core GEMM with the same contract (verification kernel: exact fp32 FMA, no tensor cores). */
+int capdec_gemm_fp32_simt(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
+                          float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
+                          int accumulate, capdec_stream_t stream);
+
+/* hi = tf32_trunc(x) (low 13 mantissa bits cleared), lo = x - hi.  n % 4 == 0. */
+int capdec_split_tf32(const float* x, float* hi, float* lo, int64_t n, capdec_stream_t stream);
+
+/* ---- noise injection: train.py:27-39 (+ :18-24 uniform-ball variant) ---------------------------------------------
+ * out = normalize( normalize(x) [unless dont_norm] + noise + offset ), rows of length D.
+ * noise: if `noise` != NULL it is used verbatim (parity mode: caller supplies torch.randn*std); otherwise a
+ * Philox Gaussian N(0, variance) (uniform_ball=0) or uniform-ball of radius sqrt(variance) (uniform_ball=1).
+ * variance == 0 -> identity copy (train.py:28-29: no normalisation at all).  offset may be NULL ([D]). */
+int capdec_noise_injection(const float* x, float* out, int B, int D, float variance, const float* noise,
+                           const float* offset, int uniform_ball, int dont_norm, uint64_t seed, uint64_t step,
+                           capdec_stream_t stream);
+
+/* ---- embedding assembly: train.py:253-255 + HF:modeling_gpt2.py:579-585,612 ----------------------------------------
+ * h[b,t,:] = (t < P ? prefix_proj[b,t,:] : wte[tokens[b,t-P],:]) + wpe[t,:], then dropout(p) (train mode).
+ * tokens int64 [B,L]; prefix_proj [B,P,d]; h [B,P+L,d].  tokens may be NULL with L = 0 (inputs_embeds path). */
+int capdec_embed_fwd(const int64_t* tokens, const float* prefix_proj, const float* wte, const float* wpe, float* h,
+                     int B, int P, int L, int d, int vocab, float p_drop, uint64_t seed, uint32_t stream_id,
+                     capdec_stream_t stream);
+/* backward: d_wte[tokens] += dh (atomic scatter; may be NULL = frozen), d_wpe[t] += sum_b dh (may be NULL),
+ * d_prefix_proj[b,t<P] = dh (may be NULL). dropout mask regenerated. */
+int capdec_embed_bwd(const int64_t* tokens, const float* dh, float* d_prefix_proj, float* d_wte, float* d_wpe, int B,
+                     int P, int L, int d, int vocab, float p_drop, uint64_t seed, uint32_t stream_id,
+                     capdec_stream_t stream);
+
+/* ---- (residual add +) LayerNorm: nn.LayerNorm(eps=1e-5) HF:modeling_gpt2.py:252-254,505 ; train.py:184-188 -------
+ * fwd: r = h_in + dropout(y) (y may be NULL -> r = h_in);  x = LN(r)*gamma + beta;  stats[row] = (mean, rstd).
+ *      h_out receives r (may alias h_in; may be NULL when y == NULL).  rows x d, d % 128 == 0, d <= 1024. */
+int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out, float* x, float* stats, const float* gamma,
+                      const float* beta, int rows, int d, float eps, float p_drop, uint64_t seed, uint32_t stream_id,
+                      capdec_stream_t stream);
+/* bwd: dr = dh_res (running residual gradient, may be NULL = 0) + LN_bwd(dx; r, stats, gamma) -> written to dh_out
+ *      (may alias dh_res); if dy != NULL: dy = dropout_mask * dr (gradient of the branch output y).
+ *      dgamma/dbeta accumulated (+=) unless NULL (frozen GPT-2, train.py:276-284). */
+int capdec_add_ln_bwd(const float* dx, const float* r, const float* stats, const float* gamma, const float* dh_res,
+                      float* dh_out, float* dy, float* dgamma, float* dbeta, int rows, int d, float p_drop,
+                      uint64_t seed, uint32_t stream_id, capdec_stream_t stream);
+
+/* ---- attention core ----------------------------------------------------------------------------------------------
+ * GPT-2 (HF:modeling_gpt2.py:54-72,185-191): qkv [B,T,3*H*hd] (q|k|v thirds, heads contiguous hd slices),
+ * causal softmax(q k^T * scale) (dropout p on probabilities) v -> ctx [B,T,H*hd].
+ * Mapper (train.py:150-167): q [B,T,H*hd] from to_queries, kv [B,S,2*H*hd] from to_keys_values, no mask.
+ * Generic strided form: element (b,t,h,:) of q at q + b*q_bs + t*q_ts + h*hd.  lse [B,H,T] saved for backward.
+ * key_len: optional int32 [B] number of valid keys (padding mask, HF attention_mask); NULL = all valid. */
+int capdec_attention_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, int B, int H, int T,
+                         int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs,
+                         int64_t o_ts, float scale, int causal, const int32_t* key_len, float p_drop, uint64_t seed,
+                         uint32_t stream_id, capdec_stream_t stream);
+int capdec_attention_bwd(const float* q, const float* k, const float* v, const float* ctx, const float* dctx,
+                         const float* lse, float* dq, float* dk, float* dv, int B, int H, int T, int S, int hd,
+                         int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts,
+                         float scale, int causal, const int32_t* key_len, float p_drop, uint64_t seed,
+                         uint32_t stream_id, capdec_stream_t stream);
+
+/* ---- masked cross entropy: train.py:349-350 (nnf.cross_entropy(..., ignore_index=0), mean over targets != 0) -----
+ * logits [rows, ld] (ld >= V, padded pitch), targets int64 [rows].  loss_sum/n_valid are device scalars (float);
+ * capdec_ce_count must run first to fill n_valid.  fwd_bwd overwrites logits with
+ * dlogits = (softmax - onehot) * grad_scale / n_valid (zero rows where target == ignore_index) and adds the row
+ * losses into loss_sum.  If write_grad == 0 logits are left intact (validation, train.py:383-386). */
+int capdec_ce_count(const int64_t* targets, int64_t n, int64_t ignore_index, float* n_valid, capdec_stream_t stream);
+int capdec_ce_fwd_bwd(float* logits, int64_t ld, const int64_t* targets, int rows, int V, int64_t ignore_index,
+                      const float* n_valid, float grad_scale, float* loss_sum, int write_grad,
+                      capdec_stream_t stream);
+
+/* ---- small fused elementwise / reduction ops ----------------------------------------------------------------------
+ * colsum: out[n] += sum_m x[m,n]  (bias gradients of every Linear/Conv1D; autograd of addmm bias) */
+int capdec_colsum_acc(const float* x, int64_t ld, float* out, int M, int N, capdec_stream_t stream);
+/* dx = dy * act'(.) ; act: 1 gelu_new (pre = pre-activation), 2 tanh (pre = activated output a: 1-a^2),
+ * 3 relu (pre = activated output) */
+int capdec_act_bwd(const float* dy, const float* pre, float* dx, int64_t n, int act, capdec_stream_t stream);
+/* row gather / scatter of d-wide rows: dst[i,:] = src[map(i),:] with map(i) = (i / L)*T + off + i % L
+ * (logits slice [:, P-1:-1] of train.py:349, expressed on the hidden states) */
+int capdec_rows_gather(const float* src, float* dst, int B, int T, int L, int off, int d, capdec_stream_t stream);
+int capdec_rows_scatter(const float* src, float* dst, int B, int T, int L, int off, int d, capdec_stream_t stream);
+/* TransformerMapper input assembly (train.py:230-233): x[b, s<C] = lin[b, s], x[b, C+s] = prefix_const[s] */
+int capdec_mapper_concat_fwd(const float* lin, const float* prefix_const, float* x, int B, int C, int P, int d,
+                             capdec_stream_t stream);
+int capdec_mapper_concat_bwd(const float* dx, float* dlin, float* dprefix_const, int B, int C, int P, int d,
+                             capdec_stream_t stream);
+
+/* ---- AdamW, HuggingFace-4.24 semantics (train.py:326,352) ----------------------------------------
+ * m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps) ; p -= lr*wd*p.
+ * grad_scale multiplies g first (1/world after the NCCL sum).  lr is read from a device scalar so that the
+ * step is CUDA-graph replayable; `t` likewise (float step count).  zero_grad != 0 clears g in the same pass. */
+int capdec_adamw_step(float* p, float* g, float* m, float* v, int64_t n, const float* lr_dev, const float* t_dev,
+                      float beta1, float beta2, float eps, float weight_decay, float grad_scale, int zero_grad,
+                      capdec_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPDEC_B200_H_ */
