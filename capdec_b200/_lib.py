@@ -44,7 +44,7 @@ SIGNATURES = {
     "capdec_rows_scatter": [_p, _p, _i, _i, _i, _i, _i, _p],
     "capdec_mapper_concat_fwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "capdec_mapper_concat_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
-    "capdec_adamw_step": [_p, _p, _p, _p, _i64, _p, _p, _f, _f, _f, _f, _f, _i, _p],
+    "capdec_adamw_step": [_p, _p, _p, _p, _i64, _p, _p, _f, _f, _f, _f, _p, _i, _p],
 }
 _RESTYPES = {"capdec_last_error": C.c_char_p, "capdec_launch_count": C.c_int64, "capdec_gemm_debug_mn_encoding": None}
 

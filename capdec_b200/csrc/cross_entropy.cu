@@ -1,0 +1,126 @@
+// capdec_b200 — masked cross entropy over the caption tokens (train.py:349-350):
+//   loss = mean_{targets != ignore} ( logsumexp(logits_row) - logits_row[target] ), plus dlogits in the same kernel.
+// HBM-bound: one CTA per logits row (V = 50257 fp32 = 201 KB: pass 2 re-reads the row from L2), 128-bit loads,
+// online max / sum-exp, warp-shuffle + smem block reduction.
+#include "../../include/capdec_b200.h"
+#include "common.cuh"
+
+namespace capdec {
+
+__global__ void ce_count_kernel(const int64_t* __restrict__ targets, int64_t n, int64_t ignore, float* __restrict__ out) {
+  __shared__ int s[32];
+  int c = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    c += (targets[i] != ignore);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    c = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (threadIdx.x == 0 && c) atomicAdd(out, (float)c);
+  }
+}
+
+constexpr int kCeThreads = 512;
+
+__device__ __forceinline__ void online_update(float& m, float& s, float x) {
+  if (x > m) { s = s * __expf(m - x) + 1.0f; m = x; } else { s += __expf(x - m); }
+}
+
+__global__ void __launch_bounds__(kCeThreads) ce_kernel(float* __restrict__ logits, int64_t ld,
+                                                        const int64_t* __restrict__ targets, int V, int64_t ignore,
+                                                        const float* __restrict__ n_valid, float grad_scale,
+                                                        float* __restrict__ loss_sum, int write_grad) {
+  __shared__ float s_m[kCeThreads / 32], s_s[kCeThreads / 32];
+  __shared__ float s_bm, s_bs;
+  const int row = blockIdx.x;
+  float* x = logits + (size_t)row * ld;
+  const int64_t tgt = targets[row];
+  const int v4 = V >> 2;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  if (tgt == ignore || tgt < 0 || tgt >= V) {  // ignored row: zero gradient, no loss (ignore_index semantics)
+    if (write_grad) {
+      for (int i = threadIdx.x; i < v4; i += kCeThreads) x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = (v4 << 2) + threadIdx.x; i < V; i += kCeThreads) x[i] = 0.f;
+    }
+    return;
+  }
+  float m = -INFINITY, s = 0.f;
+  for (int i = threadIdx.x; i < v4; i += kCeThreads) {
+    const float4 v = x4[i];
+    online_update(m, s, v.x); online_update(m, s, v.y); online_update(m, s, v.z); online_update(m, s, v.w);
+  }
+  for (int i = (v4 << 2) + threadIdx.x; i < V; i += kCeThreads) online_update(m, s, x[i]);
+  // combine (m, s) pairs across the warp, then across warps
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+    const float nm = fmaxf(m, om);
+    s = (nm == -INFINITY) ? 0.f : s * __expf(m - nm) + os * __expf(om - nm);
+    m = nm;
+  }
+  if ((threadIdx.x & 31) == 0) { s_m[threadIdx.x >> 5] = m; s_s[threadIdx.x >> 5] = s; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < kCeThreads / 32 ? s_m[threadIdx.x] : -INFINITY;
+    s = threadIdx.x < kCeThreads / 32 ? s_s[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+      const float nm = fmaxf(m, om);
+      s = (nm == -INFINITY) ? 0.f : s * __expf(m - nm) + os * __expf(om - nm);
+      m = nm;
+    }
+    if (threadIdx.x == 0) { s_bm = m; s_bs = s; }
+  }
+  __syncthreads();
+  const float bm = s_bm, bs = s_bs;
+  const float xt = x[tgt];
+  __syncthreads();  // everyone has read x[tgt] before pass 2 overwrites it
+  if (threadIdx.x == 0) atomicAdd(loss_sum, (bm + logf(bs)) - xt);
+  if (!write_grad) return;
+  const float sc = grad_scale / (n_valid ? *n_valid : 1.0f);
+  const float inv = sc / bs;
+  for (int i = threadIdx.x; i < v4; i += kCeThreads) {
+    float4 v = x4[i];
+    v.x = __expf(v.x - bm) * inv; v.y = __expf(v.y - bm) * inv; v.z = __expf(v.z - bm) * inv; v.w = __expf(v.w - bm) * inv;
+    const int base = i << 2;
+    if ((int)tgt >= base && (int)tgt < base + 4) {
+      float* pv = reinterpret_cast<float*>(&v);
+      pv[(int)tgt - base] -= sc;
+    }
+    x4[i] = v;
+  }
+  for (int i = (v4 << 2) + threadIdx.x; i < V; i += kCeThreads) x[i] = __expf(x[i] - bm) * inv - (i == (int)tgt ? sc : 0.f);
+}
+
+}  // namespace capdec
+
+using namespace capdec;
+
+extern "C" int capdec_ce_count(const int64_t* targets, int64_t n, int64_t ignore_index, float* n_valid,
+                               capdec_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CAPDEC_REQUIRE(targets && n_valid && n > 0, "ce_count: bad arguments");
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 64) blocks = 64;
+  ce_count_kernel<<<blocks, 256, 0, stream>>>(targets, n, ignore_index, n_valid);
+  g_launches.fetch_add(1);
+  CAPDEC_LAUNCH_CHECK("ce_count_kernel");
+  return CAPDEC_OK;
+}
+
+extern "C" int capdec_ce_fwd_bwd(float* logits, int64_t ld, const int64_t* targets, int rows, int V,
+                                 int64_t ignore_index, const float* n_valid, float grad_scale, float* loss_sum,
+                                 int write_grad, capdec_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CAPDEC_REQUIRE(logits && targets && loss_sum && rows > 0 && V > 0, "ce: bad arguments");
+  CAPDEC_REQUIRE(ld >= V && ld % 4 == 0 && ((uintptr_t)logits % 16) == 0, "ce: logits pitch must be a multiple of 4 floats and 16-byte aligned");
+  ce_kernel<<<rows, kCeThreads, 0, stream>>>(logits, ld, targets, V, ignore_index, n_valid, grad_scale, loss_sum, write_grad);
+  g_launches.fetch_add(1);
+  CAPDEC_LAUNCH_CHECK("ce_kernel");
+  return CAPDEC_OK;
+}

@@ -77,14 +77,22 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
   }
 }
 
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 __global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo,
                                   int64_t n4) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    // hi = RN_tf32(x), lo = RN_tf32(x - hi): both are exact TF32 values, so the tensor core's operand truncation
+    // is a no-op and the split error is unbiased (|x - hi - lo| <= 2^-22 |x|).
     float4 v = x[i], h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+    h.x = rn_tf32(v.x); l.x = rn_tf32(v.x - h.x);
+    h.y = rn_tf32(v.y); l.y = rn_tf32(v.y - h.y);
+    h.z = rn_tf32(v.z); l.z = rn_tf32(v.z - h.z);
+    h.w = rn_tf32(v.w); l.w = rn_tf32(v.w - h.w);
     hi[i] = h;
     lo[i] = l;
   }

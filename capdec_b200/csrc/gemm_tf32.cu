@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
     const int epi_tid = threadIdx.x - 4 * 32;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t store_idx = 0;  // running chunk counter: staging buffers alternate ACROSS tiles too
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles;
       const int m_blk = (tile / p.n_tiles) % p.m_tiles;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
           for (int j = 0; j < 32; ++j) v[j] += sBias[c * 32 + j];
         }
         // staging buffer(s): without aux double-buffer on c; with aux buffer 0 = activated, 1 = pre-activation
-        uint8_t* buf0 = sStage + (p.has_aux ? 0 : (c & 1)) * kStagingBytes;
+        uint8_t* buf0 = sStage + (p.has_aux ? 0 : (store_idx++ & 1)) * kStagingBytes;
         uint8_t* buf1 = sStage + kStagingBytes;
         if (epi_tid == 0) {
           if (p.has_aux) tma_store_wait_read<0>(); else tma_store_wait_read<1>();

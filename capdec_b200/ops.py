@@ -1,0 +1,235 @@
+"""Torch-tensor wrappers over the C-ABI (include/capdec_b200.h).  Plumbing only: every function hands raw device
+pointers of caller-owned tensors to a hand-written sm_100a kernel on torch's current stream.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_GELU_NEW, ACT_TANH, ACT_RELU = 0, 1, 2, 3
+
+# GEMM arithmetic: "tf32" = 1xTF32 tcgen05 (perf), "tf32x3" = 3xTF32 split on tcgen05 (fp32-grade parity mode),
+# "fp32" = CUDA-core FFMA verification kernel.
+_PRECISION = "tf32"
+
+
+def set_precision(mode: str) -> None:
+    global _PRECISION
+    if mode not in ("tf32", "tf32x3", "fp32"):
+        raise ValueError(f"unknown precision mode {mode!r}")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
+    if not t.is_cuda:
+        raise _lib.CapdecError(f"{name} must be a CUDA tensor: capdec_b200 has no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _rowmajor(t: torch.Tensor, name: str) -> int:
+    """2-D tensor with unit inner stride; returns its leading dimension (row pitch in elements)."""
+    _chk(t, name)
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f"{name} must be 2-D with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _split(t: torch.Tensor):
+    """hi/lo TF32 split of a 2-D operand into fresh zero-padded buffers with a 16-byte-aligned pitch."""
+    rows, cols = t.shape
+    ld = (cols + 3) // 4 * 4
+    src = torch.zeros(rows, ld, device=t.device, dtype=torch.float32)
+    src[:, :cols].copy_(t)
+    hi, lo = torch.empty_like(src), torch.empty_like(src)
+    _lib.check(_lib.load().capdec_split_tf32(src.data_ptr(), hi.data_ptr(), lo.data_ptr(), src.numel(), _stream()),
+               "split_tf32")
+    return hi[:, :cols], lo[:, :cols]
+
+
+def gemm(A: torch.Tensor, a_major: int, B: torch.Tensor, b_major: int, C: torch.Tensor, M: int, N: int, K: int, *,
+         bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, aux: Optional[torch.Tensor] = None,
+         accumulate: bool = False, block_n: int = 0, split_k: int = 0, precision: Optional[str] = None) -> None:
+    """C[M,N] (+)= act(A . B^T + bias).  a_major/b_major: 0 = stored [M|N, K], 1 = stored [K, M|N]."""
+    lib = _lib.load()
+    lda, ldb, ldc = _rowmajor(A, "A"), _rowmajor(B, "B"), _rowmajor(C, "C")
+    ea = (K, M) if a_major else (M, K)
+    eb = (K, N) if b_major else (N, K)
+    if tuple(A.shape) != ea or tuple(B.shape) != eb or tuple(C.shape) != (M, N):
+        raise ValueError(f"gemm shape mismatch: A{tuple(A.shape)} expected {ea}, B{tuple(B.shape)} expected {eb}, "
+                         f"C{tuple(C.shape)} expected {(M, N)}")
+    if bias is not None:
+        _chk(bias, "bias")
+    if aux is not None and _rowmajor(aux, "aux") != ldc:
+        raise ValueError("aux must share C's leading dimension")
+    mode = precision or _PRECISION
+    if mode == "fp32":
+        rc = lib.capdec_gemm_fp32_simt(A.data_ptr(), a_major, lda, B.data_ptr(), b_major, ldb, C.data_ptr(), ldc, M, N,
+                                       K, _ptr(bias), act, _ptr(aux), int(accumulate), _stream())
+        _lib.check(rc, "gemm_fp32_simt")
+        return
+    if mode == "tf32x3":
+        ah, al = _split(A)
+        bh, bl = _split(B)
+        rc = lib.capdec_gemm_tf32(ah.data_ptr(), a_major, ah.stride(0), bh.data_ptr(), b_major, bh.stride(0),
+                                  C.data_ptr(), ldc, M, N, K, _ptr(bias), act, _ptr(aux), int(accumulate), 1,
+                                  al.data_ptr(), bl.data_ptr(), block_n, split_k, _stream())
+    else:
+        rc = lib.capdec_gemm_tf32(A.data_ptr(), a_major, lda, B.data_ptr(), b_major, ldb, C.data_ptr(), ldc, M, N, K,
+                                  _ptr(bias), act, _ptr(aux), int(accumulate), 0, None, None, block_n, split_k,
+                                  _stream())
+    _lib.check(rc, "gemm_tf32")
+
+
+# ---- layer helpers: `layout` is "conv1d" (HF Conv1D weight [in,out]) or "linear" (nn.Linear weight [out,in]) --------
+def linear_fwd(x, W, layout, bias, out, act=ACT_NONE, aux=None):
+    M, K = x.shape
+    N = out.shape[1]
+    gemm(x, 0, W, 1 if layout == "conv1d" else 0, out, M, N, K, bias=bias, act=act, aux=aux)
+
+
+def linear_dgrad(dy, W, layout, dx, accumulate=False):
+    M, K = dy.shape  # K = out features (reduction)
+    N = dx.shape[1]
+    gemm(dy, 0, W, 0 if layout == "conv1d" else 1, dx, M, N, K, accumulate=accumulate)
+
+
+def linear_wgrad(x, dy, dW, layout, dbias=None):
+    rows = x.shape[0]
+    if layout == "conv1d":  # dW[in,out] += x^T dy
+        gemm(x, 1, dy, 1, dW, x.shape[1], dy.shape[1], rows, accumulate=True)
+    else:  # dW[out,in] += dy^T x
+        gemm(dy, 1, x, 1, dW, dy.shape[1], x.shape[1], rows, accumulate=True)
+    if dbias is not None:
+        colsum_acc(dy, dbias)
+
+
+def noise_injection(x, out, variance, noise=None, offset=None, uniform_ball=False, dont_norm=False, seed=0, step=0):
+    _chk(x, "x"); _chk(out, "out")
+    B, D = x.shape
+    rc = _lib.load().capdec_noise_injection(x.data_ptr(), out.data_ptr(), B, D, float(variance), _ptr(noise),
+                                            _ptr(offset), int(uniform_ball), int(dont_norm), seed, step, _stream())
+    _lib.check(rc, "noise_injection")
+
+
+def embed_fwd(tokens, prefix_proj, wte, wpe, h, B, P, L, p_drop=0.0, seed=0, stream_id=0):
+    d = h.shape[-1]
+    if tokens is not None:
+        _chk(tokens, "tokens", torch.int64)
+    rc = _lib.load().capdec_embed_fwd(_ptr(tokens), _ptr(prefix_proj), _ptr(wte), wpe.data_ptr(), h.data_ptr(), B, P, L,
+                                      d, wte.shape[0] if wte is not None else 0, float(p_drop), seed, stream_id,
+                                      _stream())
+    _lib.check(rc, "embed_fwd")
+
+
+def embed_bwd(tokens, dh, d_prefix_proj, d_wte, d_wpe, B, P, L, vocab, p_drop=0.0, seed=0, stream_id=0):
+    d = dh.shape[-1]
+    rc = _lib.load().capdec_embed_bwd(_ptr(tokens), dh.data_ptr(), _ptr(d_prefix_proj), _ptr(d_wte), _ptr(d_wpe), B, P,
+                                      L, d, vocab, float(p_drop), seed, stream_id, _stream())
+    _lib.check(rc, "embed_bwd")
+
+
+def add_ln_fwd(h_in, y, h_out, x, stats, gamma, beta, eps=1e-5, p_drop=0.0, seed=0, stream_id=0):
+    rows, d = x.shape
+    rc = _lib.load().capdec_add_ln_fwd(h_in.data_ptr(), _ptr(y), _ptr(h_out), x.data_ptr(), stats.data_ptr(),
+                                       gamma.data_ptr(), beta.data_ptr(), rows, d, eps, float(p_drop), seed, stream_id,
+                                       _stream())
+    _lib.check(rc, "add_ln_fwd")
+
+
+def add_ln_bwd(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma, dbeta, p_drop=0.0, seed=0, stream_id=0):
+    rows, d = dx.shape
+    rc = _lib.load().capdec_add_ln_bwd(dx.data_ptr(), r.data_ptr(), stats.data_ptr(), gamma.data_ptr(), _ptr(dh_res),
+                                       dh_out.data_ptr(), _ptr(dy), _ptr(dgamma), _ptr(dbeta), rows, d, float(p_drop),
+                                       seed, stream_id, _stream())
+    _lib.check(rc, "add_ln_bwd")
+
+
+def attention_fwd(q, k, v, ctx, lse, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal,
+                  key_len=None, p_drop=0.0, seed=0, stream_id=0):
+    rc = _lib.load().capdec_attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), _ptr(lse), B, H, T,
+                                          S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, float(scale), int(causal),
+                                          _ptr(key_len), float(p_drop), seed, stream_id, _stream())
+    _lib.check(rc, "attention_fwd")
+
+
+def attention_bwd(q, k, v, ctx, dctx, lse, dq, dk, dv, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale,
+                  causal, key_len=None, p_drop=0.0, seed=0, stream_id=0):
+    rc = _lib.load().capdec_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), dctx.data_ptr(),
+                                          lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, T, S, hd,
+                                          q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, float(scale), int(causal),
+                                          _ptr(key_len), float(p_drop), seed, stream_id, _stream())
+    _lib.check(rc, "attention_bwd")
+
+
+def ce_count(targets, n_valid, ignore_index=0):
+    _chk(targets, "targets", torch.int64)
+    _lib.check(_lib.load().capdec_ce_count(targets.data_ptr(), targets.numel(), ignore_index, n_valid.data_ptr(),
+                                           _stream()), "ce_count")
+
+
+def ce_fwd_bwd(logits, targets, V, loss_sum, n_valid=None, grad_scale=1.0, ignore_index=0, write_grad=True):
+    ld = _rowmajor(logits, "logits")
+    _chk(targets, "targets", torch.int64)
+    rc = _lib.load().capdec_ce_fwd_bwd(logits.data_ptr(), ld, targets.data_ptr(), logits.shape[0], V, ignore_index,
+                                       _ptr(n_valid), float(grad_scale), loss_sum.data_ptr(), int(write_grad),
+                                       _stream())
+    _lib.check(rc, "ce_fwd_bwd")
+
+
+def colsum_acc(x, out):
+    ld = _rowmajor(x, "x")
+    M, N = x.shape
+    _lib.check(_lib.load().capdec_colsum_acc(x.data_ptr(), ld, out.data_ptr(), M, N, _stream()), "colsum_acc")
+
+
+def act_bwd(dy, pre, dx, act):
+    _lib.check(_lib.load().capdec_act_bwd(dy.data_ptr(), pre.data_ptr(), dx.data_ptr(), dy.numel(), act, _stream()),
+               "act_bwd")
+
+
+def rows_gather(src, dst, B, T, L, off):
+    d = src.shape[-1]
+    _lib.check(_lib.load().capdec_rows_gather(src.data_ptr(), dst.data_ptr(), B, T, L, off, d, _stream()), "rows_gather")
+
+
+def rows_scatter(src, dst, B, T, L, off):
+    d = src.shape[-1]
+    _lib.check(_lib.load().capdec_rows_scatter(src.data_ptr(), dst.data_ptr(), B, T, L, off, d, _stream()),
+               "rows_scatter")
+
+
+def mapper_concat_fwd(lin, prefix_const, x, B, C, P):
+    d = x.shape[-1]
+    _lib.check(_lib.load().capdec_mapper_concat_fwd(lin.data_ptr(), prefix_const.data_ptr(), x.data_ptr(), B, C, P, d,
+                                                    _stream()), "mapper_concat_fwd")
+
+
+def mapper_concat_bwd(dx, dlin, dprefix_const, B, C, P):
+    d = dx.shape[-1]
+    _lib.check(_lib.load().capdec_mapper_concat_bwd(dx.data_ptr(), dlin.data_ptr(), _ptr(dprefix_const), B, C, P, d,
+                                                    _stream()), "mapper_concat_bwd")
+
+
+def adamw_step(p, g, m, v, lr_dev, t_dev, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0, grad_denom=None,
+               zero_grad=False):
+    rc = _lib.load().capdec_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                       lr_dev.data_ptr(), t_dev.data_ptr(), beta1, beta2, eps, weight_decay,
+                                       _ptr(grad_denom), int(zero_grad), _stream())
+    _lib.check(rc, "adamw_step")

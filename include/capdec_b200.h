@@ -35,8 +35,8 @@ int64_t capdec_launch_count(void);
  * lm_head (HF:modeling_gpt2.py:703-706) and all their autograd dgrad/wgrad products (train.py:351).
  *   a_major / b_major: 0 = K-major  (A stored [M,K] / B stored [N,K], K contiguous, leading dim = row pitch)
  *                      1 = MN-major (A stored [K,M] / B stored [K,N], M resp. N contiguous)
- *   precision: 0 = 1xTF32 (perf mode), 1 = 3xTF32 split (fp32-grade, needs a_lo/b_lo = x - tf32_trunc(x),
- *              produced by capdec_split_tf32)
+ *   precision: 0 = 1xTF32 (perf mode), 1 = 3xTF32 split (fp32-grade, A/B must then be the `hi` parts and a_lo/b_lo the `lo`
+ *              parts produced by capdec_split_tf32)
  *   act: 0 none, 1 gelu_new (HF:activations.py:59-66), 2 tanh (train.py:106 MLP act), 3 relu (train.py:121)
  *   aux: optional second output receiving the PRE-activation (needed by backward); ld = ldc
  *   accumulate: C += result (TMA reduce-add in L2); required for split_k > 1 (wgrad over M = B*T)
@@ -56,7 +56,7 @@ int capdec_gemm_fp32_simt(const float* A, int a_major, int64_t lda, const float*
                           float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
                           int accumulate, capdec_stream_t stream);
 
-/* hi = tf32_trunc(x) (low 13 mantissa bits cleared), lo = x - hi.  n % 4 == 0. */
+/* hi = RN_tf32(x), lo = RN_tf32(x - hi) (both exact TF32 values).  n % 4 == 0. */
 int capdec_split_tf32(const float* x, float* hi, float* lo, int64_t n, capdec_stream_t stream);
 
 /* ---- noise injection: train.py:27-39 (+ :18-24 uniform-ball variant) ---------------------------------------------
@@ -111,9 +111,10 @@ int capdec_attention_bwd(const float* q, const float* k, const float* v, const f
 
 /* ---- masked cross entropy: train.py:349-350 (nnf.cross_entropy(..., ignore_index=0), mean over targets != 0) -----
  * logits [rows, ld] (ld >= V, padded pitch), targets int64 [rows].  loss_sum/n_valid are device scalars (float);
- * capdec_ce_count must run first to fill n_valid.  fwd_bwd overwrites logits with
- * dlogits = (softmax - onehot) * grad_scale / n_valid (zero rows where target == ignore_index) and adds the row
- * losses into loss_sum.  If write_grad == 0 logits are left intact (validation, train.py:383-386). */
+ * capdec_ce_count adds the number of non-ignored targets to *n_valid.  fwd_bwd overwrites logits with
+ * dlogits = (softmax - onehot) * grad_scale / *n_valid (zero rows where target == ignore_index; n_valid == NULL
+ * means 1, i.e. sum-reduced gradients for exact data-parallel averaging) and adds the row losses into loss_sum.
+ * If write_grad == 0 logits are left intact (validation, train.py:383-386). */
 int capdec_ce_count(const int64_t* targets, int64_t n, int64_t ignore_index, float* n_valid, capdec_stream_t stream);
 int capdec_ce_fwd_bwd(float* logits, int64_t ld, const int64_t* targets, int rows, int V, int64_t ignore_index,
                       const float* n_valid, float grad_scale, float* loss_sum, int write_grad,
@@ -136,12 +137,13 @@ int capdec_mapper_concat_bwd(const float* dx, float* dlin, float* dprefix_const,
                              capdec_stream_t stream);
 
 /* ---- AdamW, HuggingFace-4.24 semantics (train.py:326,352) ----------------------------------------
- * m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps) ; p -= lr*wd*p.
- * grad_scale multiplies g first (1/world after the NCCL sum).  lr is read from a device scalar so that the
- * step is CUDA-graph replayable; `t` likewise (float step count).  zero_grad != 0 clears g in the same pass. */
+ * g' = g / *grad_denom_dev (NULL = 1: e.g. the all-reduced count of non-ignored targets) ;
+ * m = b1 m + (1-b1) g' ; v = b2 v + (1-b2) g'^2 ; p -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps) ;
+ * p -= lr*wd*p.  lr and the step count t are read from device scalars so that the step is CUDA-graph
+ * replayable.  zero_grad != 0 clears g in the same pass (train.py:354). */
 int capdec_adamw_step(float* p, float* g, float* m, float* v, int64_t n, const float* lr_dev, const float* t_dev,
-                      float beta1, float beta2, float eps, float weight_decay, float grad_scale, int zero_grad,
-                      capdec_stream_t stream);
+                      float beta1, float beta2, float eps, float weight_decay, const float* grad_denom_dev,
+                      int zero_grad, capdec_stream_t stream);
 
 #ifdef __cplusplus
 }

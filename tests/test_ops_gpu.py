@@ -1,0 +1,372 @@
+"""Kernel unit tests (GPU): every C-ABI op against a plain torch restatement of the same op on the same inputs.
+GEMM tolerances: 1xTF32 vs the TF32-truncated fp64 product (bit-level operand semantics), 3xTF32 / fp32 vs fp64.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from capdec_b200 import ops as _ops
+    _ops.set_precision("tf32")
+    return _ops
+
+
+def trunc_tf32(x):
+    return (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+def make_ab(M, N, K, a_major, b_major, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pad = lambda n: (n + 3) // 4 * 4
+    A = (torch.randn(K, pad(M), device="cuda", generator=g)[:, :M] if a_major
+         else torch.randn(M, pad(K), device="cuda", generator=g)[:, :K])
+    B = (torch.randn(K, pad(N), device="cuda", generator=g)[:, :N] if b_major
+         else torch.randn(N, pad(K), device="cuda", generator=g)[:, :K])
+    return A, (A.t() if a_major else A), B, (B.t() if b_major else B)
+
+
+def new_c(M, N):
+    return torch.full((M, (N + 3) // 4 * 4), float("nan"), device="cuda")[:, :N]
+
+
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(128, 256, 32), (200, 300, 100), (1600, 2304, 768), (384, 50257, 64),
+                                   (12800, 768, 96), (3000, 1100, 40), (5000, 2304, 64)])
+def test_gemm_tf32_matches_truncated_product(ops, shape, a_major, b_major):
+    M, N, K = shape
+    A, Al, B, Bl = make_ab(M, N, K, a_major, b_major)
+    C = new_c(M, N)
+    ops.gemm(A, a_major, B, b_major, C, M, N, K)
+    ref = trunc_tf32(Al).double() @ trunc_tf32(Bl).double().t()
+    err = (C.double() - ref).abs()
+    bad = (err > 1e-4 * ref.abs().max()).nonzero()
+    assert bad.numel() == 0, f"{bad.shape[0]} bad elements, first {bad[:5].tolist()}, rows {bad[:,0].min().item()}..{bad[:,0].max().item()} cols {bad[:,1].min().item()}..{bad[:,1].max().item()}"
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_block_n_variants(ops, bn):
+    M, N, K = 2500, 1000, 200
+    A, Al, B, Bl = make_ab(M, N, K, 0, 1)
+    C = new_c(M, N)
+    ops.gemm(A, 0, B, 1, C, M, N, K, block_n=bn)
+    ref = trunc_tf32(Al).double() @ trunc_tf32(Bl).double().t()
+    assert (C.double() - ref).abs().max() < 1e-4 * ref.abs().max()
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_gemm_epilogue_bias_act_aux(ops, act):
+    M, N, K = 700, 900, 256
+    A, Al, B, Bl = make_ab(M, N, K, 0, 0)
+    bias = torch.randn(N, device="cuda")
+    C, aux = new_c(M, N), new_c(M, N)
+    ops.gemm(A, 0, B, 0, C, M, N, K, bias=bias, act=act, aux=aux)
+    pre = (trunc_tf32(Al).double() @ trunc_tf32(Bl).double().t() + bias.double())
+    f = {0: lambda x: x, 1: lambda x: torch.nn.functional.gelu(x, approximate="tanh"), 2: torch.tanh, 3: torch.relu}[act]
+    assert (aux.double() - pre).abs().max() < 1e-3
+    assert (C.double() - f(pre)).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("split", [0, 1, 3, 8])
+def test_gemm_accumulate_splitk(ops, split):
+    M, N, K = 768, 2304, 4096
+    A, Al, B, Bl = make_ab(M, N, K, 1, 1)
+    C0 = torch.randn(M, N, device="cuda")
+    C = C0.clone()
+    ops.gemm(A, 1, B, 1, C, M, N, K, accumulate=True, split_k=split)
+    ref = C0.double() + trunc_tf32(Al).double() @ trunc_tf32(Bl).double().t()
+    assert (C.double() - ref).abs().max() < 2e-4 * ref.abs().max()
+
+
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 4e-6), ("fp32", 3e-6)])
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 1)])
+def test_gemm_fp32_grade_modes(ops, mode, tol, a_major, b_major):
+    M, N, K = 512, 770, 768
+    A, Al, B, Bl = make_ab(M, N, K, a_major, b_major)
+    C = new_c(M, N)
+    ops.gemm(A, a_major, B, b_major, C, M, N, K, precision=mode)
+    ref = Al.double() @ Bl.double().t()
+    rel = (C.double() - ref).abs().max() / ref.abs().max()
+    assert rel < tol, f"{mode}: rel err {rel:.3e}"
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    from capdec_b200._lib import CapdecError
+    A = torch.randn(64, 30, device="cuda")  # pitch 30 floats is not 16-byte aligned
+    B = torch.randn(64, 30, device="cuda")
+    C = torch.empty(64, 64, device="cuda")
+    with pytest.raises(CapdecError):
+        ops.gemm(A, 0, B, 0, C, 64, 64, 30)
+    with pytest.raises(CapdecError):
+        ops.gemm(A.cpu(), 0, B, 0, C, 64, 64, 30)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def ref_noise_injection(x, variance, noise, offset=None, dont_norm=False):
+    """train.py:27-39 with the Gaussian draw passed in."""
+    if variance == 0.0:
+        return x
+    if not dont_norm:
+        x = torch.nn.functional.normalize(x, dim=1)
+    x = x + noise
+    if offset is not None:
+        x = x + offset
+    return torch.nn.functional.normalize(x, dim=1)
+
+
+@pytest.mark.parametrize("D", [512, 640])
+@pytest.mark.parametrize("dont_norm,with_offset", [(False, False), (True, False), (False, True)])
+def test_noise_injection_with_supplied_noise(ops, D, dont_norm, with_offset):
+    B = 37
+    x = torch.randn(B, D, device="cuda") * 3
+    noise = torch.randn(B, D, device="cuda") * math.sqrt(0.016)
+    offset = torch.randn(1, D, device="cuda") * 0.1 if with_offset else None
+    out = torch.empty_like(x)
+    ops.noise_injection(x, out, 0.016, noise=noise, offset=offset, dont_norm=dont_norm)
+    ref = ref_noise_injection(x, 0.016, noise, offset, dont_norm)
+    assert (out - ref).abs().max() < 2e-6
+    # variance == 0 -> identity, NOT normalised (train.py:28-29)
+    ops.noise_injection(x, out, 0.0)
+    assert torch.equal(out, x)
+
+
+def test_noise_injection_philox_statistics(ops):
+    B, D = 4096, 512
+    x = torch.nn.functional.normalize(torch.randn(B, D, device="cuda"), dim=1)
+    out = torch.empty_like(x)
+    var = 0.016
+    ops.noise_injection(x, out, var, seed=123, step=5)
+    assert torch.allclose(out.norm(dim=1), torch.ones(B, device="cuda"), atol=1e-5)
+    # out ~ (x + n)/|x + n| ; E|x+n|^2 = 1 + D*var  => cosine(out, x) ~ 1/sqrt(1 + D var)
+    cos = (out * x).sum(1).mean().item()
+    assert abs(cos - 1.0 / math.sqrt(1 + D * var)) < 5e-3
+    out2 = torch.empty_like(x)
+    ops.noise_injection(x, out2, var, seed=123, step=5)
+    assert torch.equal(out, out2)  # counter-based: reproducible
+    ops.noise_injection(x, out2, var, seed=123, step=6)
+    assert not torch.equal(out, out2)
+    # uniform ball: |noise| <= radius
+    ops.noise_injection(x, out2, var, uniform_ball=True, dont_norm=True, seed=1, step=0)
+    assert torch.isfinite(out2).all()
+
+
+def test_embed_fwd_bwd(ops):
+    B, P, L, d, V = 5, 10, 40, 768, 50257
+    g = torch.Generator(device="cuda").manual_seed(1)
+    tokens = torch.randint(0, V, (B, L), device="cuda", generator=g)
+    tokens[0, 30:] = 0
+    wte = torch.randn(V, d, device="cuda") * 0.02
+    wpe = torch.randn(1024, d, device="cuda") * 0.02
+    pp = torch.randn(B, P, d, device="cuda")
+    h = torch.empty(B, P + L, d, device="cuda")
+    ops.embed_fwd(tokens, pp, wte, wpe, h, B, P, L)
+    ref = torch.cat([pp, wte[tokens]], dim=1) + wpe[: P + L]
+    assert torch.equal(h, ref)
+    dh = torch.randn(B, P + L, d, device="cuda")
+    dpp = torch.empty(B, P, d, device="cuda")
+    dwte = torch.zeros(V, d, device="cuda")
+    dwpe = torch.zeros(1024, d, device="cuda")
+    ops.embed_bwd(tokens, dh, dpp, dwte, dwpe, B, P, L, V)
+    assert torch.equal(dpp, dh[:, :P])
+    ref_wte = torch.zeros(V, d, device="cuda", dtype=torch.float64).index_add_(0, tokens.flatten(), dh[:, P:].reshape(-1, d).double())
+    assert (dwte.double() - ref_wte).abs().max() < 1e-5
+    assert (dwpe[: P + L].double() - dh.double().sum(0)).abs().max() < 1e-5
+    assert dwpe[P + L:].abs().max() == 0
+
+
+@pytest.mark.parametrize("rows,d", [(1000, 768), (77, 768), (64, 512), (33, 1024)])
+def test_add_ln_fwd_bwd(ops, rows, d):
+    h = torch.randn(rows, d, device="cuda")
+    y = torch.randn(rows, d, device="cuda")
+    gamma = torch.randn(d, device="cuda")
+    beta = torch.randn(d, device="cuda")
+    x = torch.empty(rows, d, device="cuda")
+    h_out = torch.empty(rows, d, device="cuda")
+    stats = torch.empty(rows, 2, device="cuda")
+    ops.add_ln_fwd(h, y, h_out, x, stats, gamma, beta)
+    hd_, yd, gd, bd = h.double().requires_grad_(), y.double().requires_grad_(), gamma.double().requires_grad_(), beta.double().requires_grad_()
+    r = hd_ + yd
+    xr = torch.nn.functional.layer_norm(r, (d,), gd, bd, 1e-5)
+    assert (h_out.double() - r).abs().max() < 1e-6
+    assert (x.double() - xr).abs().max() < 2e-5
+    dx = torch.randn(rows, d, device="cuda")
+    dres = torch.randn(rows, d, device="cuda")
+    (xr * dx.double()).sum().backward()
+    dh_out = torch.empty(rows, d, device="cuda")
+    dy = torch.empty(rows, d, device="cuda")
+    dg = torch.zeros(d, device="cuda")
+    db = torch.zeros(d, device="cuda")
+    ops.add_ln_bwd(dx, h_out, stats, gamma, dres, dh_out, dy, dg, db)
+    ref_dr = hd_.grad + dres.double()
+    assert (dh_out.double() - ref_dr).abs().max() < 1e-4
+    assert torch.equal(dy, dh_out)
+    assert (dg.double() - gd.grad).abs().max() < 2e-3 * max(1.0, gd.grad.abs().max().item())
+    assert (db.double() - bd.grad).abs().max() < 2e-3 * max(1.0, bd.grad.abs().max().item())
+    # plain LN (no branch), no residual grad, frozen params
+    ops.add_ln_fwd(h, None, None, x, stats, gamma, beta)
+    assert (x.double() - torch.nn.functional.layer_norm(h.double(), (d,), gamma.double(), beta.double(), 1e-5)).abs().max() < 2e-5
+    ops.add_ln_bwd(dx, h, stats, gamma, None, dh_out, None, None, None)
+
+
+def test_add_ln_dropout_mask_consistency(ops):
+    rows, d, p = 512, 768, 0.1
+    h = torch.zeros(rows, d, device="cuda")
+    y = torch.ones(rows, d, device="cuda")
+    gamma, beta = torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")
+    x, h_out, stats = torch.empty(rows, d, device="cuda"), torch.empty(rows, d, device="cuda"), torch.empty(rows, 2, device="cuda")
+    ops.add_ln_fwd(h, y, h_out, x, stats, gamma, beta, p_drop=p, seed=7, stream_id=3)
+    keep = h_out != 0
+    assert abs(keep.float().mean().item() - (1 - p)) < 5e-3
+    assert torch.allclose(h_out[keep], torch.full_like(h_out[keep], 1 / (1 - p)))
+    dy, dh_out = torch.empty(rows, d, device="cuda"), torch.empty(rows, d, device="cuda")
+    ops.add_ln_bwd(torch.zeros(rows, d, device="cuda"), h_out, stats, gamma, torch.ones(rows, d, device="cuda"), dh_out, dy,
+                   None, None, p_drop=p, seed=7, stream_id=3)
+    assert torch.equal(dy != 0, keep)  # backward regenerates exactly the forward mask
+    ops.add_ln_fwd(h, y, h_out, x, stats, gamma, beta, p_drop=p, seed=7, stream_id=4)
+    assert not torch.equal(h_out != 0, keep)  # a different site draws a different mask
+
+
+def ref_attention(q, k, v, scale, causal, key_len=None):
+    # q [B,H,T,hd], k,v [B,H,S,hd]; HF eager_attention_forward (modeling_gpt2.py:54-72) / train.py:150-167
+    s = (q @ k.transpose(-1, -2)) * scale
+    T, S = s.shape[-2:]
+    if causal:
+        m = torch.ones(T, S, dtype=torch.bool, device=q.device).tril(S - T)
+        s = s.masked_fill(~m, float("-inf"))
+    if key_len is not None:
+        km = torch.arange(S, device=q.device)[None, :] < key_len[:, None]
+        s = s.masked_fill(~km[:, None, None, :], float("-inf"))
+    return torch.softmax(s, dim=-1) @ v
+
+
+@pytest.mark.parametrize("B,H,T,hd,causal", [(3, 12, 50, 64, 1), (2, 12, 80, 64, 1), (2, 8, 80, 96, 0), (1, 12, 1, 64, 1),
+                                             (2, 12, 128, 64, 1)])
+def test_attention_fwd_bwd(ops, B, H, T, hd, causal):
+    d = H * hd
+    qkv = torch.randn(B, T, 3 * d, device="cuda")
+    q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+    ctx = torch.empty(B, T, d, device="cuda")
+    lse = torch.empty(B, H, T, device="cuda")
+    scale = hd ** -0.5
+    ops.attention_fwd(q, k, v, ctx, lse, B, H, T, T, hd, T * 3 * d, 3 * d, T * 3 * d, 3 * d, T * d, d, scale, causal)
+    qd = qkv.double().requires_grad_()
+    split = lambda t: t.view(B, T, H, hd).transpose(1, 2)
+    ref = ref_attention(split(qd[..., :d]), split(qd[..., d:2 * d]), split(qd[..., 2 * d:]), scale, causal)
+    ref = ref.transpose(1, 2).reshape(B, T, d)
+    assert (ctx.double() - ref).abs().max() < 2e-5
+    dctx = torch.randn(B, T, d, device="cuda")
+    (ref * dctx.double()).sum().backward()
+    dqkv = torch.empty(B, T, 3 * d, device="cuda")
+    ops.attention_bwd(q, k, v, ctx, dctx, lse, dqkv[..., :d], dqkv[..., d:2 * d], dqkv[..., 2 * d:], B, H, T, T, hd,
+                      T * 3 * d, 3 * d, T * 3 * d, 3 * d, T * d, d, scale, causal)
+    assert (dqkv.double() - qd.grad).abs().max() < 1e-4
+
+
+def test_attention_key_padding_and_dropout(ops):
+    B, H, T, hd = 4, 12, 50, 64
+    d = H * hd
+    qkv = torch.randn(B, T, 3 * d, device="cuda")
+    q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+    key_len = torch.tensor([50, 30, 18, 11], device="cuda", dtype=torch.int32)
+    ctx = torch.empty(B, T, d, device="cuda")
+    lse = torch.empty(B, H, T, device="cuda")
+    args = (B, H, T, T, hd, T * 3 * d, 3 * d, T * 3 * d, 3 * d, T * d, d, hd ** -0.5, 1)
+    ops.attention_fwd(q, k, v, ctx, lse, *args, key_len=key_len)
+    split = lambda t: t.reshape(B, T, H, hd).transpose(1, 2).double()
+    ref = ref_attention(split(q), split(k), split(v), hd ** -0.5, True, key_len).transpose(1, 2).reshape(B, T, d)
+    assert (ctx.double() - ref).abs().max() < 2e-5
+    # dropout: E[out] = no-dropout output; check the mean over many heads is unbiased to a few %
+    ctx_d = torch.empty_like(ctx)
+    ops.attention_fwd(q, k, v, ctx_d, lse, *args, p_drop=0.1, seed=11, stream_id=2)
+    ops.attention_fwd(q, k, v, ctx, lse, *args)
+    rel = (ctx_d - ctx).norm() / ctx.norm()
+    assert 0.05 < rel < 0.6
+    assert abs((ctx_d.mean() - ctx.mean()).item()) < 5e-3
+
+
+@pytest.mark.parametrize("rows,V", [(64, 50257), (10, 1000), (7, 33)])
+def test_cross_entropy_fwd_bwd(ops, rows, V):
+    ld = (V + 127) // 128 * 128
+    logits_full = torch.randn(rows, ld, device="cuda") * 3
+    logits = logits_full[:, :V]
+    targets = torch.randint(1, V, (rows,), device="cuda")
+    targets[::5] = 0
+    ref_in = logits.double().clone().requires_grad_()
+    ref = torch.nn.functional.cross_entropy(ref_in, targets, ignore_index=0)
+    ref.backward()
+    n_valid = torch.zeros(1, device="cuda")
+    loss_sum = torch.zeros(1, device="cuda")
+    ops.ce_count(targets, n_valid)
+    assert n_valid.item() == (targets != 0).sum().item()
+    ops.ce_fwd_bwd(logits, targets, V, loss_sum, n_valid=n_valid)
+    assert abs(loss_sum.item() / n_valid.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert (logits.double() - ref_in.grad).abs().max() < 1e-7 + 1e-5 * ref_in.grad.abs().max()
+    assert (logits[targets == 0] == 0).all()
+
+
+def test_colsum_actbwd_rows_concat(ops):
+    M, N = 1237, 2304
+    x = torch.randn(M, N, device="cuda")
+    out = torch.ones(N, device="cuda")
+    ops.colsum_acc(x, out)
+    assert (out.double() - (1 + x.double().sum(0))).abs().max() < 1e-3
+    pre = torch.randn(999, 3072, device="cuda").requires_grad_()
+    dy = torch.randn(999, 3072, device="cuda")
+    torch.nn.functional.gelu(pre, approximate="tanh").backward(dy)
+    dx = torch.empty_like(dy)
+    ops.act_bwd(dy, pre.detach(), dx, ops.ACT_GELU_NEW)
+    assert (dx - pre.grad).abs().max() < 1e-5
+    a = torch.tanh(pre.detach())
+    ops.act_bwd(dy, a, dx, ops.ACT_TANH)
+    assert (dx - dy * (1 - a * a)).abs().max() < 1e-6
+    r = torch.relu(pre.detach())
+    ops.act_bwd(dy, r, dx, ops.ACT_RELU)
+    assert torch.equal(dx, dy * (r > 0))
+    B, T, L, d, off = 6, 50, 40, 768, 9
+    src = torch.randn(B, T, d, device="cuda")
+    dst = torch.empty(B * L, d, device="cuda")
+    ops.rows_gather(src, dst, B, T, L, off)
+    assert torch.equal(dst.view(B, L, d), src[:, off:off + L])
+    back = torch.zeros(B, T, d, device="cuda")
+    ops.rows_scatter(dst, back, B, T, L, off)
+    assert torch.equal(back[:, off:off + L], src[:, off:off + L]) and back[:, :off].abs().max() == 0
+    C, P = 40, 40
+    lin = torch.randn(B, C, d, device="cuda")
+    pc = torch.randn(P, d, device="cuda")
+    xcat = torch.empty(B, C + P, d, device="cuda")
+    ops.mapper_concat_fwd(lin, pc, xcat, B, C, P)
+    assert torch.equal(xcat, torch.cat([lin, pc[None].expand(B, P, d)], 1))
+    dxc = torch.randn(B, C + P, d, device="cuda")
+    dlin = torch.empty(B, C, d, device="cuda")
+    dpc = torch.zeros(P, d, device="cuda")
+    ops.mapper_concat_bwd(dxc, dlin, dpc, B, C, P)
+    assert torch.equal(dlin, dxc[:, :C]) and (dpc - dxc[:, C:].sum(0)).abs().max() < 1e-5
+
+
+def test_adamw_matches_hf_semantics(ops):
+    n = 4 * 1000 + 4
+    p = torch.randn(n, device="cuda"); g = torch.randn(n, device="cuda")
+    m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    pr, mr, vr = p.double().clone(), m.double().clone(), v.double().clone()
+    lr_dev, t_dev = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    b1, b2, eps, wd = 0.9, 0.999, 1e-6, 0.01
+    denom = torch.full((1,), 4.0, device="cuda")
+    for t in range(1, 4):
+        lr = 1e-3 * t
+        lr_dev.fill_(lr); t_dev.fill_(float(t))
+        gt = torch.randn(n, device="cuda")
+        g.copy_(gt)
+        ops.adamw_step(p, g, m, v, lr_dev, t_dev, b1, b2, eps, wd, grad_denom=denom, zero_grad=True)
+        gd = gt.double() / 4.0
+        # transformers 4.24 optimization.AdamW.step
+        mr = mr * b1 + (1 - b1) * gd
+        vr = vr * b2 + (1 - b2) * gd * gd
+        step = lr * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+        pr = pr - step * mr / (vr.sqrt() + eps)
+        pr = pr - lr * wd * pr
+        assert g.abs().max() == 0
+    assert (p.double() - pr).abs().max() < 2e-6
