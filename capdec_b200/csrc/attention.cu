@@ -26,7 +26,7 @@ __device__ __forceinline__ float drop_scale_elem(uint64_t seed, uint32_t stream_
 }
 
 template <int HD>
-__global__ void attention_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
+__global__ void __launch_bounds__(512) attention_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                      const float* __restrict__ v, float* __restrict__ ctx, float* __restrict__ lse,
                                      int H, int T, int S, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts,
                                      int64_t o_bs, int64_t o_ts, float scale, int causal,
@@ -102,7 +102,7 @@ __global__ void attention_fwd_kernel(const float* __restrict__ q, const float* _
 
 // Backward.  Pass 1 (4 lanes per query row): D_i = dO_i . O_i, dQ_i.  Pass 2 (4 lanes per key row): dK_j, dV_j.
 template <int HD>
-__global__ void attention_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
+__global__ void __launch_bounds__(512) attention_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                      const float* __restrict__ v, const float* __restrict__ ctx,
                                      const float* __restrict__ dctx, const float* __restrict__ lse,
                                      float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int H,

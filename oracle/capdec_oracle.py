@@ -1,0 +1,305 @@
+"""CPU oracle for the CapDec training-step hot path — TEST INFRASTRUCTURE ONLY.
+
+A plain-torch restatement (CPU, fp32 or fp64) of exactly what the reference executes per batch
+(train.py:345-354): noise_injection -> ClipCaptionModel.forward -> logits slice -> masked cross entropy ->
+backward (torch autograd here) -> HF AdamW + linear warm-up schedule.  GPT-2 is restated from the HuggingFace
+source the reference calls (`HF:` = transformers/models/gpt2/modeling_gpt2.py, pytorch_utils.py, activations.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may import this
+module, and only as the checker / the timed CPU baseline — never on the product path (capdec_b200 raises when
+its CUDA library is missing instead of falling back here).
+
+Pinning: the reference has no tests or golden vectors.  oracle/pin_against_reference.py runs the
+reference's OWN classes (imported from /root/reference/train.py + transformers' GPT2LMHeadModel, shimmed as in
+SURVEY §8c) on the deterministic weights/inputs below, checks this restatement against them and writes
+tests/golden/*.json; tests/test_oracle_golden.py re-checks the restatement against those files on every run.
+
+Parameters are passed as a flat dict keyed by the reference's state_dict names (train.py:359-371 layout).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+Params = Dict[str, torch.Tensor]
+
+GPT2_SMALL = dict(n_layer=12, n_head=12, n_embd=768, vocab=50257, n_pos=1024, eps=1e-5)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# deterministic weights / inputs shared by the reference run, the oracle and the CUDA model
+# --------------------------------------------------------------------------------------------------------------
+def make_state_dict(seed: int = 0, mapping_type: str = "mlp", prefix_length: int = 10, clip_length: int = 10,
+                    prefix_size: int = 512, num_layers: int = 8, n_layer: int = 12, vocab: int = 50257,
+                    n_embd: int = 768, n_pos: int = 1024, weight_std: float = 0.02, dtype=torch.float32) -> Params:
+    """Seeded weights in the reference checkpoint layout.  Shapes follow SURVEY §8b.  Init follows HF GPT-2
+    (HF:modeling_gpt2.py:433-458: N(0, 0.02), c_proj N(0, 0.02/sqrt(2 n_layer))) but LayerNorm gains/biases and
+    linear biases are randomised too so that every parameter path is exercised by the parity tests."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *shape, std=1.0: (torch.randn(*shape, generator=g, dtype=torch.float32) * std).to(dtype)
+    d = n_embd
+    sd: Params = {}
+    sd["gpt.transformer.wte.weight"] = rn(vocab, d, std=weight_std)
+    sd["gpt.transformer.wpe.weight"] = rn(n_pos, d, std=weight_std)
+    for i in range(n_layer):
+        p = f"gpt.transformer.h.{i}."
+        sd[p + "ln_1.weight"] = 1.0 + rn(d, std=0.1)
+        sd[p + "ln_1.bias"] = rn(d, std=0.05)
+        sd[p + "attn.c_attn.weight"] = rn(d, 3 * d, std=weight_std)
+        sd[p + "attn.c_attn.bias"] = rn(3 * d, std=0.02)
+        sd[p + "attn.c_proj.weight"] = rn(d, d, std=weight_std / math.sqrt(2 * n_layer))
+        sd[p + "attn.c_proj.bias"] = rn(d, std=0.02)
+        sd[p + "ln_2.weight"] = 1.0 + rn(d, std=0.1)
+        sd[p + "ln_2.bias"] = rn(d, std=0.05)
+        sd[p + "mlp.c_fc.weight"] = rn(d, 4 * d, std=weight_std)
+        sd[p + "mlp.c_fc.bias"] = rn(4 * d, std=0.02)
+        sd[p + "mlp.c_proj.weight"] = rn(4 * d, d, std=weight_std / math.sqrt(2 * n_layer))
+        sd[p + "mlp.c_proj.bias"] = rn(d, std=0.02)
+    sd["gpt.transformer.ln_f.weight"] = 1.0 + rn(d, std=0.1)
+    sd["gpt.transformer.ln_f.bias"] = rn(d, std=0.05)
+    sd["gpt.lm_head.weight"] = sd["gpt.transformer.wte.weight"]  # tied (HF:modeling_gpt2.py:646-651)
+    P = prefix_length
+    if mapping_type == "mlp":  # train.py:269-270: MLP((D, d*P//2, d*P))
+        hdim = (d * P) // 2
+        sd["clip_project.model.0.weight"] = rn(hdim, prefix_size, std=1.0 / math.sqrt(prefix_size))
+        sd["clip_project.model.0.bias"] = rn(hdim, std=0.02)
+        sd["clip_project.model.2.weight"] = rn(d * P, hdim, std=1.0 / math.sqrt(hdim))
+        sd["clip_project.model.2.bias"] = rn(d * P, std=0.02)
+    else:  # train.py:238-243 TransformerMapper
+        C = clip_length
+        sd["clip_project.prefix_const"] = rn(P, d)
+        sd["clip_project.linear.weight"] = rn(C * d, prefix_size, std=1.0 / math.sqrt(prefix_size))
+        sd["clip_project.linear.bias"] = rn(C * d, std=0.02)
+        hm = int(d * 2.0)  # mlp_ratio = 2.0 (train.py:212)
+        for j in range(num_layers):
+            p = f"clip_project.transformer.layers.{j}."
+            sd[p + "norm1.weight"] = 1.0 + rn(d, std=0.1)
+            sd[p + "norm1.bias"] = rn(d, std=0.05)
+            sd[p + "attn.to_queries.weight"] = rn(d, d, std=1.0 / math.sqrt(d))
+            sd[p + "attn.to_keys_values.weight"] = rn(2 * d, d, std=1.0 / math.sqrt(d))
+            sd[p + "attn.project.weight"] = rn(d, d, std=1.0 / math.sqrt(d))
+            sd[p + "attn.project.bias"] = rn(d, std=0.02)
+            sd[p + "norm2.weight"] = 1.0 + rn(d, std=0.1)
+            sd[p + "norm2.bias"] = rn(d, std=0.05)
+            sd[p + "mlp.fc1.weight"] = rn(hm, d, std=1.0 / math.sqrt(d))
+            sd[p + "mlp.fc1.bias"] = rn(hm, std=0.02)
+            sd[p + "mlp.fc2.weight"] = rn(d, hm, std=1.0 / math.sqrt(hm))
+            sd[p + "mlp.fc2.bias"] = rn(d, std=0.02)
+    return sd
+
+
+def make_batch(seed: int, B: int, L: int = 40, prefix_size: int = 512, vocab: int = 50257, min_len: int = 8,
+               full_length: bool = False):
+    """Synthetic batch of SURVEY §8d: normalised Gaussian 'CLIP' embeddings, token ids uniform in [1, vocab),
+    per-row length ~ U{min_len..L}, right-padded with id 0; mask = cat(ones(P), tokens > 0) is built by callers
+    (train.py:55-63).  Also returns the Gaussian draw for the noise injection (unit variance; scale by std)."""
+    g = torch.Generator().manual_seed(seed)
+    prefix = torch.randn(B, prefix_size, generator=g)
+    prefix = prefix / prefix.norm(2, -1, keepdim=True)  # train.py:69-71
+    tokens = torch.randint(1, vocab, (B, L), generator=g, dtype=torch.int64)
+    if not full_length:
+        lens = torch.randint(min_len, L + 1, (B,), generator=g)
+        tokens[torch.arange(L)[None, :] >= lens[:, None]] = 0
+    noise = torch.randn(B, prefix_size, generator=g)
+    return tokens, prefix, noise
+
+
+def make_mask(tokens: torch.Tensor, prefix_length: int) -> torch.Tensor:
+    """train.py:58-63 (mask is 0 on padding; synthetic padding == id 0)."""
+    return torch.cat((torch.ones(tokens.shape[0], prefix_length), (tokens > 0).float()), dim=1)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# restatement of the model
+# --------------------------------------------------------------------------------------------------------------
+def noise_injection(x, variance=0.001, modality_offset=None, uniform_noise=False, dont_norm=False, noise=None,
+                    generator=None):
+    """train.py:27-39.  `noise` = unit-variance Gaussian draw to use instead of torch.randn (parity mode)."""
+    if variance == 0.0:
+        return x  # train.py:28-29
+    std = math.sqrt(variance)
+    if not dont_norm:
+        x = F.normalize(x, dim=1)  # train.py:31-32
+    if uniform_noise:  # train.py:18-24
+        gdraw = noise if noise is not None else torch.randn(x.shape, generator=generator, dtype=x.dtype)
+        sphere = F.normalize(gdraw, dim=1)
+        u = torch.rand(x.shape[0], generator=generator, dtype=x.dtype) ** (1.0 / x.shape[1])
+        x = x + (sphere.T * u * std).T
+    else:
+        gdraw = noise if noise is not None else torch.randn(x.shape, generator=generator, dtype=x.dtype)
+        x = x + gdraw * std  # train.py:36
+    if modality_offset is not None:
+        x = x + modality_offset  # train.py:37-38
+    return F.normalize(x, dim=1)  # train.py:39
+
+
+def gelu_new(x):
+    """HF:activations.py:59-66."""
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * torch.pow(x, 3.0))))
+
+
+def conv1d(x, w, b):
+    """HF:pytorch_utils.py:97-123: y = x @ W + b with W [in, out]."""
+    return torch.addmm(b, x.reshape(-1, x.shape[-1]), w).view(*x.shape[:-1], w.shape[1])
+
+
+def gpt2_forward(sd: Params, inputs_embeds, attention_mask=None, n_head: int = 12, eps: float = 1e-5,
+                 p_drop: float = 0.0, return_hidden: bool = False):
+    """HF GPT2LMHeadModel.forward(inputs_embeds=..., attention_mask=...) in eval mode (or p_drop via torch RNG):
+    HF:modeling_gpt2.py:579-636 (embeddings, blocks, ln_f), :262-309 (block), :54-72 + :185-226 (attention),
+    :229-243 (MLP), :703-706 (tied lm_head)."""
+    B, T, d = inputs_embeds.shape
+    hd = d // n_head
+    drop = (lambda t: F.dropout(t, p_drop, True)) if p_drop > 0 else (lambda t: t)
+    h = inputs_embeds + sd["gpt.transformer.wpe.weight"][:T].unsqueeze(0)  # position_ids = arange(T)
+    h = drop(h)
+    # additive mask: causal (-inf above the diagonal) + padding ((1 - mask) * finfo.min on keys)
+    neg = torch.finfo(h.dtype).min
+    causal = torch.ones(T, T, dtype=torch.bool).tril()
+    add_mask = torch.zeros(1, 1, T, T, dtype=h.dtype).masked_fill(~causal, neg)
+    if attention_mask is not None:
+        add_mask = add_mask + (1.0 - attention_mask.to(h.dtype))[:, None, None, :] * neg
+        add_mask = add_mask.clamp_min(neg)
+    n_layer = 0
+    while f"gpt.transformer.h.{n_layer}.ln_1.weight" in sd:
+        n_layer += 1
+    for i in range(n_layer):
+        p = f"gpt.transformer.h.{i}."
+        x = F.layer_norm(h, (d,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], eps)
+        qkv = conv1d(x, sd[p + "attn.c_attn.weight"], sd[p + "attn.c_attn.bias"])
+        q, k, v = qkv.split(d, dim=2)
+        q = q.view(B, T, n_head, hd).transpose(1, 2)
+        k = k.view(B, T, n_head, hd).transpose(1, 2)
+        v = v.view(B, T, n_head, hd).transpose(1, 2)
+        w = torch.matmul(q, k.transpose(-1, -2)) * (hd ** -0.5) + add_mask
+        w = drop(F.softmax(w, dim=-1))
+        a = torch.matmul(w, v).transpose(1, 2).reshape(B, T, d)
+        a = conv1d(a, sd[p + "attn.c_proj.weight"], sd[p + "attn.c_proj.bias"])
+        h = h + drop(a)
+        x = F.layer_norm(h, (d,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], eps)
+        m = gelu_new(conv1d(x, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"]))
+        m = conv1d(m, sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
+        h = h + drop(m)
+    hf = F.layer_norm(h, (d,), sd["gpt.transformer.ln_f.weight"], sd["gpt.transformer.ln_f.bias"], eps)
+    logits = F.linear(hf, sd["gpt.transformer.wte.weight"])  # tied lm_head, no bias
+    return (logits, hf) if return_hidden else logits
+
+
+def mlp_mapper(sd: Params, x):
+    """train.py:106-118 as built at :269-270: Linear -> Tanh -> Linear."""
+    h = torch.tanh(F.linear(x, sd["clip_project.model.0.weight"], sd["clip_project.model.0.bias"]))
+    return F.linear(h, sd["clip_project.model.2.weight"], sd["clip_project.model.2.bias"])
+
+
+def transformer_mapper(sd: Params, x, clip_length: int, num_heads: int = 8):
+    """train.py:229-243 -> :192-226 -> :170-189 -> :138-167 / :121-136 (no mask, dropout p=0)."""
+    B = x.shape[0]
+    pc = sd["clip_project.prefix_const"]
+    P, d = pc.shape
+    x = F.linear(x, sd["clip_project.linear.weight"], sd["clip_project.linear.bias"]).view(B, clip_length, d)
+    h = torch.cat((x, pc.unsqueeze(0).expand(B, P, d)), dim=1)
+    n = h.shape[1]
+    hd = d // num_heads
+    j = 0
+    while f"clip_project.transformer.layers.{j}.norm1.weight" in sd:
+        p = f"clip_project.transformer.layers.{j}."
+        y = F.layer_norm(h, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
+        q = F.linear(y, sd[p + "attn.to_queries.weight"]).reshape(B, n, num_heads, hd)
+        kv = F.linear(y, sd[p + "attn.to_keys_values.weight"]).reshape(B, n, 2, num_heads, hd)
+        k, v = kv[:, :, 0], kv[:, :, 1]
+        att = torch.einsum("bnhd,bmhd->bnmh", q, k) * (hd ** -0.5)
+        att = att.softmax(dim=2)
+        o = torch.einsum("bnmh,bmhd->bnhd", att, v).reshape(B, n, d)
+        h = h + F.linear(o, sd[p + "attn.project.weight"], sd[p + "attn.project.bias"])
+        y = F.layer_norm(h, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
+        y = F.relu(F.linear(y, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))
+        h = h + F.linear(y, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+        j += 1
+    return h[:, clip_length:]
+
+
+def clip_project(sd: Params, prefix, clip_length: Optional[int] = None):
+    if "clip_project.model.0.weight" in sd:
+        return mlp_mapper(sd, prefix)
+    return transformer_mapper(sd, prefix, clip_length)
+
+
+def clipcap_forward(sd: Params, tokens, prefix, mask=None, prefix_length: int = 10,
+                    clip_length: Optional[int] = None, p_drop: float = 0.0):
+    """ClipCaptionModel.forward, train.py:251-260 -> logits [B, P+L, V]."""
+    d = sd["gpt.transformer.wte.weight"].shape[1]
+    emb_text = sd["gpt.transformer.wte.weight"][tokens]  # train.py:253
+    proj = clip_project(sd, prefix, clip_length).view(-1, prefix_length, d)  # train.py:254
+    emb = torch.cat((proj, emb_text), dim=1)  # train.py:255
+    return gpt2_forward(sd, emb, attention_mask=mask, p_drop=p_drop)  # train.py:259
+
+
+def caption_loss(logits, tokens, prefix_length: int):
+    """train.py:349-350."""
+    lg = logits[:, prefix_length - 1: -1]
+    return F.cross_entropy(lg.reshape(-1, lg.shape[-1]), tokens.flatten(), ignore_index=0)
+
+
+def loss_and_grads(sd: Params, tokens, prefix, mask, prefix_length, clip_length=None, trainable=None):
+    """One forward/backward of train.py:348-351 through autograd. Returns (loss, logits, {name: grad})."""
+    leaves = {}
+    for k, v in sd.items():
+        if k == "gpt.lm_head.weight":
+            continue
+        if trainable is None or trainable(k):
+            leaves[k] = v.detach().clone().requires_grad_(True)
+        else:
+            leaves[k] = v.detach()
+    leaves["gpt.lm_head.weight"] = leaves["gpt.transformer.wte.weight"]
+    logits = clipcap_forward(leaves, tokens, prefix, mask, prefix_length, clip_length)
+    loss = caption_loss(logits, tokens, prefix_length)
+    loss.backward()
+    grads = {k: v.grad for k, v in leaves.items() if k != "gpt.lm_head.weight" and v.requires_grad and v.grad is not None}
+    return loss.detach(), logits.detach(), grads
+
+
+# --------------------------------------------------------------------------------------------------------------
+# optimizer restatement
+# --------------------------------------------------------------------------------------------------------------
+def hf_adamw_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0):
+    """transformers==4.24 optimization.AdamW.step (correct_bias=True), used at train.py:326,352. In place."""
+    m.mul_(beta1).add_(g, alpha=1.0 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+    denom = v.sqrt().add_(eps)
+    step_size = lr * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
+    p.addcdiv_(m, denom, value=-step_size)
+    if weight_decay > 0.0:
+        p.add_(p, alpha=-lr * weight_decay)
+
+
+def linear_warmup_lr(base_lr: float, step: int, warmup: int, total: int) -> float:
+    """get_linear_schedule_with_warmup (HF:optimization.py:101-104), value used for optimizer step number `step`
+    (0-based count of scheduler.step() calls already made; train.py:328-330,353)."""
+    if step < warmup:
+        return base_lr * float(step) / float(max(1, warmup))
+    return base_lr * max(0.0, float(total - step) / float(max(1, total - warmup)))
+
+
+class HFAdamW(torch.optim.Optimizer):
+    """Drop-in for `transformers.AdamW` (removed from transformers >= 4.5x; train.py:6 imports it)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, correct_bias=correct_bias))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                st["step"] += 1
+                hf_adamw_step(p, p.grad, st["exp_avg"], st["exp_avg_sq"], st["step"], group["lr"], *group["betas"],
+                              group["eps"], group["weight_decay"])

@@ -1,0 +1,168 @@
+"""Pin the oracle against the REAL reference and write the golden fixtures — runs only where /root/reference exists.
+
+    python oracle/pin_against_reference.py            # writes tests/golden/*.json
+
+What runs: the reference's own classes imported from /root/reference/train.py (ClipCaptionModel,
+ClipCaptionPrefix, noise_injection, MappingType) on top of the installed transformers' GPT2LMHeadModel, with the
+three shims of SURVEY §8c (AdamW symbol, from_pretrained -> GPT2LMHeadModel(GPT2Config()), device -> cpu).
+Weights/inputs come from oracle.capdec_oracle.make_state_dict / make_batch (seeded), are loaded into the
+reference model with load_state_dict(strict=True), and the reference executes train.py:348-351 verbatim.
+Recorded per case: loss, 96 sampled logits, per-parameter gradient norms and 8 sampled gradient entries each.
+The same quantities from the oracle restatement are asserted equal (fp32 tolerance) before anything is written.
+"""
+from __future__ import annotations
+
+import json
+import sys
+import types
+from pathlib import Path
+
+import torch
+import torch.nn.functional as nnf
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import capdec_oracle as O  # noqa: E402
+
+REF = Path("/root/reference")
+GOLD = ROOT / "tests" / "golden"
+
+
+def import_reference(pdrop: float = 0.0):
+    import transformers
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    orig = GPT2LMHeadModel.from_pretrained
+
+    def fake_from_pretrained(name, *a, **k):  # shim 2 (train.py:266)
+        cfg = GPT2Config(resid_pdrop=pdrop, embd_pdrop=pdrop, attn_pdrop=pdrop)
+        cfg._attn_implementation = "eager"
+        return GPT2LMHeadModel(cfg)
+
+    GPT2LMHeadModel.from_pretrained = staticmethod(fake_from_pretrained)
+    sys.path.insert(0, str(REF))
+    sys.modules.pop("train", None)
+    from transformers import GPT2Tokenizer, get_linear_schedule_with_warmup  # noqa: F401  (resolve lazies first)
+    sys.modules["transformers"].AdamW = O.HFAdamW  # shim 1 (train.py:6) — must be set right before the import
+    import train as ref_train  # noqa
+
+    ref_train.device = torch.device("cpu")  # shim 3 (train.py:15,36)
+    return ref_train  # from_pretrained stays patched: ClipCaptionModel.__init__ calls it (train.py:266)
+
+
+def sample_idx(n: int, k: int, seed: int):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, n, (min(k, n),), generator=g)
+
+
+def summarise(loss, logits, grads, seed=99):
+    rec = {"loss": float(loss), "logits_shape": list(logits.shape)}
+    li = sample_idx(logits.numel(), 96, seed)
+    rec["logits_idx"] = li.tolist()
+    rec["logits_val"] = logits.flatten()[li].double().tolist()
+    rec["logits_absmax"] = float(logits.abs().max())
+    g = {}
+    for k in sorted(grads):
+        t = grads[k]
+        gi = sample_idx(t.numel(), 8, seed + 1)
+        g[k] = {"norm": float(t.double().norm()), "idx": gi.tolist(), "val": t.flatten()[gi].double().tolist()}
+    rec["grads"] = g
+    return rec
+
+
+CASES = {
+    # name: (mapping_type, only_prefix, B, P, C, D, num_layers, full_length)
+    "mlp_full_b4": ("mlp", False, 4, 10, 10, 512, 8, False),
+    "mlp_prefix_only_b4": ("mlp", True, 4, 10, 10, 512, 8, False),
+    "transformer_full_b2": ("transformer", False, 2, 40, 40, 512, 8, False),
+    "mlp_full_d640_b3": ("mlp", False, 3, 10, 10, 640, 8, True),
+}
+
+
+def run_case(ref_train, name, cfg):
+    mtype, only_prefix, B, P, C, D, nl, full_len = cfg
+    sd = O.make_state_dict(seed=1, mapping_type=mtype, prefix_length=P, clip_length=C, prefix_size=D, num_layers=nl)
+    tokens, prefix, noise = O.make_batch(seed=2, B=B, L=40, prefix_size=D, full_length=full_len)
+    mask = O.make_mask(tokens, P)
+    var = 0.016
+    MT = ref_train.MappingType.MLP if mtype == "mlp" else ref_train.MappingType.Transformer
+    cls = ref_train.ClipCaptionPrefix if only_prefix else ref_train.ClipCaptionModel
+    torch.manual_seed(0)
+    model = cls(P, clip_length=C, prefix_size=D, num_layers=nl, mapping_type=MT)
+    missing = model.load_state_dict(sd, strict=True)
+    model.train()  # ClipCaptionPrefix keeps gpt in eval (train.py:281-284); full model has pdrop = 0 via the shim
+    # ---- the reference's own step, train.py:345-351 (noise draw made explicit through the global torch RNG) ----
+    model.zero_grad()
+    torch.manual_seed(1234)
+    pfx = ref_train.noise_injection(prefix, var)
+    torch.manual_seed(1234)
+    g_draw = torch.randn(prefix.shape)
+    pfx_oracle = O.noise_injection(prefix, var, noise=g_draw)
+    assert torch.equal(pfx, pfx_oracle), "noise_injection restatement differs"
+    outputs = model(tokens, pfx, mask)
+    logits = outputs.logits[:, P - 1: -1]
+    loss = nnf.cross_entropy(logits.reshape(-1, logits.shape[-1]), tokens.flatten(), ignore_index=0)
+    loss.backward()
+    ref_grads = {}
+    for k, p in model.named_parameters() if not only_prefix else super(cls, model).named_parameters():
+        if p.grad is not None and (not only_prefix or k.startswith("clip_project")):
+            ref_grads[k] = p.grad.detach()
+    # mask has no effect on the consumed logits / loss (SURVEY §8c probe) — re-verify and record
+    with torch.no_grad():
+        lg_nomask = model(tokens, pfx, None).logits[:, P - 1: -1]
+        loss_nomask = nnf.cross_entropy(lg_nomask.reshape(-1, lg_nomask.shape[-1]), tokens.flatten(), ignore_index=0)
+    # ---- oracle restatement on the same inputs ----
+    trainable = (lambda k: k.startswith("clip_project")) if only_prefix else None
+    o_loss, o_logits, o_grads = O.loss_and_grads(sd, tokens, pfx, mask, P, C, trainable)
+    full_logits = outputs.logits.detach()
+    assert abs(float(o_loss) - float(loss)) < 2e-6 * abs(float(loss)), (float(o_loss), float(loss))
+    valid = torch.cat((torch.ones(B, P, dtype=torch.bool), tokens > 0), dim=1)  # compare logits at unpadded positions
+    d_lg = (o_logits - full_logits)[valid].abs().max().item()
+    assert d_lg < 1e-4 * max(1.0, full_logits.abs().max().item()), d_lg
+    assert set(o_grads) == set(ref_grads), (sorted(set(o_grads) ^ set(ref_grads)))
+    worst = 0.0
+    for k in ref_grads:
+        rel = (o_grads[k] - ref_grads[k]).norm().item() / max(ref_grads[k].norm().item(), 1e-12)
+        worst = max(worst, rel)
+        assert rel < 2e-4, (k, rel)
+    rec = summarise(loss.detach(), full_logits, ref_grads)
+    rec.update({"case": name, "config": dict(mapping_type=mtype, only_prefix=only_prefix, B=B, P=P, C=C, D=D,
+                                             num_layers=nl, full_length=full_len, noise_variance=var,
+                                             sd_seed=1, batch_seed=2, noise_torch_seed=1234),
+                "loss_without_mask": float(loss_nomask), "noised_prefix_row0": pfx[0, :8].double().tolist(),
+                "oracle_vs_reference": {"loss_abs": abs(float(o_loss) - float(loss)), "logits_maxabs_valid": d_lg,
+                                        "worst_grad_rel_l2": worst},
+                "versions": {"torch": torch.__version__, "transformers": __import__("transformers").__version__,
+                             "reference_commit": "4451bfd"}})
+    return rec
+
+
+def main():
+    assert REF.exists(), "the reference checkout is only mounted in the build container"
+    GOLD.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(8)
+    ref_train = import_reference(pdrop=0.0)
+    for name, cfg in CASES.items():
+        rec = run_case(ref_train, name, cfg)
+        (GOLD / f"{name}.json").write_text(json.dumps(rec, indent=1))
+        print(name, "loss", rec["loss"], "oracle-vs-ref", rec["oracle_vs_reference"])
+    # noise_injection variants (train.py:27-39) incl. modality offset and dont_norm, seeded through torch's global RNG
+    tokens, prefix, _ = O.make_batch(seed=5, B=6, prefix_size=640)
+    x = prefix * 3.0
+    off = torch.randn(1, 640, generator=torch.Generator().manual_seed(8)) * 0.05
+    out = {}
+    for tag, kw in {"plain": {}, "offset": {"modality_offset": off}, "dont_norm": {"dont_norm": True},
+                    "zero_var": {"variance": 0.0}}.items():
+        var = kw.pop("variance", 0.016)
+        torch.manual_seed(77)
+        y = ref_train.noise_injection(x, var, **kw)
+        torch.manual_seed(77)
+        yo = O.noise_injection(x, var, noise=torch.randn(x.shape), **kw)
+        assert torch.equal(y, yo), tag
+        out[tag] = {"row0": y[0, :6].double().tolist(), "norm0": float(y[0].norm()), "sum": float(y.double().sum())}
+    (GOLD / "noise_injection.json").write_text(json.dumps({"seed": 77, "batch_seed": 5, "offset_seed": 8, "cases": out}, indent=1))
+    print("noise ok")
+
+
+if __name__ == "__main__":
+    main()

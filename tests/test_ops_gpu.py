@@ -82,7 +82,7 @@ def test_gemm_accumulate_splitk(ops, split):
     assert (C.double() - ref).abs().max() < 2e-4 * ref.abs().max()
 
 
-@pytest.mark.parametrize("mode,tol", [("tf32x3", 4e-6), ("fp32", 3e-6)])
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 2e-5), ("fp32", 3e-6)])
 @pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 1)])
 def test_gemm_fp32_grade_modes(ops, mode, tol, a_major, b_major):
     M, N, K = 512, 770, 768

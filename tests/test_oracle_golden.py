@@ -1,0 +1,89 @@
+"""CPU tests: the oracle restatement (oracle/capdec_oracle.py) against the golden vectors recorded from the
+reference's own classes (oracle/pin_against_reference.py -> tests/golden/*.json).  No GPU, no /root/reference."""
+import json
+import math
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import capdec_oracle as O
+
+GOLD = Path(__file__).resolve().parent / "golden"
+CASES = ["mlp_full_b4", "mlp_prefix_only_b4", "transformer_full_b2", "mlp_full_d640_b3"]
+
+
+def load_case(name):
+    rec = json.loads((GOLD / f"{name}.json").read_text())
+    c = rec["config"]
+    sd = O.make_state_dict(seed=c["sd_seed"], mapping_type=c["mapping_type"], prefix_length=c["P"], clip_length=c["C"],
+                           prefix_size=c["D"], num_layers=c["num_layers"])
+    tokens, prefix, _ = O.make_batch(seed=c["batch_seed"], B=c["B"], L=40, prefix_size=c["D"], full_length=c["full_length"])
+    torch.manual_seed(c["noise_torch_seed"])
+    draw = torch.randn(prefix.shape)
+    pfx = O.noise_injection(prefix, c["noise_variance"], noise=draw)
+    return rec, c, sd, tokens, pfx
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_reference_golden(name):
+    torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
+    rec, c, sd, tokens, pfx = load_case(name)
+    assert pfx[0, :8].double().tolist() == pytest.approx(rec["noised_prefix_row0"], rel=1e-6)
+    mask = O.make_mask(tokens, c["P"])
+    trainable = (lambda k: k.startswith("clip_project")) if c["only_prefix"] else None
+    loss, logits, grads = O.loss_and_grads(sd, tokens, pfx, mask, c["P"], c["C"], trainable)
+    assert float(loss) == pytest.approx(rec["loss"], rel=2e-6)
+    assert list(logits.shape) == rec["logits_shape"]
+    got = logits.flatten()[torch.tensor(rec["logits_idx"])].double()
+    # sampled logits may fall on padded positions where the reference's additive mask arithmetic is restated exactly
+    assert (got - torch.tensor(rec["logits_val"], dtype=torch.float64)).abs().max() < 2e-4 * max(1.0, rec["logits_absmax"])
+    assert set(grads) == set(rec["grads"])
+    for k, g in rec["grads"].items():
+        t = grads[k]
+        assert float(t.double().norm()) == pytest.approx(g["norm"], rel=5e-4, abs=1e-9), k
+        vals = t.flatten()[torch.tensor(g["idx"])].double()
+        assert (vals - torch.tensor(g["val"], dtype=torch.float64)).abs().max() <= 1e-3 * g["norm"] + 1e-9, k
+
+
+def test_mask_does_not_change_the_loss():
+    """SURVEY §8c probe (i): right padding + causal attention => the padding mask cannot reach a consumed logit."""
+    rec, c, sd, tokens, pfx = load_case("mlp_full_b4")
+    assert rec["loss_without_mask"] == pytest.approx(rec["loss"], rel=1e-6)
+    lg = O.clipcap_forward(sd, tokens, pfx, None, c["P"], c["C"])
+    assert float(O.caption_loss(lg, tokens, c["P"])) == pytest.approx(rec["loss"], rel=2e-6)
+
+
+def test_noise_injection_golden():
+    rec = json.loads((GOLD / "noise_injection.json").read_text())
+    _, prefix, _ = O.make_batch(seed=rec["batch_seed"], B=6, prefix_size=640)
+    x = prefix * 3.0
+    off = torch.randn(1, 640, generator=torch.Generator().manual_seed(rec["offset_seed"])) * 0.05
+    kws = {"plain": {}, "offset": {"modality_offset": off}, "dont_norm": {"dont_norm": True}, "zero_var": {"variance": 0.0}}
+    for tag, kw in kws.items():
+        var = kw.pop("variance", 0.016)
+        torch.manual_seed(rec["seed"])
+        y = O.noise_injection(x, var, noise=torch.randn(x.shape), **kw)
+        g = rec["cases"][tag]
+        assert y[0, :6].double().tolist() == pytest.approx(g["row0"], rel=1e-6)
+        assert float(y.double().sum()) == pytest.approx(g["sum"], rel=1e-6)
+    # variance 0 returns the input itself, unnormalised (train.py:28-29)
+    assert O.noise_injection(x, 0.0) is x
+
+
+def test_hf_adamw_and_schedule_restatement():
+    """HF-4.24 AdamW: eps added before bias correction; lr == 0 on the very first step of the warm-up schedule."""
+    p = torch.tensor([1.0, -2.0]); g = torch.tensor([0.5, 0.25])
+    m = torch.zeros(2); v = torch.zeros(2)
+    O.hf_adamw_step(p, g, m, v, step=1, lr=0.1)
+    denom = (0.001 * g * g).sqrt() + 1e-6
+    expect = torch.tensor([1.0, -2.0]) - 0.1 * math.sqrt(1 - 0.999) / (1 - 0.9) * (0.1 * g) / denom
+    assert torch.allclose(p, expect, rtol=1e-6)
+    assert O.linear_warmup_lr(2e-5, 0, 5000, 10000) == 0.0
+    assert O.linear_warmup_lr(2e-5, 2500, 5000, 10000) == pytest.approx(1e-5)
+    assert O.linear_warmup_lr(2e-5, 7500, 5000, 10000) == pytest.approx(1e-5)
+    w = torch.nn.Parameter(torch.ones(3))
+    opt = O.HFAdamW([w], lr=0.01)
+    w.grad = torch.ones(3)
+    opt.step()
+    assert torch.allclose(w.detach(), torch.full((3,), 1 - 0.01 * math.sqrt(0.001) / 0.1 * 0.1 / (math.sqrt(0.001) + 1e-6)), rtol=1e-5)
