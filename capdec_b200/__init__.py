@@ -1,0 +1,15 @@
+"""capdec_b200 — B200-native (sm_100a) implementation of the CapDec training-step hot path.
+
+Public surface mirrors the reference (train.py / gpt2_prefix.py): ClipCaptionModel, ClipCaptionPrefix, MappingType,
+MLP, TransformerMapper, noise_injection; plus Trainer (the fused, CUDA-graph'ed train step) and AdamW /
+get_linear_schedule_with_warmup with the reference's HuggingFace semantics.  There is no CPU fallback: the CUDA
+library (capdec_b200/libcapdec_b200.so, built by `python -m capdec_b200.build`) is required.
+"""
+from .model import (ClipCaptionModel, ClipCaptionPrefix, GPT2Config, GPT2LMHead, MappingType, MLP, TransformerMapper,
+                    noise_injection)
+from .optim import AdamW, get_linear_schedule_with_warmup
+from .trainer import Trainer
+from . import ops
+
+__all__ = ["ClipCaptionModel", "ClipCaptionPrefix", "GPT2Config", "GPT2LMHead", "MappingType", "MLP",
+           "TransformerMapper", "noise_injection", "AdamW", "get_linear_schedule_with_warmup", "Trainer", "ops"]

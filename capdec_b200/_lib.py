@@ -27,16 +27,16 @@ SIGNATURES = {
     "capdec_gemm_debug_mn_encoding": [_i, _i, _i, _i],
     "capdec_gemm_fp32_simt": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p],
     "capdec_split_tf32": [_p, _p, _p, _i64, _p],
-    "capdec_noise_injection": [_p, _p, _i, _i, _f, _p, _p, _i, _i, _u64, _u64, _p],
-    "capdec_embed_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _u64, _u32, _p],
-    "capdec_embed_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _u64, _u32, _p],
-    "capdec_add_ln_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _u64, _u32, _p],
-    "capdec_add_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _u64, _u32, _p],
+    "capdec_noise_injection": [_p, _p, _i, _i, _f, _p, _p, _i, _i, _p, _u64, _p],
+    "capdec_embed_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _u32, _p],
+    "capdec_embed_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _u32, _p],
+    "capdec_add_ln_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _p, _u32, _p],
+    "capdec_add_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _u32, _p],
     "capdec_attention_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p,
-                             _f, _u64, _u32, _p],
+                             _f, _p, _u32, _p],
     "capdec_attention_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
-                             _i64, _f, _i, _p, _f, _u64, _u32, _p],
-    "capdec_ce_count": [_p, _i64, _i64, _p, _p],
+                             _i64, _f, _i, _p, _f, _p, _u32, _p],
+    "capdec_ce_count": [_p, _i64, _i64, _p, _p, _p],
     "capdec_ce_fwd_bwd": [_p, _i64, _p, _i, _i, _i64, _p, _f, _p, _i, _p],
     "capdec_colsum_acc": [_p, _i64, _p, _i, _i, _p],
     "capdec_act_bwd": [_p, _p, _p, _i64, _i, _p],
@@ -44,6 +44,7 @@ SIGNATURES = {
     "capdec_rows_scatter": [_p, _p, _i, _i, _i, _i, _i, _p],
     "capdec_mapper_concat_fwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "capdec_mapper_concat_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "capdec_step_clock": [_p, _p, _p, _p, _f, _i, _i, _p],
     "capdec_adamw_step": [_p, _p, _p, _p, _i64, _p, _p, _f, _f, _f, _f, _p, _i, _p],
 }
 _RESTYPES = {"capdec_last_error": C.c_char_p, "capdec_launch_count": C.c_int64, "capdec_gemm_debug_mn_encoding": None}

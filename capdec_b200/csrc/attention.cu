@@ -30,8 +30,9 @@ __global__ void __launch_bounds__(512) attention_fwd_kernel(const float* __restr
                                      const float* __restrict__ v, float* __restrict__ ctx, float* __restrict__ lse,
                                      int H, int T, int S, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts,
                                      int64_t o_bs, int64_t o_ts, float scale, int causal,
-                                     const int32_t* __restrict__ key_len, float p_drop, uint64_t seed,
+                                     const int32_t* __restrict__ key_len, float p_drop, const uint64_t* seed_dev,
                                      uint32_t stream_id) {
+  const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
   constexpr int DPL = HD / 4;   // dims per lane
   constexpr int V4 = DPL / 4;   // float4 per lane
   extern __shared__ __align__(16) float smem[];
@@ -108,8 +109,9 @@ __global__ void __launch_bounds__(512) attention_bwd_kernel(const float* __restr
                                      float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int H,
                                      int T, int S, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts,
                                      int64_t o_bs, int64_t o_ts, float scale, int causal,
-                                     const int32_t* __restrict__ key_len, float p_drop, uint64_t seed,
+                                     const int32_t* __restrict__ key_len, float p_drop, const uint64_t* seed_dev,
                                      uint32_t stream_id) {
+  const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
   constexpr int DPL = HD / 4;
   constexpr int V4 = DPL / 4;
   extern __shared__ __align__(16) float smem[];
@@ -240,7 +242,7 @@ using namespace capdec;
 extern "C" int capdec_attention_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, int B,
                                     int H, int T, int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs,
                                     int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale, int causal,
-                                    const int32_t* key_len, float p_drop, uint64_t seed, uint32_t stream_id,
+                                    const int32_t* key_len, float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
                                     capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(q && k && v && ctx, "attention_fwd: null argument");
@@ -252,12 +254,12 @@ extern "C" int capdec_attention_fwd(const float* q, const float* k, const float*
     static bool set64 = false;
     if (!set64) { cudaFuncSetAttribute(attention_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); set64 = true; }
     attention_fwd_kernel<64><<<B * H, threads, smem, stream>>>(q, k, v, ctx, lse, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts,
-                                                               scale, causal, key_len, p_drop, seed, stream_id);
+                                                               scale, causal, key_len, p_drop, seed_dev, stream_id);
   } else {
     static bool set96 = false;
     if (!set96) { cudaFuncSetAttribute(attention_fwd_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); set96 = true; }
     attention_fwd_kernel<96><<<B * H, threads, smem, stream>>>(q, k, v, ctx, lse, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts,
-                                                               scale, causal, key_len, p_drop, seed, stream_id);
+                                                               scale, causal, key_len, p_drop, seed_dev, stream_id);
   }
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("attention_fwd_kernel");
@@ -268,7 +270,7 @@ extern "C" int capdec_attention_bwd(const float* q, const float* k, const float*
                                     const float* dctx, const float* lse, float* dq, float* dk, float* dv, int B, int H,
                                     int T, int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts,
                                     int64_t o_bs, int64_t o_ts, float scale, int causal, const int32_t* key_len,
-                                    float p_drop, uint64_t seed, uint32_t stream_id, capdec_stream_t stream_) {
+                                    float p_drop, const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(q && k && v && ctx && dctx && lse && dq && dk && dv, "attention_bwd: null argument");
   int rc = check_attn_args(B, H, T, S, hd, q_ts, kv_ts, o_ts);
@@ -280,12 +282,12 @@ extern "C" int capdec_attention_bwd(const float* q, const float* k, const float*
     static bool set64 = false;
     if (!set64) { cudaFuncSetAttribute(attention_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set64 = true; }
     attention_bwd_kernel<64><<<B * H, threads, smem, stream>>>(q, k, v, ctx, dctx, lse, dq, dk, dv, H, T, S, q_bs, q_ts, kv_bs,
-                                                               kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed, stream_id);
+                                                               kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id);
   } else {
     static bool set96 = false;
     if (!set96) { cudaFuncSetAttribute(attention_bwd_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set96 = true; }
     attention_bwd_kernel<96><<<B * H, threads, smem, stream>>>(q, k, v, ctx, dctx, lse, dq, dk, dv, H, T, S, q_bs, q_ts, kv_bs,
-                                                               kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed, stream_id);
+                                                               kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id);
   }
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("attention_bwd_kernel");

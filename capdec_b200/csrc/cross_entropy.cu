@@ -7,20 +7,24 @@
 
 namespace capdec {
 
-__global__ void ce_count_kernel(const int64_t* __restrict__ targets, int64_t n, int64_t ignore, float* __restrict__ out) {
+// single block: WRITES the count of non-ignored targets to *out (+= when accumulate) and zeroes *loss_sum
+__global__ void __launch_bounds__(1024) ce_count_kernel(const int64_t* __restrict__ targets, int64_t n, int64_t ignore,
+                                                        float* __restrict__ out, float* __restrict__ loss_sum) {
   __shared__ int s[32];
   int c = 0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    c += (targets[i] != ignore);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) c += (targets[i] != ignore);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
   __syncthreads();
   if (threadIdx.x < 32) {
-    c = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0;
+    c = s[threadIdx.x];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (threadIdx.x == 0 && c) atomicAdd(out, (float)c);
+    if (threadIdx.x == 0) {
+      *out = (float)c;
+      if (loss_sum) *loss_sum = 0.0f;
+    }
   }
 }
 
@@ -102,12 +106,10 @@ __global__ void __launch_bounds__(kCeThreads) ce_kernel(float* __restrict__ logi
 using namespace capdec;
 
 extern "C" int capdec_ce_count(const int64_t* targets, int64_t n, int64_t ignore_index, float* n_valid,
-                               capdec_stream_t stream_) {
+                               float* loss_sum_to_zero, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(targets && n_valid && n > 0, "ce_count: bad arguments");
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > 64) blocks = 64;
-  ce_count_kernel<<<blocks, 256, 0, stream>>>(targets, n, ignore_index, n_valid);
+  ce_count_kernel<<<1, 1024, 0, stream>>>(targets, n, ignore_index, n_valid, loss_sum_to_zero);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("ce_count_kernel");
   return CAPDEC_OK;

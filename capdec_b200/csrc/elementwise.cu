@@ -28,7 +28,8 @@ __device__ __forceinline__ void gauss4(uint64_t seed, uint32_t stream, uint64_t 
 __global__ void __launch_bounds__(256) noise_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int D,
                                                     float variance, const float* __restrict__ noise,
                                                     const float* __restrict__ offset, int uniform_ball, int dont_norm,
-                                                    uint64_t seed, uint64_t step) {
+                                                    const uint64_t* seed_dev, uint64_t step) {
+  const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= B) return;
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t* __restric
                                                         const float* __restrict__ prefix_proj,
                                                         const float* __restrict__ wte, const float* __restrict__ wpe,
                                                         float* __restrict__ h, int B, int P, int L, int d, int vocab,
-                                                        float p_drop, uint64_t seed, uint32_t stream_id) {
+                                                        float p_drop, const uint64_t* seed_dev, uint32_t stream_id) {
+  const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = P + L;
   const int row = blockIdx.x * 8 + warp;
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t* __restric
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ dh,
                                  float* __restrict__ d_prefix_proj, float* __restrict__ d_wte,
                                  float* __restrict__ d_wpe, int B, int P, int L, int d, int vocab, float p_drop,
-                                 uint64_t seed, uint32_t stream_id) {
+                                 const uint64_t* seed_dev, uint32_t stream_id) {
+  const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
   const int T = P + L;
   const int t = blockIdx.x;
   const int b0 = blockIdx.y * 32, b1 = min(B, b0 + 32);
@@ -231,17 +234,29 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float4* __restrict__
 // ------------------------------------------------------------------------------------------------------------
 // row gather / scatter (logits slice [:, P-1:-1] expressed on hidden states)
 // ------------------------------------------------------------------------------------------------------------
-// gather: dst[B*L, d] <- src[B, T, d] rows (b, off + j); scatter: the reverse into a zero-initialised dst
+// gather: dst[B*L, d] <- src[B, T, d] rows (b, off + j)
+// scatter: dst[B, T, d] <- src[B*L, d] at rows (b, off + j), every other row of dst is written as zero
 __global__ void __launch_bounds__(256) rows_copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int B,
                                                         int T, int L, int off, int d4, int scatter) {
-  const int64_t total = (int64_t)B * L * d4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % d4);
-    const int64_t rj = i / d4;
-    const int j = (int)(rj % L);
-    const int64_t b = rj / L;
-    const int64_t full = ((b * T) + off + j) * d4 + c;
-    if (scatter) dst[full] = src[i]; else dst[i] = src[full];
+  if (!scatter) {
+    const int64_t total = (int64_t)B * L * d4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int c = (int)(i % d4);
+      const int64_t rj = i / d4;
+      const int j = (int)(rj % L);
+      const int64_t b = rj / L;
+      dst[i] = src[((b * T) + off + j) * d4 + c];
+    }
+  } else {
+    const int64_t total = (int64_t)B * T * d4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int c = (int)(i % d4);
+      const int64_t rt = i / d4;
+      const int t = (int)(rt % T);
+      const int64_t b = rt / T;
+      const int j = t - off;
+      dst[i] = (j >= 0 && j < L) ? src[((b * L) + j) * d4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
@@ -313,6 +328,22 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, floa
   }
 }
 
+// device-side training clock: advances the RNG seed and evaluates get_linear_schedule_with_warmup
+// (HF:optimization.py:101-104 as used at train.py:328-330,353) so that a whole step replays as one CUDA graph.
+__global__ void step_clock_kernel(uint64_t* seed_dev, float* step_dev, float* lr_dev, float* t_dev, float base_lr,
+                                  float warmup, float total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (seed_dev) *seed_dev += 0x9E3779B97F4A7C15ull;
+    if (step_dev) {
+      const float n = *step_dev;  // number of optimizer steps already taken
+      float f = (n < warmup) ? n / fmaxf(1.0f, warmup) : fmaxf(0.0f, (total - n) / fmaxf(1.0f, total - warmup));
+      *lr_dev = base_lr * f;
+      *t_dev = n + 1.0f;  // Adam's bias-correction step number for this update
+      *step_dev = n + 1.0f;
+    }
+  }
+}
+
 static inline int grid_for(int64_t n_items, int threads, int per_sm = 8) {
   int64_t b = (n_items + threads - 1) / threads;
   const int64_t cap = (int64_t)num_sms() * per_sm;
@@ -324,40 +355,40 @@ static inline int grid_for(int64_t n_items, int threads, int per_sm = 8) {
 using namespace capdec;
 
 extern "C" int capdec_noise_injection(const float* x, float* out, int B, int D, float variance, const float* noise,
-                                      const float* offset, int uniform_ball, int dont_norm, uint64_t seed,
+                                      const float* offset, int uniform_ball, int dont_norm, const uint64_t* seed_dev,
                                       uint64_t step, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(x && out && B > 0, "noise_injection: null argument");
   CAPDEC_REQUIRE(D % 4 == 0 && D > 0 && D <= 1024, "noise_injection: D=%d must be a multiple of 4 and <= 1024", D);
   CAPDEC_REQUIRE(variance >= 0.0f, "noise_injection: negative variance");
-  noise_kernel<<<(B + 7) / 8, 256, 0, stream>>>(x, out, B, D, variance, noise, offset, uniform_ball, dont_norm, seed, step);
+  noise_kernel<<<(B + 7) / 8, 256, 0, stream>>>(x, out, B, D, variance, noise, offset, uniform_ball, dont_norm, seed_dev, step);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("noise_kernel");
   return CAPDEC_OK;
 }
 
 extern "C" int capdec_embed_fwd(const int64_t* tokens, const float* prefix_proj, const float* wte, const float* wpe,
-                                float* h, int B, int P, int L, int d, int vocab, float p_drop, uint64_t seed,
+                                float* h, int B, int P, int L, int d, int vocab, float p_drop, const uint64_t* seed_dev,
                                 uint32_t stream_id, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(wpe && h && B > 0 && P >= 0 && L >= 0 && P + L > 0 && d % 4 == 0, "embed_fwd: bad arguments");
   CAPDEC_REQUIRE((L == 0 || (tokens && wte)) && (P == 0 || prefix_proj), "embed_fwd: missing tokens/wte/prefix_proj");
   const int rows = B * (P + L);
-  embed_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(tokens, prefix_proj, wte, wpe, h, B, P, L, d, vocab, p_drop, seed, stream_id);
+  embed_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(tokens, prefix_proj, wte, wpe, h, B, P, L, d, vocab, p_drop, seed_dev, stream_id);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("embed_fwd_kernel");
   return CAPDEC_OK;
 }
 
 extern "C" int capdec_embed_bwd(const int64_t* tokens, const float* dh, float* d_prefix_proj, float* d_wte,
-                                float* d_wpe, int B, int P, int L, int d, int vocab, float p_drop, uint64_t seed,
+                                float* d_wpe, int B, int P, int L, int d, int vocab, float p_drop, const uint64_t* seed_dev,
                                 uint32_t stream_id, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(dh && B > 0 && P + L > 0 && d % 4 == 0 && d / 4 <= 1024, "embed_bwd: bad arguments");
   CAPDEC_REQUIRE(!d_wte || tokens, "embed_bwd: tokens required for the wte gradient");
   dim3 grid(P + L, (B + 31) / 32);
   const int threads = ((d / 4 + 31) / 32) * 32;
-  embed_bwd_kernel<<<grid, threads, 0, stream>>>(tokens, dh, d_prefix_proj, d_wte, d_wpe, B, P, L, d, vocab, p_drop, seed, stream_id);
+  embed_bwd_kernel<<<grid, threads, 0, stream>>>(tokens, dh, d_prefix_proj, d_wte, d_wpe, B, P, L, d, vocab, p_drop, seed_dev, stream_id);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("embed_bwd_kernel");
   return CAPDEC_OK;
@@ -390,7 +421,7 @@ extern "C" int capdec_act_bwd(const float* dy, const float* pre, float* dx, int6
 
 static int rows_copy(const float* src, float* dst, int B, int T, int L, int off, int d, int scatter, cudaStream_t stream) {
   CAPDEC_REQUIRE(src && dst && B > 0 && L > 0 && off >= 0 && off + L <= T && d % 4 == 0, "rows_gather/scatter: bad arguments");
-  rows_copy_kernel<<<grid_for((int64_t)B * L * (d / 4), 256), 256, 0, stream>>>(
+  rows_copy_kernel<<<grid_for((int64_t)B * (scatter ? T : L) * (d / 4), 256), 256, 0, stream>>>(
       reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), B, T, L, off, d / 4, scatter);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("rows_copy_kernel");
@@ -434,5 +465,16 @@ extern "C" int capdec_adamw_step(float* p, float* g, float* m, float* v, int64_t
                                                             lr_dev, t_dev, beta1, beta2, eps, weight_decay, grad_denom_dev, zero_grad);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("adamw_kernel");
+  return CAPDEC_OK;
+}
+
+extern "C" int capdec_step_clock(uint64_t* seed_dev, float* step_dev, float* lr_dev, float* t_dev, float base_lr,
+                                 int warmup_steps, int total_steps, capdec_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CAPDEC_REQUIRE(seed_dev || step_dev, "step_clock: nothing to do");
+  CAPDEC_REQUIRE(!step_dev || (lr_dev && t_dev), "step_clock: lr_dev and t_dev required with step_dev");
+  step_clock_kernel<<<1, 32, 0, stream>>>(seed_dev, step_dev, lr_dev, t_dev, base_lr, (float)warmup_steps, (float)total_steps);
+  g_launches.fetch_add(1);
+  CAPDEC_LAUNCH_CHECK("step_clock_kernel");
   return CAPDEC_OK;
 }

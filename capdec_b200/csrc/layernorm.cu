@@ -14,7 +14,8 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
                                                          float* __restrict__ h_out, float* __restrict__ x,
                                                          float* __restrict__ stats, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, int rows, int d, float eps,
-                                                         float p_drop, uint64_t seed, uint32_t stream_id) {
+                                                         float p_drop, const uint64_t* seed_dev, uint32_t stream_id) {
+  const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ dh_res, float* __restrict__ dh_out,
                                                          float* __restrict__ dy, float* __restrict__ dgamma,
                                                          float* __restrict__ dbeta, int rows, int d, float p_drop,
-                                                         uint64_t seed, uint32_t stream_id) {
+                                                         const uint64_t* seed_dev, uint32_t stream_id) {
+  const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
   __shared__ float4 s_red[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d4 = d >> 2;
@@ -184,7 +186,7 @@ using namespace capdec;
 
 extern "C" int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out, float* x, float* stats,
                                  const float* gamma, const float* beta, int rows, int d, float eps, float p_drop,
-                                 uint64_t seed, uint32_t stream_id, capdec_stream_t stream_) {
+                                 const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(h_in && x && stats && gamma && beta && rows > 0, "add_ln_fwd: null argument");
   CAPDEC_REQUIRE(d % 128 == 0 && d <= 128 * kMaxV, "add_ln_fwd: d=%d must be a multiple of 128 and <= 1024", d);
@@ -192,7 +194,7 @@ extern "C" int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out
   const int nv = d / 128;
   const int grid = (rows + 7) / 8;
   DISPATCH_NV(nv, (add_ln_fwd_kernel<NV><<<grid, 256, 0, stream>>>(h_in, y, h_out, x, stats, gamma, beta, rows, d, eps,
-                                                                   p_drop, seed, stream_id)));
+                                                                   p_drop, seed_dev, stream_id)));
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("add_ln_fwd_kernel");
   return CAPDEC_OK;
@@ -200,7 +202,7 @@ extern "C" int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out
 
 extern "C" int capdec_add_ln_bwd(const float* dx, const float* r, const float* stats, const float* gamma,
                                  const float* dh_res, float* dh_out, float* dy, float* dgamma, float* dbeta, int rows,
-                                 int d, float p_drop, uint64_t seed, uint32_t stream_id, capdec_stream_t stream_) {
+                                 int d, float p_drop, const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(dx && r && stats && gamma && dh_out && rows > 0, "add_ln_bwd: null argument");
   CAPDEC_REQUIRE(d % 128 == 0 && d <= 128 * kMaxV, "add_ln_bwd: d=%d must be a multiple of 128 and <= 1024", d);
@@ -210,7 +212,7 @@ extern "C" int capdec_add_ln_bwd(const float* dx, const float* r, const float* s
   const int cap = num_sms() * 4;
   if (grid > cap) grid = cap;
   DISPATCH_NV(nv, (add_ln_bwd_kernel<NV><<<grid, 256, 0, stream>>>(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma,
-                                                                   dbeta, rows, d, p_drop, seed, stream_id)));
+                                                                   dbeta, rows, d, p_drop, seed_dev, stream_id)));
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("add_ln_bwd_kernel");
   return CAPDEC_OK;

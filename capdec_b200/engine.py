@@ -1,0 +1,472 @@
+"""Forward / backward orchestration of the CapDec train step over the C-ABI kernels (host plumbing, no arithmetic).
+
+One `Engine` per model.  Activations live in a preallocated arena keyed by (B, P, L); every launch goes to torch's
+current stream, so a whole step is CUDA-graph capturable.  Two entry points share the same kernels:
+
+  * `loss_and_grads(tokens, prefix)` — the fast path used by `Trainer`: LM head only on the L consumed positions
+    (train.py:349), fused CE fwd+bwd, gradients written straight into the flat gradient buffer;
+  * `logits_autograd(tokens, prefix, mask)` — the drop-in path behind `ClipCaptionModel.forward` (train.py:251-260):
+    materialises `.logits` [B, P+L, V] and hooks the hand-written backward into torch autograd so the reference's
+    `loss.backward()` (train.py:351) works unmodified.
+
+Reference map: embedding assembly train.py:253-255; GPT-2 block HF:modeling_gpt2.py:262-309; attention :54-72,185-226;
+MLP :229-243; ln_f/lm_head :628,703-706; mapper MLP train.py:106-118; TransformerMapper train.py:229-243.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import CapdecError
+
+# dropout site ids (Philox stream): 1 = embeddings, 16 + 4*layer + {0: attention probs, 1: attn resid, 2: mlp resid}
+_SITE_EMBD = 1
+
+
+def _site(layer: int, k: int) -> int:
+    return 16 + 4 * layer + k
+
+
+class Engine:
+    def __init__(self, model):
+        self.m = model
+        self.flat = model._flatten()
+        self.dev = self.flat.params.device
+        cfg = model.gpt.config
+        self.cfg = cfg
+        self.d = cfg.n_embd
+        self.H = cfg.n_head
+        self.hd = self.d // self.H
+        self.F = 4 * self.d
+        self.V = cfg.vocab_size
+        self.Vp = (self.V + 127) // 128 * 128  # logits pitch (16-byte aligned rows for TMA)
+        self.nl = cfg.n_layer
+        self.P = model.prefix_length
+        self.D = model.prefix_size
+        self.is_mlp = model.mapping_type.value == "mlp"
+        if self.d % 128 or self.hd not in (64, 96):
+            raise CapdecError(f"unsupported GPT-2 geometry d={self.d} heads={self.H}")
+        self._params()
+        self.seed = ops.make_seed(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, self.dev)
+        self.arenas = {}
+        self._mapper_arenas = {}
+
+    # ------------------------------------------------------------------------------------------------------------
+    # parameter / gradient views
+    # ------------------------------------------------------------------------------------------------------------
+    def _params(self):
+        fl = self.flat
+        self.p = {n: fl.params[o: o + k].view(s) for n, (o, k, s) in fl.layout.items()}
+        if fl.grads is None:
+            fl.grads = torch.zeros_like(fl.params)
+        self.g = {n: fl.grads[o: o + k].view(s) for n, (o, k, s) in fl.layout.items()}
+        if not self.is_mlp:
+            # to_queries [d,d] and to_keys_values [2d,d] are adjacent in the flat buffer -> one fused [3d,d] weight
+            self.wqkv, self.gqkv = [], []
+            j = 0
+            while f"clip_project.transformer.layers.{j}.attn.to_queries.weight" in fl.layout:
+                oq, kq, _ = fl.layout[f"clip_project.transformer.layers.{j}.attn.to_queries.weight"]
+                ok, kk, _ = fl.layout[f"clip_project.transformer.layers.{j}.attn.to_keys_values.weight"]
+                assert ok == oq + kq, "mapper q / kv weights must be adjacent in the flat buffer"
+                self.wqkv.append(fl.params[oq: oq + kq + kk].view(3 * self.d, self.d))
+                self.gqkv.append(fl.grads[oq: oq + kq + kk].view(3 * self.d, self.d))
+                j += 1
+            self.n_mapper_layers = j
+            self.C = self.m.clip_project.clip_length
+            self.mH = self.m.clip_project.num_heads
+            self.mhd = self.d // self.mH
+
+    def grad_views(self):
+        return self.g
+
+    def zero_grads(self, mapper_only: bool = False):
+        fl = self.flat
+        end = fl.tail + fl.n_mapper if mapper_only else fl.grads.numel()
+        fl.grads[:end].zero_()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # arenas
+    # ------------------------------------------------------------------------------------------------------------
+    def _arena(self, B: int, L: int, P: Optional[int] = None):
+        P = self.P if P is None else P
+        key = (B, P, L)
+        a = self.arenas.get(key)
+        if a is not None:
+            return a
+        T = P + L
+        if T > 128:
+            raise CapdecError(f"sequence of {T} positions exceeds the single-tile attention limit (128)")
+        M = B * T
+        d, F = self.d, self.F
+        e = lambda *s: torch.empty(*s, device=self.dev, dtype=torch.float32)
+        a = SimpleNamespace(B=B, P=P, L=L, T=T, M=M)
+        a.h = [e(M, d) for _ in range(self.nl + 1)]       # residual stream entering layer l (h[nl] = input of ln_f)
+        a.x1 = [e(M, d) for _ in range(self.nl)]
+        a.st1 = [e(M, 2) for _ in range(self.nl)]
+        a.qkv = [e(M, 3 * d) for _ in range(self.nl)]
+        a.lse = [e(B * self.H * T) for _ in range(self.nl)]
+        a.ctx = [e(M, d) for _ in range(self.nl)]
+        a.h1 = [e(M, d) for _ in range(self.nl)]
+        a.x2 = [e(M, d) for _ in range(self.nl)]
+        a.st2 = [e(M, 2) for _ in range(self.nl)]
+        a.u = [e(M, F) for _ in range(self.nl)]
+        a.g = [e(M, F) for _ in range(self.nl)]
+        a.y = e(M, d)
+        a.xf = e(M, d)
+        a.stf = e(M, 2)
+        a.pp = e(B, P * d) if P > 0 else None
+        # backward scratch
+        a.dh = e(M, d)
+        a.dy = e(M, d)
+        a.dx = e(M, d)
+        a.dF = e(M, F)
+        a.dqkv = e(M, 3 * d)
+        a.dctx = e(M, d)
+        a.dpp = e(B, P * d) if P > 0 else None
+        # LM head on the consumed rows only (fast path)
+        if L > 0:
+            a.xsel = e(B * L, d)
+            a.dxsel = e(B * L, d)
+            a.logits_sel = e(B * L, self.Vp)
+        a.logits_full = None
+        a.tokens = None
+        self.arenas[key] = a
+        return a
+
+    def _mapper_arena(self, B: int):
+        a = self._mapper_arenas.get(B)
+        if a is not None:
+            return a
+        d, P = self.d, self.P
+        e = lambda *s: torch.empty(*s, device=self.dev, dtype=torch.float32)
+        a = SimpleNamespace(B=B)
+        a.x_in = e(B, self.D)
+        if self.is_mlp:
+            hdim = (d * P) // 2
+            a.a1 = e(B, hdim)
+            a.da1 = e(B, hdim)
+        else:
+            C, S = self.C, self.C + P
+            Mm = B * S
+            nl = self.n_mapper_layers
+            a.S, a.Mm = S, Mm
+            a.lin = e(B, C * d)
+            a.dlin = e(B, C * d)
+            a.hm = [e(Mm, d) for _ in range(nl + 1)]   # residual entering layer j; hm[nl] = mapper output stream
+            a.y1 = [e(Mm, d) for _ in range(nl)]
+            a.s1 = [e(Mm, 2) for _ in range(nl)]
+            a.qkv = [e(Mm, 3 * d) for _ in range(nl)]
+            a.lse = [e(B * self.mH * S) for _ in range(nl)]
+            a.o = [e(Mm, d) for _ in range(nl)]
+            a.hm1 = [e(Mm, d) for _ in range(nl)]
+            a.y2 = [e(Mm, d) for _ in range(nl)]
+            a.s2 = [e(Mm, 2) for _ in range(nl)]
+            a.f = [e(Mm, 2 * d) for _ in range(nl)]
+            a.t = e(Mm, d)
+            a.scratch = e(Mm, d)
+            a.sscr = e(Mm, 2)
+            a.dhm = e(Mm, d)
+            a.dt = e(Mm, d)
+            a.df = e(Mm, 2 * d)
+            a.dqkv = e(Mm, 3 * d)
+            a.do = e(Mm, d)
+        self._mapper_arenas[B] = a
+        return a
+
+    # ------------------------------------------------------------------------------------------------------------
+    # mapper
+    # ------------------------------------------------------------------------------------------------------------
+    def _mapper_fwd(self, x, pp):
+        """x [B, D] -> pp [B, P*d] (train.py:254 `clip_project(prefix)`)."""
+        B = x.shape[0]
+        ma = self._mapper_arena(B)
+        p = self.p
+        if self.is_mlp:
+            ops.linear_fwd(x, p["clip_project.model.0.weight"], "linear", p["clip_project.model.0.bias"], ma.a1,
+                           act=ops.ACT_TANH)
+            ops.linear_fwd(ma.a1, p["clip_project.model.2.weight"], "linear", p["clip_project.model.2.bias"], pp)
+            return
+        d, C, P, S, Mm = self.d, self.C, self.P, ma.S, ma.Mm
+        ops.linear_fwd(x, p["clip_project.linear.weight"], "linear", p["clip_project.linear.bias"], ma.lin)
+        ops.mapper_concat_fwd(ma.lin, p["clip_project.prefix_const"], ma.hm[0], B, C, P)
+        nl = self.n_mapper_layers
+        for j in range(nl):
+            pre = f"clip_project.transformer.layers.{j}."
+            if j == 0:
+                ops.add_ln_fwd(ma.hm[0], None, None, ma.y1[0], ma.s1[0], p[pre + "norm1.weight"], p[pre + "norm1.bias"])
+            ops.gemm(ma.y1[j], 0, self.wqkv[j], 0, ma.qkv[j], Mm, 3 * d, d)
+            q, k, v = ma.qkv[j][:, :d], ma.qkv[j][:, d:2 * d], ma.qkv[j][:, 2 * d:]
+            ops.attention_fwd(q, k, v, ma.o[j], ma.lse[j], B, self.mH, S, S, self.mhd, S * 3 * d, 3 * d, S * 3 * d, 3 * d,
+                              S * d, d, self.mhd ** -0.5, 0)
+            ops.linear_fwd(ma.o[j], p[pre + "attn.project.weight"], "linear", p[pre + "attn.project.bias"], ma.t)
+            ops.add_ln_fwd(ma.hm[j], ma.t, ma.hm1[j], ma.y2[j], ma.s2[j], p[pre + "norm2.weight"], p[pre + "norm2.bias"])
+            ops.linear_fwd(ma.y2[j], p[pre + "mlp.fc1.weight"], "linear", p[pre + "mlp.fc1.bias"], ma.f[j], act=ops.ACT_RELU)
+            ops.linear_fwd(ma.f[j], p[pre + "mlp.fc2.weight"], "linear", p[pre + "mlp.fc2.bias"], ma.t)
+            if j + 1 < nl:
+                nx = f"clip_project.transformer.layers.{j + 1}."
+                ops.add_ln_fwd(ma.hm1[j], ma.t, ma.hm[j + 1], ma.y1[j + 1], ma.s1[j + 1], p[nx + "norm1.weight"],
+                               p[nx + "norm1.bias"])
+            else:  # last residual add (no LayerNorm follows, train.py:178): reuse the fused kernel, discard its LN output
+                ops.add_ln_fwd(ma.hm1[j], ma.t, ma.hm[nl], ma.scratch, ma.sscr, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
+        ops.rows_gather(ma.hm[nl], pp.view(B * P, d), B, S, P, C)  # out = transformer(prefix)[:, clip_length:]
+
+    def _mapper_bwd(self, x, dpp):
+        B = x.shape[0]
+        ma = self._mapper_arena(B)
+        p, g = self.p, self.g
+        if self.is_mlp:
+            w2, w1 = "clip_project.model.2.", "clip_project.model.0."
+            ops.linear_wgrad(ma.a1, dpp, g[w2 + "weight"], "linear", g[w2 + "bias"])
+            ops.linear_dgrad(dpp, p[w2 + "weight"], "linear", ma.da1)
+            ops.act_bwd(ma.da1, ma.a1, ma.da1, ops.ACT_TANH)
+            ops.linear_wgrad(x, ma.da1, g[w1 + "weight"], "linear", g[w1 + "bias"])
+            return
+        d, C, P, S, Mm = self.d, self.C, self.P, ma.S, ma.Mm
+        nl = self.n_mapper_layers
+        ops.rows_scatter(dpp.view(B * P, d), ma.dhm, B, S, P, C)
+        for j in reversed(range(nl)):
+            pre = f"clip_project.transformer.layers.{j}."
+            # fc2
+            ops.linear_wgrad(ma.f[j], ma.dhm, g[pre + "mlp.fc2.weight"], "linear", g[pre + "mlp.fc2.bias"])
+            ops.linear_dgrad(ma.dhm, p[pre + "mlp.fc2.weight"], "linear", ma.df)
+            ops.act_bwd(ma.df, ma.f[j], ma.df, ops.ACT_RELU)
+            ops.linear_wgrad(ma.y2[j], ma.df, g[pre + "mlp.fc1.weight"], "linear", g[pre + "mlp.fc1.bias"])
+            ops.linear_dgrad(ma.df, p[pre + "mlp.fc1.weight"], "linear", ma.dt)
+            ops.add_ln_bwd(ma.dt, ma.hm1[j], ma.s2[j], p[pre + "norm2.weight"], ma.dhm, ma.dhm, None,
+                           g[pre + "norm2.weight"], g[pre + "norm2.bias"])
+            # attention branch
+            ops.linear_wgrad(ma.o[j], ma.dhm, g[pre + "attn.project.weight"], "linear", g[pre + "attn.project.bias"])
+            ops.linear_dgrad(ma.dhm, p[pre + "attn.project.weight"], "linear", ma.do)
+            q, k, v = ma.qkv[j][:, :d], ma.qkv[j][:, d:2 * d], ma.qkv[j][:, 2 * d:]
+            dq, dk, dv = ma.dqkv[:, :d], ma.dqkv[:, d:2 * d], ma.dqkv[:, 2 * d:]
+            ops.attention_bwd(q, k, v, ma.o[j], ma.do, ma.lse[j], dq, dk, dv, B, self.mH, S, S, self.mhd, S * 3 * d, 3 * d,
+                              S * 3 * d, 3 * d, S * d, d, self.mhd ** -0.5, 0)
+            ops.linear_wgrad(ma.y1[j], ma.dqkv, self.gqkv[j], "linear")
+            ops.linear_dgrad(ma.dqkv, self.wqkv[j], "linear", ma.dt)
+            ops.add_ln_bwd(ma.dt, ma.hm[j], ma.s1[j], p[pre + "norm1.weight"], ma.dhm, ma.dhm, None,
+                           g[pre + "norm1.weight"], g[pre + "norm1.bias"])
+        ops.mapper_concat_bwd(ma.dhm, ma.dlin, g["clip_project.prefix_const"], B, C, P)
+        ops.linear_wgrad(x, ma.dlin, g["clip_project.linear.weight"], "linear", g["clip_project.linear.bias"])
+
+    def mapper_infer(self, x):
+        """`model.clip_project(prefix)` (predictions_runner.py:228, gpt2_prefix_eval.py:271) — forward only."""
+        x = x.detach().to(device=self.dev, dtype=torch.float32).contiguous()
+        B = x.shape[0]
+        pp = torch.empty(B, self.P * self.d, device=self.dev)
+        self._mapper_fwd(x, pp)
+        return pp if self.is_mlp else pp.view(B, self.P, self.d)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # GPT-2 trunk
+    # ------------------------------------------------------------------------------------------------------------
+    def _drop_p(self):
+        """(embd, attn, resid) dropout probabilities in effect: GPT-2's `training` flag decides (train.py:281-284)."""
+        if self.m.gpt.training:
+            c = self.cfg
+            return float(c.embd_pdrop), float(c.attn_pdrop), float(c.resid_pdrop)
+        return 0.0, 0.0, 0.0
+
+    def _trunk_fwd(self, a, key_len=None):
+        """a.h[0] (embeddings + positions) -> a.xf = ln_f(h_L).  HF:modeling_gpt2.py:612-628."""
+        p = self.p
+        B, T, M, d, F = a.B, a.T, a.M, self.d, self.F
+        _, p_attn, p_res = a.pdrop
+        ops.add_ln_fwd(a.h[0], None, None, a.x1[0], a.st1[0], p["gpt.transformer.h.0.ln_1.weight"],
+                       p["gpt.transformer.h.0.ln_1.bias"], eps=self.cfg.layer_norm_epsilon)
+        for l in range(self.nl):
+            pre = f"gpt.transformer.h.{l}."
+            ops.linear_fwd(a.x1[l], p[pre + "attn.c_attn.weight"], "conv1d", p[pre + "attn.c_attn.bias"], a.qkv[l])
+            q, k, v = a.qkv[l][:, :d], a.qkv[l][:, d:2 * d], a.qkv[l][:, 2 * d:]
+            ops.attention_fwd(q, k, v, a.ctx[l], a.lse[l], B, self.H, T, T, self.hd, T * 3 * d, 3 * d, T * 3 * d, 3 * d,
+                              T * d, d, self.hd ** -0.5, 1, key_len=key_len, p_drop=p_attn, seed=self.seed,
+                              stream_id=_site(l, 0))
+            ops.linear_fwd(a.ctx[l], p[pre + "attn.c_proj.weight"], "conv1d", p[pre + "attn.c_proj.bias"], a.y)
+            ops.add_ln_fwd(a.h[l], a.y, a.h1[l], a.x2[l], a.st2[l], p[pre + "ln_2.weight"], p[pre + "ln_2.bias"],
+                           eps=self.cfg.layer_norm_epsilon, p_drop=p_res, seed=self.seed, stream_id=_site(l, 1))
+            ops.linear_fwd(a.x2[l], p[pre + "mlp.c_fc.weight"], "conv1d", p[pre + "mlp.c_fc.bias"], a.g[l],
+                           act=ops.ACT_GELU_NEW, aux=a.u[l])
+            ops.linear_fwd(a.g[l], p[pre + "mlp.c_proj.weight"], "conv1d", p[pre + "mlp.c_proj.bias"], a.y)
+            if l + 1 < self.nl:
+                nx = f"gpt.transformer.h.{l + 1}."
+                ops.add_ln_fwd(a.h1[l], a.y, a.h[l + 1], a.x1[l + 1], a.st1[l + 1], p[nx + "ln_1.weight"],
+                               p[nx + "ln_1.bias"], eps=self.cfg.layer_norm_epsilon, p_drop=p_res, seed=self.seed,
+                               stream_id=_site(l, 2))
+            else:
+                ops.add_ln_fwd(a.h1[l], a.y, a.h[self.nl], a.xf, a.stf, p["gpt.transformer.ln_f.weight"],
+                               p["gpt.transformer.ln_f.bias"], eps=self.cfg.layer_norm_epsilon, p_drop=p_res,
+                               seed=self.seed, stream_id=_site(l, 2))
+
+    def _trunk_bwd(self, a, dxf, train_gpt: bool, key_len=None):
+        """dxf = dL/d(ln_f output) [M, d] -> a.dh = dL/d(h[0]); GPT-2 parameter gradients accumulated if train_gpt."""
+        p, g = self.p, self.g
+        B, T, M, d, F = a.B, a.T, a.M, self.d, self.F
+        _, p_attn, p_res = a.pdrop
+        gw = (lambda n: g[n]) if train_gpt else (lambda n: None)
+        dy = a.dy if p_res > 0 else None     # branch-output gradient buffer (mask * dh); aliases dh when p = 0
+        cur = (lambda: a.dy) if p_res > 0 else (lambda: a.dh)
+        ops.add_ln_bwd(dxf, a.h[self.nl], a.stf, p["gpt.transformer.ln_f.weight"], None, a.dh, dy,
+                       gw("gpt.transformer.ln_f.weight"), gw("gpt.transformer.ln_f.bias"), p_drop=p_res, seed=self.seed,
+                       stream_id=_site(self.nl - 1, 2))
+        for l in reversed(range(self.nl)):
+            pre = f"gpt.transformer.h.{l}."
+            dy2 = cur()
+            # mlp.c_proj
+            if train_gpt:
+                ops.linear_wgrad(a.g[l], dy2, g[pre + "mlp.c_proj.weight"], "conv1d", g[pre + "mlp.c_proj.bias"])
+            ops.linear_dgrad(dy2, p[pre + "mlp.c_proj.weight"], "conv1d", a.dF)
+            ops.act_bwd(a.dF, a.u[l], a.dF, ops.ACT_GELU_NEW)
+            if train_gpt:
+                ops.linear_wgrad(a.x2[l], a.dF, g[pre + "mlp.c_fc.weight"], "conv1d", g[pre + "mlp.c_fc.bias"])
+            ops.linear_dgrad(a.dF, p[pre + "mlp.c_fc.weight"], "conv1d", a.dx)
+            ops.add_ln_bwd(a.dx, a.h1[l], a.st2[l], p[pre + "ln_2.weight"], a.dh, a.dh, dy, gw(pre + "ln_2.weight"),
+                           gw(pre + "ln_2.bias"), p_drop=p_res, seed=self.seed, stream_id=_site(l, 1))
+            dy1 = cur()
+            # attention
+            if train_gpt:
+                ops.linear_wgrad(a.ctx[l], dy1, g[pre + "attn.c_proj.weight"], "conv1d", g[pre + "attn.c_proj.bias"])
+            ops.linear_dgrad(dy1, p[pre + "attn.c_proj.weight"], "conv1d", a.dctx)
+            q, k, v = a.qkv[l][:, :d], a.qkv[l][:, d:2 * d], a.qkv[l][:, 2 * d:]
+            dq, dk, dv = a.dqkv[:, :d], a.dqkv[:, d:2 * d], a.dqkv[:, 2 * d:]
+            ops.attention_bwd(q, k, v, a.ctx[l], a.dctx, a.lse[l], dq, dk, dv, B, self.H, T, T, self.hd, T * 3 * d, 3 * d,
+                              T * 3 * d, 3 * d, T * d, d, self.hd ** -0.5, 1, key_len=key_len, p_drop=p_attn,
+                              seed=self.seed, stream_id=_site(l, 0))
+            if train_gpt:
+                ops.linear_wgrad(a.x1[l], a.dqkv, g[pre + "attn.c_attn.weight"], "conv1d", g[pre + "attn.c_attn.bias"])
+            ops.linear_dgrad(a.dqkv, p[pre + "attn.c_attn.weight"], "conv1d", a.dx)
+            if l > 0:
+                ops.add_ln_bwd(a.dx, a.h[l], a.st1[l], p[pre + "ln_1.weight"], a.dh, a.dh, dy, gw(pre + "ln_1.weight"),
+                               gw(pre + "ln_1.bias"), p_drop=p_res, seed=self.seed, stream_id=_site(l - 1, 2))
+            else:
+                ops.add_ln_bwd(a.dx, a.h[0], a.st1[0], p[pre + "ln_1.weight"], a.dh, a.dh, None, gw(pre + "ln_1.weight"),
+                               gw(pre + "ln_1.bias"))
+
+    # ------------------------------------------------------------------------------------------------------------
+    # fast path: loss + gradients (sum-reduced CE gradients, divided by the token count inside AdamW)
+    # ------------------------------------------------------------------------------------------------------------
+    def forward_hidden(self, tokens, prefix, key_len=None):
+        """tokens int64 [B,L], prefix fp32 [B,D] (already noise-injected) -> arena with a.xf = ln_f output."""
+        B, L = tokens.shape
+        a = self._arena(B, L)
+        a.pdrop = self._drop_p()
+        a.tokens, a.prefix = tokens, prefix
+        p = self.p
+        self._mapper_fwd(prefix, a.pp)
+        ops.embed_fwd(tokens, a.pp, p["gpt.transformer.wte.weight"], p["gpt.transformer.wpe.weight"], a.h[0], B, self.P, L,
+                      p_drop=a.pdrop[0], seed=self.seed, stream_id=_SITE_EMBD)
+        self._trunk_fwd(a, key_len)
+        return a
+
+    def backward_hidden(self, a, dxf, train_gpt: bool, key_len=None):
+        """Everything below ln_f: trunk, embedding scatter, mapper."""
+        g = self.g
+        self._trunk_bwd(a, dxf, train_gpt, key_len)
+        ops.embed_bwd(a.tokens, a.dh, a.dpp, g["gpt.transformer.wte.weight"] if train_gpt else None,
+                      g["gpt.transformer.wpe.weight"] if train_gpt else None, a.B, self.P, a.L, self.V,
+                      p_drop=a.pdrop[0], seed=self.seed, stream_id=_SITE_EMBD)
+        self._mapper_bwd(a.prefix, a.dpp)
+
+    def loss_and_grads(self, tokens, prefix, train_gpt: Optional[bool] = None, mean_reduce: bool = False):
+        """One forward+backward of train.py:348-351.  Gradients are ACCUMULATED into the flat gradient buffer,
+        sum-reduced over tokens unless `mean_reduce` (then divided by the local count of non-ignored targets).
+        tail[0] <- number of non-ignored targets, tail[1] <- sum of token losses.  Returns the tail view."""
+        if train_gpt is None:
+            train_gpt = self.m.gpt_trainable()
+        fl = self.flat
+        B, L = tokens.shape
+        a = self.forward_hidden(tokens, prefix)
+        p, g = self.p, self.g
+        P, T, d = self.P, a.T, self.d
+        tail = fl.grads[:4]
+        n_valid, loss_sum = tail[0:1], tail[1:2]
+        targets = tokens.reshape(-1)
+        ops.ce_count(targets, n_valid, loss_sum)
+        ops.rows_gather(a.xf, a.xsel, B, T, L, P - 1)                      # hidden states of logits[:, P-1:-1]
+        logits = a.logits_sel[:, : self.V]
+        ops.linear_fwd(a.xsel, p["gpt.transformer.wte.weight"], "linear", None, logits)   # tied lm_head
+        ops.ce_fwd_bwd(logits, targets, self.V, loss_sum, n_valid=n_valid if mean_reduce else None)
+        if train_gpt:
+            ops.linear_wgrad(a.xsel, logits, g["gpt.transformer.wte.weight"], "linear")
+        ops.linear_dgrad(logits, p["gpt.transformer.wte.weight"], "linear", a.dxsel)
+        ops.rows_scatter(a.dxsel, a.dx, B, T, L, P - 1)
+        # a.dx is reused as scratch inside the trunk; ln_f backward consumes it first
+        self.backward_hidden(a, a.dx, train_gpt)
+        return tail
+
+    # ------------------------------------------------------------------------------------------------------------
+    # drop-in path: full logits + autograd hook
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _key_len(mask, T):
+        if mask is None:
+            return None
+        m = mask.reshape(mask.shape[0], -1)[:, :T] > 0
+        klen = m.sum(dim=1).to(torch.int32)
+        # only right padding can be expressed as a key length (which is what ClipCocoDataset produces, train.py:55-63)
+        return klen.contiguous()
+
+    def _full_logits(self, a):
+        if a.logits_full is None:
+            a.logits_full = torch.empty(a.M, self.Vp, device=self.dev, dtype=torch.float32)
+        lg = a.logits_full[:, : self.V]
+        ops.linear_fwd(a.xf, self.p["gpt.transformer.wte.weight"], "linear", None, lg)
+        return lg
+
+    def logits_autograd(self, tokens, prefix, mask=None):
+        if not tokens.is_cuda:
+            raise CapdecError("capdec_b200 has no CPU path: tokens/prefix must be CUDA tensors")
+        tokens = tokens.contiguous()
+        prefix = prefix.detach().to(torch.float32).contiguous()
+        params = [v for _, v in sorted(self._trainable().items())]
+        return _LogitsFn.apply(self, tokens, prefix, mask, *params)
+
+    def _trainable(self):
+        named = dict(torch.nn.Module.named_parameters(self.m))
+        if not self.m.gpt_trainable():
+            named = {k: v for k, v in named.items() if k.startswith("clip_project.")}
+        return {k: v for k, v in named.items() if v.requires_grad}
+
+    def gpt_logits_from_embeds(self, inputs_embeds, attention_mask=None):
+        """`model.gpt(inputs_embeds=...)` for decoding (gpt2_prefix_eval.py:76,163) — forward only, no grad."""
+        x = inputs_embeds.detach().to(device=self.dev, dtype=torch.float32).contiguous()
+        B, T, d = x.shape
+        a = self._arena(B, 0, P=T)
+        a.pdrop = self._drop_p()
+        ops.embed_fwd(None, x, None, self.p["gpt.transformer.wpe.weight"], a.h[0], B, T, 0, p_drop=a.pdrop[0],
+                      seed=self.seed, stream_id=_SITE_EMBD)
+        self._trunk_fwd(a, self._key_len(attention_mask, T))
+        return self._full_logits(a).view(B, T, self.V).clone()
+
+
+class _LogitsFn(torch.autograd.Function):
+    """`ClipCaptionModel.forward` for torch autograd: forward materialises logits [B,T,V]; backward runs the
+    hand-written backward chain and hands each parameter its gradient (a view of the flat gradient buffer)."""
+
+    @staticmethod
+    def forward(ctx, eng: Engine, tokens, prefix, mask, *params):
+        B, L = tokens.shape
+        key_len = Engine._key_len(mask, eng.P + L)
+        a = eng.forward_hidden(tokens, prefix, key_len)
+        lg = eng._full_logits(a)
+        ctx.eng, ctx.arena, ctx.key_len = eng, a, key_len
+        ctx.names = sorted(eng._trainable().keys())
+        return lg.view(B, a.T, eng.V)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        eng, a = ctx.eng, ctx.arena
+        train_gpt = eng.m.gpt_trainable()
+        g, p = eng.g, eng.p
+        # fresh gradients for this backward (autograd accumulates them into .grad itself)
+        eng.zero_grads(mapper_only=not train_gpt)
+        dl = a.logits_full[:, : eng.V]
+        dl.copy_(dlogits.reshape(a.M, eng.V))
+        if train_gpt:
+            ops.linear_wgrad(a.xf, dl, g["gpt.transformer.wte.weight"], "linear")
+        ops.linear_dgrad(dl, p["gpt.transformer.wte.weight"], "linear", a.dx)
+        eng.backward_hidden(a, a.dx, train_gpt, ctx.key_len)
+        grads = [g[n].clone() for n in ctx.names]
+        return (None, None, None, None, *grads)

@@ -120,68 +120,89 @@ def linear_wgrad(x, dy, dW, layout, dbias=None):
         colsum_acc(dy, dbias)
 
 
-def noise_injection(x, out, variance, noise=None, offset=None, uniform_ball=False, dont_norm=False, seed=0, step=0):
+def make_seed(value: int, device="cuda") -> torch.Tensor:
+    """Device-resident 64-bit Philox seed (int64 storage, read as uint64 by the kernels)."""
+    return torch.tensor([value], dtype=torch.int64, device=device)
+
+
+def _seed_ptr(seed, p_active: bool):
+    if seed is None:
+        if p_active:
+            raise ValueError("a device seed tensor (ops.make_seed) is required when dropout / Philox noise is active")
+        return None
+    if not (isinstance(seed, torch.Tensor) and seed.is_cuda and seed.dtype == torch.int64 and seed.numel() >= 1):
+        raise TypeError("seed must be a CUDA int64 tensor (see ops.make_seed)")
+    return seed.data_ptr()
+
+
+def noise_injection(x, out, variance, noise=None, offset=None, uniform_ball=False, dont_norm=False, seed=None, step=0):
     _chk(x, "x"); _chk(out, "out")
     B, D = x.shape
     rc = _lib.load().capdec_noise_injection(x.data_ptr(), out.data_ptr(), B, D, float(variance), _ptr(noise),
-                                            _ptr(offset), int(uniform_ball), int(dont_norm), seed, step, _stream())
+                                            _ptr(offset), int(uniform_ball), int(dont_norm),
+                                            _seed_ptr(seed, noise is None and variance > 0), step, _stream())
     _lib.check(rc, "noise_injection")
 
 
-def embed_fwd(tokens, prefix_proj, wte, wpe, h, B, P, L, p_drop=0.0, seed=0, stream_id=0):
+def embed_fwd(tokens, prefix_proj, wte, wpe, h, B, P, L, p_drop=0.0, seed=None, stream_id=0):
     d = h.shape[-1]
     if tokens is not None:
         _chk(tokens, "tokens", torch.int64)
     rc = _lib.load().capdec_embed_fwd(_ptr(tokens), _ptr(prefix_proj), _ptr(wte), wpe.data_ptr(), h.data_ptr(), B, P, L,
-                                      d, wte.shape[0] if wte is not None else 0, float(p_drop), seed, stream_id,
+                                      d, wte.shape[0] if wte is not None else 0, float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id,
                                       _stream())
     _lib.check(rc, "embed_fwd")
 
 
-def embed_bwd(tokens, dh, d_prefix_proj, d_wte, d_wpe, B, P, L, vocab, p_drop=0.0, seed=0, stream_id=0):
+def embed_bwd(tokens, dh, d_prefix_proj, d_wte, d_wpe, B, P, L, vocab, p_drop=0.0, seed=None, stream_id=0):
     d = dh.shape[-1]
     rc = _lib.load().capdec_embed_bwd(_ptr(tokens), dh.data_ptr(), _ptr(d_prefix_proj), _ptr(d_wte), _ptr(d_wpe), B, P,
-                                      L, d, vocab, float(p_drop), seed, stream_id, _stream())
+                                      L, d, vocab, float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id, _stream())
     _lib.check(rc, "embed_bwd")
 
 
-def add_ln_fwd(h_in, y, h_out, x, stats, gamma, beta, eps=1e-5, p_drop=0.0, seed=0, stream_id=0):
+def add_ln_fwd(h_in, y, h_out, x, stats, gamma, beta, eps=1e-5, p_drop=0.0, seed=None, stream_id=0):
     rows, d = x.shape
     rc = _lib.load().capdec_add_ln_fwd(h_in.data_ptr(), _ptr(y), _ptr(h_out), x.data_ptr(), stats.data_ptr(),
-                                       gamma.data_ptr(), beta.data_ptr(), rows, d, eps, float(p_drop), seed, stream_id,
+                                       gamma.data_ptr(), beta.data_ptr(), rows, d, eps, float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id,
                                        _stream())
     _lib.check(rc, "add_ln_fwd")
 
 
-def add_ln_bwd(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma, dbeta, p_drop=0.0, seed=0, stream_id=0):
+def add_ln_bwd(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma, dbeta, p_drop=0.0, seed=None, stream_id=0):
     rows, d = dx.shape
     rc = _lib.load().capdec_add_ln_bwd(dx.data_ptr(), r.data_ptr(), stats.data_ptr(), gamma.data_ptr(), _ptr(dh_res),
                                        dh_out.data_ptr(), _ptr(dy), _ptr(dgamma), _ptr(dbeta), rows, d, float(p_drop),
-                                       seed, stream_id, _stream())
+                                       _seed_ptr(seed, p_drop > 0), stream_id, _stream())
     _lib.check(rc, "add_ln_bwd")
 
 
 def attention_fwd(q, k, v, ctx, lse, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal,
-                  key_len=None, p_drop=0.0, seed=0, stream_id=0):
+                  key_len=None, p_drop=0.0, seed=None, stream_id=0):
     rc = _lib.load().capdec_attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), _ptr(lse), B, H, T,
                                           S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, float(scale), int(causal),
-                                          _ptr(key_len), float(p_drop), seed, stream_id, _stream())
+                                          _ptr(key_len), float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id, _stream())
     _lib.check(rc, "attention_fwd")
 
 
 def attention_bwd(q, k, v, ctx, dctx, lse, dq, dk, dv, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale,
-                  causal, key_len=None, p_drop=0.0, seed=0, stream_id=0):
+                  causal, key_len=None, p_drop=0.0, seed=None, stream_id=0):
     rc = _lib.load().capdec_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), dctx.data_ptr(),
                                           lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, T, S, hd,
                                           q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, float(scale), int(causal),
-                                          _ptr(key_len), float(p_drop), seed, stream_id, _stream())
+                                          _ptr(key_len), float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id, _stream())
     _lib.check(rc, "attention_bwd")
 
 
-def ce_count(targets, n_valid, ignore_index=0):
+def ce_count(targets, n_valid, loss_sum_to_zero=None, ignore_index=0):
     _chk(targets, "targets", torch.int64)
     _lib.check(_lib.load().capdec_ce_count(targets.data_ptr(), targets.numel(), ignore_index, n_valid.data_ptr(),
-                                           _stream()), "ce_count")
+                                           _ptr(loss_sum_to_zero), _stream()), "ce_count")
+
+
+def step_clock(seed=None, step_dev=None, lr_dev=None, t_dev=None, base_lr=0.0, warmup_steps=0, total_steps=1):
+    _lib.check(_lib.load().capdec_step_clock(_ptr(seed), _ptr(step_dev), _ptr(lr_dev), _ptr(t_dev), float(base_lr),
+                                             int(warmup_steps), int(total_steps), _stream()), "step_clock")
 
 
 def ce_fwd_bwd(logits, targets, V, loss_sum, n_valid=None, grad_scale=1.0, ignore_index=0, write_grad=True):

@@ -1,0 +1,115 @@
+"""The train step of train.py:345-354 as one replayable unit (our public API for training / the benchmark):
+
+    H2D(tokens, prefix) -> step clock (RNG + LR schedule) -> noise_injection -> forward -> masked CE -> backward
+    -> [NCCL all-reduce of the flat gradient buffer] -> fused HF-AdamW (+ zero_grad)
+
+Everything between the H2D copies and the optimizer is captured in CUDA graphs (shapes are static per config).
+Data parallel: one process per GPU, captions sharded across ranks, ONE all-reduce per step over the
+flat buffer [n_valid, loss_sum, 0, 0 | grads...]: CE gradients are sum-reduced per rank and divided by the GLOBAL
+count of non-ignored targets inside the AdamW kernel, so N ranks reproduce the single-GPU global-batch mean exactly.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import CapdecError
+
+
+class Trainer:
+    def __init__(self, model, batch_size: int, seq_len: int = 40, lr: float = 2e-5, warmup_steps: int = 5000,
+                 total_steps: int = 100000, noise_variance: float = 0.0, uniform_noise: bool = False,
+                 dont_norm: bool = False, modality_offset: Optional[torch.Tensor] = None, betas=(0.9, 0.999),
+                 eps: float = 1e-6, weight_decay: float = 0.0, use_cuda_graph: bool = True, process_group=None):
+        self.model = model
+        self.eng = model.engine()
+        self.dev = self.eng.dev
+        self.B, self.L = batch_size, seq_len
+        self.lr, self.warmup, self.total = lr, warmup_steps, total_steps
+        self.noise_variance, self.uniform_noise, self.dont_norm = noise_variance, uniform_noise, dont_norm
+        self.offset = None
+        if modality_offset is not None:
+            self.offset = modality_offset.to(device=self.dev, dtype=torch.float32).reshape(-1).contiguous()
+        self.betas, self.eps, self.wd = betas, eps, weight_decay
+        self.train_gpt = model.gpt_trainable()
+        fl = self.eng.flat
+        self.n_train = fl.n_mapper + (fl.n_gpt if self.train_gpt else 0)
+        lo, hi = fl.tail, fl.tail + self.n_train
+        self.p_flat, self.g_flat = fl.params[lo:hi], fl.grads[lo:hi]
+        self.m_flat, self.v_flat = torch.zeros_like(self.p_flat), torch.zeros_like(self.p_flat)
+        self.reduce_buf = fl.grads[:hi]                      # [tail | trainable grads]: the single all-reduce payload
+        self.tail = fl.grads[:4]
+        self.step_dev = torch.zeros(1, device=self.dev)
+        self.lr_dev = torch.zeros(1, device=self.dev)
+        self.t_dev = torch.zeros(1, device=self.dev)
+        self.tokens_d = torch.zeros(batch_size, seq_len, dtype=torch.int64, device=self.dev)
+        self.prefix_d = torch.zeros(batch_size, self.eng.D, device=self.dev)
+        self.prefix_n = torch.zeros(batch_size, self.eng.D, device=self.dev)
+        self.stats = torch.zeros(4, device=self.dev)          # [n_valid, loss_sum, ., .] of the last step (global)
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+            # per-rank RNG stream for noise + dropout: same weights, different masks
+            self.eng.seed.add_(7919 * (1 + torch.distributed.get_rank(process_group)))
+        self.use_graph = use_cuda_graph
+        self._g_fb = self._g_opt = None
+        self._warm = 0
+        fl.grads.zero_()
+
+    # ---- pieces ------------------------------------------------------------------------------------------------
+    def _fwd_bwd(self):
+        eng = self.eng
+        ops.step_clock(eng.seed, self.step_dev, self.lr_dev, self.t_dev, self.lr, self.warmup, self.total)
+        if self.noise_variance > 0.0:
+            ops.noise_injection(self.prefix_d, self.prefix_n, self.noise_variance, offset=self.offset,
+                                uniform_ball=self.uniform_noise, dont_norm=self.dont_norm, seed=eng.seed)
+            pfx = self.prefix_n
+        else:
+            pfx = self.prefix_d                                 # train.py:28-29: variance 0 -> untouched
+        eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False)
+
+    def _opt(self):
+        self.stats.copy_(self.tail)
+        ops.adamw_step(self.p_flat, self.g_flat, self.m_flat, self.v_flat, self.lr_dev, self.t_dev, self.betas[0],
+                       self.betas[1], self.eps, self.wd, grad_denom=self.stats[0:1], zero_grad=True)
+
+    def _capture(self, fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    def step_device(self):
+        """One step on the batch already resident in `tokens_d` / `prefix_d`."""
+        if self.use_graph and self._warm >= 2:
+            if self._g_fb is None:
+                torch.cuda.synchronize()
+                self._g_fb = self._capture(self._fwd_bwd)
+                self._g_opt = self._capture(self._opt)
+            self._g_fb.replay()
+            if self.world > 1:
+                torch.distributed.all_reduce(self.reduce_buf, group=self.pg)
+            self._g_opt.replay()
+        else:
+            self._warm += 1
+            self._fwd_bwd()
+            if self.world > 1:
+                torch.distributed.all_reduce(self.reduce_buf, group=self.pg)
+            self._opt()
+        return self.stats
+
+    def step(self, tokens: torch.Tensor, prefix: torch.Tensor):
+        """tokens int64 [B, L], prefix fp32 [B, D] (host pinned or device).  Returns the device stats tensor
+        [n_valid, loss_sum, ., .]; `Trainer.loss()` turns it into the mean token loss (forces a sync)."""
+        if tuple(tokens.shape) != (self.B, self.L) or prefix.shape[0] != self.B:
+            raise CapdecError(f"Trainer was built for batch {self.B} x {self.L}, got tokens {tuple(tokens.shape)}")
+        self.tokens_d.copy_(tokens, non_blocking=True)
+        self.prefix_d.copy_(prefix, non_blocking=True)
+        return self.step_device()
+
+    def loss(self) -> float:
+        s = self.stats.tolist()
+        return s[1] / s[0] if s[0] > 0 else float("nan")

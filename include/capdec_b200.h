@@ -11,7 +11,10 @@
  *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator); callee never allocates;
  *   - launches are asynchronous on `stream` (pass torch.cuda.current_stream()); CUDA-graph capturable;
  *   - return 0 on success, <0 on error; capdec_last_error() returns a thread-local message; nothing throws;
- *   - all tensors fp32 row-major unless noted; token ids are int64 (as torch.int64 in train.py:57).
+ *   - all tensors fp32 row-major unless noted; token ids are int64 (as torch.int64 in train.py:57);
+ *   - RNG: `seed_dev` is a DEVICE pointer to a 64-bit Philox seed (NULL = 0); dropout masks / noise are functions of
+ *     (*seed_dev, stream_id, element index) and are regenerated in backward, never stored.  Keeping the seed in
+ *     device memory (advanced by capdec_step_clock) gives fresh masks on every CUDA-graph replay.
  */
 #ifndef CAPDEC_B200_H_
 #define CAPDEC_B200_H_
@@ -65,33 +68,33 @@ int capdec_split_tf32(const float* x, float* hi, float* lo, int64_t n, capdec_st
  * Philox Gaussian N(0, variance) (uniform_ball=0) or uniform-ball of radius sqrt(variance) (uniform_ball=1).
  * variance == 0 -> identity copy (train.py:28-29: no normalisation at all).  offset may be NULL ([D]). */
 int capdec_noise_injection(const float* x, float* out, int B, int D, float variance, const float* noise,
-                           const float* offset, int uniform_ball, int dont_norm, uint64_t seed, uint64_t step,
+                           const float* offset, int uniform_ball, int dont_norm, const uint64_t* seed_dev, uint64_t step,
                            capdec_stream_t stream);
 
 /* ---- embedding assembly: train.py:253-255 + HF:modeling_gpt2.py:579-585,612 ----------------------------------------
  * h[b,t,:] = (t < P ? prefix_proj[b,t,:] : wte[tokens[b,t-P],:]) + wpe[t,:], then dropout(p) (train mode).
  * tokens int64 [B,L]; prefix_proj [B,P,d]; h [B,P+L,d].  tokens may be NULL with L = 0 (inputs_embeds path). */
 int capdec_embed_fwd(const int64_t* tokens, const float* prefix_proj, const float* wte, const float* wpe, float* h,
-                     int B, int P, int L, int d, int vocab, float p_drop, uint64_t seed, uint32_t stream_id,
+                     int B, int P, int L, int d, int vocab, float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
                      capdec_stream_t stream);
 /* backward: d_wte[tokens] += dh (atomic scatter; may be NULL = frozen), d_wpe[t] += sum_b dh (may be NULL),
  * d_prefix_proj[b,t<P] = dh (may be NULL). dropout mask regenerated. */
 int capdec_embed_bwd(const int64_t* tokens, const float* dh, float* d_prefix_proj, float* d_wte, float* d_wpe, int B,
-                     int P, int L, int d, int vocab, float p_drop, uint64_t seed, uint32_t stream_id,
+                     int P, int L, int d, int vocab, float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
                      capdec_stream_t stream);
 
 /* ---- (residual add +) LayerNorm: nn.LayerNorm(eps=1e-5) HF:modeling_gpt2.py:252-254,505 ; train.py:184-188 -------
  * fwd: r = h_in + dropout(y) (y may be NULL -> r = h_in);  x = LN(r)*gamma + beta;  stats[row] = (mean, rstd).
  *      h_out receives r (may alias h_in; may be NULL when y == NULL).  rows x d, d % 128 == 0, d <= 1024. */
 int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out, float* x, float* stats, const float* gamma,
-                      const float* beta, int rows, int d, float eps, float p_drop, uint64_t seed, uint32_t stream_id,
+                      const float* beta, int rows, int d, float eps, float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
                       capdec_stream_t stream);
 /* bwd: dr = dh_res (running residual gradient, may be NULL = 0) + LN_bwd(dx; r, stats, gamma) -> written to dh_out
  *      (may alias dh_res); if dy != NULL: dy = dropout_mask * dr (gradient of the branch output y).
  *      dgamma/dbeta accumulated (+=) unless NULL (frozen GPT-2, train.py:276-284). */
 int capdec_add_ln_bwd(const float* dx, const float* r, const float* stats, const float* gamma, const float* dh_res,
                       float* dh_out, float* dy, float* dgamma, float* dbeta, int rows, int d, float p_drop,
-                      uint64_t seed, uint32_t stream_id, capdec_stream_t stream);
+                      const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
 
 /* ---- attention core ----------------------------------------------------------------------------------------------
  * GPT-2 (HF:modeling_gpt2.py:54-72,185-191): qkv [B,T,3*H*hd] (q|k|v thirds, heads contiguous hd slices),
@@ -101,21 +104,22 @@ int capdec_add_ln_bwd(const float* dx, const float* r, const float* stats, const
  * key_len: optional int32 [B] number of valid keys (padding mask, HF attention_mask); NULL = all valid. */
 int capdec_attention_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, int B, int H, int T,
                          int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs,
-                         int64_t o_ts, float scale, int causal, const int32_t* key_len, float p_drop, uint64_t seed,
-                         uint32_t stream_id, capdec_stream_t stream);
+                         int64_t o_ts, float scale, int causal, const int32_t* key_len, float p_drop,
+                         const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
 int capdec_attention_bwd(const float* q, const float* k, const float* v, const float* ctx, const float* dctx,
                          const float* lse, float* dq, float* dk, float* dv, int B, int H, int T, int S, int hd,
                          int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts,
-                         float scale, int causal, const int32_t* key_len, float p_drop, uint64_t seed,
-                         uint32_t stream_id, capdec_stream_t stream);
+                         float scale, int causal, const int32_t* key_len, float p_drop,
+                         const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
 
 /* ---- masked cross entropy: train.py:349-350 (nnf.cross_entropy(..., ignore_index=0), mean over targets != 0) -----
  * logits [rows, ld] (ld >= V, padded pitch), targets int64 [rows].  loss_sum/n_valid are device scalars (float);
- * capdec_ce_count adds the number of non-ignored targets to *n_valid.  fwd_bwd overwrites logits with
+ * capdec_ce_count writes the number of non-ignored targets to *n_valid and zeroes *loss_sum_to_zero (may be NULL).  fwd_bwd overwrites logits with
  * dlogits = (softmax - onehot) * grad_scale / *n_valid (zero rows where target == ignore_index; n_valid == NULL
  * means 1, i.e. sum-reduced gradients for exact data-parallel averaging) and adds the row losses into loss_sum.
  * If write_grad == 0 logits are left intact (validation, train.py:383-386). */
-int capdec_ce_count(const int64_t* targets, int64_t n, int64_t ignore_index, float* n_valid, capdec_stream_t stream);
+int capdec_ce_count(const int64_t* targets, int64_t n, int64_t ignore_index, float* n_valid, float* loss_sum_to_zero,
+                    capdec_stream_t stream);
 int capdec_ce_fwd_bwd(float* logits, int64_t ld, const int64_t* targets, int rows, int V, int64_t ignore_index,
                       const float* n_valid, float grad_scale, float* loss_sum, int write_grad,
                       capdec_stream_t stream);
@@ -144,6 +148,13 @@ int capdec_mapper_concat_bwd(const float* dx, float* dlin, float* dprefix_const,
 int capdec_adamw_step(float* p, float* g, float* m, float* v, int64_t n, const float* lr_dev, const float* t_dev,
                       float beta1, float beta2, float eps, float weight_decay, const float* grad_denom_dev,
                       int zero_grad, capdec_stream_t stream);
+
+/* ---- device-side training clock (train.py:328-330,352-354) --------------------------------------------------------
+ * *seed_dev += golden ratio (next step's RNG stream); if step_dev != NULL: n = *step_dev (updates done so far),
+ * *lr_dev = base_lr * linear-warm-up/decay factor(n) (HF get_linear_schedule_with_warmup), *t_dev = n + 1 (Adam bias
+ * correction step), *step_dev = n + 1.  One thread; exists so that the whole step is CUDA-graph replayable. */
+int capdec_step_clock(uint64_t* seed_dev, float* step_dev, float* lr_dev, float* t_dev, float base_lr,
+                      int warmup_steps, int total_steps, capdec_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,256 @@
+"""End-to-end parity (GPU): the CUDA path behind the reference's class surface vs the CPU oracle (itself pinned
+bit-exactly to the reference's own classes, tests/golden) on identical seeded weights and inputs.
+
+Stated tolerances (SURVEY §8c budget; measured values are appended to gpurun_out/parity_report.jsonl):
+  fp32   (CUDA-core GEMMs)        loss rel <= 3e-6, logits max-abs <= 1e-4 * max|logit|, per-tensor grad rel-L2 <= 3e-4
+  tf32x3 (3xTF32 on tcgen05)      loss rel <= 2e-5, logits rel-L2 <= 1e-4,               per-tensor grad rel-L2 <= 3e-3
+  tf32   (1xTF32 on tcgen05,perf) loss rel <= 2e-4, logits rel-L2 <= 5e-3,               per-tensor grad rel-L2 <= 3e-2
+"""
+import json
+import os
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import capdec_oracle as O  # noqa: E402  (checker only)
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+TOL = {"fp32": dict(loss=3e-6, logits_abs=1e-4, logits_l2=2e-5, grad=3e-4),
+       "tf32x3": dict(loss=2e-5, logits_abs=1e-3, logits_l2=1e-4, grad=3e-3),
+       "tf32": dict(loss=2e-4, logits_abs=5e-2, logits_l2=5e-3, grad=3e-2)}
+
+
+def report(rec):
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    with open(out / "parity_report.jsonl", "a") as f:
+        f.write(json.dumps(rec) + "\n")
+
+
+def build(case, train_mode=False):
+    import capdec_b200 as cb
+    rec = json.loads((GOLD / f"{case}.json").read_text())
+    c = rec["config"]
+    sd = O.make_state_dict(seed=c["sd_seed"], mapping_type=c["mapping_type"], prefix_length=c["P"], clip_length=c["C"],
+                           prefix_size=c["D"], num_layers=c["num_layers"])
+    tokens, prefix, _ = O.make_batch(seed=c["batch_seed"], B=c["B"], L=40, prefix_size=c["D"], full_length=c["full_length"])
+    torch.manual_seed(c["noise_torch_seed"])
+    draw = torch.randn(prefix.shape)
+    cls = cb.ClipCaptionPrefix if c["only_prefix"] else cb.ClipCaptionModel
+    mt = cb.MappingType.MLP if c["mapping_type"] == "mlp" else cb.MappingType.Transformer
+    cfg = cb.GPT2Config(resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    model = cls(c["P"], clip_length=c["C"], prefix_size=c["D"], num_layers=c["num_layers"], mapping_type=mt, gpt_config=cfg)
+    model.load_state_dict(sd)
+    model = model.to("cuda")
+    model.train()
+    return rec, c, sd, tokens, prefix, draw, model
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("case", ["mlp_full_b4", "mlp_prefix_only_b4", "transformer_full_b2", "mlp_full_d640_b3"])
+def test_fast_path_loss_and_grads_match_oracle_and_golden(case, mode):
+    import capdec_b200 as cb
+    rec, c, sd, tokens, prefix, draw, model = build(case)
+    cb.ops.set_precision(mode)
+    try:
+        eng = model.engine()
+        P = c["P"]
+        # noise injection kernel with the reference's Gaussian draw (train.py:36)
+        std = c["noise_variance"] ** 0.5
+        pfx = torch.empty_like(prefix, device="cuda")
+        cb.ops.noise_injection(prefix.cuda(), pfx, c["noise_variance"], noise=(draw * std).cuda())
+        pfx_ref = O.noise_injection(prefix, c["noise_variance"], noise=draw)
+        assert (pfx.cpu() - pfx_ref).abs().max() < 1e-6
+        assert pfx[0, :8].cpu().double().tolist() == pytest.approx(rec["noised_prefix_row0"], abs=1e-6)
+        eng.zero_grads()
+        tail = eng.loss_and_grads(tokens.cuda(), pfx, mean_reduce=True)
+        torch.cuda.synchronize()
+        n_valid, loss_sum = tail[0].item(), tail[1].item()
+        assert n_valid == (tokens != 0).sum().item()
+        loss = loss_sum / n_valid
+        tol = TOL[mode]
+        # --- vs golden (reference's own run) ---
+        assert abs(loss - rec["loss"]) <= tol["loss"] * abs(rec["loss"]), (loss, rec["loss"])
+        # --- vs oracle on this box's CPU ---
+        trainable = (lambda k: k.startswith("clip_project")) if c["only_prefix"] else None
+        o_loss, o_logits, o_grads = O.loss_and_grads(sd, tokens, pfx_ref, O.make_mask(tokens, P), P, c["C"], trainable)
+        assert abs(loss - float(o_loss)) <= tol["loss"] * abs(float(o_loss))
+        g = eng.grad_views()
+        worst, worst_name = 0.0, None
+        for k, og in o_grads.items():
+            r = rel_l2(g[k].cpu(), og)
+            if r > worst:
+                worst, worst_name = r, k
+            gr = rec["grads"][k]
+            vals = g[k].flatten()[torch.tensor(gr["idx"], device="cuda")].cpu().double()
+            assert (vals - torch.tensor(gr["val"], dtype=torch.float64)).abs().max() <= 3 * tol["grad"] * gr["norm"] + 1e-9, k
+        report(dict(test="fast_path", case=case, mode=mode, loss=loss, loss_ref=rec["loss"],
+                    loss_rel=abs(loss - rec["loss"]) / abs(rec["loss"]), worst_grad_rel_l2=worst, worst_grad=worst_name))
+        assert worst <= tol["grad"], (worst_name, worst)
+        if c["only_prefix"]:  # frozen GPT-2: no gradient may have been written (train.py:276-284)
+            fl = eng.flat
+            assert fl.grads[fl.tail + fl.n_mapper:].abs().max().item() == 0.0
+    finally:
+        cb.ops.set_precision("tf32")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("case", ["mlp_full_b4", "transformer_full_b2", "mlp_prefix_only_b4"])
+def test_drop_in_forward_backward_like_train_py(case, mode):
+    """The reference's own lines train.py:348-351 executed against our classes: logits, loss and .grad."""
+    import capdec_b200 as cb
+    import torch.nn.functional as nnf
+    rec, c, sd, tokens, prefix, draw, model = build(case)
+    cb.ops.set_precision(mode)
+    try:
+        P = c["P"]
+        pfx_ref = O.noise_injection(prefix, c["noise_variance"], noise=draw)
+        tok_d, pfx_d, mask_d = tokens.cuda(), pfx_ref.cuda(), O.make_mask(tokens, P).cuda()
+        model.zero_grad()
+        outputs = model(tok_d, pfx_d, mask_d)
+        logits = outputs.logits[:, P - 1: -1]
+        loss = nnf.cross_entropy(logits.reshape(-1, logits.shape[-1]), tok_d.flatten(), ignore_index=0)
+        full = outputs.logits.detach().cpu().clone()
+        loss.backward()
+        tol = TOL[mode]
+        assert list(full.shape) == rec["logits_shape"]
+        got = full.flatten()[torch.tensor(rec["logits_idx"])].double()
+        ref = torch.tensor(rec["logits_val"], dtype=torch.float64)
+        valid = torch.cat((torch.ones(c["B"], P, dtype=torch.bool), tokens > 0), dim=1)
+        vmask = valid.unsqueeze(-1).expand_as(full).flatten()[torch.tensor(rec["logits_idx"])]
+        assert (got - ref)[vmask].abs().max() <= tol["logits_abs"] * max(1.0, rec["logits_absmax"])
+        o_logits = O.clipcap_forward(sd, tokens, pfx_ref, O.make_mask(tokens, P), P, c["C"])
+        l2 = rel_l2(full[valid], o_logits[valid])
+        assert l2 <= tol["logits_l2"], l2
+        assert abs(loss.item() - rec["loss"]) <= tol["loss"] * abs(rec["loss"])
+        named = dict(torch.nn.Module.named_parameters(model))
+        worst = 0.0
+        for k, gr in rec["grads"].items():
+            assert named[k].grad is not None, k
+            assert abs(named[k].grad.double().norm().item() - gr["norm"]) <= 2 * tol["grad"] * gr["norm"] + 1e-9, k
+            vals = named[k].grad.flatten()[torch.tensor(gr["idx"], device="cuda")].cpu().double()
+            worst = max(worst, ((vals - torch.tensor(gr["val"], dtype=torch.float64)).abs().max() / gr["norm"]).item())
+        report(dict(test="drop_in", case=case, mode=mode, logits_rel_l2=l2, loss=loss.item(), loss_ref=rec["loss"],
+                    worst_sampled_grad_err_over_norm=worst))
+        if c["only_prefix"]:
+            assert all(v.grad is None for k, v in named.items() if k.startswith("gpt."))
+            assert len(list(model.parameters())) == 4  # train.py:278-279
+    finally:
+        cb.ops.set_precision("tf32")
+
+
+def test_state_dict_layout_and_class_surface():
+    import capdec_b200 as cb
+    model = cb.ClipCaptionModel(10, prefix_size=512).to("cuda")
+    sd = model.state_dict()
+    assert len(sd) == 153 and "gpt.lm_head.weight" in sd and "clip_project.model.2.bias" in sd
+    assert sd["gpt.lm_head.weight"].data_ptr() == sd["gpt.transformer.wte.weight"].data_ptr()
+    assert sd["gpt.transformer.h.0.attn.c_attn.weight"].shape == (768, 2304)
+    assert model.gpt_embedding_size == 768 and model.prefix_length == 10
+    assert next(model.parameters()).device.type == "cuda"
+    # second constructor flavour (gpt2_prefix.py:157-158) and checkpoints carrying 4.24-era mask buffers
+    m2 = cb.ClipCaptionModel(10, prefix_dim=640, mapping_type="mlp")
+    old = m2.state_dict_hf424()
+    assert "gpt.transformer.h.0.attn.masked_bias" in old
+    m2.load_state_dict(old)
+    ids = torch.tensor([[1, 2, 3]], device="cuda")
+    emb = model.gpt.transformer.wte(ids)
+    assert emb.shape == (1, 3, 768)
+    assert model.gpt.get_input_embeddings().weight.shape == (50257, 768)
+    # inference surface: clip_project(prefix) and gpt(inputs_embeds=...) (predictions_runner.py:228, gpt2_prefix_eval.py:76)
+    model.eval()
+    with torch.no_grad():
+        pe = model.clip_project(torch.randn(2, 512, device="cuda")).reshape(2, 10, -1)
+        out = model.gpt(inputs_embeds=torch.cat((pe, model.gpt.transformer.wte(ids.expand(2, 3))), dim=1))
+    assert out.logits.shape == (2, 13, 50257) and torch.isfinite(out.logits).all()
+    with pytest.raises(cb._lib.CapdecError):
+        cb.ClipCaptionModel(10).engine()  # CPU model: no fallback
+
+
+def test_inference_surface_matches_oracle():
+    import capdec_b200 as cb
+    rec, c, sd, tokens, prefix, draw, model = build("mlp_full_b4")
+    cb.ops.set_precision("fp32")
+    try:
+        model.eval()
+        with torch.no_grad():
+            pp = model.clip_project(prefix.cuda())
+            ref_pp = O.mlp_mapper(sd, prefix)
+            assert (pp.cpu() - ref_pp).abs().max() < 1e-4
+            emb = torch.cat((pp.view(-1, 10, 768), model.gpt.transformer.wte(tokens.cuda()[:, :7])), dim=1)
+            lg = model.gpt(inputs_embeds=emb).logits
+        ref = O.gpt2_forward(sd, emb.cpu())
+        assert rel_l2(lg.cpu(), ref) < 2e-5
+    finally:
+        cb.ops.set_precision("tf32")
+
+
+def test_trainer_three_steps_match_oracle_adamw_trajectory():
+    """Trainer (graphs off/on) vs the oracle running train.py:345-354 with the HF-AdamW restatement."""
+    import capdec_b200 as cb
+    rec, c, sd, tokens, prefix, draw, model = build("mlp_full_b4")
+    cb.ops.set_precision("fp32")
+    try:
+        steps, lr, warm, total = 3, 1e-3, 2, 10
+        # oracle trajectory (no noise: variance 0 -> prefix untouched)
+        params = {k: v.clone() for k, v in sd.items() if k != "gpt.lm_head.weight"}
+        m = {k: torch.zeros_like(v) for k, v in params.items()}
+        v_ = {k: torch.zeros_like(v) for k, v in params.items()}
+        ref_losses = []
+        for s in range(steps):
+            full = dict(params); full["gpt.lm_head.weight"] = full["gpt.transformer.wte.weight"]
+            loss, _, grads = O.loss_and_grads(full, tokens, prefix, None, c["P"], c["C"])
+            ref_losses.append(float(loss))
+            cur_lr = O.linear_warmup_lr(lr, s, warm, total)
+            for k in params:
+                O.hf_adamw_step(params[k], grads[k], m[k], v_[k], s + 1, cur_lr)
+        results = {}
+        for use_graph in (False, True):
+            mdl = cb.ClipCaptionModel(c["P"], prefix_size=c["D"], gpt_config=cb.GPT2Config(resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0))
+            mdl.load_state_dict(sd)
+            mdl = mdl.to("cuda").train()
+            tr = cb.Trainer(mdl, batch_size=c["B"], seq_len=40, lr=lr, warmup_steps=warm, total_steps=total,
+                            noise_variance=0.0, use_cuda_graph=use_graph)
+            losses = []
+            for s in range(steps + (2 if use_graph else 0)):   # graph mode: 2 eager warm-up steps precede capture
+                tr.step(tokens.pin_memory(), prefix.pin_memory())
+                losses.append(tr.loss())
+            results[use_graph] = (losses, {k: p.detach().cpu().clone() for k, p in torch.nn.Module.named_parameters(mdl)})
+        losses, final = results[False]
+        for a, b in zip(losses, ref_losses):
+            assert abs(a - b) <= 1e-5 * abs(b), (losses, ref_losses)
+        worst = max(rel_l2(final[k], params[k]) for k in params)
+        report(dict(test="trainer_trajectory", losses=losses, ref_losses=ref_losses, worst_param_rel_l2=worst))
+        assert worst < 1e-4
+        assert losses[1] < losses[0] or losses[2] < losses[0]   # lr(step 0) == 0, then it must learn
+        # CUDA-graph replay reproduces the eager steps
+        assert results[True][0][:steps] == pytest.approx(losses, rel=1e-6)
+    finally:
+        cb.ops.set_precision("tf32")
+
+
+def test_dropout_train_mode_runs_and_is_fresh_per_step():
+    import capdec_b200 as cb
+    rec, c, sd, tokens, prefix, draw, _ = build("mlp_full_b4")
+    mdl = cb.ClipCaptionModel(c["P"], prefix_size=c["D"])        # default GPT2Config: p = 0.1 at 37 sites
+    mdl.load_state_dict(sd)
+    mdl = mdl.to("cuda").train()
+    tr = cb.Trainer(mdl, batch_size=c["B"], seq_len=40, lr=0.0, warmup_steps=0, total_steps=10, noise_variance=0.016)
+    losses = []
+    for _ in range(5):                                             # lr = 0: weights frozen, only the RNG moves
+        tr.step(tokens.cuda(), prefix.cuda())
+        losses.append(tr.loss())
+    assert all(l == l and abs(l - rec["loss"]) < 0.5 for l in losses), losses
+    assert len(set(round(l, 6) for l in losses)) == 5, losses     # fresh masks/noise every step, incl. graph replays
+    mdl.eval()
+    eng = mdl.engine()
+    a = [eng.loss_and_grads(tokens.cuda(), prefix.cuda(), mean_reduce=True).clone() for _ in range(2)]
+    assert torch.equal(a[0][:2], a[1][:2])                         # eval: deterministic

@@ -139,18 +139,18 @@ def test_noise_injection_philox_statistics(ops):
     x = torch.nn.functional.normalize(torch.randn(B, D, device="cuda"), dim=1)
     out = torch.empty_like(x)
     var = 0.016
-    ops.noise_injection(x, out, var, seed=123, step=5)
+    ops.noise_injection(x, out, var, seed=ops.make_seed(123), step=5)
     assert torch.allclose(out.norm(dim=1), torch.ones(B, device="cuda"), atol=1e-5)
     # out ~ (x + n)/|x + n| ; E|x+n|^2 = 1 + D*var  => cosine(out, x) ~ 1/sqrt(1 + D var)
     cos = (out * x).sum(1).mean().item()
     assert abs(cos - 1.0 / math.sqrt(1 + D * var)) < 5e-3
     out2 = torch.empty_like(x)
-    ops.noise_injection(x, out2, var, seed=123, step=5)
+    ops.noise_injection(x, out2, var, seed=ops.make_seed(123), step=5)
     assert torch.equal(out, out2)  # counter-based: reproducible
-    ops.noise_injection(x, out2, var, seed=123, step=6)
+    ops.noise_injection(x, out2, var, seed=ops.make_seed(123), step=6)
     assert not torch.equal(out, out2)
     # uniform ball: |noise| <= radius
-    ops.noise_injection(x, out2, var, uniform_ball=True, dont_norm=True, seed=1, step=0)
+    ops.noise_injection(x, out2, var, uniform_ball=True, dont_norm=True, seed=ops.make_seed(1), step=0)
     assert torch.isfinite(out2).all()
 
 
@@ -214,19 +214,20 @@ def test_add_ln_fwd_bwd(ops, rows, d):
 
 def test_add_ln_dropout_mask_consistency(ops):
     rows, d, p = 512, 768, 0.1
+    seed7 = ops.make_seed(7)
     h = torch.zeros(rows, d, device="cuda")
     y = torch.ones(rows, d, device="cuda")
     gamma, beta = torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")
     x, h_out, stats = torch.empty(rows, d, device="cuda"), torch.empty(rows, d, device="cuda"), torch.empty(rows, 2, device="cuda")
-    ops.add_ln_fwd(h, y, h_out, x, stats, gamma, beta, p_drop=p, seed=7, stream_id=3)
+    ops.add_ln_fwd(h, y, h_out, x, stats, gamma, beta, p_drop=p, seed=seed7, stream_id=3)
     keep = h_out != 0
     assert abs(keep.float().mean().item() - (1 - p)) < 5e-3
     assert torch.allclose(h_out[keep], torch.full_like(h_out[keep], 1 / (1 - p)))
     dy, dh_out = torch.empty(rows, d, device="cuda"), torch.empty(rows, d, device="cuda")
     ops.add_ln_bwd(torch.zeros(rows, d, device="cuda"), h_out, stats, gamma, torch.ones(rows, d, device="cuda"), dh_out, dy,
-                   None, None, p_drop=p, seed=7, stream_id=3)
+                   None, None, p_drop=p, seed=seed7, stream_id=3)
     assert torch.equal(dy != 0, keep)  # backward regenerates exactly the forward mask
-    ops.add_ln_fwd(h, y, h_out, x, stats, gamma, beta, p_drop=p, seed=7, stream_id=4)
+    ops.add_ln_fwd(h, y, h_out, x, stats, gamma, beta, p_drop=p, seed=seed7, stream_id=4)
     assert not torch.equal(h_out != 0, keep)  # a different site draws a different mask
 
 
@@ -281,7 +282,7 @@ def test_attention_key_padding_and_dropout(ops):
     assert (ctx.double() - ref).abs().max() < 2e-5
     # dropout: E[out] = no-dropout output; check the mean over many heads is unbiased to a few %
     ctx_d = torch.empty_like(ctx)
-    ops.attention_fwd(q, k, v, ctx_d, lse, *args, p_drop=0.1, seed=11, stream_id=2)
+    ops.attention_fwd(q, k, v, ctx_d, lse, *args, p_drop=0.1, seed=ops.make_seed(11), stream_id=2)
     ops.attention_fwd(q, k, v, ctx, lse, *args)
     rel = (ctx_d - ctx).norm() / ctx.norm()
     assert 0.05 < rel < 0.6
@@ -298,9 +299,10 @@ def test_cross_entropy_fwd_bwd(ops, rows, V):
     ref_in = logits.double().clone().requires_grad_()
     ref = torch.nn.functional.cross_entropy(ref_in, targets, ignore_index=0)
     ref.backward()
-    n_valid = torch.zeros(1, device="cuda")
-    loss_sum = torch.zeros(1, device="cuda")
-    ops.ce_count(targets, n_valid)
+    n_valid = torch.full((1,), 77.0, device="cuda")
+    loss_sum = torch.full((1,), 5.0, device="cuda")
+    ops.ce_count(targets, n_valid, loss_sum)
+    assert loss_sum.item() == 0.0
     assert n_valid.item() == (targets != 0).sum().item()
     ops.ce_fwd_bwd(logits, targets, V, loss_sum, n_valid=n_valid)
     assert abs(loss_sum.item() / n_valid.item() - ref.item()) < 1e-5 * abs(ref.item())
@@ -370,3 +372,16 @@ def test_adamw_matches_hf_semantics(ops):
         pr = pr - lr * wd * pr
         assert g.abs().max() == 0
     assert (p.double() - pr).abs().max() < 2e-6
+
+
+def test_step_clock_schedule_and_seed(ops):
+    seed = ops.make_seed(5)
+    step, lr, t = (torch.zeros(1, device="cuda") for _ in range(3))
+    lrs = []
+    for n in range(6):
+        ops.step_clock(seed, step, lr, t, base_lr=2e-5, warmup_steps=2, total_steps=6)
+        lrs.append(lr.item())
+        assert t.item() == n + 1
+    # get_linear_schedule_with_warmup(warmup=2, total=6): 0, .5, 1, .75, .5, .25 (x base)
+    assert lrs == pytest.approx([0.0, 1e-5, 2e-5, 1.5e-5, 1e-5, 0.5e-5], rel=1e-6)
+    assert seed.item() != 5
