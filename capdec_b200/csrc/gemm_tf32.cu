@@ -95,11 +95,19 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// kPair = false: one CTA per 128 x block_n tile (tcgen05 cta_group::1).
+// kPair = true : a CTA PAIR (cluster of 2, cta_group::2) per 256 x block_n tile.  CTA r of the pair TMA-loads its own
+//                128 A rows and its own block_n/2 B columns into ITS shared memory; the leader (rank 0) issues one
+//                M=256 MMA per k-step that reads both CTAs' smem and writes both CTAs' TMEM.  Per CTA the operand
+//                traffic drops from (128 + block_n) to (128 + block_n/2) rows per k-block: the 1-CTA kernel is bound
+//                by L2->SM bandwidth with fp32 operands, so this is the main lever (GEMM section).
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_constant__ GemmDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve-up (all tile buffers 1024-byte aligned for the 128B swizzle patterns)
+  // carve-up (all tile buffers 1024-byte aligned for the 128B swizzle patterns); identical in both CTAs of a pair
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = p.block_n * kBlockK * 4;
+  const int bn_local = kPair ? p.block_n / 2 : p.block_n;  // B columns this CTA stages
+  const int b_bytes = bn_local * kBlockK * 4;
   const int stage_bytes = kABytes + b_bytes;
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.stages * kABytes;
@@ -113,6 +121,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+  constexpr int kCtas = kPair ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tmA[0]);
@@ -126,36 +137,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], kCtas);  // pair: leader's arrive.expect_tx + the peer's remote arrive
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kEpiThreads);
+      mbar_init(&tmem_empty_bar[i], kCtas * kEpiThreads);  // pair: both CTAs' epilogues report to the leader
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (kPair) { tmem_alloc_pair(tmem_slot, kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;   // m_tiles counts 256-row tiles when kPair
+  const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int kTileM = kPair ? 2 * kBlockM : kBlockM;
 
   if (warp == 0) {
-    // ============================== TMA producer ==============================
+    // ============================== TMA producer (every CTA feeds its own smem) ==============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int n_blk = tile % p.n_tiles;
         const int m_blk = (tile / p.n_tiles) % p.m_tiles;
         const int split = tile / (p.n_tiles * p.m_tiles);
-        const int m0 = m_blk * kBlockM, n0 = n_blk * p.block_n;
+        const int m0 = m_blk * kTileM + (int)cta_rank * kBlockM;
+        const int n0 = n_blk * p.block_n + (int)cta_rank * (kPair ? bn_local : 0);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int seg = 0; seg < p.nseg; ++seg) {
@@ -163,22 +178,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
           const CUtensorMap* mapB = (seg == 2) ? &p.tmB[1] : &p.tmB[0];
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
             const int k0 = kb * kBlockK;
             uint8_t* a_dst = sA + stage * kABytes;
             uint8_t* b_dst = sB + stage * b_bytes;
+            uint64_t* fb = &full_bar[stage];
+            if constexpr (!kPair) mbar_arrive_expect_tx(fb, (uint32_t)stage_bytes);
+            auto load = [&](void* dst, const CUtensorMap* m, int x, int y) {
+              if constexpr (kPair) tma_load_2d_pair(dst, m, fb, x, y); else tma_load_2d(dst, m, fb, x, y);
+            };
             if (!p.a_mn) {
-              tma_load_2d(a_dst, mapA, &full_bar[stage], k0, m0);
+              load(a_dst, mapA, k0, m0);
             } else {
 #pragma unroll
-              for (int i = 0; i < kBlockM / 32; ++i)
-                tma_load_2d(a_dst + i * 4096, mapA, &full_bar[stage], m0 + 32 * i, k0);
+              for (int i = 0; i < kBlockM / 32; ++i) load(a_dst + i * 4096, mapA, m0 + 32 * i, k0);
             }
             if (!p.b_mn) {
-              tma_load_2d(b_dst, mapB, &full_bar[stage], k0, n0);
+              load(b_dst, mapB, k0, n0);
             } else {
-              for (int i = 0; i < p.block_n / 32; ++i)
-                tma_load_2d(b_dst + i * 4096, mapB, &full_bar[stage], n0 + 32 * i, k0);
+              for (int i = 0; i < bn_local / 32; ++i) load(b_dst + i * 4096, mapB, n0 + 32 * i, k0);
+            }
+            if constexpr (kPair) {
+              if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(2 * stage_bytes));  // bytes of BOTH CTAs land here
+              else mbar_arrive_remote(fb, 0);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -187,13 +208,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ============================== MMA issuer (one thread) ==============================
-    if (lane == 0) {
+    // ============================== MMA issuer (one thread of the leader CTA) ==============================
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int split = tile / (p.n_tiles * p.m_tiles);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -213,31 +234,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
                                      (uint64_t)(p.adesc_lo16 | ((a_start + k * p.a_kstep) & 0x3FFFu));
               const uint64_t bdesc = ((uint64_t)p.bdesc_hi << 32) |
                                      (uint64_t)(p.bdesc_lo16 | ((b_start + k * p.b_kstep) & 0x3FFFu));
-              umma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
+              if constexpr (kPair) umma_tf32_pair(d_tmem, adesc, bdesc, p.idesc, accumulate);
+              else umma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
               accumulate = 1;
             }
-            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            // smem slot reusable (in both CTAs) once these MMAs retire
+            if constexpr (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue(s)
+        if constexpr (kPair) umma_commit_pair(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ============================== epilogue (4 warps = 128 TMEM lanes) ==============================
+    // ============================== epilogue (4 warps = this CTA's 128 TMEM lanes) ==============================
     const int q = warp & 3;                   // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;            // row of the 128-row tile owned by this thread
+    const int row = q * 32 + lane;            // row of this CTA's 128-row slab owned by this thread
     const int epi_tid = threadIdx.x - 4 * 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t store_idx = 0;  // running chunk counter: staging buffers alternate ACROSS tiles too
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int n_blk = tile % p.n_tiles;
       const int m_blk = (tile / p.n_tiles) % p.m_tiles;
       const int split = tile / (p.n_tiles * p.m_tiles);
-      const int m0 = m_blk * kBlockM, n0 = n_blk * p.block_n;
+      const int m0 = m_blk * kTileM + (int)cta_rank * kBlockM, n0 = n_blk * p.block_n;
       const bool use_bias = (p.bias != nullptr) && (split == 0);
       if (use_bias) {
         for (int i = epi_tid; i < p.block_n; i += kEpiThreads) sBias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
@@ -252,15 +276,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
         tmem_ld_wait();
         if (c == n_chunks - 1) {
-          // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+          // all TMEM reads of this accumulator stage are done -> hand it back to the (leader's) MMA warp
           tc_fence_before();
-          mbar_arrive(&tmem_empty_bar[acc]);
+          if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]);
         }
         if (use_bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += sBias[c * 32 + j];
         }
-        // staging buffer(s): without aux double-buffer on c; with aux buffer 0 = activated, 1 = pre-activation
+        // staging buffer(s): without aux double-buffer on the running index; with aux buffer 0 = activated, 1 = pre-activation
         uint8_t* buf0 = sStage + (p.has_aux ? 0 : (store_idx++ & 1)) * kStagingBytes;
         uint8_t* buf1 = sStage + kStagingBytes;
         if (epi_tid == 0) {
@@ -296,10 +320,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();  // pair: nobody exits while the peer may still touch its smem/barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -374,9 +398,12 @@ static OperandEnc operand_encoding(bool mn_major) {
   return e;
 }
 
-static void choose_tiling(int M, int N, int kb_total, int accumulate, int& block_n, int& splits) {
-  const int nsm = num_sms();
-  const int m_tiles = (M + kBlockM - 1) / kBlockM;
+static int g_force_pair = -1;  // bring-up override: -1 auto, 0 never, 1 always
+
+static void choose_tiling(int M, int N, int kb_total, int accumulate, bool pair, int& block_n, int& splits) {
+  const int nsm = pair ? num_sms() / 2 : num_sms();
+  const int tile_m = pair ? 2 * kBlockM : kBlockM;
+  const int m_tiles = (M + tile_m - 1) / tile_m;
   auto cost = [&](int bn, int s) {
     const long tiles = (long)m_tiles * ((N + bn - 1) / bn) * s;
     const long waves = (tiles + nsm - 1) / nsm;
@@ -392,6 +419,7 @@ static void choose_tiling(int M, int N, int kb_total, int accumulate, int& block
   for (int bi = 0; bi < 3; ++bi) {
     const int bn = bns[bi];
     if (block_n > 0 && bn != block_n) continue;
+    if (pair && bn < 128) continue;  // pair: each CTA stages bn/2 >= 64 columns
     const int smax = (splits > 0) ? splits : (accumulate ? 32 : 1);
     for (int s = (splits > 0 ? splits : 1); s <= smax; ++s) {
       if (s > 1 && kb_total / s < 4) break;
@@ -410,6 +438,8 @@ using namespace capdec;
 extern "C" const char* capdec_last_error(void) { return g_err; }
 extern "C" int capdec_version(void) { return 100; }
 extern "C" int64_t capdec_launch_count(void) { return g_launches.load(); }
+
+extern "C" void capdec_gemm_debug_force_pair(int mode) { g_force_pair = mode; }
 
 extern "C" void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, int sbo_bytes, int tma_swizzle) {
   g_mn_layout = layout_type;
@@ -435,7 +465,8 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm_tf32_kernel)");
     attr_set = true;
   }
@@ -444,15 +475,20 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   p.kb_total = (K + kBlockK - 1) / kBlockK;
+  // CTA pairs (cta_group::2, 256-row tiles) whenever the problem has at least 256 rows and 128 columns
+  bool pair = (M > kBlockM) && (N >= 128) && (block_n == 0 || block_n >= 128);
+  if (g_force_pair == 0) pair = false;
+  if (g_force_pair == 1 && (block_n == 0 || block_n >= 128)) pair = true;
+  const int tile_m = pair ? 2 * kBlockM : kBlockM;
   int bn = block_n, splits = split_k;
   if (!accumulate) splits = 1;
-  choose_tiling(M, N, p.kb_total, accumulate, bn, splits);
+  choose_tiling(M, N, p.kb_total, accumulate, pair, bn, splits);
   CAPDEC_REQUIRE(splits == 1 || (accumulate && act == 0 && !aux), "gemm: split-K needs accumulate=1, act=0, no aux");
   p.block_n = bn;
   p.splits = splits;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // drop empty splits
-  p.m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.m_tiles = (M + tile_m - 1) / tile_m;
   p.n_tiles = (N + bn - 1) / bn;
   p.nseg = precision ? 3 : 1;
   p.act = act;
@@ -462,7 +498,8 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   p.b_mn = b_major ? 1 : 0;
   p.bias = bias;
 
-  const int b_bytes = bn * kBlockK * 4;
+  const int bn_local = pair ? bn / 2 : bn;
+  const int b_bytes = bn_local * kBlockK * 4;
   const int fixed = 2 * kStagingBytes + 256 * 4 + (2 * kMaxStages + 4) * 8 + 16 + 1024 /* alignment slack */;
   int stages = (kSmemLimit - fixed) / (kABytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -475,7 +512,7 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   // instruction descriptor: D=F32 (bits 4-5 = 1), A/B = TF32 (2) at bits 7-9 / 10-12, majors at 15/16,
   // N>>3 at bits 17-22, M>>4 at bits 24-28
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_major ? 1 : 0) << 15) |
-            ((uint32_t)(b_major ? 1 : 0) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            ((uint32_t)(b_major ? 1 : 0) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(tile_m >> 4) << 24);
 
   int rc;
   for (int s = 0; s < p.nseg && s < 2; ++s) {
@@ -484,7 +521,7 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
     if (!a_major) rc = make_map(&p.tmA[s], a, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBlockK, kBlockM, ea.swz);
     else rc = make_map(&p.tmA[s], a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, kBlockK, ea.swz);
     if (rc) return rc;
-    if (!b_major) rc = make_map(&p.tmB[s], b, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBlockK, (uint32_t)bn, eb.swz);
+    if (!b_major) rc = make_map(&p.tmB[s], b, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBlockK, (uint32_t)bn_local, eb.swz);
     else rc = make_map(&p.tmB[s], b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, kBlockK, eb.swz);
     if (rc) return rc;
   }
@@ -496,8 +533,28 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   }
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  gemm_tf32_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  if (!pair) {
+    const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+    gemm_tf32_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(p);
+  } else {
+    const int max_pairs = num_sms() / 2;
+    const int pairs = total_tiles < max_pairs ? total_tiles : max_pairs;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<true>, p);
+    if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm_tf32_kernel<pair>)");
+  }
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("gemm_tf32_kernel");
   return CAPDEC_OK;

@@ -53,6 +53,9 @@ int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const float* B, i
 /* debug/bring-up override of the UMMA shared-memory descriptor encoding for MN-major operands
  * (layout_type, LBO bytes, SBO bytes, TMA swizzle enum); pass -1 to keep the default. Not used in production. */
 void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, int sbo_bytes, int tma_swizzle);
+/* tile engine selection override: -1 auto (CTA pairs / cta_group::2 whenever M > 128 and N >= 128), 0 = always one CTA
+ * per 128-row tile (cta_group::1), 1 = always CTA pairs.  Used by the tests to cover both engines. */
+void capdec_gemm_debug_force_pair(int mode);
 
 /* fp32 CUDA-core GEMM with the same contract (verification kernel: exact fp32 FMA, no tensor cores). */
 int capdec_gemm_fp32_simt(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,

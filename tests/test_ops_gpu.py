@@ -48,6 +48,27 @@ def test_gemm_tf32_matches_truncated_product(ops, shape, a_major, b_major):
     assert bad.numel() == 0, f"{bad.shape[0]} bad elements, first {bad[:5].tolist()}, rows {bad[:,0].min().item()}..{bad[:,0].max().item()} cols {bad[:,1].min().item()}..{bad[:,1].max().item()}"
 
 
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(256, 256, 32), (12800, 2304, 768), (1000, 50257, 96), (768, 2304, 3200), (300, 200, 64)])
+def test_gemm_both_tile_engines(ops, shape, a_major, b_major, pair):
+    """cta_group::1 (one CTA per 128-row tile) and cta_group::2 (CTA pair per 256-row tile) give the same numbers."""
+    from capdec_b200 import _lib
+    M, N, K = shape
+    A, Al, B, Bl = make_ab(M, N, K, a_major, b_major)
+    C = new_c(M, N)
+    _lib.load().capdec_gemm_debug_force_pair(pair)
+    try:
+        ops.gemm(A, a_major, B, b_major, C, M, N, K)
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().capdec_gemm_debug_force_pair(-1)
+    ref = trunc_tf32(Al).double() @ trunc_tf32(Bl).double().t()
+    err = (C.double() - ref).abs()
+    bad = (err > 1e-4 * ref.abs().max()).nonzero()
+    assert bad.numel() == 0, f"{bad.shape[0]} bad elements, rows {bad[:,0].min().item()}..{bad[:,0].max().item()} cols {bad[:,1].min().item()}..{bad[:,1].max().item()}"
+
+
 @pytest.mark.parametrize("bn", [64, 128, 256])
 def test_gemm_block_n_variants(ops, bn):
     M, N, K = 2500, 1000, 200
