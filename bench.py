@@ -104,7 +104,7 @@ class ClockSampler:
 def cpu_train_step_rate(sample_captions: int, steps: int, warmup: int):
     import torch
     from oracle import capdec_oracle as O
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, int(os.environ.get("CAPDEC_CPU_THREADS", "32")))  # >32 threads oversubscribe this size
     torch.set_num_threads(cores)
     sd = O.make_state_dict(seed=0, mapping_type="mlp", prefix_length=P_LEN, prefix_size=D_CLIP)
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "gpt.lm_head.weight"}
@@ -122,7 +122,7 @@ def cpu_train_step_rate(sample_captions: int, steps: int, warmup: int):
         loss = O.caption_loss(logits, tokens, P_LEN)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     for s in range(warmup):
         one(s)

@@ -15,6 +15,7 @@
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the mainloop of tile i+1.
 // 3xTF32 ("parity") mode runs three K passes (hi*hi, lo*hi, hi*lo) into the same TMEM accumulator.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -477,6 +478,8 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   p.kb_total = (K + kBlockK - 1) / kBlockK;
   // CTA pairs (cta_group::2, 256-row tiles) whenever the problem has at least 256 rows and 128 columns
   bool pair = (M > kBlockM) && (N >= 128) && (block_n == 0 || block_n >= 128);
+  static const char* env_pair = getenv("CAPDEC_GEMM_PAIR");  // bring-up switch: 0 = cta_group::1 only, 1 = force pairs
+  if (env_pair && g_force_pair < 0) { if (env_pair[0] == '0') pair = false; else if (block_n == 0 || block_n >= 128) pair = true; }
   if (g_force_pair == 0) pair = false;
   if (g_force_pair == 1 && (block_n == 0 || block_n >= 128)) pair = true;
   const int tile_m = pair ? 2 * kBlockM : kBlockM;
