@@ -32,15 +32,15 @@ SIGNATURES = {
     "capdec_embed_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _u32, _p],
     "capdec_embed_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _u32, _p],
     "capdec_add_ln_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _p, _u32, _p],
-    "capdec_add_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _u32, _p],
+    "capdec_add_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _u32, _p],
     "capdec_attention_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p,
                              _f, _p, _u32, _p],
-    "capdec_attention_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
+    "capdec_attention_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
                              _i64, _f, _i, _p, _f, _p, _u32, _p],
     "capdec_ce_count": [_p, _i64, _i64, _p, _p, _p],
     "capdec_ce_fwd_bwd": [_p, _i64, _p, _i, _i, _i64, _p, _f, _p, _i, _p],
     "capdec_colsum_acc": [_p, _i64, _p, _i, _i, _p],
-    "capdec_act_bwd": [_p, _p, _p, _i64, _i, _p],
+    "capdec_act_bwd": [_p, _p, _p, _p, _i, _i, _i, _p],
     "capdec_rows_gather": [_p, _p, _i, _i, _i, _i, _i, _p],
     "capdec_rows_scatter": [_p, _p, _i, _i, _i, _i, _i, _p],
     "capdec_mapper_concat_fwd": [_p, _p, _p, _i, _i, _i, _i, _p],

@@ -106,8 +106,8 @@ template <int HD>
 __global__ void __launch_bounds__(512) attention_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                      const float* __restrict__ v, const float* __restrict__ ctx,
                                      const float* __restrict__ dctx, const float* __restrict__ lse,
-                                     float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int H,
-                                     int T, int S, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts,
+                                     float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
+                                     float* __restrict__ dbias_qkv, int H, int T, int S, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts,
                                      int64_t o_bs, int64_t o_ts, float scale, int causal,
                                      const int32_t* __restrict__ key_len, float p_drop, const uint64_t* seed_dev,
                                      uint32_t stream_id) {
@@ -121,8 +121,10 @@ __global__ void __launch_bounds__(512) attention_bwd_kernel(const float* __restr
   float* sdO = sQ + (size_t)T * HD;
   float* sLse = sdO + (size_t)T * HD;
   float* sD = sLse + T;
+  float* sDb = sD + T;  // [3][HD] column sums of dq | dk | dv (bias gradient of the fused QKV projection)
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const int hd4 = HD / 4;
+  for (int i = threadIdx.x; i < 3 * HD; i += blockDim.x) sDb[i] = 0.f;
   for (int i = threadIdx.x; i < S * hd4; i += blockDim.x) {
     const int j = i / hd4, c = i % hd4;
     const size_t g = (size_t)b * kv_bs + (size_t)j * kv_ts + (size_t)h * HD + 4 * c;
@@ -185,6 +187,10 @@ __global__ void __launch_bounds__(512) attention_bwd_kernel(const float* __restr
     for (int i = 0; i < V4; ++i)
       *reinterpret_cast<float4*>(dqp + 4 * i) =
           make_float4(dqa[4 * i] * scale, dqa[4 * i + 1] * scale, dqa[4 * i + 2] * scale, dqa[4 * i + 3] * scale);
+    if (dbias_qkv) {
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) atomicAdd(&sDb[sub * DPL + i], dqa[i] * scale);
+    }
   }
   __syncthreads();
   // ---------------- pass 2: key rows ----------------
@@ -224,6 +230,18 @@ __global__ void __launch_bounds__(512) attention_bwd_kernel(const float* __restr
       *reinterpret_cast<float4*>(dkp + 4 * i) = make_float4(dka[4 * i], dka[4 * i + 1], dka[4 * i + 2], dka[4 * i + 3]);
       *reinterpret_cast<float4*>(dvp + 4 * i) = make_float4(dva[4 * i], dva[4 * i + 1], dva[4 * i + 2], dva[4 * i + 3]);
     }
+    if (dbias_qkv) {
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) {
+        atomicAdd(&sDb[HD + sub * DPL + i], dka[i]);
+        atomicAdd(&sDb[2 * HD + sub * DPL + i], dva[i]);
+      }
+    }
+  }
+  if (dbias_qkv) {  // one global atomic per (head, column): dbias laid out [q | k | v] x [H*HD] like c_attn.bias
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * HD; i += blockDim.x)
+      atomicAdd(dbias_qkv + (size_t)(i / HD) * H * HD + (size_t)h * HD + (i % HD), sDb[i]);
   }
 }
 
@@ -267,8 +285,8 @@ extern "C" int capdec_attention_fwd(const float* q, const float* k, const float*
 }
 
 extern "C" int capdec_attention_bwd(const float* q, const float* k, const float* v, const float* ctx,
-                                    const float* dctx, const float* lse, float* dq, float* dk, float* dv, int B, int H,
-                                    int T, int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts,
+                                    const float* dctx, const float* lse, float* dq, float* dk, float* dv, float* dbias_qkv, int B,
+                                    int H, int T, int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts,
                                     int64_t o_bs, int64_t o_ts, float scale, int causal, const int32_t* key_len,
                                     float p_drop, const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -277,16 +295,16 @@ extern "C" int capdec_attention_bwd(const float* q, const float* k, const float*
   if (rc) return rc;
   const int mx = T > S ? T : S;
   const int threads = ((4 * mx + 31) / 32) * 32;
-  const size_t smem = ((size_t)2 * S * hd + (size_t)2 * T * hd + 2 * T) * sizeof(float);
+  const size_t smem = ((size_t)2 * S * hd + (size_t)2 * T * hd + 2 * T + 3 * hd) * sizeof(float);
   if (hd == 64) {
     static bool set64 = false;
     if (!set64) { cudaFuncSetAttribute(attention_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set64 = true; }
-    attention_bwd_kernel<64><<<B * H, threads, smem, stream>>>(q, k, v, ctx, dctx, lse, dq, dk, dv, H, T, S, q_bs, q_ts, kv_bs,
+    attention_bwd_kernel<64><<<B * H, threads, smem, stream>>>(q, k, v, ctx, dctx, lse, dq, dk, dv, dbias_qkv, H, T, S, q_bs, q_ts, kv_bs,
                                                                kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id);
   } else {
     static bool set96 = false;
     if (!set96) { cudaFuncSetAttribute(attention_bwd_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set96 = true; }
-    attention_bwd_kernel<96><<<B * H, threads, smem, stream>>>(q, k, v, ctx, dctx, lse, dq, dk, dv, H, T, S, q_bs, q_ts, kv_bs,
+    attention_bwd_kernel<96><<<B * H, threads, smem, stream>>>(q, k, v, ctx, dctx, lse, dq, dk, dv, dbias_qkv, H, T, S, q_bs, q_ts, kv_bs,
                                                                kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id);
   }
   g_launches.fetch_add(1);

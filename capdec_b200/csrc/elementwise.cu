@@ -210,24 +210,41 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// activation backward
+// activation backward (+ fused bias gradient: dbias[n] += sum_m dx[m,n]); same thread layout as colsum_kernel
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) act_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ pre,
-                                                      float4* __restrict__ dx, int64_t n4, int act) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 g = ld_stream(dy + i), p = ld_stream(pre + i);
-    float4 o;
-    if (act == 1) {
-      o.x = g.x * gelu_new_grad(p.x); o.y = g.y * gelu_new_grad(p.y);
-      o.z = g.z * gelu_new_grad(p.z); o.w = g.w * gelu_new_grad(p.w);
-    } else if (act == 2) {
-      o.x = g.x * (1.f - p.x * p.x); o.y = g.y * (1.f - p.y * p.y);
-      o.z = g.z * (1.f - p.z * p.z); o.w = g.w * (1.f - p.w * p.w);
-    } else {
-      o.x = p.x > 0.f ? g.x : 0.f; o.y = p.y > 0.f ? g.y : 0.f;
-      o.z = p.z > 0.f ? g.z : 0.f; o.w = p.w > 0.f ? g.w : 0.f;
+__device__ __forceinline__ float act_grad(float g, float p, int act) {
+  if (act == 1) return g * gelu_new_grad(p);
+  if (act == 2) return g * (1.f - p * p);
+  return p > 0.f ? g : 0.f;
+}
+
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre,
+                                                      float* __restrict__ dx, float* __restrict__ dbias, int M, int N,
+                                                      int rows_per_block, int act) {
+  __shared__ float4 s[8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cl) * 4;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < N) {
+    for (int m = m0 + rl; m < m1; m += 8) {
+      const size_t off = (size_t)m * N + col;
+      const float4 g = ld_stream(reinterpret_cast<const float4*>(dy + off));
+      const float4 p = ld_stream(reinterpret_cast<const float4*>(pre + off));
+      float4 o;
+      o.x = act_grad(g.x, p.x, act); o.y = act_grad(g.y, p.y, act);
+      o.z = act_grad(g.z, p.z, act); o.w = act_grad(g.w, p.w, act);
+      *reinterpret_cast<float4*>(dx + off) = o;
+      a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
     }
-    dx[i] = o;
+  }
+  if (!dbias) return;
+  s[rl][cl] = a;
+  __syncthreads();
+  if (rl == 0 && col < N) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { const float4 t = s[w][cl]; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+    atomicAdd(dbias + col + 0, a.x); atomicAdd(dbias + col + 1, a.y); atomicAdd(dbias + col + 2, a.z); atomicAdd(dbias + col + 3, a.w);
   }
 }
 
@@ -409,11 +426,17 @@ extern "C" int capdec_colsum_acc(const float* x, int64_t ld, float* out, int M, 
   return CAPDEC_OK;
 }
 
-extern "C" int capdec_act_bwd(const float* dy, const float* pre, float* dx, int64_t n, int act, capdec_stream_t stream_) {
+extern "C" int capdec_act_bwd(const float* dy, const float* pre, float* dx, float* dbias, int M, int N, int act,
+                              capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CAPDEC_REQUIRE(dy && pre && dx && n > 0 && n % 4 == 0 && act >= 1 && act <= 3, "act_bwd: bad arguments");
-  act_bwd_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(pre),
-                                                           reinterpret_cast<float4*>(dx), n / 4, act);
+  CAPDEC_REQUIRE(dy && pre && dx && M > 0 && N > 0 && N % 4 == 0 && act >= 1 && act <= 3, "act_bwd: bad arguments");
+  const int gx = (N + 127) / 128;
+  int gy = (num_sms() * 8 + gx - 1) / gx;
+  int rpb = (M + gy - 1) / gy;
+  rpb = ((rpb + 7) / 8) * 8;
+  if (rpb < 8) rpb = 8;
+  gy = (M + rpb - 1) / rpb;
+  act_bwd_kernel<<<dim3(gx, gy), 256, 0, stream>>>(dy, pre, dx, dbias, M, N, rpb, act);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("act_bwd_kernel");
   return CAPDEC_OK;

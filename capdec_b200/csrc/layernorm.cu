@@ -81,19 +81,21 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ dh_res, float* __restrict__ dh_out,
                                                          float* __restrict__ dy, float* __restrict__ dgamma,
-                                                         float* __restrict__ dbeta, int rows, int d, float p_drop,
+                                                         float* __restrict__ dbeta, float* __restrict__ dbias_branch,
+                                                         int rows, int d, float p_drop,
                                                          const uint64_t* seed_dev, uint32_t stream_id) {
   const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
   __shared__ float4 s_red[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d4 = d >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  float4 gam[NV], dg[NV], db[NV];
+  float4 gam[NV], dg[NV], db[NV], dbr[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     gam[i] = __ldg(g4 + lane + 32 * i);
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dbr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float inv_keep = 1.0f / (1.0f - p_drop);
   const float inv_d = 1.0f / (float)d;
@@ -135,23 +137,26 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
         o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
       }
       out4[c] = o;
-      if (dy4) {
+      if (dy4 || dbias_branch) {
         if (p_drop > 0.0f) {
           float s[4];
           dropout_scale4(seed, stream_id, (uint64_t)row * d4 + c, p_drop, inv_keep, s);
           o.x *= s[0]; o.y *= s[1]; o.z *= s[2]; o.w *= s[3];
         }
-        dy4[c] = o;
+        if (dy4) dy4[c] = o;
+        dbr[i].x += o.x; dbr[i].y += o.y; dbr[i].z += o.z; dbr[i].w += o.w;  // bias gradient of the branch's last Linear
       }
     }
   }
-  if (dgamma) {
+  if (dgamma || dbias_branch) {
     // block reduce the 8 warps' partials, one atomicAdd per column per block
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      for (int pass = 0; pass < 2; ++pass) {
+      for (int pass = 0; pass < 3; ++pass) {
+        if (pass < 2 && !dgamma) continue;
+        if (pass == 2 && !dbias_branch) continue;
         __syncthreads();
-        s_red[warp][lane] = pass == 0 ? dg[i] : db[i];
+        s_red[warp][lane] = pass == 0 ? dg[i] : (pass == 1 ? db[i] : dbr[i]);
         __syncthreads();
         if (warp == 0) {
           float4 a = s_red[0][lane];
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
             const float4 t = s_red[w][lane];
             a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
           }
-          float* dst = (pass == 0 ? dgamma : dbeta) + 4 * (lane + 32 * i);
+          float* dst = (pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias_branch)) + 4 * (lane + 32 * i);
           atomicAdd(dst + 0, a.x); atomicAdd(dst + 1, a.y); atomicAdd(dst + 2, a.z); atomicAdd(dst + 3, a.w);
         }
       }
@@ -201,8 +206,8 @@ extern "C" int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out
 }
 
 extern "C" int capdec_add_ln_bwd(const float* dx, const float* r, const float* stats, const float* gamma,
-                                 const float* dh_res, float* dh_out, float* dy, float* dgamma, float* dbeta, int rows,
-                                 int d, float p_drop, const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream_) {
+                                 const float* dh_res, float* dh_out, float* dy, float* dgamma, float* dbeta,
+                                 float* dbias_branch, int rows, int d, float p_drop, const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(dx && r && stats && gamma && dh_out && rows > 0, "add_ln_bwd: null argument");
   CAPDEC_REQUIRE(d % 128 == 0 && d <= 128 * kMaxV, "add_ln_bwd: d=%d must be a multiple of 128 and <= 1024", d);
@@ -212,7 +217,7 @@ extern "C" int capdec_add_ln_bwd(const float* dx, const float* r, const float* s
   const int cap = num_sms() * 4;
   if (grid > cap) grid = cap;
   DISPATCH_NV(nv, (add_ln_bwd_kernel<NV><<<grid, 256, 0, stream>>>(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma,
-                                                                   dbeta, rows, d, p_drop, seed_dev, stream_id)));
+                                                                   dbeta, dbias_branch, rows, d, p_drop, seed_dev, stream_id)));
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("add_ln_bwd_kernel");
   return CAPDEC_OK;

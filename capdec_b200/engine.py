@@ -222,24 +222,25 @@ class Engine:
             w2, w1 = "clip_project.model.2.", "clip_project.model.0."
             ops.linear_wgrad(ma.a1, dpp, g[w2 + "weight"], "linear", g[w2 + "bias"])
             ops.linear_dgrad(dpp, p[w2 + "weight"], "linear", ma.da1)
-            ops.act_bwd(ma.da1, ma.a1, ma.da1, ops.ACT_TANH)
-            ops.linear_wgrad(x, ma.da1, g[w1 + "weight"], "linear", g[w1 + "bias"])
+            ops.act_bwd(ma.da1, ma.a1, ma.da1, ops.ACT_TANH, dbias=g[w1 + "bias"])
+            ops.linear_wgrad(x, ma.da1, g[w1 + "weight"], "linear")
             return
         d, C, P, S, Mm = self.d, self.C, self.P, ma.S, ma.Mm
         nl = self.n_mapper_layers
         ops.rows_scatter(dpp.view(B * P, d), ma.dhm, B, S, P, C)
         for j in reversed(range(nl)):
             pre = f"clip_project.transformer.layers.{j}."
-            # fc2
-            ops.linear_wgrad(ma.f[j], ma.dhm, g[pre + "mlp.fc2.weight"], "linear", g[pre + "mlp.fc2.bias"])
+            # fc2 (its bias gradient comes fused from the add_ln_bwd that produced dhm; last layer: explicit colsum)
+            ops.linear_wgrad(ma.f[j], ma.dhm, g[pre + "mlp.fc2.weight"], "linear",
+                             g[pre + "mlp.fc2.bias"] if j == nl - 1 else None)
             ops.linear_dgrad(ma.dhm, p[pre + "mlp.fc2.weight"], "linear", ma.df)
-            ops.act_bwd(ma.df, ma.f[j], ma.df, ops.ACT_RELU)
-            ops.linear_wgrad(ma.y2[j], ma.df, g[pre + "mlp.fc1.weight"], "linear", g[pre + "mlp.fc1.bias"])
+            ops.act_bwd(ma.df, ma.f[j], ma.df, ops.ACT_RELU, dbias=g[pre + "mlp.fc1.bias"])
+            ops.linear_wgrad(ma.y2[j], ma.df, g[pre + "mlp.fc1.weight"], "linear")
             ops.linear_dgrad(ma.df, p[pre + "mlp.fc1.weight"], "linear", ma.dt)
             ops.add_ln_bwd(ma.dt, ma.hm1[j], ma.s2[j], p[pre + "norm2.weight"], ma.dhm, ma.dhm, None,
-                           g[pre + "norm2.weight"], g[pre + "norm2.bias"])
+                           g[pre + "norm2.weight"], g[pre + "norm2.bias"], dbias_branch=g[pre + "attn.project.bias"])
             # attention branch
-            ops.linear_wgrad(ma.o[j], ma.dhm, g[pre + "attn.project.weight"], "linear", g[pre + "attn.project.bias"])
+            ops.linear_wgrad(ma.o[j], ma.dhm, g[pre + "attn.project.weight"], "linear")
             ops.linear_dgrad(ma.dhm, p[pre + "attn.project.weight"], "linear", ma.do)
             q, k, v = ma.qkv[j][:, :d], ma.qkv[j][:, d:2 * d], ma.qkv[j][:, 2 * d:]
             dq, dk, dv = ma.dqkv[:, :d], ma.dqkv[:, d:2 * d], ma.dqkv[:, 2 * d:]
@@ -247,8 +248,9 @@ class Engine:
                               S * 3 * d, 3 * d, S * d, d, self.mhd ** -0.5, 0)
             ops.linear_wgrad(ma.y1[j], ma.dqkv, self.gqkv[j], "linear")
             ops.linear_dgrad(ma.dqkv, self.wqkv[j], "linear", ma.dt)
+            prev_fc2_bias = g[f"clip_project.transformer.layers.{j - 1}.mlp.fc2.bias"] if j > 0 else None
             ops.add_ln_bwd(ma.dt, ma.hm[j], ma.s1[j], p[pre + "norm1.weight"], ma.dhm, ma.dhm, None,
-                           g[pre + "norm1.weight"], g[pre + "norm1.bias"])
+                           g[pre + "norm1.weight"], g[pre + "norm1.bias"], dbias_branch=prev_fc2_bias)
         ops.mapper_concat_bwd(ma.dhm, ma.dlin, g["clip_project.prefix_const"], B, C, P)
         ops.linear_wgrad(x, ma.dlin, g["clip_project.linear.weight"], "linear", g["clip_project.linear.bias"])
 
@@ -308,38 +310,42 @@ class Engine:
         gw = (lambda n: g[n]) if train_gpt else (lambda n: None)
         dy = a.dy if p_res > 0 else None     # branch-output gradient buffer (mask * dh); aliases dh when p = 0
         cur = (lambda: a.dy) if p_res > 0 else (lambda: a.dh)
+        # bias gradients of attn.c_proj / mlp.c_proj / c_fc / c_attn come fused out of add_ln_bwd / act_bwd / attention_bwd
         ops.add_ln_bwd(dxf, a.h[self.nl], a.stf, p["gpt.transformer.ln_f.weight"], None, a.dh, dy,
                        gw("gpt.transformer.ln_f.weight"), gw("gpt.transformer.ln_f.bias"), p_drop=p_res, seed=self.seed,
-                       stream_id=_site(self.nl - 1, 2))
+                       stream_id=_site(self.nl - 1, 2),
+                       dbias_branch=gw(f"gpt.transformer.h.{self.nl - 1}.mlp.c_proj.bias"))
         for l in reversed(range(self.nl)):
             pre = f"gpt.transformer.h.{l}."
             dy2 = cur()
             # mlp.c_proj
             if train_gpt:
-                ops.linear_wgrad(a.g[l], dy2, g[pre + "mlp.c_proj.weight"], "conv1d", g[pre + "mlp.c_proj.bias"])
+                ops.linear_wgrad(a.g[l], dy2, g[pre + "mlp.c_proj.weight"], "conv1d")
             ops.linear_dgrad(dy2, p[pre + "mlp.c_proj.weight"], "conv1d", a.dF)
-            ops.act_bwd(a.dF, a.u[l], a.dF, ops.ACT_GELU_NEW)
+            ops.act_bwd(a.dF, a.u[l], a.dF, ops.ACT_GELU_NEW, dbias=gw(pre + "mlp.c_fc.bias"))
             if train_gpt:
-                ops.linear_wgrad(a.x2[l], a.dF, g[pre + "mlp.c_fc.weight"], "conv1d", g[pre + "mlp.c_fc.bias"])
+                ops.linear_wgrad(a.x2[l], a.dF, g[pre + "mlp.c_fc.weight"], "conv1d")
             ops.linear_dgrad(a.dF, p[pre + "mlp.c_fc.weight"], "conv1d", a.dx)
             ops.add_ln_bwd(a.dx, a.h1[l], a.st2[l], p[pre + "ln_2.weight"], a.dh, a.dh, dy, gw(pre + "ln_2.weight"),
-                           gw(pre + "ln_2.bias"), p_drop=p_res, seed=self.seed, stream_id=_site(l, 1))
+                           gw(pre + "ln_2.bias"), p_drop=p_res, seed=self.seed, stream_id=_site(l, 1),
+                           dbias_branch=gw(pre + "attn.c_proj.bias"))
             dy1 = cur()
             # attention
             if train_gpt:
-                ops.linear_wgrad(a.ctx[l], dy1, g[pre + "attn.c_proj.weight"], "conv1d", g[pre + "attn.c_proj.bias"])
+                ops.linear_wgrad(a.ctx[l], dy1, g[pre + "attn.c_proj.weight"], "conv1d")
             ops.linear_dgrad(dy1, p[pre + "attn.c_proj.weight"], "conv1d", a.dctx)
             q, k, v = a.qkv[l][:, :d], a.qkv[l][:, d:2 * d], a.qkv[l][:, 2 * d:]
             dq, dk, dv = a.dqkv[:, :d], a.dqkv[:, d:2 * d], a.dqkv[:, 2 * d:]
             ops.attention_bwd(q, k, v, a.ctx[l], a.dctx, a.lse[l], dq, dk, dv, B, self.H, T, T, self.hd, T * 3 * d, 3 * d,
                               T * 3 * d, 3 * d, T * d, d, self.hd ** -0.5, 1, key_len=key_len, p_drop=p_attn,
-                              seed=self.seed, stream_id=_site(l, 0))
+                              seed=self.seed, stream_id=_site(l, 0), dbias_qkv=gw(pre + "attn.c_attn.bias"))
             if train_gpt:
-                ops.linear_wgrad(a.x1[l], a.dqkv, g[pre + "attn.c_attn.weight"], "conv1d", g[pre + "attn.c_attn.bias"])
+                ops.linear_wgrad(a.x1[l], a.dqkv, g[pre + "attn.c_attn.weight"], "conv1d")
             ops.linear_dgrad(a.dqkv, p[pre + "attn.c_attn.weight"], "conv1d", a.dx)
             if l > 0:
                 ops.add_ln_bwd(a.dx, a.h[l], a.st1[l], p[pre + "ln_1.weight"], a.dh, a.dh, dy, gw(pre + "ln_1.weight"),
-                               gw(pre + "ln_1.bias"), p_drop=p_res, seed=self.seed, stream_id=_site(l - 1, 2))
+                               gw(pre + "ln_1.bias"), p_drop=p_res, seed=self.seed, stream_id=_site(l - 1, 2),
+                               dbias_branch=gw(f"gpt.transformer.h.{l - 1}.mlp.c_proj.bias"))
             else:
                 ops.add_ln_bwd(a.dx, a.h[0], a.st1[0], p[pre + "ln_1.weight"], a.dh, a.dh, None, gw(pre + "ln_1.weight"),
                                gw(pre + "ln_1.bias"))

@@ -111,6 +111,8 @@ def linear_dgrad(dy, W, layout, dx, accumulate=False):
 
 
 def linear_wgrad(x, dy, dW, layout, dbias=None):
+    """dW += x^T dy (conv1d) / dy^T x (linear); dbias (optional) += column sums of dy via a separate pass — the engine
+    normally gets bias gradients from the fused producers (add_ln_bwd / act_bwd / attention_bwd) instead."""
     rows = x.shape[0]
     if layout == "conv1d":  # dW[in,out] += x^T dy
         gemm(x, 1, dy, 1, dW, x.shape[1], dy.shape[1], rows, accumulate=True)
@@ -169,10 +171,12 @@ def add_ln_fwd(h_in, y, h_out, x, stats, gamma, beta, eps=1e-5, p_drop=0.0, seed
     _lib.check(rc, "add_ln_fwd")
 
 
-def add_ln_bwd(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma, dbeta, p_drop=0.0, seed=None, stream_id=0):
+def add_ln_bwd(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma, dbeta, p_drop=0.0, seed=None, stream_id=0,
+               dbias_branch=None):
     rows, d = dx.shape
     rc = _lib.load().capdec_add_ln_bwd(dx.data_ptr(), r.data_ptr(), stats.data_ptr(), gamma.data_ptr(), _ptr(dh_res),
-                                       dh_out.data_ptr(), _ptr(dy), _ptr(dgamma), _ptr(dbeta), rows, d, float(p_drop),
+                                       dh_out.data_ptr(), _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(dbias_branch), rows, d,
+                                       float(p_drop),
                                        _seed_ptr(seed, p_drop > 0), stream_id, _stream())
     _lib.check(rc, "add_ln_bwd")
 
@@ -186,9 +190,10 @@ def attention_fwd(q, k, v, ctx, lse, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o
 
 
 def attention_bwd(q, k, v, ctx, dctx, lse, dq, dk, dv, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale,
-                  causal, key_len=None, p_drop=0.0, seed=None, stream_id=0):
+                  causal, key_len=None, p_drop=0.0, seed=None, stream_id=0, dbias_qkv=None):
     rc = _lib.load().capdec_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), dctx.data_ptr(),
-                                          lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, T, S, hd,
+                                          lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _ptr(dbias_qkv),
+                                          B, H, T, S, hd,
                                           q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, float(scale), int(causal),
                                           _ptr(key_len), float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id, _stream())
     _lib.check(rc, "attention_bwd")
@@ -220,8 +225,11 @@ def colsum_acc(x, out):
     _lib.check(_lib.load().capdec_colsum_acc(x.data_ptr(), ld, out.data_ptr(), M, N, _stream()), "colsum_acc")
 
 
-def act_bwd(dy, pre, dx, act):
-    _lib.check(_lib.load().capdec_act_bwd(dy.data_ptr(), pre.data_ptr(), dx.data_ptr(), dy.numel(), act, _stream()),
+def act_bwd(dy, pre, dx, act, dbias=None):
+    M, N = dy.shape
+    if not (dy.is_contiguous() and pre.is_contiguous() and dx.is_contiguous()):
+        raise ValueError("act_bwd expects contiguous [M, N] tensors")
+    _lib.check(_lib.load().capdec_act_bwd(dy.data_ptr(), pre.data_ptr(), dx.data_ptr(), _ptr(dbias), M, N, act, _stream()),
                "act_bwd")
 
 

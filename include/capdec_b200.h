@@ -94,9 +94,12 @@ int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out, float* x,
                       capdec_stream_t stream);
 /* bwd: dr = dh_res (running residual gradient, may be NULL = 0) + LN_bwd(dx; r, stats, gamma) -> written to dh_out
  *      (may alias dh_res); if dy != NULL: dy = dropout_mask * dr (gradient of the branch output y).
- *      dgamma/dbeta accumulated (+=) unless NULL (frozen GPT-2, train.py:276-284). */
+ *      dgamma/dbeta accumulated (+=) unless NULL (frozen GPT-2, train.py:276-284).
+ *      dbias_branch (may be NULL): += sum over rows of (dropout_mask * dr) = the bias gradient of the Linear/Conv1D
+ *      whose output was the branch y (attn.c_proj / mlp.c_proj / mapper project / fc2), fused here to save a pass. */
 int capdec_add_ln_bwd(const float* dx, const float* r, const float* stats, const float* gamma, const float* dh_res,
-                      float* dh_out, float* dy, float* dgamma, float* dbeta, int rows, int d, float p_drop,
+                      float* dh_out, float* dy, float* dgamma, float* dbeta, float* dbias_branch, int rows, int d,
+                      float p_drop,
                       const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
 
 /* ---- attention core ----------------------------------------------------------------------------------------------
@@ -109,8 +112,10 @@ int capdec_attention_fwd(const float* q, const float* k, const float* v, float* 
                          int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs,
                          int64_t o_ts, float scale, int causal, const int32_t* key_len, float p_drop,
                          const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
+/* dbias_qkv (may be NULL): [3*H*hd] += column sums of (dq | dk | dv) over all rows = c_attn.bias gradient */
 int capdec_attention_bwd(const float* q, const float* k, const float* v, const float* ctx, const float* dctx,
-                         const float* lse, float* dq, float* dk, float* dv, int B, int H, int T, int S, int hd,
+                         const float* lse, float* dq, float* dk, float* dv, float* dbias_qkv, int B, int H, int T,
+                         int S, int hd,
                          int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts,
                          float scale, int causal, const int32_t* key_len, float p_drop,
                          const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
@@ -130,9 +135,11 @@ int capdec_ce_fwd_bwd(float* logits, int64_t ld, const int64_t* targets, int row
 /* ---- small fused elementwise / reduction ops ----------------------------------------------------------------------
  * colsum: out[n] += sum_m x[m,n]  (bias gradients of every Linear/Conv1D; autograd of addmm bias) */
 int capdec_colsum_acc(const float* x, int64_t ld, float* out, int M, int N, capdec_stream_t stream);
-/* dx = dy * act'(.) ; act: 1 gelu_new (pre = pre-activation), 2 tanh (pre = activated output a: 1-a^2),
- * 3 relu (pre = activated output) */
-int capdec_act_bwd(const float* dy, const float* pre, float* dx, int64_t n, int act, capdec_stream_t stream);
+/* dx[M,N] = dy * act'(.) ; act: 1 gelu_new (pre = pre-activation), 2 tanh (pre = activated output a: 1-a^2),
+ * 3 relu (pre = activated output).  dbias (may be NULL): [N] += column sums of dx (bias gradient of the Linear that
+ * produced the pre-activation), fused to save a pass.  dx may alias dy.  Contiguous [M,N], N % 4 == 0. */
+int capdec_act_bwd(const float* dy, const float* pre, float* dx, float* dbias, int M, int N, int act,
+                   capdec_stream_t stream);
 /* row gather / scatter of d-wide rows: dst[i,:] = src[map(i),:] with map(i) = (i / L)*T + off + i % L
  * (logits slice [:, P-1:-1] of train.py:349, expressed on the hidden states) */
 int capdec_rows_gather(const float* src, float* dst, int B, int T, int L, int off, int d, capdec_stream_t stream);

@@ -221,8 +221,10 @@ def test_add_ln_fwd_bwd(ops, rows, d):
     dy = torch.empty(rows, d, device="cuda")
     dg = torch.zeros(d, device="cuda")
     db = torch.zeros(d, device="cuda")
-    ops.add_ln_bwd(dx, h_out, stats, gamma, dres, dh_out, dy, dg, db)
+    dbr = torch.zeros(d, device="cuda")
+    ops.add_ln_bwd(dx, h_out, stats, gamma, dres, dh_out, dy, dg, db, dbias_branch=dbr)
     ref_dr = hd_.grad + dres.double()
+    assert (dbr.double() - ref_dr.sum(0)).abs().max() < 2e-3 * max(1.0, ref_dr.sum(0).abs().max().item())
     assert (dh_out.double() - ref_dr).abs().max() < 1e-4
     assert torch.equal(dy, dh_out)
     assert (dg.double() - gd.grad).abs().max() < 2e-3 * max(1.0, gd.grad.abs().max().item())
@@ -283,9 +285,12 @@ def test_attention_fwd_bwd(ops, B, H, T, hd, causal):
     dctx = torch.randn(B, T, d, device="cuda")
     (ref * dctx.double()).sum().backward()
     dqkv = torch.empty(B, T, 3 * d, device="cuda")
+    dbias = torch.zeros(3 * d, device="cuda")
     ops.attention_bwd(q, k, v, ctx, dctx, lse, dqkv[..., :d], dqkv[..., d:2 * d], dqkv[..., 2 * d:], B, H, T, T, hd,
-                      T * 3 * d, 3 * d, T * 3 * d, 3 * d, T * d, d, scale, causal)
+                      T * 3 * d, 3 * d, T * 3 * d, 3 * d, T * d, d, scale, causal, dbias_qkv=dbias)
     assert (dqkv.double() - qd.grad).abs().max() < 1e-4
+    ref_db = qd.grad.sum(dim=(0, 1))
+    assert (dbias.double() - ref_db).abs().max() < 1e-3 * max(1.0, ref_db.abs().max().item())
 
 
 def test_attention_key_padding_and_dropout(ops):
@@ -341,8 +346,10 @@ def test_colsum_actbwd_rows_concat(ops):
     dy = torch.randn(999, 3072, device="cuda")
     torch.nn.functional.gelu(pre, approximate="tanh").backward(dy)
     dx = torch.empty_like(dy)
-    ops.act_bwd(dy, pre.detach(), dx, ops.ACT_GELU_NEW)
+    dbias = torch.ones(3072, device="cuda")
+    ops.act_bwd(dy, pre.detach(), dx, ops.ACT_GELU_NEW, dbias=dbias)
     assert (dx - pre.grad).abs().max() < 1e-5
+    assert (dbias.double() - (1 + pre.grad.double().sum(0))).abs().max() < 1e-3
     a = torch.tanh(pre.detach())
     ops.act_bwd(dy, a, dx, ops.ACT_TANH)
     assert (dx - dy * (1 - a * a)).abs().max() < 1e-6
