@@ -37,6 +37,10 @@ SIGNATURES = {
                              _f, _p, _u32, _p],
     "capdec_attention_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
                              _i64, _f, _i, _p, _f, _p, _u32, _p],
+    "capdec_attention_tc_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p,
+                                _f, _p, _u32, _p],
+    "capdec_attention_tc_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
+                                _i64, _f, _i, _p, _f, _p, _u32, _p],
     "capdec_ce_count": [_p, _i64, _i64, _p, _p, _p],
     "capdec_ce_fwd_bwd": [_p, _i64, _p, _i, _i, _i64, _p, _f, _p, _i, _p],
     "capdec_colsum_acc": [_p, _i64, _p, _i, _i, _p],

@@ -17,12 +17,13 @@ __device__ __forceinline__ float group4_sum(float v, uint32_t mask) {
   return v;
 }
 
-// dropout keep-scale of probability element (row_base + j) of this (b,h)
-__device__ __forceinline__ float drop_scale_elem(uint64_t seed, uint32_t stream_id, uint64_t elem, float p, float inv_keep) {
+// dropout keep-scale of probability element (grow = (b*H+h)*T + i, column j); same (row, col) -> Philox mapping as the
+// tensor-core kernels (attention_tc.cu): quad = grow*32 + (j>>4)*4 + ((j&7)>>1), component = ((j>>3)&1)*2 + (j&1)
+__device__ __forceinline__ float drop_scale_elem(uint64_t seed, uint32_t stream_id, uint64_t grow, int j, float p, float inv_keep) {
   uint32_t r[4];
-  Philox::gen(seed, stream_id, elem >> 2, r);
+  Philox::gen(seed, stream_id, grow * 32 + (uint64_t)((j >> 4) * 4 + ((j & 7) >> 1)), r);
   const uint32_t thr = (uint32_t)(p * 4294967296.0f);
-  return (r[elem & 3] >= thr) ? inv_keep : 0.0f;
+  return (r[((j >> 3) & 1) * 2 + (j & 1)] >= thr) ? inv_keep : 0.0f;
 }
 
 template <int HD>
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(512) attention_fwd_kernel(const float* __restr
   if (key_len) jmax = min(jmax, key_len[b]);
   float m = -INFINITY, l = 0.f;
   const float inv_keep = 1.0f / (1.0f - p_drop);
-  const uint64_t row_base = ((uint64_t)bh * T + row) * (uint64_t)S;
+  const uint64_t grow = (uint64_t)bh * T + row;
   for (int j = 0; j < jmax; ++j) {
     const float4* kp = reinterpret_cast<const float4*>(sK + (size_t)j * HD + sub * DPL);
     float part = 0.f;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(512) attention_fwd_kernel(const float* __restr
     l = l * alpha + pe;
     m = m_new;
     float pv = pe;
-    if (p_drop > 0.f) pv *= drop_scale_elem(seed, stream_id, row_base + j, p_drop, inv_keep);
+    if (p_drop > 0.f) pv *= drop_scale_elem(seed, stream_id, grow, j, p_drop, inv_keep);
     const float4* vp = reinterpret_cast<const float4*>(sV + (size_t)j * HD + sub * DPL);
 #pragma unroll
     for (int i = 0; i < V4; ++i) {
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(512) attention_bwd_kernel(const float* __restr
     const float lse_i = sLse[r];
     int jmax = causal ? min(S, r + 1 + (S - T)) : S;
     jmax = min(jmax, klen);
-    const uint64_t row_base = ((uint64_t)bh * T + r) * (uint64_t)S;
+    const uint64_t grow = (uint64_t)bh * T + r;
     for (int j = 0; j < jmax; ++j) {
       const float* kp = sK + (size_t)j * HD + sub * DPL;
       const float* vp = sV + (size_t)j * HD + sub * DPL;
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(512) attention_bwd_kernel(const float* __restr
       const float s = group4_sum(sp, gmask);
       float dp = group4_sum(dpp, gmask);
       const float p = __expf(s - lse_i);
-      if (p_drop > 0.f) dp *= drop_scale_elem(seed, stream_id, row_base + j, p_drop, inv_keep);
+      if (p_drop > 0.f) dp *= drop_scale_elem(seed, stream_id, grow, j, p_drop, inv_keep);
       const float ds = p * (dp - Di);
 #pragma unroll
       for (int i = 0; i < DPL; ++i) dqa[i] = fmaf(ds, kp[i], dqa[i]);
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(512) attention_bwd_kernel(const float* __restr
       const float p = __expf(s - sLse[i]);
       float pd = p;
       if (p_drop > 0.f) {
-        const float sc = drop_scale_elem(seed, stream_id, ((uint64_t)bh * T + i) * (uint64_t)S + j, p_drop, inv_keep);
+        const float sc = drop_scale_elem(seed, stream_id, (uint64_t)bh * T + i, j, p_drop, inv_keep);
         pd *= sc;
         dp *= sc;
       }

@@ -181,8 +181,24 @@ def add_ln_bwd(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma, dbeta, p_drop=0.
     _lib.check(rc, "add_ln_bwd")
 
 
+def _use_tc(impl):
+    """attention implementation: 'tc' = mma.sync TF32 tensor-core kernel, 'ffma' = exact fp32 CUDA-core kernel;
+    default follows the GEMM precision mode (tf32 -> tc, fp32 / tf32x3 -> ffma)."""
+    if impl is None:
+        return _PRECISION == "tf32"
+    return impl == "tc"
+
+
 def attention_fwd(q, k, v, ctx, lse, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal,
-                  key_len=None, p_drop=0.0, seed=None, stream_id=0):
+                  key_len=None, p_drop=0.0, seed=None, stream_id=0, impl=None):
+    if _use_tc(impl):
+        rc = _lib.load().capdec_attention_tc_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), _ptr(lse), B, H,
+                                                 T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, float(scale), int(causal),
+                                                 _ptr(key_len), float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id,
+                                                 _stream())
+        if rc != -3:
+            _lib.check(rc, "attention_tc_fwd")
+            return
     rc = _lib.load().capdec_attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), _ptr(lse), B, H, T,
                                           S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, float(scale), int(causal),
                                           _ptr(key_len), float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id, _stream())
@@ -190,7 +206,16 @@ def attention_fwd(q, k, v, ctx, lse, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o
 
 
 def attention_bwd(q, k, v, ctx, dctx, lse, dq, dk, dv, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale,
-                  causal, key_len=None, p_drop=0.0, seed=None, stream_id=0, dbias_qkv=None):
+                  causal, key_len=None, p_drop=0.0, seed=None, stream_id=0, dbias_qkv=None, impl=None):
+    if _use_tc(impl):
+        rc = _lib.load().capdec_attention_tc_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), dctx.data_ptr(),
+                                                 lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                                 _ptr(dbias_qkv), B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts,
+                                                 float(scale), int(causal), _ptr(key_len), float(p_drop),
+                                                 _seed_ptr(seed, p_drop > 0), stream_id, _stream())
+        if rc != -3:
+            _lib.check(rc, "attention_tc_bwd")
+            return
     rc = _lib.load().capdec_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), dctx.data_ptr(),
                                           lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _ptr(dbias_qkv),
                                           B, H, T, S, hd,

@@ -120,6 +120,18 @@ int capdec_attention_bwd(const float* q, const float* k, const float* v, const f
                          float scale, int causal, const int32_t* key_len, float p_drop,
                          const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
 
+/* Tensor-core variants (mma.sync m16n8k8, TF32 in / FP32 accumulate) with the identical contract and dropout
+ * mapping; used in the 1xTF32 precision mode.  Return -3 (unsupported) if the tile exceeds shared memory. */
+int capdec_attention_tc_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, int B, int H, int T,
+                            int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs,
+                            int64_t o_ts, float scale, int causal, const int32_t* key_len, float p_drop,
+                            const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
+int capdec_attention_tc_bwd(const float* q, const float* k, const float* v, const float* ctx, const float* dctx,
+                            const float* lse, float* dq, float* dk, float* dv, float* dbias_qkv, int B, int H, int T,
+                            int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs,
+                            int64_t o_ts, float scale, int causal, const int32_t* key_len, float p_drop,
+                            const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
+
 /* ---- masked cross entropy: train.py:349-350 (nnf.cross_entropy(..., ignore_index=0), mean over targets != 0) -----
  * logits [rows, ld] (ld >= V, padded pitch), targets int64 [rows].  loss_sum/n_valid are device scalars (float);
  * capdec_ce_count writes the number of non-ignored targets to *n_valid and zeroes *loss_sum_to_zero (may be NULL).  fwd_bwd overwrites logits with
