@@ -1,0 +1,40 @@
+"""Launch one GEMM shape of the C2 step repeatedly (for `ncu --set full -k regex:gemm_tf32 -s 5 -c 3 ...`)."""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import capdec_b200 as cb  # noqa: E402
+
+SHAPES = {  # name: (M, N, K, a_major, b_major, accumulate)
+    "qkv": (12800, 2304, 768, 0, 1, 0), "fc": (12800, 3072, 768, 0, 1, 0), "fc_proj": (12800, 768, 3072, 0, 1, 0),
+    "qkv_wgrad": (768, 2304, 12800, 1, 1, 1), "lm_head": (10240, 50257, 768, 0, 0, 0),
+}
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "qkv"
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    M, N, K, am, bm, acc = SHAPES[name]
+    pad = lambda n: (n + 127) // 128 * 128
+    A = torch.randn((K, pad(M)) if am else (M, pad(K)), device="cuda")[:, : (M if am else K)]
+    B = torch.randn((K, pad(N)) if bm else (N, pad(K)), device="cuda")[:, : (N if bm else K)]
+    C = torch.zeros(M, pad(N), device="cuda")[:, :N]
+    bias = None if acc else torch.zeros(N, device="cuda")
+    for _ in range(iters):
+        cb.ops.gemm(A, am, B, bm, C, M, N, K, bias=bias, accumulate=bool(acc))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        cb.ops.gemm(A, am, B, bm, C, M, N, K, bias=bias, accumulate=bool(acc))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"{name}: {ms * 1e3:.1f} us, {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()
