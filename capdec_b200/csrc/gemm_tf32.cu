@@ -85,6 +85,7 @@ struct __align__(64) GemmDev {
   uint32_t adesc_hi, bdesc_hi;      // upper 32 bits of the smem descriptors (SBO, version, layout)
   uint32_t adesc_lo16, bdesc_lo16;  // LBO field (bits 16..29 of the low word), pre-shifted
   uint32_t a_kstep, b_kstep;        // start-address increment per UMMA_K step, in 16-byte units
+  uint32_t dbg;                     // bring-up switches (CAPDEC_GEMM_DBG): 1 skip TMA loads, 2 skip MMA, 4 skip stores, 8 skip epilogue
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -183,6 +184,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
             uint8_t* a_dst = sA + stage * kABytes;
             uint8_t* b_dst = sB + stage * b_bytes;
             uint64_t* fb = &full_bar[stage];
+            if (p.dbg & 1u) {  // timing experiment: no loads, just hand the (stale) stage to the MMA warp
+              if constexpr (kPair) { if (leader) mbar_arrive(fb); else mbar_arrive_remote(fb, 0); } else mbar_arrive(fb);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+              continue;
+            }
             if constexpr (!kPair) mbar_arrive_expect_tx(fb, (uint32_t)stage_bytes);
             auto load = [&](void* dst, const CUtensorMap* m, int x, int y) {
               if constexpr (kPair) tma_load_2d_pair(dst, m, fb, x, y); else tma_load_2d(dst, m, fb, x, y);
@@ -235,8 +241,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
                                      (uint64_t)(p.adesc_lo16 | ((a_start + k * p.a_kstep) & 0x3FFFu));
               const uint64_t bdesc = ((uint64_t)p.bdesc_hi << 32) |
                                      (uint64_t)(p.bdesc_lo16 | ((b_start + k * p.b_kstep) & 0x3FFFu));
-              if constexpr (kPair) umma_tf32_pair(d_tmem, adesc, bdesc, p.idesc, accumulate);
-              else umma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
+              if (!(p.dbg & 2u)) {
+                if constexpr (kPair) umma_tf32_pair(d_tmem, adesc, bdesc, p.idesc, accumulate);
+                else umma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
+              }
               accumulate = 1;
             }
             // smem slot reusable (in both CTAs) once these MMAs retire
@@ -271,7 +279,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       tc_fence_after();
       named_bar_sync(1, kEpiThreads);  // bias tile visible
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols);
-      const int n_chunks = min(p.block_n, p.N - n0 + 31) / 32;  // skip chunks fully past N
+      int n_chunks = min(p.block_n, p.N - n0 + 31) / 32;  // skip chunks fully past N
+      if (p.dbg & 8u) {  // timing experiment: no epilogue at all
+        tc_fence_before();
+        if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]);
+        n_chunks = 0;
+      }
       for (int c = 0; c < n_chunks; ++c) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
@@ -308,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         }
         fence_proxy_async_smem();
         named_bar_sync(1, kEpiThreads);
-        if (epi_tid == 0) {
+        if (epi_tid == 0 && !(p.dbg & 4u)) {
           if (p.accumulate) tma_reduce_add_2d(&p.tmC, buf0, n0 + c * 32, m0);
           else tma_store_2d(&p.tmC, buf0, n0 + c * 32, m0);
           if (p.has_aux) tma_store_2d(&p.tmAux, buf1, n0 + c * 32, m0);
@@ -500,6 +513,8 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   p.a_mn = a_major ? 1 : 0;
   p.b_mn = b_major ? 1 : 0;
   p.bias = bias;
+  static const char* env_dbg = getenv("CAPDEC_GEMM_DBG");
+  p.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
 
   const int bn_local = pair ? bn / 2 : bn;
   const int b_bytes = bn_local * kBlockK * 4;
