@@ -97,16 +97,24 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
-// kPair = false: one CTA per 128 x block_n tile (tcgen05 cta_group::1).
-// kPair = true : a CTA PAIR (cluster of 2, cta_group::2) per 256 x block_n tile.  CTA r of the pair TMA-loads its own
-//                128 A rows and its own block_n/2 B columns into ITS shared memory; the leader (rank 0) issues one
-//                M=256 MMA per k-step that reads both CTAs' smem and writes both CTAs' TMEM.  Per CTA the operand
-//                traffic drops from (128 + block_n) to (128 + block_n/2) rows per k-block: the 1-CTA kernel is bound
-//                by L2->SM bandwidth with fp32 operands, so this is the main lever (GEMM section).
-template <bool kPair>
+// Tile engines (template kMode):
+//   0  one CTA per 128 x block_n tile (tcgen05 cta_group::1).
+//   1  a CTA PAIR (cluster of 2, cta_group::2) per 256 x block_n tile.  CTA r of the pair TMA-loads its own 128 A rows
+//      and its own block_n/2 B columns into ITS shared memory; the leader issues one M=256 MMA per k-step that reads
+//      both CTAs' smem and writes both CTAs' TMEM.  Operand bytes per CTA drop from (128 + block_n) to
+//      (128 + block_n/2) rows per k-block.
+//   2  a QUAD (cluster of 4 = two pairs side by side in N) per 256 x (2*block_n) tile: the two pairs need the SAME A
+//      rows, so each CTA loads only HALF of its A slab and TMA-multicasts it to its twin in the other pair.
+//   3  a QUAD stacked in M (512 x block_n): the pairs need the same B columns; B halves are multicast instead.
+// Why: with fp32 operands these GEMMs are bound by L2->SM bandwidth (~8.3 TB/s measured: loads-only experiment in
+// profiles/r1_gemm_pipeline_experiments.md), not by the tensor pipe; FLOP per L2 byte is 43 / 64 / 87 for modes 0/1/2-3.
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_constant__ GemmDev p) {
+  constexpr bool kPair = kMode >= 1;
+  constexpr bool kQuad = kMode >= 2;
+  constexpr bool kShareB = kMode == 3;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve-up (all tile buffers 1024-byte aligned for the 128B swizzle patterns); identical in both CTAs of a pair
+  // carve-up (all tile buffers 1024-byte aligned for the 128B swizzle patterns); identical in every CTA of a cluster
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int bn_local = kPair ? p.block_n / 2 : p.block_n;  // B columns this CTA stages
   const int b_bytes = bn_local * kBlockK * 4;
@@ -124,8 +132,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
-  const bool leader = (cta_rank == 0);
-  constexpr int kCtas = kPair ? 2 : 1;
+  const uint32_t half = cta_rank & 1u;          // which 128 rows / which B half inside the pair
+  const uint32_t pair_idx = cta_rank >> 1;      // which pair inside the quad
+  const uint32_t pair_leader = cta_rank & ~1u;  // cluster rank of this pair's MMA-issuing CTA
+  const bool leader = (half == 0);
+  constexpr int kCtasPerPair = kPair ? 2 : 1;
+  constexpr int kPairsPerCluster = kQuad ? 2 : 1;
+  constexpr int kCtasPerCluster = kCtasPerPair * kPairsPerCluster;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tmA[0]);
@@ -139,12 +152,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&full_bar[i], kCtas);  // pair: leader's arrive.expect_tx + the peer's remote arrive
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&full_bar[i], kCtasPerPair);      // pair: leader's arrive.expect_tx + the peer's remote arrive
+      mbar_init(&empty_bar[i], kPairsPerCluster);  // quad: both pairs' MMAs must have retired (multicast writes my smem)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kCtas * kEpiThreads);  // pair: both CTAs' epilogues report to the leader
+      mbar_init(&tmem_empty_bar[i], kCtasPerPair * kEpiThreads);  // pair: both CTAs' epilogues report to the leader
     }
     fence_barrier_init();
   }
@@ -157,13 +170,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;   // m_tiles counts 256-row tiles when kPair
-  const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  constexpr int kTileM = kPair ? 2 * kBlockM : kBlockM;
+  // cluster-level tile grid: m_tiles x n_tiles cluster tiles (each kCM x kCN*block_n), times split-K
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int tile0 = (int)(blockIdx.x / kCtasPerCluster);
+  const int tile_step = (int)(gridDim.x / kCtasPerCluster);
+  constexpr int kPairM = kPair ? 2 * kBlockM : kBlockM;                       // rows per pair tile
+  constexpr int kTileM = (kQuad && kShareB) ? 2 * kPairM : kPairM;            // rows per cluster tile
+  const int tile_n = (kQuad && !kShareB) ? 2 * p.block_n : p.block_n;         // columns per cluster tile
+  // this CTA's pair tile inside the cluster tile
+  const int pm_off = (kQuad && kShareB) ? (int)pair_idx * kPairM : 0;
+  const int pn_off = (kQuad && !kShareB) ? (int)pair_idx * p.block_n : 0;
+  const uint16_t mc_mask = (uint16_t)((1u << half) | (1u << (half + 2)));   // me and my twin in the other pair
+  const uint16_t commit_empty_mask = kQuad ? (uint16_t)0xF : (uint16_t)0x3;
+  const uint16_t commit_pair_mask = (uint16_t)(0x3u << (2 * pair_idx));
 
   if (warp == 0) {
-    // ============================== TMA producer (every CTA feeds its own smem) ==============================
+    // ============================== TMA producer (every CTA feeds its own smem, and its twin's when multicasting) ====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -171,8 +193,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         const int n_blk = tile % p.n_tiles;
         const int m_blk = (tile / p.n_tiles) % p.m_tiles;
         const int split = tile / (p.n_tiles * p.m_tiles);
-        const int m0 = m_blk * kTileM + (int)cta_rank * kBlockM;
-        const int n0 = n_blk * p.block_n + (int)cta_rank * (kPair ? bn_local : 0);
+        const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM;               // my 128 A rows
+        const int n0 = n_blk * tile_n + pn_off + (kPair ? (int)half * bn_local : 0);  // my bn_local B columns
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int seg = 0; seg < p.nseg; ++seg) {
@@ -185,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
             uint8_t* b_dst = sB + stage * b_bytes;
             uint64_t* fb = &full_bar[stage];
             if (p.dbg & 1u) {  // timing experiment: no loads, just hand the (stale) stage to the MMA warp
-              if constexpr (kPair) { if (leader) mbar_arrive(fb); else mbar_arrive_remote(fb, 0); } else mbar_arrive(fb);
+              if constexpr (kPair) { if (leader) mbar_arrive(fb); else mbar_arrive_remote(fb, pair_leader); } else mbar_arrive(fb);
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
               continue;
             }
@@ -193,20 +215,43 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
             auto load = [&](void* dst, const CUtensorMap* m, int x, int y) {
               if constexpr (kPair) tma_load_2d_pair(dst, m, fb, x, y); else tma_load_2d(dst, m, fb, x, y);
             };
-            if (!p.a_mn) {
-              load(a_dst, mapA, k0, m0);
-            } else {
+            auto load_mc = [&](void* dst, const CUtensorMap* m, int x, int y) { tma_load_2d_pair_mc(dst, m, fb, x, y, mc_mask); };
+            // ---- A ----
+            if constexpr (kQuad && !kShareB) {   // my half of the shared A slab -> me + twin
+              if (!p.a_mn) load_mc(a_dst + pair_idx * (kABytes / 2), mapA, k0, m0 + (int)pair_idx * (kBlockM / 2));
+              else {
 #pragma unroll
-              for (int i = 0; i < kBlockM / 32; ++i) load(a_dst + i * 4096, mapA, m0 + 32 * i, k0);
-            }
-            if (!p.b_mn) {
-              load(b_dst, mapB, k0, n0);
+                for (int i = 0; i < kBlockM / 64; ++i) {
+                  const int sl = (int)pair_idx * (kBlockM / 64) + i;
+                  load_mc(a_dst + sl * 4096, mapA, m0 + 32 * sl, k0);
+                }
+              }
             } else {
-              for (int i = 0; i < bn_local / 32; ++i) load(b_dst + i * 4096, mapB, n0 + 32 * i, k0);
+              if (!p.a_mn) load(a_dst, mapA, k0, m0);
+              else {
+#pragma unroll
+                for (int i = 0; i < kBlockM / 32; ++i) load(a_dst + i * 4096, mapA, m0 + 32 * i, k0);
+              }
+            }
+            // ---- B ----
+            if constexpr (kQuad && kShareB) {    // my half of the shared B slab -> me + twin
+              if (!p.b_mn) load_mc(b_dst + pair_idx * (b_bytes / 2), mapB, k0, n0 + (int)pair_idx * (bn_local / 2));
+              else {
+                const int ns = bn_local / 64;
+                for (int i = 0; i < ns; ++i) {
+                  const int sl = (int)pair_idx * ns + i;
+                  load_mc(b_dst + sl * 4096, mapB, n0 + 32 * sl, k0);
+                }
+              }
+            } else {
+              if (!p.b_mn) load(b_dst, mapB, k0, n0);
+              else {
+                for (int i = 0; i < bn_local / 32; ++i) load(b_dst + i * 4096, mapB, n0 + 32 * i, k0);
+              }
             }
             if constexpr (kPair) {
-              if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(2 * stage_bytes));  // bytes of BOTH CTAs land here
-              else mbar_arrive_remote(fb, 0);
+              if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(2 * stage_bytes));  // bytes landing in BOTH CTAs of my pair
+              else mbar_arrive_remote(fb, pair_leader);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -215,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ============================== MMA issuer (one thread of the leader CTA) ==============================
+    // ============================== MMA issuer (one thread of each pair's leader CTA) ==============================
     if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
@@ -247,13 +292,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
               }
               accumulate = 1;
             }
-            // smem slot reusable (in both CTAs) once these MMAs retire
-            if constexpr (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+            // smem slot reusable (in every CTA that writes into my pair's smem) once these MMAs retire
+            if constexpr (kPair) umma_commit_mc(&empty_bar[stage], commit_empty_mask); else umma_commit(&empty_bar[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
-        // accumulator complete -> epilogue(s)
-        if constexpr (kPair) umma_commit_pair(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
+        // accumulator complete -> epilogue(s) of my pair
+        if constexpr (kPair) umma_commit_mc(&tmem_full_bar[acc], commit_pair_mask); else umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -270,7 +315,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       const int n_blk = tile % p.n_tiles;
       const int m_blk = (tile / p.n_tiles) % p.m_tiles;
       const int split = tile / (p.n_tiles * p.m_tiles);
-      const int m0 = m_blk * kTileM + (int)cta_rank * kBlockM, n0 = n_blk * p.block_n;
+      const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM;
+      const int n0 = n_blk * tile_n + pn_off;   // the pair's full block_n columns (each CTA stores its 128 rows x block_n)
       const bool use_bias = (p.bias != nullptr) && (split == 0);
       if (use_bias) {
         for (int i = epi_tid; i < p.block_n; i += kEpiThreads) sBias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
@@ -279,10 +325,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       tc_fence_after();
       named_bar_sync(1, kEpiThreads);  // bias tile visible
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols);
-      int n_chunks = min(p.block_n, p.N - n0 + 31) / 32;  // skip chunks fully past N
-      if (p.dbg & 8u) {  // timing experiment: no epilogue at all
+      int n_chunks = (p.N > n0) ? min(p.block_n, p.N - n0 + 31) / 32 : 0;  // skip chunks (or whole tiles) past N
+      if ((p.dbg & 8u) || n_chunks == 0) {  // nothing to store: release the accumulator right away
         tc_fence_before();
-        if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]);
+        if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], pair_leader); else mbar_arrive(&tmem_empty_bar[acc]);
         n_chunks = 0;
       }
       for (int c = 0; c < n_chunks; ++c) {
@@ -292,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         if (c == n_chunks - 1) {
           // all TMEM reads of this accumulator stage are done -> hand it back to the (leader's) MMA warp
           tc_fence_before();
-          if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]);
+          if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], pair_leader); else mbar_arrive(&tmem_empty_bar[acc]);
         }
         if (use_bias) {
 #pragma unroll
@@ -334,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   }
 
   tc_fence_before();
-  if constexpr (kPair) cluster_sync_all(); else __syncthreads();  // pair: nobody exits while the peer may still touch its smem/barriers
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();  // nobody exits while a peer may still touch its smem/barriers
   if (warp == 2) {
     tc_fence_after();
     if constexpr (kPair) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
@@ -412,17 +458,18 @@ static OperandEnc operand_encoding(bool mn_major) {
   return e;
 }
 
-static int g_force_pair = -1;  // bring-up override: -1 auto, 0 never, 1 always
+static int g_force_pair = -1;  // bring-up override: -1 auto, 0 never, 1 always (pairs), 2/3 force quad modes
 
-static void choose_tiling(int M, int N, int kb_total, int accumulate, bool pair, int& block_n, int& splits) {
-  const int nsm = pair ? num_sms() / 2 : num_sms();
-  const int tile_m = pair ? 2 * kBlockM : kBlockM;
+// pick block_n and split-K for a given engine: `units` = concurrently running tile owners (SMs, pairs or quads),
+// tile_m rows and nmul*block_n columns per cluster tile
+static void choose_tiling(int M, int N, int kb_total, int accumulate, int units, int tile_m, int nmul, int min_bn,
+                          int& block_n, int& splits) {
   const int m_tiles = (M + tile_m - 1) / tile_m;
   auto cost = [&](int bn, int s) {
-    const long tiles = (long)m_tiles * ((N + bn - 1) / bn) * s;
-    const long waves = (tiles + nsm - 1) / nsm;
+    const long tiles = (long)m_tiles * ((N + nmul * bn - 1) / (nmul * bn)) * s;
+    const long waves = (tiles + units - 1) / units;
     const double kb = (double)((kb_total + s - 1) / s);
-    // per-tile time ~ k-blocks x (MMA cycles ~ bn, but small tiles are L2-feed bound) + epilogue
+    // per-tile time ~ k-blocks x (operand bytes per k-block, the L2 feed is the limiter) + epilogue
     const double per_kb = (bn >= 256) ? 1.0 : (bn == 128 ? 0.62 : 0.40);
     const double epi = (bn / 256.0) * 5.0;
     return waves * (kb * per_kb + epi + 1.5);
@@ -433,7 +480,7 @@ static void choose_tiling(int M, int N, int kb_total, int accumulate, bool pair,
   for (int bi = 0; bi < 3; ++bi) {
     const int bn = bns[bi];
     if (block_n > 0 && bn != block_n) continue;
-    if (pair && bn < 128) continue;  // pair: each CTA stages bn/2 >= 64 columns
+    if (bn < min_bn) continue;
     const int smax = (splits > 0) ? splits : (accumulate ? 32 : 1);
     for (int s = (splits > 0 ? splits : 1); s <= smax; ++s) {
       if (s > 1 && kb_total / s < 4) break;
@@ -441,8 +488,55 @@ static void choose_tiling(int M, int N, int kb_total, int accumulate, bool pair,
       if (c < best * 0.999) { best = c; best_bn = bn; best_s = s; }
     }
   }
-  block_n = best_bn > 0 ? best_bn : 128;
+  block_n = best_bn > 0 ? best_bn : (min_bn > 128 ? min_bn : 128);
   splits = best_s > 0 ? best_s : 1;
+}
+
+template <int kMode>
+static int max_clusters(int cluster_size, int smem_bytes) {
+  static int cached[4] = {0, 0, 0, 0};
+  if (cached[kMode] > 0) return cached[kMode];
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cluster_size * 64);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = cluster_size;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<kMode>, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = num_sms() / cluster_size;
+  }
+  cached[kMode] = n;
+  return n;
+}
+
+template <int kMode>
+static int launch_clustered(const GemmDev& p, int cluster_size, int total_tiles, int smem_bytes, cudaStream_t stream) {
+  const int maxc = max_clusters<kMode>(cluster_size, smem_bytes);
+  const int nc = total_tiles < maxc ? total_tiles : maxc;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cluster_size * nc);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = cluster_size;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<kMode>, p);
+  if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm_tf32_kernel)");
+  return CAPDEC_OK;
 }
 
 }  // namespace capdec
@@ -453,7 +547,7 @@ extern "C" const char* capdec_last_error(void) { return g_err; }
 extern "C" int capdec_version(void) { return 100; }
 extern "C" int64_t capdec_launch_count(void) { return g_launches.load(); }
 
-extern "C" void capdec_gemm_debug_force_pair(int mode) { g_force_pair = mode; }
+extern "C" void capdec_gemm_debug_force_pair(int mode) { g_force_pair = mode; }  // -1 auto, 0..3 engine
 
 extern "C" void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, int sbo_bytes, int tma_swizzle) {
   g_mn_layout = layout_type;
@@ -479,8 +573,10 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm_tf32_kernel)");
     attr_set = true;
   }
@@ -489,23 +585,42 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   p.kb_total = (K + kBlockK - 1) / kBlockK;
-  // CTA pairs (cta_group::2, 256-row tiles) whenever the problem has at least 256 rows and 128 columns
-  bool pair = (M > kBlockM) && (N >= 128) && (block_n == 0 || block_n >= 128);
-  static const char* env_pair = getenv("CAPDEC_GEMM_PAIR");  // bring-up switch: 0 = cta_group::1 only, 1 = force pairs
-  if (env_pair && g_force_pair < 0) { if (env_pair[0] == '0') pair = false; else if (block_n == 0 || block_n >= 128) pair = true; }
-  if (g_force_pair == 0) pair = false;
-  if (g_force_pair == 1 && (block_n == 0 || block_n >= 128)) pair = true;
-  const int tile_m = pair ? 2 * kBlockM : kBlockM;
-  int bn = block_n, splits = split_k;
-  if (!accumulate) splits = 1;
-  choose_tiling(M, N, p.kb_total, accumulate, pair, bn, splits);
+  // ---- engine selection: 0 single CTA, 1 CTA pair, 2 quad sharing A (pairs side by side in N), 3 quad sharing B ----
+  int mode = ((M > kBlockM) && (N >= 128) && (block_n == 0 || block_n >= 128)) ? 1 : 0;
+  static const char* env_pair = getenv("CAPDEC_GEMM_PAIR");  // bring-up switch: 0 = cta_group::1 only, 1 = pairs only
+  static const char* env_mode = getenv("CAPDEC_GEMM_MODE");  // bring-up switch: force engine 0..3 where legal
+  int forced = g_force_pair >= 0 ? g_force_pair : (env_mode ? atoi(env_mode) : (env_pair ? atoi(env_pair) : -1));
+  int bn = block_n, splits = accumulate ? split_k : 1;
+  if (forced == 0) mode = 0;
+  if (mode >= 1) {
+    const bool quad_ok = (M > 2 * kBlockM || N > 256);
+    if (forced < 0 && quad_ok) {
+      // prefer a quad when the problem is large; share the operand whose tile count wastes less on rounding to pairs
+      const int bn_guess = (block_n > 0) ? block_n : 256;
+      const int mt = (M + 255) / 256, nt = (N + bn_guess - 1) / bn_guess;
+      if ((long)mt * nt >= 64) {
+        const double waste_a = (double)(((nt + 1) / 2) * 2) / nt, waste_b = (double)(((mt + 1) / 2) * 2) / mt;
+        if (waste_a <= waste_b && waste_a <= 1.15) mode = 2;
+        else if (waste_b <= 1.15) mode = 3;
+      }
+    } else if (forced == 2 || forced == 3) {
+      mode = forced;
+    }
+  }
+  const int tile_m = (mode == 0) ? kBlockM : (mode == 3 ? 4 * kBlockM : 2 * kBlockM);   // rows per cluster tile
+  const int pair_m = (mode == 0) ? kBlockM : 2 * kBlockM;                               // rows per MMA (instruction M)
+  const int nmul = (mode == 2) ? 2 : 1;
+  const int cluster_size = (mode == 0) ? 1 : (mode == 1 ? 2 : 4);
+  const int units = (mode >= 2) ? 33 : num_sms() / cluster_size;   // quads: 132 of the 148 SMs are schedulable in 4-clusters
+  const int min_bn = (mode == 0) ? 64 : 128;
+  choose_tiling(M, N, p.kb_total, accumulate, units, tile_m, nmul, min_bn, bn, splits);
   CAPDEC_REQUIRE(splits == 1 || (accumulate && act == 0 && !aux), "gemm: split-K needs accumulate=1, act=0, no aux");
   p.block_n = bn;
   p.splits = splits;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // drop empty splits
   p.m_tiles = (M + tile_m - 1) / tile_m;
-  p.n_tiles = (N + bn - 1) / bn;
+  p.n_tiles = (N + nmul * bn - 1) / (nmul * bn);
   p.nseg = precision ? 3 : 1;
   p.act = act;
   p.has_aux = aux ? 1 : 0;
@@ -516,7 +631,7 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   static const char* env_dbg = getenv("CAPDEC_GEMM_DBG");
   p.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
 
-  const int bn_local = pair ? bn / 2 : bn;
+  const int bn_local = (mode == 0) ? bn : bn / 2;
   const int b_bytes = bn_local * kBlockK * 4;
   const int fixed = 2 * kStagingBytes + 256 * 4 + (2 * kMaxStages + 4) * 8 + 16 + 1024 /* alignment slack */;
   int stages = (kSmemLimit - fixed) / (kABytes + b_bytes);
@@ -530,16 +645,19 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   // instruction descriptor: D=F32 (bits 4-5 = 1), A/B = TF32 (2) at bits 7-9 / 10-12, majors at 15/16,
   // N>>3 at bits 17-22, M>>4 at bits 24-28
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_major ? 1 : 0) << 15) |
-            ((uint32_t)(b_major ? 1 : 0) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(tile_m >> 4) << 24);
+            ((uint32_t)(b_major ? 1 : 0) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(pair_m >> 4) << 24);
 
+  // TMA boxes: K-major operands move {32 fp32, rows}; a quad that shares the operand moves half the rows per CTA
+  const uint32_t a_rows = (mode == 2) ? kBlockM / 2 : kBlockM;
+  const uint32_t b_rows = (mode == 3) ? (uint32_t)bn_local / 2 : (uint32_t)bn_local;
   int rc;
   for (int s = 0; s < p.nseg && s < 2; ++s) {
     const float* a = s ? a_lo : A;
     const float* b = s ? b_lo : B;
-    if (!a_major) rc = make_map(&p.tmA[s], a, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBlockK, kBlockM, ea.swz);
+    if (!a_major) rc = make_map(&p.tmA[s], a, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBlockK, a_rows, ea.swz);
     else rc = make_map(&p.tmA[s], a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, kBlockK, ea.swz);
     if (rc) return rc;
-    if (!b_major) rc = make_map(&p.tmB[s], b, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBlockK, (uint32_t)bn_local, eb.swz);
+    if (!b_major) rc = make_map(&p.tmB[s], b, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBlockK, b_rows, eb.swz);
     else rc = make_map(&p.tmB[s], b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, kBlockK, eb.swz);
     if (rc) return rc;
   }
@@ -551,27 +669,18 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   }
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
-  if (!pair) {
+  if (mode == 0) {
     const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-    gemm_tf32_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(p);
+    gemm_tf32_kernel<0><<<grid, kThreads, smem_bytes, stream>>>(p);
+  } else if (mode == 1) {
+    rc = launch_clustered<1>(p, 2, total_tiles, smem_bytes, stream);
+    if (rc) return rc;
+  } else if (mode == 2) {
+    rc = launch_clustered<2>(p, 4, total_tiles, smem_bytes, stream);
+    if (rc) return rc;
   } else {
-    const int max_pairs = num_sms() / 2;
-    const int pairs = total_tiles < max_pairs ? total_tiles : max_pairs;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<true>, p);
-    if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm_tf32_kernel<pair>)");
+    rc = launch_clustered<3>(p, 4, total_tiles, smem_bytes, stream);
+    if (rc) return rc;
   }
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("gemm_tf32_kernel");

@@ -48,11 +48,13 @@ def test_gemm_tf32_matches_truncated_product(ops, shape, a_major, b_major):
     assert bad.numel() == 0, f"{bad.shape[0]} bad elements, first {bad[:5].tolist()}, rows {bad[:,0].min().item()}..{bad[:,0].max().item()} cols {bad[:,1].min().item()}..{bad[:,1].max().item()}"
 
 
-@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("pair", [0, 1, 2, 3])
 @pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize("shape", [(256, 256, 32), (12800, 2304, 768), (1000, 50257, 96), (768, 2304, 3200), (300, 200, 64)])
+@pytest.mark.parametrize("shape", [(256, 256, 32), (12800, 2304, 768), (1000, 50257, 96), (768, 2304, 3200), (300, 200, 64),
+                                   (1300, 768, 3072), (520, 1030, 200)])
 def test_gemm_both_tile_engines(ops, shape, a_major, b_major, pair):
-    """cta_group::1 (one CTA per 128-row tile) and cta_group::2 (CTA pair per 256-row tile) give the same numbers."""
+    """All tile engines give the same numbers: 0 = cta_group::1 (one CTA per 128-row tile), 1 = cta_group::2 CTA pair,
+    2 / 3 = cluster of two pairs with the shared A / B operand TMA-multicast."""
     from capdec_b200 import _lib
     M, N, K = shape
     A, Al, B, Bl = make_ab(M, N, K, a_major, b_major)

@@ -11,6 +11,8 @@ import capdec_b200 as cb  # noqa: E402
 SHAPES = {  # name: (M, N, K, a_major, b_major, accumulate)
     "qkv": (12800, 2304, 768, 0, 1, 0), "fc": (12800, 3072, 768, 0, 1, 0), "fc_proj": (12800, 768, 3072, 0, 1, 0),
     "qkv_wgrad": (768, 2304, 12800, 1, 1, 1), "lm_head": (10240, 50257, 768, 0, 0, 0),
+    "attn_proj": (12800, 768, 768, 0, 1, 0), "qkv_dgrad": (12800, 768, 2304, 0, 0, 0), "fc_dgrad": (12800, 768, 3072, 0, 0, 0),
+    "fc_wgrad": (768, 3072, 12800, 1, 1, 1), "lm_dgrad": (10240, 768, 50257, 0, 1, 0), "lm_wgrad": (50257, 768, 10240, 1, 1, 1),
 }
 
 
@@ -33,7 +35,8 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    print(f"{name}: {ms * 1e3:.1f} us, {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+    import os
+    print(f"{name} mode={os.environ.get('CAPDEC_GEMM_MODE', 'auto')}: {ms * 1e3:.1f} us, {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
 
 
 if __name__ == "__main__":
