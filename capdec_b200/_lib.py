@@ -24,6 +24,7 @@ SIGNATURES = {
     "capdec_version": [],
     "capdec_launch_count": [],
     "capdec_gemm_tf32": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _i, _p],
+    "capdec_gemm_tf32_ex": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _i, _p, _p, _p],
     "capdec_gemm_debug_mn_encoding": [_i, _i, _i, _i],
     "capdec_gemm_debug_force_pair": [_i],
     "capdec_gemm_fp32_simt": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p],
@@ -42,7 +43,10 @@ SIGNATURES = {
     "capdec_attention_tc_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
                                 _i64, _f, _i, _p, _f, _p, _u32, _p],
     "capdec_ce_count": [_p, _i64, _i64, _p, _p, _p],
-    "capdec_ce_fwd_bwd": [_p, _i64, _p, _i, _i, _i64, _p, _f, _p, _i, _p],
+    "capdec_ce_fwd_bwd": [_p, _i64, _p, _i, _i, _i64, _p, _f, _p, _i, _p, _p],
+    "capdec_compact_targets": [_p, _i, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _p],
+    "capdec_rows_gather_idx": [_p, _p, _p, _p, _i, _i, _p],
+    "capdec_rows_scatter_idx": [_p, _p, _p, _i, _i, _p],
     "capdec_colsum_acc": [_p, _i64, _p, _i, _i, _p],
     "capdec_act_bwd": [_p, _p, _p, _p, _i, _i, _i, _p],
     "capdec_rows_gather": [_p, _p, _i, _i, _i, _i, _i, _p],

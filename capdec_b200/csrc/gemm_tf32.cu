@@ -85,6 +85,8 @@ struct __align__(64) GemmDev {
   uint32_t adesc_hi, bdesc_hi;      // upper 32 bits of the smem descriptors (SBO, version, layout)
   uint32_t adesc_lo16, bdesc_lo16;  // LBO field (bits 16..29 of the low word), pre-shifted
   uint32_t a_kstep, b_kstep;        // start-address increment per UMMA_K step, in 16-byte units
+  const int* m_limit;               // optional device scalar: rows >= *m_limit are not computed (whole tiles skipped)
+  const int* k_limit;               // optional device scalar: reduction stops at *k_limit (rounded up to a k-block)
   uint32_t dbg;                     // bring-up switches (CAPDEC_GEMM_DBG): 1 skip TMA loads, 2 skip MMA, 4 skip stores, 8 skip epilogue
 };
 
@@ -170,6 +172,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // data-dependent extents (LM head over the non-ignored caption tokens only): every role skips the same tiles
+  const int m_lim = p.m_limit ? __ldg(p.m_limit) : p.M;
+  const int kb_lim = p.k_limit ? min(p.kb_total, (__ldg(p.k_limit) + kBlockK - 1) / kBlockK) : p.kb_total;
   // cluster-level tile grid: m_tiles x n_tiles cluster tiles (each kCM x kCN*block_n), times split-K
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   const int tile0 = (int)(blockIdx.x / kCtasPerCluster);
@@ -196,7 +201,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM;               // my 128 A rows
         const int n0 = n_blk * tile_n + pn_off + (kPair ? (int)half * bn_local : 0);  // my bn_local B columns
         const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int kb1 = min(kb0 + p.kb_per_split, kb_lim);
+        if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
         for (int seg = 0; seg < p.nseg; ++seg) {
           const CUtensorMap* mapA = (seg == 1) ? &p.tmA[1] : &p.tmA[0];
           const CUtensorMap* mapB = (seg == 2) ? &p.tmB[1] : &p.tmB[0];
@@ -268,8 +274,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       uint32_t acc_phase = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int split = tile / (p.n_tiles * p.m_tiles);
+        const int m_blk = (tile / p.n_tiles) % p.m_tiles;
         const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int kb1 = min(kb0 + p.kb_per_split, kb_lim);
+        if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
@@ -315,6 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       const int n_blk = tile % p.n_tiles;
       const int m_blk = (tile / p.n_tiles) % p.m_tiles;
       const int split = tile / (p.n_tiles * p.m_tiles);
+      if (m_blk * kTileM >= m_lim || split * p.kb_per_split >= min(split * p.kb_per_split + p.kb_per_split, kb_lim)) continue;
       const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM;
       const int n0 = n_blk * tile_n + pn_off;   // the pair's full block_n columns (each CTA stores its 128 rows x block_n)
       const bool use_bias = (p.bias != nullptr) && (split == 0);
@@ -556,10 +565,25 @@ extern "C" void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, in
   g_mn_swz = tma_swizzle;
 }
 
+extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
+                                   float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
+                                   int accumulate, int precision, const float* a_lo, const float* b_lo, int block_n,
+                                   int split_k, const int32_t* m_limit_dev, const int32_t* k_limit_dev,
+                                   capdec_stream_t stream_);
+
 extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
                                 float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
                                 int accumulate, int precision, const float* a_lo, const float* b_lo, int block_n,
                                 int split_k, capdec_stream_t stream_) {
+  return capdec_gemm_tf32_ex(A, a_major, lda, B, b_major, ldb, C, ldc, M, N, K, bias, act, aux, accumulate, precision,
+                             a_lo, b_lo, block_n, split_k, nullptr, nullptr, stream_);
+}
+
+extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
+                                   float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
+                                   int accumulate, int precision, const float* a_lo, const float* b_lo, int block_n,
+                                   int split_k, const int32_t* m_limit_dev, const int32_t* k_limit_dev,
+                                   capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(A && B && C, "gemm: null operand");
   CAPDEC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
@@ -595,14 +619,12 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   if (mode >= 1) {
     const bool quad_ok = (M > 2 * kBlockM || N > 256);
     if (forced < 0 && quad_ok) {
-      // prefer a quad when the problem is large; share the operand whose tile count wastes less on rounding to pairs
-      const int bn_guess = (block_n > 0) ? block_n : 256;
-      const int mt = (M + 255) / 256, nt = (N + bn_guess - 1) / bn_guess;
-      if ((long)mt * nt >= 64) {
-        const double waste_a = (double)(((nt + 1) / 2) * 2) / nt, waste_b = (double)(((mt + 1) / 2) * 2) / mt;
-        if (waste_a <= waste_b && waste_a <= 1.15) mode = 2;
-        else if (waste_b <= 1.15) mode = 3;
-      }
+      // Measured on B200 (profiles/r1_gemm_modes.md): stacking the two pairs in M and multicasting B (mode 3) wins
+      // 10-16 % whenever there are enough 256-row tiles to fill the 33 resident quads; sharing A (mode 2) loses to
+      // wave quantisation on every shape of this model, and few-row problems (wgrad, M = 768) stay on plain pairs.
+      const int mt = (M + 255) / 256;
+      const double waste_b = (double)(((mt + 1) / 2) * 2) / mt;
+      if (mt >= 8 && waste_b <= 1.15) mode = 3;
     } else if (forced == 2 || forced == 3) {
       mode = forced;
     }
@@ -628,6 +650,8 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
   p.a_mn = a_major ? 1 : 0;
   p.b_mn = b_major ? 1 : 0;
   p.bias = bias;
+  p.m_limit = m_limit_dev;
+  p.k_limit = k_limit_dev;
   static const char* env_dbg = getenv("CAPDEC_GEMM_DBG");
   p.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
 

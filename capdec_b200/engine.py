@@ -129,9 +129,15 @@ class Engine:
         a.dpp = e(B, P * d) if P > 0 else None
         # LM head on the consumed rows only (fast path)
         if L > 0:
-            a.xsel = e(B * L, d)
-            a.dxsel = e(B * L, d)
-            a.logits_sel = e(B * L, self.Vp)
+            z = lambda *s_, dt=torch.float32: torch.zeros(*s_, device=self.dev, dtype=dt)
+            a.xsel = z(B * L, d)
+            a.dxsel = z(B * L, d)
+            a.logits_sel = z(B * L, self.Vp)
+            # compaction of the non-ignored target rows (train.py:350 ignore_index=0)
+            a.row_src = z(B * L, dt=torch.int32)
+            a.dst_of = z(M, dt=torch.int32)
+            a.targets_c = z(B * L, dt=torch.int64)
+            a.counts = z(2, dt=torch.int32)
         a.logits_full = None
         a.tokens = None
         self.arenas[key] = a
@@ -389,15 +395,30 @@ class Engine:
         tail = fl.grads[:4]
         n_valid, loss_sum = tail[0:1], tail[1:2]
         targets = tokens.reshape(-1)
-        ops.ce_count(targets, n_valid, loss_sum)
-        ops.rows_gather(a.xf, a.xsel, B, T, L, P - 1)                      # hidden states of logits[:, P-1:-1]
+        wte = p["gpt.transformer.wte.weight"]
         logits = a.logits_sel[:, : self.V]
-        ops.linear_fwd(a.xsel, p["gpt.transformer.wte.weight"], "linear", None, logits)   # tied lm_head
-        ops.ce_fwd_bwd(logits, targets, self.V, loss_sum, n_valid=n_valid if mean_reduce else None)
-        if train_gpt:
-            ops.linear_wgrad(a.xsel, logits, g["gpt.transformer.wte.weight"], "linear")
-        ops.linear_dgrad(logits, p["gpt.transformer.wte.weight"], "linear", a.dxsel)
-        ops.rows_scatter(a.dxsel, a.dx, B, T, L, P - 1)
+        if ops.get_precision() == "tf32":
+            # LM head + CE only over the rows whose target is not ignored: compact them on device, keep every shape
+            # static and let the GEMMs / CE read the row count from a device scalar (CUDA-graph friendly).
+            ops.compact_targets(targets, B, L, T, P - 1, a.row_src, a.dst_of, a.targets_c, a.counts, n_valid, loss_sum)
+            nv = a.counts[0:1]
+            ops.rows_gather_idx(a.xf, a.xsel, a.row_src, a.counts)
+            ops.gemm(a.xsel, 0, wte, 0, logits, B * L, self.V, d, m_limit=nv)                       # tied lm_head
+            ops.ce_fwd_bwd(logits, a.targets_c, self.V, loss_sum, n_valid=n_valid if mean_reduce else None, row_limit=nv)
+            if train_gpt:
+                ops.gemm(logits, 1, a.xsel, 1, g["gpt.transformer.wte.weight"], self.V, d, B * L, accumulate=True,
+                         k_limit=nv)
+            ops.gemm(logits, 0, wte, 1, a.dxsel, B * L, d, self.V, m_limit=nv)
+            ops.rows_scatter_idx(a.dxsel, a.dx, a.dst_of)
+        else:
+            ops.ce_count(targets, n_valid, loss_sum)
+            ops.rows_gather(a.xf, a.xsel, B, T, L, P - 1)                      # hidden states of logits[:, P-1:-1]
+            ops.linear_fwd(a.xsel, wte, "linear", None, logits)               # tied lm_head
+            ops.ce_fwd_bwd(logits, targets, self.V, loss_sum, n_valid=n_valid if mean_reduce else None)
+            if train_gpt:
+                ops.linear_wgrad(a.xsel, logits, g["gpt.transformer.wte.weight"], "linear")
+            ops.linear_dgrad(logits, wte, "linear", a.dxsel)
+            ops.rows_scatter(a.dxsel, a.dx, B, T, L, P - 1)
         # a.dx is reused as scratch inside the trunk; ln_f backward consumes it first
         self.backward_hidden(a, a.dx, train_gpt)
         return tail

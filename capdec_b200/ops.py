@@ -65,8 +65,12 @@ def _split(t: torch.Tensor):
 
 def gemm(A: torch.Tensor, a_major: int, B: torch.Tensor, b_major: int, C: torch.Tensor, M: int, N: int, K: int, *,
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, aux: Optional[torch.Tensor] = None,
-         accumulate: bool = False, block_n: int = 0, split_k: int = 0, precision: Optional[str] = None) -> None:
-    """C[M,N] (+)= act(A . B^T + bias).  a_major/b_major: 0 = stored [M|N, K], 1 = stored [K, M|N]."""
+         accumulate: bool = False, block_n: int = 0, split_k: int = 0, precision: Optional[str] = None,
+         m_limit: Optional[torch.Tensor] = None, k_limit: Optional[torch.Tensor] = None) -> None:
+    """C[M,N] (+)= act(A . B^T + bias).  a_major/b_major: 0 = stored [M|N, K], 1 = stored [K, M|N].
+    m_limit / k_limit: optional int32 device scalars bounding the rows computed / the reduction length at run time
+    (tcgen05 path only; the fp32 / 3xTF32 parity modes compute the full static extent, which is equivalent as long as
+    the caller keeps the skipped region's contribution at zero)."""
     lib = _lib.load()
     lda, ldb, ldc = _rowmajor(A, "A"), _rowmajor(B, "B"), _rowmajor(C, "C")
     ea = (K, M) if a_major else (M, K)
@@ -91,9 +95,9 @@ def gemm(A: torch.Tensor, a_major: int, B: torch.Tensor, b_major: int, C: torch.
                                   C.data_ptr(), ldc, M, N, K, _ptr(bias), act, _ptr(aux), int(accumulate), 1,
                                   al.data_ptr(), bl.data_ptr(), block_n, split_k, _stream())
     else:
-        rc = lib.capdec_gemm_tf32(A.data_ptr(), a_major, lda, B.data_ptr(), b_major, ldb, C.data_ptr(), ldc, M, N, K,
-                                  _ptr(bias), act, _ptr(aux), int(accumulate), 0, None, None, block_n, split_k,
-                                  _stream())
+        rc = lib.capdec_gemm_tf32_ex(A.data_ptr(), a_major, lda, B.data_ptr(), b_major, ldb, C.data_ptr(), ldc, M, N, K,
+                                     _ptr(bias), act, _ptr(aux), int(accumulate), 0, None, None, block_n, split_k,
+                                     _ptr(m_limit), _ptr(k_limit), _stream())
     _lib.check(rc, "gemm_tf32")
 
 
@@ -230,17 +234,39 @@ def ce_count(targets, n_valid, loss_sum_to_zero=None, ignore_index=0):
                                            _ptr(loss_sum_to_zero), _stream()), "ce_count")
 
 
+def compact_targets(targets, B, L, T, off, row_src, dst_of, targets_c, counts, n_valid, loss_sum_to_zero=None,
+                    ignore_index=0):
+    _chk(targets, "targets", torch.int64)
+    rc = _lib.load().capdec_compact_targets(targets.data_ptr(), B, L, T, off, ignore_index, row_src.data_ptr(),
+                                            dst_of.data_ptr(), targets_c.data_ptr(), counts.data_ptr(),
+                                            n_valid.data_ptr(), _ptr(loss_sum_to_zero), _stream())
+    _lib.check(rc, "compact_targets")
+
+
+def rows_gather_idx(src, dst, row_src, counts):
+    rc = _lib.load().capdec_rows_gather_idx(src.data_ptr(), dst.data_ptr(), row_src.data_ptr(), counts.data_ptr(),
+                                            dst.shape[0], dst.shape[1], _stream())
+    _lib.check(rc, "rows_gather_idx")
+
+
+def rows_scatter_idx(src, dst, dst_of):
+    rc = _lib.load().capdec_rows_scatter_idx(src.data_ptr(), dst.data_ptr(), dst_of.data_ptr(), dst.shape[0],
+                                             dst.shape[1], _stream())
+    _lib.check(rc, "rows_scatter_idx")
+
+
 def step_clock(seed=None, step_dev=None, lr_dev=None, t_dev=None, base_lr=0.0, warmup_steps=0, total_steps=1):
     _lib.check(_lib.load().capdec_step_clock(_ptr(seed), _ptr(step_dev), _ptr(lr_dev), _ptr(t_dev), float(base_lr),
                                              int(warmup_steps), int(total_steps), _stream()), "step_clock")
 
 
-def ce_fwd_bwd(logits, targets, V, loss_sum, n_valid=None, grad_scale=1.0, ignore_index=0, write_grad=True):
+def ce_fwd_bwd(logits, targets, V, loss_sum, n_valid=None, grad_scale=1.0, ignore_index=0, write_grad=True,
+               row_limit=None):
     ld = _rowmajor(logits, "logits")
     _chk(targets, "targets", torch.int64)
     rc = _lib.load().capdec_ce_fwd_bwd(logits.data_ptr(), ld, targets.data_ptr(), logits.shape[0], V, ignore_index,
                                        _ptr(n_valid), float(grad_scale), loss_sum.data_ptr(), int(write_grad),
-                                       _stream())
+                                       _ptr(row_limit), _stream())
     _lib.check(rc, "ce_fwd_bwd")
 
 

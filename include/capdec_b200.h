@@ -50,6 +50,15 @@ int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const float* B, i
                      int precision, const float* a_lo, const float* b_lo, int block_n, int split_k,
                      capdec_stream_t stream);
 
+/* Same, with data-dependent extents read from DEVICE scalars at run time (shapes stay static, CUDA-graph friendly):
+ * rows >= *m_limit_dev are not computed (whole 256/512-row cluster tiles are skipped), the reduction stops at
+ * *k_limit_dev (rounded up to 32; the caller guarantees that rows of the K-tail hold zeros in one operand).
+ * Used for the LM head over the NON-IGNORED caption tokens only (train.py:349-350). Either pointer may be NULL. */
+int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb, float* C,
+                        int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux, int accumulate,
+                        int precision, const float* a_lo, const float* b_lo, int block_n, int split_k,
+                        const int32_t* m_limit_dev, const int32_t* k_limit_dev, capdec_stream_t stream);
+
 /* debug/bring-up override of the UMMA shared-memory descriptor encoding for MN-major operands
  * (layout_type, LBO bytes, SBO bytes, TMA swizzle enum); pass -1 to keep the default. Not used in production. */
 void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, int sbo_bytes, int tma_swizzle);
@@ -142,7 +151,19 @@ int capdec_ce_count(const int64_t* targets, int64_t n, int64_t ignore_index, flo
                     capdec_stream_t stream);
 int capdec_ce_fwd_bwd(float* logits, int64_t ld, const int64_t* targets, int rows, int V, int64_t ignore_index,
                       const float* n_valid, float grad_scale, float* loss_sum, int write_grad,
+                      const int32_t* row_limit_dev /* NULL or device scalar: rows >= it are skipped */,
                       capdec_stream_t stream);
+/* Compaction of the consumed logits rows: targets int64 [B,L] -> row_src[r] (hidden row b*T+off+j feeding compact row
+ * r), dst_of[b*T+t] (compact row or -1), targets_c[r], counts = {n_valid, n_valid rounded up to 32}; also writes
+ * *n_valid (float) and zeroes *loss_sum_to_zero.  Replaces capdec_ce_count on the compacted path. */
+int capdec_compact_targets(const int64_t* targets, int B, int L, int T, int off, int64_t ignore_index,
+                           int32_t* row_src, int32_t* dst_of, int64_t* targets_c, int32_t* counts, float* n_valid,
+                           float* loss_sum_to_zero, capdec_stream_t stream);
+/* dst[r] = src[row_src[r]] for r < counts[0], zero rows up to counts[1]; dst has max_rows rows of width d */
+int capdec_rows_gather_idx(const float* src, float* dst, const int32_t* row_src, const int32_t* counts, int max_rows,
+                           int d, capdec_stream_t stream);
+/* dst[row] = dst_of[row] >= 0 ? src[dst_of[row]] : 0 for every one of `rows` rows */
+int capdec_rows_scatter_idx(const float* src, float* dst, const int32_t* dst_of, int rows, int d, capdec_stream_t stream);
 
 /* ---- small fused elementwise / reduction ops ----------------------------------------------------------------------
  * colsum: out[n] += sum_m x[m,n]  (bias gradients of every Linear/Conv1D; autograd of addmm bias) */

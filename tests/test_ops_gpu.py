@@ -454,3 +454,64 @@ def test_step_clock_schedule_and_seed(ops):
     # get_linear_schedule_with_warmup(warmup=2, total=6): 0, .5, 1, .75, .5, .25 (x base)
     assert lrs == pytest.approx([0.0, 1e-5, 2e-5, 1.5e-5, 1e-5, 0.5e-5], rel=1e-6)
     assert seed.item() != 5
+
+
+def test_compact_targets_and_limited_gemm(ops):
+    """Row compaction of the non-ignored targets + GEMMs / CE bounded by a device scalar (LM head on valid rows only)."""
+    B, L, P, d, V = 7, 40, 10, 768, 1000
+    T = P + L
+    g = torch.Generator(device="cuda").manual_seed(3)
+    tokens = torch.randint(1, V, (B, L), device="cuda", generator=g)
+    lens = torch.randint(3, L + 1, (B,), device="cuda", generator=g)
+    tokens[torch.arange(L, device="cuda")[None, :] >= lens[:, None]] = 0
+    tokens[2, 5] = 0  # a genuine id-0 token in the middle is ignored too (train.py:350)
+    row_src = torch.zeros(B * L, dtype=torch.int32, device="cuda")
+    dst_of = torch.zeros(B * T, dtype=torch.int32, device="cuda")
+    tc = torch.zeros(B * L, dtype=torch.int64, device="cuda")
+    counts = torch.zeros(2, dtype=torch.int32, device="cuda")
+    n_valid = torch.zeros(1, device="cuda"); loss_sum = torch.ones(1, device="cuda")
+    ops.compact_targets(tokens.reshape(-1), B, L, T, P - 1, row_src, dst_of, tc, counts, n_valid, loss_sum)
+    flat = tokens.reshape(-1)
+    idx = (flat != 0).nonzero().flatten()
+    nv = idx.numel()
+    assert counts.tolist() == [nv, (nv + 31) // 32 * 32] and n_valid.item() == nv and loss_sum.item() == 0
+    exp_src = (idx // L) * T + (P - 1) + idx % L
+    assert torch.equal(row_src[:nv].long(), exp_src) and torch.equal(tc[:nv], flat[idx])
+    exp_dst = torch.full((B * T,), -1, dtype=torch.int32, device="cuda")
+    exp_dst[exp_src] = torch.arange(nv, dtype=torch.int32, device="cuda")
+    assert torch.equal(dst_of, exp_dst)
+    xf = torch.randn(B * T, d, device="cuda")
+    xsel = torch.full((B * L, d), float("nan"), device="cuda")
+    ops.rows_gather_idx(xf, xsel, row_src, counts)
+    assert torch.equal(xsel[:nv], xf[exp_src]) and (xsel[nv:counts[1].item()] == 0).all()
+    back = torch.empty(B * T, d, device="cuda")
+    ops.rows_scatter_idx(xsel, back, dst_of)
+    ref = torch.zeros_like(back); ref[exp_src] = xf[exp_src]
+    assert torch.equal(back, ref)
+    # m_limit: rows beyond the limit's tile are untouched, rows below are correct
+    M, N, K = 1200, 520, 96
+    A, Al, Bm, Bl = make_ab(M, N, K, 0, 0)
+    lim = torch.tensor([300], dtype=torch.int32, device="cuda")
+    C = torch.full((M, N), 7.0, device="cuda")
+    ops.gemm(A, 0, Bm, 0, C, M, N, K, m_limit=lim)
+    refC = trunc_tf32(Al).double() @ trunc_tf32(Bl).double().t()
+    assert (C[:300].double() - refC[:300]).abs().max() < 1e-4 * refC.abs().max()
+    assert (C[1024:] == 7.0).all()
+    # k_limit: reduction stops at the limit (operand rows of the k-tail are zero)
+    M, N, K = 700, 768, 640
+    A, Al, Bm, Bl = make_ab(M, N, K, 1, 1)
+    A[333:352] = 0  # the caller's contract for the K-tail [limit, roundup32(limit))
+    kl = torch.tensor([333], dtype=torch.int32, device="cuda")
+    C = torch.zeros(M, N, device="cuda")
+    ops.gemm(A, 1, Bm, 1, C, M, N, K, accumulate=True, k_limit=kl)
+    refC = trunc_tf32(A[:333].t().contiguous()).double() @ trunc_tf32(Bm[:333].t().contiguous()).double().t()
+    assert (C.double() - refC).abs().max() < 1e-4 * refC.abs().max()
+    # CE with a row limit
+    logits = torch.randn(64, 1024, device="cuda")[:, :V]
+    tg = torch.randint(1, V, (64,), device="cuda")
+    keep = logits.clone()
+    rl = torch.tensor([40], dtype=torch.int32, device="cuda")
+    ls = torch.zeros(1, device="cuda")
+    ops.ce_fwd_bwd(logits, tg, V, ls, row_limit=rl)
+    assert torch.equal(logits[40:], keep[40:])
+    assert abs(ls.item() - torch.nn.functional.cross_entropy(keep[:40].double(), tg[:40], reduction="sum").item()) < 1e-2
