@@ -64,6 +64,7 @@ constexpr int kThreads = 256;
 constexpr int kEpiThreads = 128;
 constexpr int kABytes = kBlockM * kBlockK * 4;  // 16 KB
 constexpr int kStagingBytes = 128 * 128;        // 128 rows x 32 fp32
+constexpr int kNumStaging = 4;                  // 2 ping-pong buffers for C (+ 2 for the aux output)
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;  // columns per accumulator stage
@@ -81,6 +82,7 @@ struct __align__(64) GemmDev {
   int nseg;
   int act, has_aux, accumulate;
   int a_mn, b_mn;
+  int a_3d, b_3d;                   // MN-major operand fetched as ONE 3-D TMA box {32, 32 k-rows, slabs} per stage
   uint32_t idesc;
   uint32_t adesc_hi, bdesc_hi;      // upper 32 bits of the smem descriptors (SBO, version, layout)
   uint32_t adesc_lo16, bdesc_lo16;  // LBO field (bits 16..29 of the low word), pre-shifted
@@ -90,10 +92,21 @@ struct __align__(64) GemmDev {
   uint32_t dbg;                     // bring-up switches (CAPDEC_GEMM_DBG): 1 skip TMA loads, 2 skip MMA, 4 skip stores, 8 skip epilogue
 };
 
-__device__ __forceinline__ float apply_act(float x, int act) {
+__device__ __forceinline__ float tanh_fast(float x) {  // MUFU.TANH, max rel. error 2^-11: same grade as a TF32 operand
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// `exact` (3xTF32 parity mode) uses tanhf; the 1xTF32 mode uses the single-instruction approximation — libdevice tanhf
+// costs ~40 instructions per element and made the c_fc epilogue 3x longer than its mainloop (profiles/r1_step_profile_v3.md)
+__device__ __forceinline__ float apply_act(float x, int act, bool exact) {
   switch (act) {
-    case 1: return gelu_new_fwd(x);
-    case 2: return tanhf(x);
+    case 1: {
+      if (exact) return gelu_new_fwd(x);
+      const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+      return 0.5f * x * (1.0f + tanh_fast(u));
+    }
+    case 2: return exact ? tanhf(x) : tanh_fast(x);
     case 3: return fmaxf(x, 0.0f);
     default: return x;
   }
@@ -123,8 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   const int stage_bytes = kABytes + b_bytes;
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.stages * kABytes;
-  uint8_t* sStage = smem + p.stages * stage_bytes;  // 2 x 16 KB epilogue staging
-  float* sBias = reinterpret_cast<float*>(sStage + 2 * kStagingBytes);
+  uint8_t* sStage = smem + p.stages * stage_bytes;  // epilogue staging: C ping-pong [+ aux ping-pong]
+  float* sBias = reinterpret_cast<float*>(sStage + (p.has_aux ? 4 : 2) * kStagingBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 256);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
@@ -175,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   // data-dependent extents (LM head over the non-ignored caption tokens only): every role skips the same tiles
   const int m_lim = p.m_limit ? __ldg(p.m_limit) : p.M;
   const int kb_lim = p.k_limit ? min(p.kb_total, (__ldg(p.k_limit) + kBlockK - 1) / kBlockK) : p.kb_total;
+  const int kb_per_split = p.k_limit ? max(1, (kb_lim + p.splits - 1) / p.splits) : p.kb_per_split;  // rebalance the splits
   // cluster-level tile grid: m_tiles x n_tiles cluster tiles (each kCM x kCN*block_n), times split-K
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   const int tile0 = (int)(blockIdx.x / kCtasPerCluster);
@@ -200,8 +214,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         const int split = tile / (p.n_tiles * p.m_tiles);
         const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM;               // my 128 A rows
         const int n0 = n_blk * tile_n + pn_off + (kPair ? (int)half * bn_local : 0);  // my bn_local B columns
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, kb_lim);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, kb_lim);
         if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
         for (int seg = 0; seg < p.nseg; ++seg) {
           const CUtensorMap* mapA = (seg == 1) ? &p.tmA[1] : &p.tmA[0];
@@ -222,9 +236,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
               if constexpr (kPair) tma_load_2d_pair(dst, m, fb, x, y); else tma_load_2d(dst, m, fb, x, y);
             };
             auto load_mc = [&](void* dst, const CUtensorMap* m, int x, int y) { tma_load_2d_pair_mc(dst, m, fb, x, y, mc_mask); };
+            auto load3 = [&](void* dst, const CUtensorMap* m, int y, int z) {   // {32 floats, 32 k-rows from y, slabs from z}
+              if constexpr (kPair) tma_load_3d_pair(dst, m, fb, 0, y, z); else tma_load_3d(dst, m, fb, 0, y, z);
+            };
+            auto load3_mc = [&](void* dst, const CUtensorMap* m, int y, int z) { tma_load_3d_pair_mc(dst, m, fb, 0, y, z, mc_mask); };
             // ---- A ----
             if constexpr (kQuad && !kShareB) {   // my half of the shared A slab -> me + twin
               if (!p.a_mn) load_mc(a_dst + pair_idx * (kABytes / 2), mapA, k0, m0 + (int)pair_idx * (kBlockM / 2));
+              else if (p.a_3d) load3_mc(a_dst + pair_idx * (kABytes / 2), mapA, k0, m0 / 32 + (int)pair_idx * (kBlockM / 64));
               else {
 #pragma unroll
                 for (int i = 0; i < kBlockM / 64; ++i) {
@@ -234,6 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
               }
             } else {
               if (!p.a_mn) load(a_dst, mapA, k0, m0);
+              else if (p.a_3d) load3(a_dst, mapA, k0, m0 / 32);
               else {
 #pragma unroll
                 for (int i = 0; i < kBlockM / 32; ++i) load(a_dst + i * 4096, mapA, m0 + 32 * i, k0);
@@ -242,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
             // ---- B ----
             if constexpr (kQuad && kShareB) {    // my half of the shared B slab -> me + twin
               if (!p.b_mn) load_mc(b_dst + pair_idx * (b_bytes / 2), mapB, k0, n0 + (int)pair_idx * (bn_local / 2));
+              else if (p.b_3d) load3_mc(b_dst + pair_idx * (b_bytes / 2), mapB, k0, n0 / 32 + (int)pair_idx * (bn_local / 64));
               else {
                 const int ns = bn_local / 64;
                 for (int i = 0; i < ns; ++i) {
@@ -251,6 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
               }
             } else {
               if (!p.b_mn) load(b_dst, mapB, k0, n0);
+              else if (p.b_3d) load3(b_dst, mapB, k0, n0 / 32);
               else {
                 for (int i = 0; i < bn_local / 32; ++i) load(b_dst + i * 4096, mapB, n0 + 32 * i, k0);
               }
@@ -275,8 +297,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int split = tile / (p.n_tiles * p.m_tiles);
         const int m_blk = (tile / p.n_tiles) % p.m_tiles;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, kb_lim);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, kb_lim);
         if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 2);
         tc_fence_after();
@@ -323,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       const int n_blk = tile % p.n_tiles;
       const int m_blk = (tile / p.n_tiles) % p.m_tiles;
       const int split = tile / (p.n_tiles * p.m_tiles);
-      if (m_blk * kTileM >= m_lim || split * p.kb_per_split >= min(split * p.kb_per_split + p.kb_per_split, kb_lim)) continue;
+      if (m_blk * kTileM >= m_lim || split * kb_per_split >= kb_lim) continue;
       const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM;
       const int n0 = n_blk * tile_n + pn_off;   // the pair's full block_n columns (each CTA stores its 128 rows x block_n)
       const bool use_bias = (p.bias != nullptr) && (split == 0);
@@ -354,11 +376,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
           for (int j = 0; j < 32; ++j) v[j] += sBias[c * 32 + j];
         }
         // staging buffer(s): without aux double-buffer on the running index; with aux buffer 0 = activated, 1 = pre-activation
-        uint8_t* buf0 = sStage + (p.has_aux ? 0 : (store_idx++ & 1)) * kStagingBytes;
-        uint8_t* buf1 = sStage + kStagingBytes;
-        if (epi_tid == 0) {
-          if (p.has_aux) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
-        }
+        const uint32_t pp = store_idx++ & 1;
+        uint8_t* buf0 = sStage + pp * kStagingBytes;
+        uint8_t* buf1 = sStage + (2 + pp) * kStagingBytes;
+        if (epi_tid == 0) tma_store_wait_read<1>();  // the group committed two chunks ago has finished reading its buffers
         named_bar_sync(1, kEpiThreads);
         if (p.has_aux) {
           float4* d1 = reinterpret_cast<float4*>(buf1 + row * 128);
@@ -367,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         }
         if (p.act != 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.nseg > 1);
         }
         {
           float4* d0 = reinterpret_cast<float4*>(buf0 + row * 128);
@@ -437,6 +458,22 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim
     return CAPDEC_ERR_CUDA;
   }
   return CAPDEC_OK;
+}
+
+// 3-D view of an MN-major operand: [MN/32 slabs][K rows][32 floats]; one box = {32, 32 k-rows, nslabs} lands in shared
+// memory slab after slab (4 KB each), i.e. exactly the layout the UMMA descriptor expects.  Needs MN % 32 == 0.
+static int make_map_mn3d(CUtensorMap* m, const void* ptr, uint64_t mn, uint64_t k_rows, uint64_t pitch_elems,
+                         uint32_t nslabs, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return CAPDEC_ERR_CUDA;
+  cuuint64_t dims[3] = {32, k_rows, mn / 32};
+  cuuint64_t strides[2] = {pitch_elems * 4, 128};
+  cuuint32_t box[3] = {32, kBlockK, nslabs};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CAPDEC_OK : CAPDEC_ERR_UNSUPPORTED;
 }
 
 // bring-up overrides for the MN-major encoding (see capdec_gemm_debug_mn_encoding)
@@ -624,7 +661,9 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
       // wave quantisation on every shape of this model, and few-row problems (wgrad, M = 768) stay on plain pairs.
       const int mt = (M + 255) / 256;
       const double waste_b = (double)(((mt + 1) / 2) * 2) / mt;
-      if (mt >= 8 && waste_b <= 1.15) mode = 3;
+      // ... and only when B is MN-major: there multicast halves the number of small (4 KB) TMA boxes per k-block; with a
+      // K-major B (one 16 KB box) the in-step profile shows mode 3 ~10 % SLOWER than pairs (132 vs 148 SMs, no fewer requests)
+      if (mt >= 8 && waste_b <= 1.15 && b_major) mode = 3;
     } else if (forced == 2 || forced == 3) {
       mode = forced;
     }
@@ -657,7 +696,7 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
 
   const int bn_local = (mode == 0) ? bn : bn / 2;
   const int b_bytes = bn_local * kBlockK * 4;
-  const int fixed = 2 * kStagingBytes + 256 * 4 + (2 * kMaxStages + 4) * 8 + 16 + 1024 /* alignment slack */;
+  const int fixed = (aux ? 4 : 2) * kStagingBytes + 256 * 4 + (2 * kMaxStages + 4) * 8 + 16 + 1024 /* alignment slack */;
   int stages = (kSmemLimit - fixed) / (kABytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
@@ -674,15 +713,27 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
   // TMA boxes: K-major operands move {32 fp32, rows}; a quad that shares the operand moves half the rows per CTA
   const uint32_t a_rows = (mode == 2) ? kBlockM / 2 : kBlockM;
   const uint32_t b_rows = (mode == 3) ? (uint32_t)bn_local / 2 : (uint32_t)bn_local;
+  static const char* env_3d = getenv("CAPDEC_GEMM_3D");   // bring-up switch: 0 disables the 3-D MN-major boxes
+  const bool allow3d = !(env_3d && env_3d[0] == '0') && g_mn_swz < 0;
+  const uint32_t a_slabs = (mode == 2) ? kBlockM / 64 : kBlockM / 32;
+  const uint32_t b_slabs = (mode == 3) ? (uint32_t)bn_local / 64 : (uint32_t)bn_local / 32;
+  p.a_3d = (a_major && allow3d && (M % 32) == 0) ? 1 : 0;
+  p.b_3d = (b_major && allow3d && (N % 32) == 0) ? 1 : 0;
   int rc;
   for (int s = 0; s < p.nseg && s < 2; ++s) {
     const float* a = s ? a_lo : A;
     const float* b = s ? b_lo : B;
     if (!a_major) rc = make_map(&p.tmA[s], a, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBlockK, a_rows, ea.swz);
-    else rc = make_map(&p.tmA[s], a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, kBlockK, ea.swz);
+    else {
+      rc = p.a_3d ? make_map_mn3d(&p.tmA[s], a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, a_slabs, ea.swz) : CAPDEC_ERR_UNSUPPORTED;
+      if (rc) { p.a_3d = 0; rc = make_map(&p.tmA[s], a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, kBlockK, ea.swz); }
+    }
     if (rc) return rc;
     if (!b_major) rc = make_map(&p.tmB[s], b, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBlockK, b_rows, eb.swz);
-    else rc = make_map(&p.tmB[s], b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, kBlockK, eb.swz);
+    else {
+      rc = p.b_3d ? make_map_mn3d(&p.tmB[s], b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, b_slabs, eb.swz) : CAPDEC_ERR_UNSUPPORTED;
+      if (rc) { p.b_3d = 0; rc = make_map(&p.tmB[s], b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, kBlockK, eb.swz); }
+    }
     if (rc) return rc;
   }
   rc = make_map(&p.tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);

@@ -347,11 +347,11 @@ def test_attention_key_padding_and_dropout(ops, impl):
     # finite-difference check of dV under the frozen mask (output is linear in V)
     dv_num = torch.zeros(B, T, d, device="cuda")
     probe = torch.randn(B, T, d, device="cuda")
-    v2 = (v + 1e-2 * probe).contiguous()
+    v2 = (v + 1.0 * probe).contiguous()   # the output is linear in V: a large step keeps TF32 rounding out of the quotient
     qkv2 = qkv.clone(); qkv2[..., 2 * d:] = v2
     c2 = torch.empty_like(ctx)
     ops.attention_fwd(qkv2[..., :d], qkv2[..., d:2 * d], qkv2[..., 2 * d:], c2, lse, *args, p_drop=0.1, seed=seed, stream_id=2, impl=impl)
-    lhs = ((c2 - ctx_d) * dctx).sum().item() / 1e-2
+    lhs = ((c2 - ctx_d) * dctx).sum().item() / 1.0
     rhs = (dqkv[..., 2 * d:] * probe).sum().item()
     assert abs(lhs - rhs) < 3e-2 * max(1.0, abs(rhs)), (lhs, rhs)
 
