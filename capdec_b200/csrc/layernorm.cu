@@ -74,90 +74,103 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
   }
 }
 
-// persistent: each warp strides over rows.  The column reductions (dgamma, dbeta, bias gradient of the branch) are
-// accumulated with shared-memory float atomics (conflict-free: a warp instruction touches 32 distinct banks) instead of
-// per-lane register accumulators: that keeps the kernel at ~80 registers -> 3 CTAs/SM, which is what a streaming
-// kernel needs to cover HBM latency (the register-accumulator version ran at 2.6 TB/s, this one is HBM-bound).
-template <int NV>
-__global__ void __launch_bounds__(256, 3) add_ln_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ r,
-                                                            const float* __restrict__ stats,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ dh_res, float* __restrict__ dh_out,
-                                                            float* __restrict__ dy, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, float* __restrict__ dbias_branch,
-                                                            int rows, int d, float p_drop,
-                                                            const uint64_t* seed_dev, uint32_t stream_id) {
+// Backward, column-parallel: thread c of a CTA owns float4 column c of every row the CTA processes (d/4 threads), so
+// the column reductions (dgamma, dbeta, bias gradient of the branch) are 12 private registers per thread and need no
+// atomics until the very end; the two ROW reductions (mean of g, mean of g*xhat) are done for kR rows at a time with
+// one shuffle tree + one shared-memory exchange.  ~4x fewer instructions than a warp-per-row kernel with shared-memory
+// atomics (17.5 M -> ~4.6 M warp instructions at C2) and enough CTAs per SM to stream at HBM speed.
+constexpr int kR = 4;  // rows per batch
+
+__global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ r,
+                                                         const float* __restrict__ stats,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ dh_res, float* __restrict__ dh_out,
+                                                         float* __restrict__ dy, float* __restrict__ dgamma,
+                                                         float* __restrict__ dbeta, float* __restrict__ dbias_branch,
+                                                         int rows, int d, int rows_per_cta, float p_drop,
+                                                         const uint64_t* seed_dev, uint32_t stream_id) {
   const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
-  __shared__ float s_acc[3][NV * 128];  // dgamma | dbeta | dbias_branch partial sums of this CTA
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float s_part[2][8][2 * kR];              // [batch parity][warp][c1_0..c1_{R-1}, c2_0..c2_{R-1}]
+  const int c = threadIdx.x;                          // float4 column
   const int d4 = d >> 2;
-  for (int i = threadIdx.x; i < 3 * NV * 128; i += 256) (&s_acc[0][0])[i] = 0.f;
-  __syncthreads();
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
   const float inv_keep = 1.0f / (1.0f - p_drop);
   const float inv_d = 1.0f / (float)d;
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
-    const float4* dx4 = reinterpret_cast<const float4*>(dx) + (size_t)row * d4;
-    const float4* r4 = reinterpret_cast<const float4*>(r) + (size_t)row * d4;
-    const float mean = stats[2 * (size_t)row], rstd = stats[2 * (size_t)row + 1];
-    float4 g[NV], xh[NV];
-    float c1 = 0.f, c2 = 0.f;
+  float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg, dbr = dg;
+  const int row0 = blockIdx.x * rows_per_cta, row1 = min(rows, row0 + rows_per_cta);
+  int parity = 0;
+  for (int rb = row0; rb < row1; rb += kR, parity ^= 1) {
+    float4 g[kR], xh[kR];
+    float part[2 * kR];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      const float4 dv = ld_stream(dx4 + c), rv = ld_stream(r4 + c);
-      const float4 gm = __ldg(g4 + c);
-      xh[i].x = (rv.x - mean) * rstd; xh[i].y = (rv.y - mean) * rstd;
-      xh[i].z = (rv.z - mean) * rstd; xh[i].w = (rv.w - mean) * rstd;
-      if (dgamma) {
-        float* a0 = &s_acc[0][4 * c];
-        float* a1 = &s_acc[1][4 * c];
-        atomicAdd(a0 + 0, dv.x * xh[i].x); atomicAdd(a0 + 1, dv.y * xh[i].y);
-        atomicAdd(a0 + 2, dv.z * xh[i].z); atomicAdd(a0 + 3, dv.w * xh[i].w);
-        atomicAdd(a1 + 0, dv.x); atomicAdd(a1 + 1, dv.y); atomicAdd(a1 + 2, dv.z); atomicAdd(a1 + 3, dv.w);
+    for (int i = 0; i < kR; ++i) {
+      const int row = rb + i;
+      if (row < row1) {
+        const float4 dv = ld_stream(reinterpret_cast<const float4*>(dx) + (size_t)row * d4 + c);
+        const float4 rv = ld_stream(reinterpret_cast<const float4*>(r) + (size_t)row * d4 + c);
+        const float mean = __ldg(stats + 2 * (size_t)row), rstd = __ldg(stats + 2 * (size_t)row + 1);
+        xh[i].x = (rv.x - mean) * rstd; xh[i].y = (rv.y - mean) * rstd;
+        xh[i].z = (rv.z - mean) * rstd; xh[i].w = (rv.w - mean) * rstd;
+        dg.x += dv.x * xh[i].x; dg.y += dv.y * xh[i].y; dg.z += dv.z * xh[i].z; dg.w += dv.w * xh[i].w;
+        db.x += dv.x; db.y += dv.y; db.z += dv.z; db.w += dv.w;
+        g[i].x = dv.x * gm.x; g[i].y = dv.y * gm.y; g[i].z = dv.z * gm.z; g[i].w = dv.w * gm.w;
+        part[i] = (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        part[kR + i] = (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+      } else {
+        g[i] = xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        part[i] = part[kR + i] = 0.f;
       }
-      g[i].x = dv.x * gm.x; g[i].y = dv.y * gm.y; g[i].z = dv.z * gm.z; g[i].w = dv.w * gm.w;
-      c1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-      c2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
     }
-    c1 = warp_sum(c1) * inv_d;
-    c2 = warp_sum(c2) * inv_d;
-    const float4* res4 = dh_res ? reinterpret_cast<const float4*>(dh_res) + (size_t)row * d4 : nullptr;
-    float4* out4 = reinterpret_cast<float4*>(dh_out) + (size_t)row * d4;
-    float4* dy4 = dy ? reinterpret_cast<float4*>(dy) + (size_t)row * d4 : nullptr;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
+    for (int j = 0; j < 2 * kR; ++j) part[j] = warp_sum(part[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 2 * kR; ++j) s_part[parity][warp][j] = part[j];
+    }
+    __syncthreads();  // one barrier per batch: the partials are double-buffered by batch parity
+#pragma unroll
+    for (int j = 0; j < 2 * kR; ++j) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += s_part[parity][w][j];
+      part[j] = t * inv_d;
+    }
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+      const int row = rb + i;
+      if (row >= row1) break;
+      const float rstd = __ldg(stats + 2 * (size_t)row + 1);
+      const float c1 = part[i], c2 = part[kR + i];
       float4 o;
       o.x = rstd * (g[i].x - c1 - xh[i].x * c2);
       o.y = rstd * (g[i].y - c1 - xh[i].y * c2);
       o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
       o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
-      if (res4) {
-        const float4 rr = ld_stream(res4 + c);
+      if (dh_res) {
+        const float4 rr = ld_stream(reinterpret_cast<const float4*>(dh_res) + (size_t)row * d4 + c);
         o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
       }
-      out4[c] = o;
-      if (dy4 || dbias_branch) {
+      reinterpret_cast<float4*>(dh_out)[(size_t)row * d4 + c] = o;
+      if (dy || dbias_branch) {
         if (p_drop > 0.0f) {
-          float s[4];
-          dropout_scale4(seed, stream_id, (uint64_t)row * d4 + c, p_drop, inv_keep, s);
-          o.x *= s[0]; o.y *= s[1]; o.z *= s[2]; o.w *= s[3];
+          float sc[4];
+          dropout_scale4(seed, stream_id, (uint64_t)row * d4 + c, p_drop, inv_keep, sc);
+          o.x *= sc[0]; o.y *= sc[1]; o.z *= sc[2]; o.w *= sc[3];
         }
-        if (dy4) dy4[c] = o;
-        if (dbias_branch) {  // bias gradient of the branch's last Linear
-          float* a2 = &s_acc[2][4 * c];
-          atomicAdd(a2 + 0, o.x); atomicAdd(a2 + 1, o.y); atomicAdd(a2 + 2, o.z); atomicAdd(a2 + 3, o.w);
-        }
+        if (dy) reinterpret_cast<float4*>(dy)[(size_t)row * d4 + c] = o;
+        dbr.x += o.x; dbr.y += o.y; dbr.z += o.z; dbr.w += o.w;  // bias gradient of the branch's last Linear
       }
     }
   }
-  if (dgamma || dbias_branch) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < d; i += 256) {
-      if (dgamma) { atomicAdd(dgamma + i, s_acc[0][i]); atomicAdd(dbeta + i, s_acc[1][i]); }
-      if (dbias_branch) atomicAdd(dbias_branch + i, s_acc[2][i]);
-    }
+  if (dgamma) {
+    float* a = dgamma + 4 * c;
+    float* b = dbeta + 4 * c;
+    atomicAdd(a + 0, dg.x); atomicAdd(a + 1, dg.y); atomicAdd(a + 2, dg.z); atomicAdd(a + 3, dg.w);
+    atomicAdd(b + 0, db.x); atomicAdd(b + 1, db.y); atomicAdd(b + 2, db.z); atomicAdd(b + 3, db.w);
+  }
+  if (dbias_branch) {
+    float* a = dbias_branch + 4 * c;
+    atomicAdd(a + 0, dbr.x); atomicAdd(a + 1, dbr.y); atomicAdd(a + 2, dbr.z); atomicAdd(a + 3, dbr.w);
   }
 }
 
@@ -200,12 +213,14 @@ extern "C" int capdec_add_ln_bwd(const float* dx, const float* r, const float* s
   CAPDEC_REQUIRE(dx && r && stats && gamma && dh_out && rows > 0, "add_ln_bwd: null argument");
   CAPDEC_REQUIRE(d % 128 == 0 && d <= 128 * kMaxV, "add_ln_bwd: d=%d must be a multiple of 128 and <= 1024", d);
   CAPDEC_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "add_ln_bwd: dgamma and dbeta must both be set or both NULL");
-  const int nv = d / 128;
-  int grid = (rows + 7) / 8;
-  const int cap = num_sms() * 3;
-  if (grid > cap) grid = cap;
-  DISPATCH_NV(nv, (add_ln_bwd_kernel<NV><<<grid, 256, 0, stream>>>(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma,
-                                                                   dbeta, dbias_branch, rows, d, p_drop, seed_dev, stream_id)));
+  const int threads = d / 4;                     // one float4 column per thread (d = 768 -> 192 threads)
+  int ctas = num_sms() * 4;
+  int rpc = (rows + ctas - 1) / ctas;
+  rpc = ((rpc + kR - 1) / kR) * kR;
+  if (rpc < kR) rpc = kR;
+  ctas = (rows + rpc - 1) / rpc;
+  add_ln_bwd_kernel<<<ctas, threads, 0, stream>>>(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma, dbeta, dbias_branch, rows,
+                                                  d, rpc, p_drop, seed_dev, stream_id);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("add_ln_bwd_kernel");
   return CAPDEC_OK;
