@@ -25,6 +25,7 @@ SIGNATURES = {
     "capdec_launch_count": [],
     "capdec_gemm_tf32": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _i, _p],
     "capdec_gemm_tf32_ex": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _i, _p, _p, _p],
+    "capdec_gemm_tf32_mul": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p],
     "capdec_gemm_debug_mn_encoding": [_i, _i, _i, _i],
     "capdec_gemm_debug_force_pair": [_i],
     "capdec_gemm_fp32_simt": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p],

@@ -75,6 +75,7 @@ struct __align__(64) GemmDev {
   CUtensorMap tmB[2];
   CUtensorMap tmC;
   CUtensorMap tmAux;
+  CUtensorMap tmMul;   // optional epilogue INPUT (same shape as C): C = acc * act'(mul)
   const float* bias;
   int M, N, K;
   int block_n, stages;
@@ -87,6 +88,8 @@ struct __align__(64) GemmDev {
   uint32_t adesc_hi, bdesc_hi;      // upper 32 bits of the smem descriptors (SBO, version, layout)
   uint32_t adesc_lo16, bdesc_lo16;  // LBO field (bits 16..29 of the low word), pre-shifted
   uint32_t a_kstep, b_kstep;        // start-address increment per UMMA_K step, in 16-byte units
+  float* colsum;                    // optional [N]: += column sums of the stored C (bias gradient), mul epilogue only
+  int mul_act;                      // 0 none; 1 gelu_new'(pre-activation), 2 tanh' = 1 - a^2 (activated a), 3 relu' (activated a)
   const int* m_limit;               // optional device scalar: rows >= *m_limit are not computed (whole tiles skipped)
   const int* k_limit;               // optional device scalar: reduction stops at *k_limit (rounded up to a k-block)
   uint32_t dbg;                     // bring-up switches (CAPDEC_GEMM_DBG): 1 skip TMA loads, 2 skip MMA, 4 skip stores, 8 skip epilogue
@@ -97,18 +100,40 @@ __device__ __forceinline__ float tanh_fast(float x) {  // MUFU.TANH, max rel. er
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// `exact` (3xTF32 parity mode) uses tanhf; the 1xTF32 mode uses the single-instruction approximation — libdevice tanhf
-// costs ~40 instructions per element and made the c_fc epilogue 3x longer than its mainloop (profiles/r1_step_profile_v3.md)
-__device__ __forceinline__ float apply_act(float x, int act, bool exact) {
-  switch (act) {
-    case 1: {
-      if (exact) return gelu_new_fwd(x);
-      const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-      return 0.5f * x * (1.0f + tanh_fast(u));
+__device__ __forceinline__ float gelu_grad_fast(float x) {  // d/dx gelu_new with MUFU.TANH (1xTF32 mode only)
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float t = tanh_fast(k0 * (x + k1 * x * x2));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x2);
+}
+// Activation over a 32-column register chunk.  The `act` / `exact` dispatch is hoisted OUT of the element loop: with
+// the switch inside the unrolled loop the compiler emitted a branch tree per element and the c_fc epilogue took 3x its
+// mainloop (313 vs 110 us, profiles/r1_gemm_pipeline_experiments.md).  `exact` (3xTF32 parity mode) uses tanhf; the
+// 1xTF32 mode uses MUFU.TANH (2^-11 relative error, the grade of a TF32 operand).
+__device__ __forceinline__ void apply_act32(float (&v)[32], int act, bool exact) {
+  if (act == 1) {
+    if (exact) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_new_fwd(v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = v[j];
+        const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+        v[j] = 0.5f * x * (1.0f + tanh_fast(u));
+      }
     }
-    case 2: return exact ? tanhf(x) : tanh_fast(x);
-    case 3: return fmaxf(x, 0.0f);
-    default: return x;
+  } else if (act == 2) {
+    if (exact) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = tanh_fast(v[j]);
+    }
+  } else if (act == 3) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
 }
 
@@ -137,12 +162,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.stages * kABytes;
   uint8_t* sStage = smem + p.stages * stage_bytes;  // epilogue staging: C ping-pong [+ aux ping-pong]
-  float* sBias = reinterpret_cast<float*>(sStage + (p.has_aux ? 4 : 2) * kStagingBytes);
+  const int n_staging = (p.has_aux || p.mul_act) ? 4 : 2;
+  float* sBias = reinterpret_cast<float*>(sStage + n_staging * kStagingBytes);
+  float* sCol = sBias;                              // per-tile column sums (mul epilogue; never together with a bias)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 256);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* mul_bar = tmem_empty_bar + 2;           // TMA loads of the epilogue input chunks (ping-pong)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mul_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -164,6 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       prefetch_tensormap(&p.tmB[1]);
     }
     if (p.has_aux) prefetch_tensormap(&p.tmAux);
+    if (p.mul_act) prefetch_tensormap(&p.tmMul);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
@@ -171,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       mbar_init(&empty_bar[i], kPairsPerCluster);  // quad: both pairs' MMAs must have retired (multicast writes my smem)
     }
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&mul_bar[i], 1);
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], kCtasPerPair * kEpiThreads);  // pair: both CTAs' epilogues report to the leader
     }
@@ -341,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t store_idx = 0;  // running chunk counter: staging buffers alternate ACROSS tiles too
+    uint32_t mul_idx = 0;    // running count of epilogue-input chunks already consumed (buffer = idx & 1, phase = idx >> 1)
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int n_blk = tile % p.n_tiles;
       const int m_blk = (tile / p.n_tiles) % p.m_tiles;
@@ -354,6 +385,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase, 4);
       tc_fence_after();
+      if (p.mul_act) {
+        for (int i = epi_tid; i < 256; i += kEpiThreads) sCol[i] = 0.f;
+      }
       named_bar_sync(1, kEpiThreads);  // bias tile visible
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols);
       int n_chunks = (p.N > n0) ? min(p.block_n, p.N - n0 + 31) / 32 : 0;  // skip chunks (or whole tiles) past N
@@ -362,9 +396,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], pair_leader); else mbar_arrive(&tmem_empty_bar[acc]);
         n_chunks = 0;
       }
+      if (p.mul_act && n_chunks > 0 && epi_tid == 0) {  // prefetch the first epilogue-input chunk of this tile
+        uint64_t* mb = &mul_bar[mul_idx & 1];
+        mbar_arrive_expect_tx(mb, kStagingBytes);
+        tma_load_2d(sStage + (2 + (mul_idx & 1)) * kStagingBytes, &p.tmMul, mb, n0, m0);
+      }
       for (int c = 0; c < n_chunks; ++c) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
+        if (p.mul_act && c + 1 < n_chunks && epi_tid == 0) {  // next chunk's input: its buffer was last read one chunk ago
+          uint64_t* mb = &mul_bar[(mul_idx + 1) & 1];
+          mbar_arrive_expect_tx(mb, kStagingBytes);
+          tma_load_2d(sStage + (2 + ((mul_idx + 1) & 1)) * kStagingBytes, &p.tmMul, mb, n0 + (c + 1) * 32, m0);
+        }
         tmem_ld_wait();
         if (c == n_chunks - 1) {
           // all TMEM reads of this accumulator stage are done -> hand it back to the (leader's) MMA warp
@@ -374,6 +418,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         if (use_bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += sBias[c * 32 + j];
+        }
+        if (p.mul_act) {  // v *= act'(input chunk), read back from the 128B-swizzled TMA layout
+          mbar_wait(&mul_bar[mul_idx & 1], (mul_idx >> 1) & 1, 5);
+          const float4* u4 = reinterpret_cast<const float4*>(sStage + (2 + (mul_idx & 1)) * kStagingBytes + row * 128);
+          ++mul_idx;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 u = u4[j ^ (row & 7)];
+            if (p.mul_act == 1) {
+              v[4 * j] *= gelu_grad_fast(u.x); v[4 * j + 1] *= gelu_grad_fast(u.y);
+              v[4 * j + 2] *= gelu_grad_fast(u.z); v[4 * j + 3] *= gelu_grad_fast(u.w);
+            } else if (p.mul_act == 2) {
+              v[4 * j] *= 1.f - u.x * u.x; v[4 * j + 1] *= 1.f - u.y * u.y;
+              v[4 * j + 2] *= 1.f - u.z * u.z; v[4 * j + 3] *= 1.f - u.w * u.w;
+            } else {
+              v[4 * j] = u.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = u.y > 0.f ? v[4 * j + 1] : 0.f;
+              v[4 * j + 2] = u.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = u.w > 0.f ? v[4 * j + 3] : 0.f;
+            }
+          }
         }
         // staging buffer(s): without aux double-buffer on the running index; with aux buffer 0 = activated, 1 = pre-activation
         const uint32_t pp = store_idx++ & 1;
@@ -386,10 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 8; ++j) d1[j ^ (row & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        if (p.act != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.nseg > 1);
-        }
+        if (p.act != 0) apply_act32(v, p.act, p.nseg > 1);
         {
           float4* d0 = reinterpret_cast<float4*>(buf0 + row * 128);
 #pragma unroll
@@ -397,12 +457,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         }
         fence_proxy_async_smem();
         named_bar_sync(1, kEpiThreads);
+        if (p.colsum) {  // bias gradient: lane = column of this chunk, each warp sums its 32 rows out of the staged tile
+          float cs = 0.f;
+          const int rbase = q * 32;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r2 = rbase + rr;
+            if (m0 + r2 < p.M)
+              cs += *reinterpret_cast<const float*>(buf0 + r2 * 128 + (((lane >> 2) ^ (r2 & 7)) << 4) + ((lane & 3) << 2));
+          }
+          atomicAdd(&sCol[c * 32 + lane], cs);
+        }
         if (epi_tid == 0 && !(p.dbg & 4u)) {
           if (p.accumulate) tma_reduce_add_2d(&p.tmC, buf0, n0 + c * 32, m0);
           else tma_store_2d(&p.tmC, buf0, n0 + c * 32, m0);
           if (p.has_aux) tma_store_2d(&p.tmAux, buf1, n0 + c * 32, m0);
           tma_store_commit();
         }
+      }
+      if (p.colsum && n_chunks > 0) {
+        named_bar_sync(1, kEpiThreads);
+        for (int i = epi_tid; i < n_chunks * 32; i += kEpiThreads)
+          if (n0 + i < p.N) atomicAdd(p.colsum + n0 + i, sCol[i]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -616,6 +692,24 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
                              a_lo, b_lo, block_n, split_k, nullptr, nullptr, stream_);
 }
 
+static thread_local const float* t_mul_in = nullptr;
+static thread_local int t_mul_act = 0;
+static thread_local float* t_colsum = nullptr;
+
+// C = (A . B^T) * act'(mul_in), colsum[n] += sum_m C[m,n]: the dgrad GEMM that feeds an activation's backward, with the
+// bias gradient of the layer below fused (HF:modeling_gpt2.py:238-243 c_fc -> gelu_new; train.py:106-118 tanh; :121 relu)
+extern "C" int capdec_gemm_tf32_mul(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
+                                    float* C, int64_t ldc, int M, int N, int K, const float* mul_in, int mul_act,
+                                    float* colsum, int block_n, capdec_stream_t stream_) {
+  CAPDEC_REQUIRE(mul_in && mul_act >= 1 && mul_act <= 3, "gemm_mul: bad epilogue input");
+  CAPDEC_REQUIRE(((uintptr_t)mul_in % 16) == 0, "gemm_mul: mul_in must be 16-byte aligned");
+  t_mul_in = mul_in; t_mul_act = mul_act; t_colsum = colsum;
+  int rc = capdec_gemm_tf32_ex(A, a_major, lda, B, b_major, ldb, C, ldc, M, N, K, nullptr, 0, nullptr, 0, 0, nullptr,
+                               nullptr, block_n, 1, nullptr, nullptr, stream_);
+  t_mul_in = nullptr; t_mul_act = 0; t_colsum = nullptr;
+  return rc;
+}
+
 extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
                                    float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
                                    int accumulate, int precision, const float* a_lo, const float* b_lo, int block_n,
@@ -690,13 +784,15 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
   p.b_mn = b_major ? 1 : 0;
   p.bias = bias;
   p.m_limit = m_limit_dev;
+  p.mul_act = t_mul_act;
+  p.colsum = t_colsum;
   p.k_limit = k_limit_dev;
   static const char* env_dbg = getenv("CAPDEC_GEMM_DBG");
   p.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
 
   const int bn_local = (mode == 0) ? bn : bn / 2;
   const int b_bytes = bn_local * kBlockK * 4;
-  const int fixed = (aux ? 4 : 2) * kStagingBytes + 256 * 4 + (2 * kMaxStages + 4) * 8 + 16 + 1024 /* alignment slack */;
+  const int fixed = ((aux || t_mul_act) ? 4 : 2) * kStagingBytes + 256 * 4 + (2 * kMaxStages + 6) * 8 + 16 + 1008 /* alignment slack */;
   int stages = (kSmemLimit - fixed) / (kABytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
@@ -740,6 +836,10 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
   if (rc) return rc;
   if (aux) {
     rc = make_map(&p.tmAux, aux, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  if (t_mul_act) {
+    rc = make_map(&p.tmMul, t_mul_in, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
 

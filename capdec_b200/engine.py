@@ -227,8 +227,7 @@ class Engine:
         if self.is_mlp:
             w2, w1 = "clip_project.model.2.", "clip_project.model.0."
             ops.linear_wgrad(ma.a1, dpp, g[w2 + "weight"], "linear", g[w2 + "bias"])
-            ops.linear_dgrad(dpp, p[w2 + "weight"], "linear", ma.da1)
-            ops.act_bwd(ma.da1, ma.a1, ma.da1, ops.ACT_TANH, dbias=g[w1 + "bias"])
+            ops.linear_dgrad_act(dpp, p[w2 + "weight"], "linear", ma.da1, ma.a1, ops.ACT_TANH, dbias=g[w1 + "bias"])
             ops.linear_wgrad(x, ma.da1, g[w1 + "weight"], "linear")
             return
         d, C, P, S, Mm = self.d, self.C, self.P, ma.S, ma.Mm
@@ -239,8 +238,8 @@ class Engine:
             # fc2 (its bias gradient comes fused from the add_ln_bwd that produced dhm; last layer: explicit colsum)
             ops.linear_wgrad(ma.f[j], ma.dhm, g[pre + "mlp.fc2.weight"], "linear",
                              g[pre + "mlp.fc2.bias"] if j == nl - 1 else None)
-            ops.linear_dgrad(ma.dhm, p[pre + "mlp.fc2.weight"], "linear", ma.df)
-            ops.act_bwd(ma.df, ma.f[j], ma.df, ops.ACT_RELU, dbias=g[pre + "mlp.fc1.bias"])
+            ops.linear_dgrad_act(ma.dhm, p[pre + "mlp.fc2.weight"], "linear", ma.df, ma.f[j], ops.ACT_RELU,
+                                 dbias=g[pre + "mlp.fc1.bias"])
             ops.linear_wgrad(ma.y2[j], ma.df, g[pre + "mlp.fc1.weight"], "linear")
             ops.linear_dgrad(ma.df, p[pre + "mlp.fc1.weight"], "linear", ma.dt)
             ops.add_ln_bwd(ma.dt, ma.hm1[j], ma.s2[j], p[pre + "norm2.weight"], ma.dhm, ma.dhm, None,
@@ -327,8 +326,8 @@ class Engine:
             # mlp.c_proj
             if train_gpt:
                 ops.linear_wgrad(a.g[l], dy2, g[pre + "mlp.c_proj.weight"], "conv1d")
-            ops.linear_dgrad(dy2, p[pre + "mlp.c_proj.weight"], "conv1d", a.dF)
-            ops.act_bwd(a.dF, a.u[l], a.dF, ops.ACT_GELU_NEW, dbias=gw(pre + "mlp.c_fc.bias"))
+            ops.linear_dgrad_act(dy2, p[pre + "mlp.c_proj.weight"], "conv1d", a.dF, a.u[l], ops.ACT_GELU_NEW,
+                                 dbias=gw(pre + "mlp.c_fc.bias"))
             if train_gpt:
                 ops.linear_wgrad(a.x2[l], a.dF, g[pre + "mlp.c_fc.weight"], "conv1d")
             ops.linear_dgrad(a.dF, p[pre + "mlp.c_fc.weight"], "conv1d", a.dx)

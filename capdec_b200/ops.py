@@ -101,6 +101,27 @@ def gemm(A: torch.Tensor, a_major: int, B: torch.Tensor, b_major: int, C: torch.
     _lib.check(rc, "gemm_tf32")
 
 
+def gemm_mul(A, a_major, B, b_major, C, M, N, K, mul_in, mul_act, colsum=None, block_n=0):
+    """C = (A . B^T) * act'(mul_in), colsum += column sums of C — dgrad + activation backward + bias gradient in one
+    tcgen05 launch (1xTF32 mode)."""
+    lda, ldb, ldc = _rowmajor(A, "A"), _rowmajor(B, "B"), _rowmajor(C, "C")
+    if _rowmajor(mul_in, "mul_in") != ldc or tuple(mul_in.shape) != (M, N):
+        raise ValueError("mul_in must have C's shape and leading dimension")
+    rc = _lib.load().capdec_gemm_tf32_mul(A.data_ptr(), a_major, lda, B.data_ptr(), b_major, ldb, C.data_ptr(), ldc, M, N,
+                                          K, mul_in.data_ptr(), mul_act, _ptr(colsum), block_n, _stream())
+    _lib.check(rc, "gemm_tf32_mul")
+
+
+def linear_dgrad_act(dy, W, layout, dx, act_in, act, dbias=None):
+    """dx = (dy . W^T) * act'(act_in) (+ dbias += colsum(dx)).  tf32: one fused launch; parity modes: dgrad then act_bwd."""
+    if _PRECISION == "tf32":
+        M, K = dy.shape
+        gemm_mul(dy, 0, W, 0 if layout == "conv1d" else 1, dx, M, dx.shape[1], K, act_in, act, dbias)
+    else:
+        linear_dgrad(dy, W, layout, dx)
+        act_bwd(dx, act_in, dx, act, dbias=dbias)
+
+
 # ---- layer helpers: `layout` is "conv1d" (HF Conv1D weight [in,out]) or "linear" (nn.Linear weight [out,in]) --------
 def linear_fwd(x, W, layout, bias, out, act=ACT_NONE, aux=None):
     M, K = x.shape

@@ -59,6 +59,14 @@ int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B
                         int precision, const float* a_lo, const float* b_lo, int block_n, int split_k,
                         const int32_t* m_limit_dev, const int32_t* k_limit_dev, capdec_stream_t stream);
 
+/* dgrad GEMM with a fused activation backward and bias gradient:  C[M,N] = (A . B^T) * act'(mul_in[M,N]),
+ * colsum[n] += sum_m C[m,n] (may be NULL).  mul_act: 1 = gelu_new'(pre-activation u) (HF:activations.py:59-66),
+ * 2 = tanh' = 1 - a^2 with a the activated output (train.py:106), 3 = relu mask from the activated output
+ * (train.py:121).  mul_in shares C's leading dimension.  1xTF32 only (the parity modes use capdec_act_bwd). */
+int capdec_gemm_tf32_mul(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb, float* C,
+                         int64_t ldc, int M, int N, int K, const float* mul_in, int mul_act, float* colsum,
+                         int block_n, capdec_stream_t stream);
+
 /* debug/bring-up override of the UMMA shared-memory descriptor encoding for MN-major operands
  * (layout_type, LBO bytes, SBO bytes, TMA swizzle enum); pass -1 to keep the default. Not used in production. */
 void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, int sbo_bytes, int tma_swizzle);

@@ -515,3 +515,32 @@ def test_compact_targets_and_limited_gemm(ops):
     ops.ce_fwd_bwd(logits, tg, V, ls, row_limit=rl)
     assert torch.equal(logits[40:], keep[40:])
     assert abs(ls.item() - torch.nn.functional.cross_entropy(keep[:40].double(), tg[:40], reduction="sum").item()) < 1e-2
+
+
+@pytest.mark.parametrize("act", [1, 2, 3])
+@pytest.mark.parametrize("layout", ["conv1d", "linear"])
+def test_gemm_fused_activation_backward_and_bias_grad(ops, act, layout):
+    """dgrad GEMM x act'(.) with the bias-gradient column sums fused in the epilogue == separate dgrad + act_bwd."""
+    M, K, N = 1300, 768, 1100   # dx [M,N] = dy [M,K] . W^T, tails in M and N
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dy = torch.randn(M, K, device="cuda", generator=g)
+    W = (torch.randn(N, K, device="cuda", generator=g) if layout == "conv1d" else torch.randn(K, N, device="cuda", generator=g)) * 0.05
+    pre = torch.randn(M, N, device="cuda", generator=g)
+    act_in = pre if act == 1 else (torch.tanh(pre) if act == 2 else torch.relu(pre))
+    dx = torch.empty(M, N, device="cuda")
+    db = torch.full((N,), 3.0, device="cuda")
+    ops.linear_dgrad_act(dy, W, layout, dx, act_in, act, dbias=db)
+    Wl = W if layout == "conv1d" else W.t()
+    lin = trunc_tf32(dy).double() @ trunc_tf32(Wl.contiguous()).double().t()
+    p64 = pre.double()
+    if act == 1:
+        p64r = p64.clone().requires_grad_()
+        torch.nn.functional.gelu(p64r, approximate="tanh").sum().backward()
+        d = p64r.grad
+    elif act == 2:
+        d = 1 - torch.tanh(p64) ** 2
+    else:
+        d = (p64 > 0).double()
+    ref = lin * d
+    assert (dx.double() - ref).abs().max() < 2e-4 * max(1.0, ref.abs().max().item())
+    assert (db.double() - (3.0 + ref.sum(0))).abs().max() < 2e-3 * max(1.0, ref.sum(0).abs().max().item())
