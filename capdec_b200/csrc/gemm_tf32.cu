@@ -64,7 +64,7 @@ constexpr int kThreads = 256;
 constexpr int kEpiThreads = 128;
 constexpr int kABytes = kBlockM * kBlockK * 4;  // 16 KB
 constexpr int kStagingBytes = 128 * 128;        // 128 rows x 32 fp32
-constexpr int kNumStaging = 4;                  // 2 ping-pong buffers for C (+ 2 for the aux output)
+constexpr int kWarpStagingBytes = 32 * 128;     // one epilogue warp's box: 32 rows x 32 fp32 (4 per 16 KB slot)
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;  // columns per accumulator stage
@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* mul_bar = tmem_empty_bar + 2;           // TMA loads of the epilogue input chunks (ping-pong)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mul_bar + 2);
+  uint64_t* mul_bar = tmem_empty_bar + 2;           // TMA loads of the epilogue input boxes (2 per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mul_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       mbar_init(&full_bar[i], kCtasPerPair);      // pair: leader's arrive.expect_tx + the peer's remote arrive
       mbar_init(&empty_bar[i], kPairsPerCluster);  // quad: both pairs' MMAs must have retired (multicast writes my smem)
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&mul_bar[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&mul_bar[i], 1);
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], kCtasPerPair * kEpiThreads);  // pair: both CTAs' epilogues report to the leader
     }
@@ -365,49 +365,55 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
     __syncwarp();
   } else if (warp >= 4) {
     // ============================== epilogue (4 warps = this CTA's 128 TMEM lanes) ==============================
+    // Every warp runs its OWN pipeline over its 32 rows: tcgen05.ld -> bias / activation -> swizzled 4 KB staging box ->
+    // TMA store of a {32 cols, 32 rows} box.  No cross-warp barrier inside the chunk loop (two per tile remain, for the
+    // bias tile and the column sums); staging is ping-pong per warp, gated by the warp leader's bulk-group counter.
     const int q = warp & 3;                   // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;            // row of this CTA's 128-row slab owned by this thread
     const int epi_tid = threadIdx.x - 4 * 32;
+    uint8_t* wst = sStage + q * (n_staging * kWarpStagingBytes);   // this warp's staging: C[0], C[1], (X[0], X[1])
+    uint64_t* my_mul_bar = mul_bar + 2 * q;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t store_idx = 0;  // running chunk counter: staging buffers alternate ACROSS tiles too
-    uint32_t mul_idx = 0;    // running count of epilogue-input chunks already consumed (buffer = idx & 1, phase = idx >> 1)
+    uint32_t mul_idx = 0;    // running count of epilogue-input chunks consumed (buffer = idx & 1, phase = (idx >> 1) & 1)
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int n_blk = tile % p.n_tiles;
       const int m_blk = (tile / p.n_tiles) % p.m_tiles;
       const int split = tile / (p.n_tiles * p.m_tiles);
       if (m_blk * kTileM >= m_lim || split * kb_per_split >= kb_lim) continue;
-      const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM;
+      const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM + q * 32;   // first row of this WARP's 32-row box
       const int n0 = n_blk * tile_n + pn_off;   // the pair's full block_n columns (each CTA stores its 128 rows x block_n)
       const bool use_bias = (p.bias != nullptr) && (split == 0);
       if (use_bias) {
+        named_bar_sync(1, kEpiThreads);  // the warps run independently: nobody may still be reading the previous bias tile
         for (int i = epi_tid; i < p.block_n; i += kEpiThreads) sBias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
+      }
+      if (p.colsum) {
+        for (int i = epi_tid; i < 256; i += kEpiThreads) sCol[i] = 0.f;
+      }
+      int n_chunks = (p.N > n0) ? min(p.block_n, p.N - n0 + 31) / 32 : 0;  // skip chunks (or whole tiles) past N
+      if (p.mul_act && n_chunks > 0 && lane == 0) {  // prefetch the first epilogue-input box of this tile
+        uint64_t* mb = &my_mul_bar[mul_idx & 1];
+        mbar_arrive_expect_tx(mb, kWarpStagingBytes);
+        tma_load_2d(wst + (2 + (mul_idx & 1)) * kWarpStagingBytes, &p.tmMul, mb, n0, m0);
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase, 4);
       tc_fence_after();
-      if (p.mul_act) {
-        for (int i = epi_tid; i < 256; i += kEpiThreads) sCol[i] = 0.f;
-      }
-      named_bar_sync(1, kEpiThreads);  // bias tile visible
+      if (use_bias || p.colsum) named_bar_sync(1, kEpiThreads);  // bias tile / zeroed column sums visible to all 4 warps
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols);
-      int n_chunks = (p.N > n0) ? min(p.block_n, p.N - n0 + 31) / 32 : 0;  // skip chunks (or whole tiles) past N
       if ((p.dbg & 8u) || n_chunks == 0) {  // nothing to store: release the accumulator right away
         tc_fence_before();
         if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], pair_leader); else mbar_arrive(&tmem_empty_bar[acc]);
         n_chunks = 0;
       }
-      if (p.mul_act && n_chunks > 0 && epi_tid == 0) {  // prefetch the first epilogue-input chunk of this tile
-        uint64_t* mb = &mul_bar[mul_idx & 1];
-        mbar_arrive_expect_tx(mb, kStagingBytes);
-        tma_load_2d(sStage + (2 + (mul_idx & 1)) * kStagingBytes, &p.tmMul, mb, n0, m0);
-      }
       for (int c = 0; c < n_chunks; ++c) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
-        if (p.mul_act && c + 1 < n_chunks && epi_tid == 0) {  // next chunk's input: its buffer was last read one chunk ago
-          uint64_t* mb = &mul_bar[(mul_idx + 1) & 1];
-          mbar_arrive_expect_tx(mb, kStagingBytes);
-          tma_load_2d(sStage + (2 + ((mul_idx + 1) & 1)) * kStagingBytes, &p.tmMul, mb, n0 + (c + 1) * 32, m0);
+        if (p.mul_act && c + 1 < n_chunks && lane == 0) {  // next chunk's input box: its buffer was last read one chunk ago
+          uint64_t* mb = &my_mul_bar[(mul_idx + 1) & 1];
+          mbar_arrive_expect_tx(mb, kWarpStagingBytes);
+          tma_load_2d(wst + (2 + ((mul_idx + 1) & 1)) * kWarpStagingBytes, &p.tmMul, mb, n0 + (c + 1) * 32, m0);
         }
         tmem_ld_wait();
         if (c == n_chunks - 1) {
@@ -419,13 +425,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += sBias[c * 32 + j];
         }
-        if (p.mul_act) {  // v *= act'(input chunk), read back from the 128B-swizzled TMA layout
-          mbar_wait(&mul_bar[mul_idx & 1], (mul_idx >> 1) & 1, 5);
-          const float4* u4 = reinterpret_cast<const float4*>(sStage + (2 + (mul_idx & 1)) * kStagingBytes + row * 128);
+        if (p.mul_act) {  // v *= act'(input box), read back from the 128B-swizzled TMA layout (row = lane)
+          mbar_wait(&my_mul_bar[mul_idx & 1], (mul_idx >> 1) & 1, 5);
+          const float4* u4 = reinterpret_cast<const float4*>(wst + (2 + (mul_idx & 1)) * kWarpStagingBytes + lane * 128);
           ++mul_idx;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 u = u4[j ^ (row & 7)];
+            const float4 u = u4[j ^ (lane & 7)];
             if (p.mul_act == 1) {
               v[4 * j] *= gelu_grad_fast(u.x); v[4 * j + 1] *= gelu_grad_fast(u.y);
               v[4 * j + 2] *= gelu_grad_fast(u.z); v[4 * j + 3] *= gelu_grad_fast(u.w);
@@ -438,37 +444,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
             }
           }
         }
-        // staging buffer(s): without aux double-buffer on the running index; with aux buffer 0 = activated, 1 = pre-activation
         const uint32_t pp = store_idx++ & 1;
-        uint8_t* buf0 = sStage + pp * kStagingBytes;
-        uint8_t* buf1 = sStage + (2 + pp) * kStagingBytes;
-        if (epi_tid == 0) tma_store_wait_read<1>();  // the group committed two chunks ago has finished reading its buffers
-        named_bar_sync(1, kEpiThreads);
+        uint8_t* buf0 = wst + pp * kWarpStagingBytes;          // C box
+        uint8_t* buf1 = wst + (2 + pp) * kWarpStagingBytes;    // aux (pre-activation) box
+        if (lane == 0) tma_store_wait_read<1>();  // the group this lane committed two chunks ago has released buf[pp]
+        __syncwarp();
         if (p.has_aux) {
-          float4* d1 = reinterpret_cast<float4*>(buf1 + row * 128);
+          float4* d1 = reinterpret_cast<float4*>(buf1 + lane * 128);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) d1[j ^ (row & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 8; ++j) d1[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         if (p.act != 0) apply_act32(v, p.act, p.nseg > 1);
         {
-          float4* d0 = reinterpret_cast<float4*>(buf0 + row * 128);
+          float4* d0 = reinterpret_cast<float4*>(buf0 + lane * 128);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) d0[j ^ (row & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 8; ++j) d0[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, kEpiThreads);
-        if (p.colsum) {  // bias gradient: lane = column of this chunk, each warp sums its 32 rows out of the staged tile
+        __syncwarp();
+        if (p.colsum) {  // bias gradient: lane = column of this chunk, summed over this warp's 32 staged rows
           float cs = 0.f;
-          const int rbase = q * 32;
 #pragma unroll 8
           for (int rr = 0; rr < 32; ++rr) {
-            const int r2 = rbase + rr;
-            if (m0 + r2 < p.M)
-              cs += *reinterpret_cast<const float*>(buf0 + r2 * 128 + (((lane >> 2) ^ (r2 & 7)) << 4) + ((lane & 3) << 2));
+            if (m0 + rr < p.M)
+              cs += *reinterpret_cast<const float*>(buf0 + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
           }
           atomicAdd(&sCol[c * 32 + lane], cs);
         }
-        if (epi_tid == 0 && !(p.dbg & 4u)) {
+        if (lane == 0 && !(p.dbg & 4u)) {
           if (p.accumulate) tma_reduce_add_2d(&p.tmC, buf0, n0 + c * 32, m0);
           else tma_store_2d(&p.tmC, buf0, n0 + c * 32, m0);
           if (p.has_aux) tma_store_2d(&p.tmAux, buf1, n0 + c * 32, m0);
@@ -479,10 +482,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         named_bar_sync(1, kEpiThreads);
         for (int i = epi_tid; i < n_chunks * 32; i += kEpiThreads)
           if (n0 + i < p.N) atomicAdd(p.colsum + n0 + i, sCol[i]);
+        named_bar_sync(1, kEpiThreads);  // sCol is re-zeroed by other threads at the next tile
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (epi_tid == 0) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -792,7 +796,7 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
 
   const int bn_local = (mode == 0) ? bn : bn / 2;
   const int b_bytes = bn_local * kBlockK * 4;
-  const int fixed = ((aux || t_mul_act) ? 4 : 2) * kStagingBytes + 256 * 4 + (2 * kMaxStages + 6) * 8 + 16 + 1008 /* alignment slack */;
+  const int fixed = ((aux || t_mul_act) ? 4 : 2) * kStagingBytes + 256 * 4 + (2 * kMaxStages + 12) * 8 + 16 + 960 /* alignment slack */;
   int stages = (kSmemLimit - fixed) / (kABytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
@@ -832,14 +836,14 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
     }
     if (rc) return rc;
   }
-  rc = make_map(&p.tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = make_map(&p.tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);  // per-warp {32 x 32} boxes
   if (rc) return rc;
   if (aux) {
-    rc = make_map(&p.tmAux, aux, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_map(&p.tmAux, aux, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   if (t_mul_act) {
-    rc = make_map(&p.tmMul, t_mul_in, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_map(&p.tmMul, t_mul_in, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
 
