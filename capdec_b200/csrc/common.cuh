@@ -71,6 +71,11 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                : "memory");
 }
 
+// 128-bit vector reduction into global memory (split-K / tied-embedding accumulation)
+__device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // gelu_new (HF activations.py:59-66): 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
 __device__ __forceinline__ float gelu_new_fwd(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;

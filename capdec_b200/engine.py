@@ -83,6 +83,20 @@ class Engine:
     def grad_views(self):
         return self.g
 
+    def layer_grad_slices(self):
+        """Flat-gradient slices in the order backward completes them: block L-1 (+ ln_f) ... block 0, then the rest
+        ([tail | mapper | wte | wpe], final only after the embedding scatter).  Used to overlap the data-parallel
+        all-reduce with the backward pass."""
+        fl = self.flat
+        lo = lambda n: fl.layout[n][0]
+        slices = []
+        for l in range(self.nl):
+            start = lo(f"gpt.transformer.h.{l}.ln_1.weight")
+            end = lo(f"gpt.transformer.h.{l + 1}.ln_1.weight") if l + 1 < self.nl else fl.grads.numel()
+            slices.append(fl.grads[start:end])
+        head = fl.grads[: lo("gpt.transformer.h.0.ln_1.weight")]
+        return slices, head
+
     def zero_grads(self, mapper_only: bool = False):
         fl = self.flat
         end = fl.tail + fl.n_mapper if mapper_only else fl.grads.numel()
@@ -307,7 +321,7 @@ class Engine:
                                p["gpt.transformer.ln_f.bias"], eps=self.cfg.layer_norm_epsilon, p_drop=p_res,
                                seed=self.seed, stream_id=_site(l, 2))
 
-    def _trunk_bwd(self, a, dxf, train_gpt: bool, key_len=None):
+    def _trunk_bwd(self, a, dxf, train_gpt: bool, key_len=None, on_layer_done=None):
         """dxf = dL/d(ln_f output) [M, d] -> a.dh = dL/d(h[0]); GPT-2 parameter gradients accumulated if train_gpt."""
         p, g = self.p, self.g
         B, T, M, d, F = a.B, a.T, a.M, self.d, self.F
@@ -354,6 +368,8 @@ class Engine:
             else:
                 ops.add_ln_bwd(a.dx, a.h[0], a.st1[0], p[pre + "ln_1.weight"], a.dh, a.dh, None, gw(pre + "ln_1.weight"),
                                gw(pre + "ln_1.bias"))
+            if on_layer_done is not None and train_gpt:
+                on_layer_done(l)   # every gradient of GPT-2 block l (and ln_f when l is the last block) is final now
 
     # ------------------------------------------------------------------------------------------------------------
     # fast path: loss + gradients (sum-reduced CE gradients, divided by the token count inside AdamW)
@@ -371,16 +387,17 @@ class Engine:
         self._trunk_fwd(a, key_len)
         return a
 
-    def backward_hidden(self, a, dxf, train_gpt: bool, key_len=None):
+    def backward_hidden(self, a, dxf, train_gpt: bool, key_len=None, on_layer_done=None):
         """Everything below ln_f: trunk, embedding scatter, mapper."""
         g = self.g
-        self._trunk_bwd(a, dxf, train_gpt, key_len)
+        self._trunk_bwd(a, dxf, train_gpt, key_len, on_layer_done)
         ops.embed_bwd(a.tokens, a.dh, a.dpp, g["gpt.transformer.wte.weight"] if train_gpt else None,
                       g["gpt.transformer.wpe.weight"] if train_gpt else None, a.B, self.P, a.L, self.V,
                       p_drop=a.pdrop[0], seed=self.seed, stream_id=_SITE_EMBD)
         self._mapper_bwd(a.prefix, a.dpp)
 
-    def loss_and_grads(self, tokens, prefix, train_gpt: Optional[bool] = None, mean_reduce: bool = False):
+    def loss_and_grads(self, tokens, prefix, train_gpt: Optional[bool] = None, mean_reduce: bool = False,
+                       on_layer_done=None):
         """One forward+backward of train.py:348-351.  Gradients are ACCUMULATED into the flat gradient buffer,
         sum-reduced over tokens unless `mean_reduce` (then divided by the local count of non-ignored targets).
         tail[0] <- number of non-ignored targets, tail[1] <- sum of token losses.  Returns the tail view."""
@@ -419,7 +436,7 @@ class Engine:
             ops.linear_dgrad(logits, wte, "linear", a.dxsel)
             ops.rows_scatter(a.dxsel, a.dx, B, T, L, P - 1)
         # a.dx is reused as scratch inside the trunk; ln_f backward consumes it first
-        self.backward_hidden(a, a.dx, train_gpt)
+        self.backward_hidden(a, a.dx, train_gpt, on_layer_done=on_layer_done)
         return tail
 
     # ------------------------------------------------------------------------------------------------------------

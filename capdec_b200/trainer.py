@@ -10,6 +10,7 @@ count of non-ignored targets inside the AdamW kernel, so N ranks reproduce the s
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -54,6 +55,12 @@ class Trainer:
             self.world = torch.distributed.get_world_size(process_group)
             # per-rank RNG stream for noise + dropout: same weights, different masks
             self.eng.seed.add_(7919 * (1 + torch.distributed.get_rank(process_group)))
+        # data-parallel all-reduce overlapped with backward: one bucket per GPT-2 block, reduced on a side stream as
+        # soon as the block's gradients are final; only [tail | mapper | wte | wpe] (ready last) stays exposed
+        self.overlap = (self.world > 1 and self.train_gpt and os.environ.get("CAPDEC_DP_OVERLAP", "1") != "0")
+        if self.overlap:
+            self.comm = torch.cuda.Stream(device=self.dev)
+            self.buckets, self.head_bucket = self.eng.layer_grad_slices()
         self.use_graph = use_cuda_graph
         self._g_fb = self._g_opt = None
         self._warm = 0
@@ -69,7 +76,18 @@ class Trainer:
             pfx = self.prefix_n
         else:
             pfx = self.prefix_d                                 # train.py:28-29: variance 0 -> untouched
-        eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False)
+        eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False,
+                           on_layer_done=self._reduce_layer if self.overlap else None)
+        if self.overlap:
+            torch.distributed.all_reduce(self.head_bucket, group=self.pg)       # ready last: not overlappable
+            torch.cuda.current_stream().wait_stream(self.comm)
+
+    def _reduce_layer(self, l: int):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.comm.wait_event(ev)
+        with torch.cuda.stream(self.comm):
+            torch.distributed.all_reduce(self.buckets[l], group=self.pg)
 
     def _opt(self):
         self.stats.copy_(self.tail)
@@ -90,13 +108,13 @@ class Trainer:
                 self._g_fb = self._capture(self._fwd_bwd)
                 self._g_opt = self._capture(self._opt)
             self._g_fb.replay()
-            if self.world > 1:
+            if self.world > 1 and not self.overlap:
                 torch.distributed.all_reduce(self.reduce_buf, group=self.pg)
             self._g_opt.replay()
         else:
             self._warm += 1
             self._fwd_bwd()
-            if self.world > 1:
+            if self.world > 1 and not self.overlap:
                 torch.distributed.all_reduce(self.reduce_buf, group=self.pg)
             self._opt()
         return self.stats
