@@ -71,7 +71,7 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                : "memory");
 }
 
-// 128-bit vector reduction into global memory (split-K / tied-embedding accumulation)
+// 128-bit vector reduction into global memory
 __device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }

@@ -174,14 +174,10 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ tokens, const float
     } else if (d_wte) {
       int64_t tok = tokens[(size_t)b * L + (t - P)];
       tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
-      float* dst = d_wte + (size_t)tok * d + 4 * c;
-      atomicAdd(dst + 0, g.x); atomicAdd(dst + 1, g.y); atomicAdd(dst + 2, g.z); atomicAdd(dst + 3, g.w);
+      red_add_v4(d_wte + (size_t)tok * d + 4 * c, g);   // one 128-bit reduction per thread instead of four scalar atomics
     }
   }
-  if (d_wpe) {
-    float* dst = d_wpe + (size_t)t * d + 4 * c;
-    atomicAdd(dst + 0, acc.x); atomicAdd(dst + 1, acc.y); atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w);
-  }
+  if (d_wpe) red_add_v4(d_wpe + (size_t)t * d + 4 * c, acc);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -77,9 +77,6 @@ struct __align__(64) GemmDev {
   CUtensorMap tmAux;
   CUtensorMap tmMul;   // optional epilogue INPUT (same shape as C): C = acc * act'(mul)
   const float* bias;
-  float* C;            // output (and optional aux) written by the epilogue with vector stores / red.add
-  float* aux;
-  int64_t ldc;
   int M, N, K;
   int block_n, stages;
   int m_tiles, n_tiles, splits, kb_per_split, kb_total;
@@ -447,14 +444,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
             }
           }
         }
-        // Stage the 32x32 box through shared memory to turn "one row per lane" into full 128-byte lines, then write it
-        // with plain vector stores (8 lanes per row, 4 rows per instruction).  Fire-and-forget st.global / red.global
-        // instead of TMA stores: a TMA store holds its smem source for ~1 us, which capped the epilogue at two boxes
-        // in flight per warp (~1.5 k clk per chunk, profiles/r1_gemm_pipeline_experiments.md).
         const uint32_t pp = store_idx++ & 1;
         uint8_t* buf0 = wst + pp * kWarpStagingBytes;          // C box
         uint8_t* buf1 = wst + (2 + pp) * kWarpStagingBytes;    // aux (pre-activation) box
-        __syncwarp();                                           // the box two chunks ago has been read back by all lanes
+        if (lane == 0) tma_store_wait_read<1>();  // the group this lane committed two chunks ago has released buf[pp]
+        __syncwarp();
         if (p.has_aux) {
           float4* d1 = reinterpret_cast<float4*>(buf1 + lane * 128);
 #pragma unroll
@@ -466,6 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 8; ++j) d0[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+        fence_proxy_async_smem();
         __syncwarp();
         if (p.colsum) {  // bias gradient: lane = column of this chunk, summed over this warp's 32 staged rows
           float cs = 0.f;
@@ -476,31 +471,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
           }
           atomicAdd(&sCol[c * 32 + lane], cs);
         }
-        if (!(p.dbg & 4u)) {
-          const int cg = lane & 7;                     // 16-byte column group inside the 128-byte row
-          const int col = n0 + c * 32 + cg * 4;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + (lane >> 3);
-            const int grow = m0 + rr;
-            if (grow < p.M && col < p.N) {
-              const float4 val = *reinterpret_cast<const float4*>(buf0 + rr * 128 + ((cg ^ (rr & 7)) << 4));
-              float* dst = p.C + (size_t)grow * p.ldc + col;
-              if (col + 3 < p.N) {
-                if (p.accumulate) red_add_v4(dst, val); else *reinterpret_cast<float4*>(dst) = val;
-                if (p.has_aux) {
-                  const float4 av = *reinterpret_cast<const float4*>(buf1 + rr * 128 + ((cg ^ (rr & 7)) << 4));
-                  *reinterpret_cast<float4*>(p.aux + (size_t)grow * p.ldc + col) = av;
-                }
-              } else {  // ragged last column group (N % 4 != 0, e.g. V = 50257)
-                const float* vs = reinterpret_cast<const float*>(&val);
-                for (int e = 0; e < p.N - col; ++e) {
-                  if (p.accumulate) atomicAdd(dst + e, vs[e]); else dst[e] = vs[e];
-                  if (p.has_aux) p.aux[(size_t)grow * p.ldc + col + e] = *reinterpret_cast<const float*>(buf1 + rr * 128 + ((cg ^ (rr & 7)) << 4) + 4 * e);
-                }
-              }
-            }
-          }
+        if (lane == 0 && !(p.dbg & 4u)) {
+          if (p.accumulate) tma_reduce_add_2d(&p.tmC, buf0, n0 + c * 32, m0);
+          else tma_store_2d(&p.tmC, buf0, n0 + c * 32, m0);
+          if (p.has_aux) tma_store_2d(&p.tmAux, buf1, n0 + c * 32, m0);
+          tma_store_commit();
         }
       }
       if (p.colsum && n_chunks > 0) {
@@ -511,6 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -811,9 +787,6 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
   p.a_mn = a_major ? 1 : 0;
   p.b_mn = b_major ? 1 : 0;
   p.bias = bias;
-  p.C = C;
-  p.aux = aux;
-  p.ldc = ldc;
   p.m_limit = m_limit_dev;
   p.mul_act = t_mul_act;
   p.colsum = t_colsum;

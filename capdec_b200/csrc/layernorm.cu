@@ -101,8 +101,15 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
   const int row0 = blockIdx.x * rows_per_cta, row1 = min(rows, row0 + rows_per_cta);
   int parity = 0;
   for (int rb = row0; rb < row1; rb += kR, parity ^= 1) {
-    float4 g[kR], xh[kR];
+    float4 g[kR], xh[kR], res[kR];
     float part[2 * kR];
+    // issue every global load of the batch up front (dx, r AND the residual gradient): 12 independent 16-byte loads per thread
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+      const int row = rb + i;
+      res[i] = (dh_res && row < row1) ? ld_stream(reinterpret_cast<const float4*>(dh_res) + (size_t)row * d4 + c)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int i = 0; i < kR; ++i) {
       const int row = rb + i;
@@ -146,10 +153,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
       o.y = rstd * (g[i].y - c1 - xh[i].y * c2);
       o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
       o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
-      if (dh_res) {
-        const float4 rr = ld_stream(reinterpret_cast<const float4*>(dh_res) + (size_t)row * d4 + c);
-        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-      }
+      o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w;
       reinterpret_cast<float4*>(dh_out)[(size_t)row * d4 + c] = o;
       if (dy || dbias_branch) {
         if (p_drop > 0.0f) {
