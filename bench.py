@@ -193,7 +193,12 @@ def run_gpu(args):
     from capdec_b200 import _lib
     cb.ops.set_precision("tf32")
     torch.manual_seed(0)
-    model = cb.ClipCaptionModel(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP)   # HF-style random init
+    if args.workload == "c1":      # --only_prefix: GPT-2 frozen and in eval mode (train.py:276-284)
+        model = cb.ClipCaptionPrefix(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP)
+    elif args.workload == "c3":    # --mapping_type transformer, prefix_length = prefix_length_clip = 40, 8 layers
+        model = cb.ClipCaptionModel(P_LEN, clip_length=40, prefix_size=D_CLIP, num_layers=8, mapping_type=cb.MappingType.Transformer)
+    else:
+        model = cb.ClipCaptionModel(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP)   # HF-style random init
     model = model.to("cuda").train()                                                           # dropout p=0.1 live
     B = BS_PER_GPU
     tr = cb.Trainer(model, batch_size=B, seq_len=SEQ, lr=2e-5, warmup_steps=5000, total_steps=100000,
@@ -251,14 +256,17 @@ def run_gpu(args):
         e2e = captions / (ms_e2e * 1e-3)
         tf32_peak = pk["bf16"] / 2.0
         qkv_tf, qkv_ms = qkv_gemm_roofline(cb, torch)
-        step_tf = flops_per_caption() * B / (ms_dev / args.steps * 1e-3) / 1e12
-        cpu_rate, cores, cpu_s = cpu_train_step_rate(16, 2, 1) if world == 1 else (None, None, None)
+        step_tf = flops_per_caption(P=P_LEN) * B / (ms_dev / args.steps * 1e-3) / 1e12
+        cpu_rate, cores, cpu_s = cpu_train_step_rate(16, 2, 1) if (world == 1 and args.workload == "c2") else (None, None, None)
         line = {
             "metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": "C2: MLP mapper P=10 + GPT-2-small fine-tuned end-to-end, bs=256/GPU, seq_len=40, "
-                                   "noise_variance=0.016, dropout 0.1 live, HF-AdamW + warm-up schedule in the step",
+            "config": {"workload": {"c1": "C1: MLP mapper P=10, GPT-2 frozen (--only_prefix), bs=32, seq_len=40, noise_variance=0.016",
+                                    "c2": "C2: MLP mapper P=10 + GPT-2-small fine-tuned end-to-end, bs=256/GPU, seq_len=40, "
+                                          "noise_variance=0.016, dropout 0.1 live, HF-AdamW + warm-up schedule in the step",
+                                    "c3": "C3: TransformerMapper (8 layers, P=C=40) + GPT-2-small fine-tuned, bs=256/GPU, seq_len=40, dropout 0.1 live",
+                                    "c4": "C4: MLP mapper P=10 + GPT-2-small fine-tuned, bs=512/GPU, seq_len=40, dropout 0.1 live"}[args.workload],
                        "global_batch": B * world, "seq_len": SEQ, "parallelism": f"dp{world}",
                        "l2": "working set per step (0.62 GB weights + 7.5 GB activations) >> 126 MB L2; 8 distinct host batches",
                        "arithmetic": "fp32 storage, TF32 tcgen05 GEMMs with fp32 TMEM accumulation, fp32 everywhere else"},
@@ -289,7 +297,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="capdec_b200", choices=["capdec_b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"],
+                    help="BASELINE.json config: c2 (default, the headline metric), c1 = --only_prefix bs=32, "
+                         "c3 = TransformerMapper P=40 bs=256, c4 = MLP bs=512/GPU")
     args = ap.parse_args()
+    global P_LEN, BS_PER_GPU
+    if args.workload == "c1":
+        BS_PER_GPU = 32
+    elif args.workload == "c3":
+        P_LEN = 40
+    elif args.workload == "c4":
+        BS_PER_GPU = 512
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) rows_scatter_idx_kernel(const float4* __r
   }
 }
 
-constexpr int kCeThreads = 512;
+constexpr int kCeThreads = 1024;  // 2 CTAs/SM: 296 rows x 201 KB = 60 MB in flight, so pass 2 re-reads its row from L2 (512 threads thrashed the 126 MB L2)
 
 __device__ __forceinline__ void online_update(float& m, float& s, float x) {
   if (x > m) { s = s * __expf(m - x) + 1.0f; m = x; } else { s += __expf(x - m); }

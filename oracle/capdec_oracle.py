@@ -262,6 +262,53 @@ def loss_and_grads(sd: Params, tokens, prefix, mask, prefix_length, clip_length=
 
 
 # --------------------------------------------------------------------------------------------------------------
+# decoding: beam search exactly as gpt2_prefix_eval.py:50-115, full re-forward per step like the reference
+# --------------------------------------------------------------------------------------------------------------
+def generate_beam(sd: Params, embed, beam_size: int = 5, entry_length: int = 67, temperature: float = 1.0,
+                  stop_token_index: int = 13):
+    """Returns (token id lists ordered by final score, scores / seq_lengths in that order, seq_lengths in that order).
+    The reference decodes the ids with the GPT-2 tokenizer (gpt2_prefix_eval.py:111-112); ids are the comparable part."""
+    wte = sd["gpt.transformer.wte.weight"]
+    tokens = None
+    scores = None
+    seq_lengths = torch.ones(beam_size)
+    is_stopped = torch.zeros(beam_size, dtype=torch.bool)
+    generated = embed  # [1, P, d]
+    for _ in range(entry_length):
+        logits = gpt2_forward(sd, generated)                                         # :75-76
+        logits = logits[:, -1, :] / (temperature if temperature > 0 else 1.0)         # :77
+        logits = logits.softmax(-1).log()                                            # :78-79
+        if scores is None:
+            scores, next_tokens = logits.topk(beam_size, -1)                         # :81
+            generated = generated.expand(beam_size, *generated.shape[1:])
+            next_tokens, scores = next_tokens.permute(1, 0), scores.squeeze(0)
+            tokens = next_tokens
+        else:
+            logits[is_stopped] = -float("inf")                                       # :90
+            logits[is_stopped, 0] = 0                                                # :91
+            scores_sum = scores[:, None] + logits
+            seq_lengths[~is_stopped] += 1
+            scores_sum_average = scores_sum / seq_lengths[:, None]
+            scores_sum_average, next_tokens = scores_sum_average.view(-1).topk(beam_size, -1)
+            next_tokens_source = next_tokens // scores_sum.shape[1]                  # :96
+            seq_lengths = seq_lengths[next_tokens_source]
+            next_tokens = (next_tokens % scores_sum.shape[1]).unsqueeze(1)
+            tokens = torch.cat((tokens[next_tokens_source], next_tokens), dim=1)
+            generated = generated[next_tokens_source]
+            scores = scores_sum_average * seq_lengths
+            is_stopped = is_stopped[next_tokens_source]
+        nxt = wte[next_tokens.squeeze()].view(generated.shape[0], 1, -1)             # :105
+        generated = torch.cat((generated, nxt), dim=1)
+        is_stopped = is_stopped + next_tokens.eq(stop_token_index).squeeze()
+        if is_stopped.all():
+            break
+    scores = scores / seq_lengths                                                     # :110
+    order = scores.argsort(descending=True)
+    out = [tokens[i, : int(seq_lengths[i])].tolist() for i in order]
+    return out, scores[order].tolist(), seq_lengths[order].tolist()
+
+
+# --------------------------------------------------------------------------------------------------------------
 # optimizer restatement
 # --------------------------------------------------------------------------------------------------------------
 def hf_adamw_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0):

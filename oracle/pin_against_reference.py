@@ -164,5 +164,47 @@ def main():
     print("noise ok")
 
 
+class _FakeTokenizer:
+    """No GPT-2 vocab files offline: ids are the comparable part. encode('.') -> [13] as for the real tokenizer."""
+
+    def encode(self, text):
+        return [13] if text == "." else [ord(ch) % 50257 for ch in text]
+
+    def decode(self, ids):
+        return " ".join(str(int(i)) for i in ids)
+
+
+def pin_generate_beam():
+    """gpt2_prefix_eval.generate_beam (the reference's own function) vs the oracle restatement -> tests/golden/beam.json"""
+    for name in ("clip", "pycocotools", "pycocotools.coco", "matplotlib", "matplotlib.pyplot", "skimage", "skimage.io"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["pycocotools.coco"].COCO = object
+    import transformers
+    sys.modules["transformers"].AdamW = O.HFAdamW
+    import gpt2_prefix_eval as ev  # noqa
+    import gpt2_prefix as gp  # noqa
+    P, D = 10, 640
+    sd = O.make_state_dict(seed=1, mapping_type="mlp", prefix_length=P, prefix_size=D, weight_std=0.08)  # sharper logits
+    torch.manual_seed(0)
+    model = gp.ClipCaptionModel(P, prefix_dim=D, mapping_type=gp.MappingType.MLP)
+    model.gpt.config._attn_implementation = "eager"
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    recs = []
+    for case in range(3):
+        _, prefix, _ = O.make_batch(seed=20 + case, B=1, prefix_size=D)
+        with torch.no_grad():
+            embed = model.clip_project(prefix).reshape(1, P, -1)
+            texts = ev.generate_beam(model, _FakeTokenizer(), embed=embed, entry_length=12, stop_token="." )
+        ref_ids = [[int(t) for t in txt.split()] for txt in texts]
+        ids, scores, lens = O.generate_beam(sd, O.mlp_mapper(sd, prefix).view(1, P, -1), entry_length=12, stop_token_index=13)
+        assert ids == ref_ids, (ids, ref_ids)
+        recs.append({"batch_seed": 20 + case, "ids": ref_ids, "scores": scores, "seq_lengths": lens})
+    (GOLD / "beam.json").write_text(json.dumps({"config": dict(P=P, D=D, sd_seed=1, weight_std=0.08, entry_length=12,
+                                                                 beam_size=5, stop_token_index=13), "cases": recs}, indent=1))
+    print("generate_beam ok", [r["ids"][0][:6] for r in recs])
+
+
 if __name__ == "__main__":
     main()
+    pin_generate_beam()
