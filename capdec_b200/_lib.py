@@ -54,6 +54,12 @@ SIGNATURES = {
     "capdec_rows_scatter": [_p, _p, _i, _i, _i, _i, _i, _p],
     "capdec_mapper_concat_fwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "capdec_mapper_concat_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "capdec_beam_init": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "capdec_kv_prefill": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "capdec_decode_embed": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "capdec_decode_attention": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
+    "capdec_row_topk": [_p, _i64, _i, _i, _f, _i, _p, _p, _p, _p],
+    "capdec_beam_select": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "capdec_step_clock": [_p, _p, _p, _p, _f, _i, _i, _p],
     "capdec_adamw_step": [_p, _p, _p, _p, _i64, _p, _p, _f, _f, _f, _f, _p, _i, _p],
 }

@@ -334,3 +334,47 @@ def adamw_step(p, g, m, v, lr_dev, t_dev, beta1=0.9, beta2=0.999, eps=1e-6, weig
                                        lr_dev.data_ptr(), t_dev.data_ptr(), beta1, beta2, eps, weight_decay,
                                        _ptr(grad_denom), int(zero_grad), _stream())
     _lib.check(rc, "adamw_step")
+
+
+# ---- KV-cached beam search (decode.cu) ---------------------------------------------------------------------------
+def beam_init(st, n_img, beam, P, Tmax):
+    rc = _lib.load().capdec_beam_init(st.step.data_ptr(), st.scores.data_ptr(), st.seq_len.data_ptr(),
+                                      st.stopped.data_ptr(), st.src.data_ptr(), st.img_done.data_ptr(),
+                                      st.ticket.data_ptr(), n_img, beam, P, Tmax, _stream())
+    _lib.check(rc, "beam_init")
+
+
+def kv_prefill(qkv, kcache, vcache, n_img, beam, P, Tmax, d):
+    _chk(qkv, "qkv")
+    rc = _lib.load().capdec_kv_prefill(qkv.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), n_img, beam, P, Tmax, d,
+                                       _stream())
+    _lib.check(rc, "kv_prefill")
+
+
+def decode_embed(st, wte, wpe, x, P):
+    rc = _lib.load().capdec_decode_embed(st.step.data_ptr(), st.hist_tok.data_ptr(), wte.data_ptr(), wpe.data_ptr(),
+                                         x.data_ptr(), x.shape[0], P, x.shape[1], _stream())
+    _lib.check(rc, "decode_embed")
+
+
+def decode_attention(qkv, kcache, vcache, st, ctx, H, hd, P, Tmax, scale):
+    rc = _lib.load().capdec_decode_attention(qkv.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), st.src.data_ptr(),
+                                             st.step.data_ptr(), ctx.data_ptr(), qkv.shape[0], H, hd, P, Tmax,
+                                             float(scale), _stream())
+    _lib.check(rc, "decode_attention")
+
+
+def row_topk(logits, V, temperature, k, cand_val, cand_idx, row_lse):
+    ld = _rowmajor(logits, "logits")
+    rc = _lib.load().capdec_row_topk(logits.data_ptr(), ld, logits.shape[0], V, float(temperature), k,
+                                     cand_val.data_ptr(), cand_idx.data_ptr(), row_lse.data_ptr(), _stream())
+    _lib.check(rc, "row_topk")
+
+
+def beam_select(st, n_img, beam, P, Tmax, V, stop_token):
+    rc = _lib.load().capdec_beam_select(st.cand_val.data_ptr(), st.cand_idx.data_ptr(), st.row_lse.data_ptr(),
+                                        st.step.data_ptr(), st.scores.data_ptr(), st.seq_len.data_ptr(),
+                                        st.stopped.data_ptr(), st.src.data_ptr(), st.hist_tok.data_ptr(),
+                                        st.hist_parent.data_ptr(), st.img_done.data_ptr(), st.ticket.data_ptr(), n_img,
+                                        beam, P, Tmax, V, int(stop_token), _stream())
+    _lib.check(rc, "beam_select")

@@ -57,7 +57,7 @@ class Trainer:
             self.eng.seed.add_(7919 * (1 + torch.distributed.get_rank(process_group)))
         # data-parallel all-reduce overlapped with backward: one bucket per GPT-2 block, reduced on a side stream as
         # soon as the block's gradients are final; only [tail | mapper | wte | wpe] (ready last) stays exposed
-        self.overlap = (self.world > 1 and self.train_gpt and os.environ.get("CAPDEC_DP_OVERLAP", "1") != "0")
+        self.overlap = (self.world > 1 and self.train_gpt and os.environ.get("CAPDEC_DP_OVERLAP", "0") == "1")
         if self.overlap:
             self.comm = torch.cuda.Stream(device=self.dev)
             self.buckets, self.head_bucket = self.eng.layer_grad_slices()

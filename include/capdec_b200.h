@@ -173,6 +173,32 @@ int capdec_rows_gather_idx(const float* src, float* dst, const int32_t* row_src,
 /* dst[row] = dst_of[row] >= 0 ? src[dst_of[row]] : 0 for every one of `rows` rows */
 int capdec_rows_scatter_idx(const float* src, float* dst, const int32_t* dst_of, int rows, int d, capdec_stream_t stream);
 
+/* ---- KV-cached batched beam search (replaces gpt2_prefix_eval.py:50-115 generate_beam) -----------------
+ * R = n_img*beam physical rows; caches are per layer [R][Tmax][d]; `src` is the int32 [2][R][Tmax] lineage table
+ * (position t of logical beam b lives in physical row src[c&1][b][t]); `step` is the device-resident count c of
+ * selections done, which every kernel below reads so that one decode step is a replayable CUDA graph.
+ * beam_init: c=0, scores=0, seq_len=1 (:59), stopped=0 (:60), prefix lineage -> row img*beam. */
+int capdec_beam_init(int32_t* step, float* scores, float* seq_len, int32_t* stopped, int32_t* src, int32_t* img_done,
+                     int32_t* ticket, int n_img, int beam, int P, int Tmax, capdec_stream_t stream);
+/* K/V thirds of the prefill's fused QKV rows [n_img*P, 3d] -> cache rows img*beam, positions 0..P-1 */
+int capdec_kv_prefill(const float* qkv, float* kcache, float* vcache, int n_img, int beam, int P, int Tmax, int d,
+                      capdec_stream_t stream);
+/* x[b,:] = wte[hist_tok[c-1][b]] + wpe[P+c-1]   (:105 `model.gpt.transformer.wte(next_tokens)` + HF position embedding) */
+int capdec_decode_embed(const int32_t* step, const int32_t* hist_tok, const float* wte, const float* wpe, float* x, int rows,
+                        int P, int d, capdec_stream_t stream);
+/* one query per row over its lineage in the cache; appends this token's K/V at (row, P+c-1).  head_dim 64. */
+int capdec_decode_attention(const float* qkv, float* kcache, float* vcache, const int32_t* src, const int32_t* step,
+                            float* ctx, int rows, int H, int head_dim, int P, int Tmax, float scale, capdec_stream_t stream);
+/* per logits row: lse of logits/temperature (:77-79) and its k largest entries (value, index), 8 slots per row */
+int capdec_row_topk(const float* logits, int64_t ld, int rows, int V, float temperature, int k, float* cand_val,
+                    int32_t* cand_idx, float* row_lse, capdec_stream_t stream);
+/* per image: top-`beam` of (scores + logp)/seq_len over beam*V (:80-100), stop bookkeeping (:106), lineage update,
+ * history (hist_tok/hist_parent [max_sel][R]), img_done[img] = all beams stopped (:107), then c += 1. */
+int capdec_beam_select(const float* cand_val, const int32_t* cand_idx, const float* row_lse, int32_t* step, float* scores,
+                       float* seq_len, int32_t* stopped, int32_t* src, int32_t* hist_tok, int32_t* hist_parent,
+                       int32_t* img_done, int32_t* ticket, int n_img, int beam, int P, int Tmax, int V, int stop_token,
+                       capdec_stream_t stream);
+
 /* ---- small fused elementwise / reduction ops ----------------------------------------------------------------------
  * colsum: out[n] += sum_m x[m,n]  (bias gradients of every Linear/Conv1D; autograd of addmm bias) */
 int capdec_colsum_acc(const float* x, int64_t ld, float* out, int M, int N, capdec_stream_t stream);

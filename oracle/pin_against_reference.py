@@ -168,7 +168,9 @@ class _FakeTokenizer:
     """No GPT-2 vocab files offline: ids are the comparable part. encode('.') -> [13] as for the real tokenizer."""
 
     def encode(self, text):
-        return [13] if text == "." else [ord(ch) % 50257 for ch in text]
+        if text == ".":
+            return [13]
+        return [int(text)] if text.isdigit() else [ord(ch) % 50257 for ch in text]
 
     def decode(self, ids):
         return " ".join(str(int(i)) for i in ids)
@@ -191,17 +193,30 @@ def pin_generate_beam():
     model.load_state_dict(sd, strict=True)
     model.eval()
     recs = []
-    for case in range(3):
+
+    def run(case, stop, temperature):
         _, prefix, _ = O.make_batch(seed=20 + case, B=1, prefix_size=D)
         with torch.no_grad():
             embed = model.clip_project(prefix).reshape(1, P, -1)
-            texts = ev.generate_beam(model, _FakeTokenizer(), embed=embed, entry_length=12, stop_token="." )
+            texts = ev.generate_beam(model, _FakeTokenizer(), embed=embed, entry_length=12, temperature=temperature,
+                                     stop_token="." if stop == 13 else str(stop))
         ref_ids = [[int(t) for t in txt.split()] for txt in texts]
-        ids, scores, lens = O.generate_beam(sd, O.mlp_mapper(sd, prefix).view(1, P, -1), entry_length=12, stop_token_index=13)
+        ids, scores, lens = O.generate_beam(sd, O.mlp_mapper(sd, prefix).view(1, P, -1), entry_length=12,
+                                            temperature=temperature, stop_token_index=stop)
         assert ids == ref_ids, (ids, ref_ids)
-        recs.append({"batch_seed": 20 + case, "ids": ref_ids, "scores": scores, "seq_lengths": lens})
+        recs.append({"batch_seed": 20 + case, "stop_token_index": stop, "temperature": temperature, "ids": ref_ids,
+                     "scores": scores, "seq_lengths": lens})
+        return ref_ids
+
+    for case in range(3):
+        ids = run(case, 13, 1.0)
+        # early stops: make tokens that the beams actually emit the stop token (exercises :90-91, :106-108)
+        run(case, ids[-1][1], 0.7)
+        sharp = run(case, 13, 0.05)      # peaked distribution: the best beam's log-probs are ~0 ...
+        run(case, sharp[0][2], 0.05)     # ... so when its 3rd token is the stop token it stays in the beam, stopped
+        run(case, sharp[0][0], 0.05)
     (GOLD / "beam.json").write_text(json.dumps({"config": dict(P=P, D=D, sd_seed=1, weight_std=0.08, entry_length=12,
-                                                                 beam_size=5, stop_token_index=13), "cases": recs}, indent=1))
+                                                                 beam_size=5), "cases": recs}, indent=1))
     print("generate_beam ok", [r["ids"][0][:6] for r in recs])
 
 

@@ -87,3 +87,17 @@ def test_hf_adamw_and_schedule_restatement():
     w.grad = torch.ones(3)
     opt.step()
     assert torch.allclose(w.detach(), torch.full((3,), 1 - 0.01 * math.sqrt(0.001) / 0.1 * 0.1 / (math.sqrt(0.001) + 1e-6)), rtol=1e-5)
+
+
+def test_oracle_beam_search_reproduces_the_reference_ids():
+    """tests/golden/beam.json holds the ids the reference's own generate_beam produced (pin_generate_beam)."""
+    rec = json.loads((GOLD / "beam.json").read_text())
+    c = rec["config"]
+    sd = O.make_state_dict(seed=c["sd_seed"], mapping_type="mlp", prefix_length=c["P"], prefix_size=c["D"],
+                           weight_std=c["weight_std"])
+    for case in rec["cases"][3:5]:  # one sharp-temperature run and its early-stop variant (seconds each on CPU)
+        _, prefix, _ = O.make_batch(seed=case["batch_seed"], B=1, prefix_size=c["D"])
+        ids, scores, lens = O.generate_beam(sd, O.mlp_mapper(sd, prefix).view(1, c["P"], -1), c["beam_size"],
+                                            c["entry_length"], case["temperature"], case["stop_token_index"])
+        assert ids == case["ids"] and lens == case["seq_lengths"]
+        assert max(abs(a - b) for a, b in zip(scores, case["scores"])) < 1e-5
