@@ -25,7 +25,7 @@ SIGNATURES = {
     "capdec_launch_count": [],
     "capdec_gemm_tf32": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _i, _p],
     "capdec_gemm_tf32_ex": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _i, _p, _p, _p],
-    "capdec_gemm_tf32_mul": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p],
+    "capdec_gemm_tf32_mul": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p, _p],
     "capdec_gemm_debug_mn_encoding": [_i, _i, _i, _i],
     "capdec_gemm_debug_force_pair": [_i],
     "capdec_gemm_fp32_simt": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p],
@@ -33,19 +33,19 @@ SIGNATURES = {
     "capdec_noise_injection": [_p, _p, _i, _i, _f, _p, _p, _i, _i, _p, _u64, _p],
     "capdec_embed_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _u32, _p],
     "capdec_embed_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _u32, _p],
-    "capdec_add_ln_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _p, _u32, _p],
-    "capdec_add_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _u32, _p],
+    "capdec_add_ln_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _p, _u32, _p, _p],
+    "capdec_add_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _u32, _p, _p],
     "capdec_attention_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p,
                              _f, _p, _u32, _p],
     "capdec_attention_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
                              _i64, _f, _i, _p, _f, _p, _u32, _p],
     "capdec_attention_tc_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p,
-                                _f, _p, _u32, _p],
+                                _f, _p, _u32, _p, _p],
     "capdec_attention_tc_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
-                                _i64, _f, _i, _p, _f, _p, _u32, _p],
+                                _i64, _f, _i, _p, _f, _p, _u32, _p, _p],
     "capdec_ce_count": [_p, _i64, _i64, _p, _p, _p],
     "capdec_ce_fwd_bwd": [_p, _i64, _p, _i, _i, _i64, _p, _f, _p, _i, _p, _p],
-    "capdec_compact_targets": [_p, _i, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _p],
+    "capdec_compact_targets": [_p, _i, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p],
     "capdec_rows_gather_idx": [_p, _p, _p, _p, _i, _i, _p],
     "capdec_rows_scatter_idx": [_p, _p, _p, _i, _i, _p],
     "capdec_colsum_acc": [_p, _i64, _p, _i, _i, _p],
@@ -60,6 +60,10 @@ SIGNATURES = {
     "capdec_decode_attention": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
     "capdec_row_topk": [_p, _i64, _i, _i, _f, _i, _p, _p, _p, _p],
     "capdec_beam_select": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "capdec_pack_plan": [_p, _i, _i, _i, _p, _p, _p, _p],
+    "capdec_embed_fwd_packed": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _u32, _p],
+    "capdec_embed_bwd_packed": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _u32, _p],
+    "capdec_zero_tail_rows": [_p, _i64, _p, _p],
     "capdec_step_clock": [_p, _p, _p, _p, _f, _i, _i, _p],
     "capdec_adamw_step": [_p, _p, _p, _p, _i64, _p, _p, _f, _f, _f, _f, _p, _i, _p],
 }

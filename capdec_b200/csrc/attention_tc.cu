@@ -66,12 +66,23 @@ __device__ __forceinline__ void attn_drop4(uint64_t seed, uint32_t stream_id, ui
 template <int HD, int NT_MAX>
 __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                const float* __restrict__ v, float* __restrict__ ctx,
-                                                               float* __restrict__ lse, int H, int T, int S, int64_t q_bs,
+                                                               float* __restrict__ lse, int H, int T_arg, int S_arg, int64_t q_bs,
                                                                int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs,
                                                                int64_t o_ts, float scale, int causal,
                                                                const int32_t* __restrict__ key_len, float p_drop,
-                                                               const uint64_t* seed_dev, uint32_t stream_id) {
+                                                               const uint64_t* seed_dev, uint32_t stream_id, const int32_t* __restrict__ cu_rows) {
   const uint64_t seed = seed_dev ? *seed_dev : 0ull;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  // dense: sequence b owns rows [b*T, (b+1)*T).  packed (cu_rows != NULL): rows [cu_rows[b], cu_rows[b+1]) — only the
+  // live positions of each caption exist; T = S = that count.  lse / dropout keep the dense pitch TL.
+  int T = T_arg, S = S_arg;
+  const int TL = T_arg;
+  size_t q_b = (size_t)b * q_bs, kv_b = (size_t)b * kv_bs, o_b = (size_t)b * o_bs;
+  if (cu_rows) {
+    const int row_lo = cu_rows[b];
+    T = S = cu_rows[b + 1] - row_lo;
+    q_b = (size_t)row_lo * q_ts; kv_b = (size_t)row_lo * kv_ts; o_b = (size_t)row_lo * o_ts;
+  }
   extern __shared__ __align__(16) float smem[];
   const int Tp = (T + 15) & ~15, Sp = (S + 7) & ~7;
   constexpr int LQ = HD + 4, LV = HD + 8;
@@ -80,20 +91,19 @@ __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __re
   float* sK = sQ + (size_t)Tp * LQ;
   float* sV = sK + (size_t)Sp * LQ;
   float* sP = sV + (size_t)Sp * LV;  // [4 warps][16][LP]
-  const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr int hd4 = HD / 4;
   for (int i = threadIdx.x; i < Tp * hd4; i += 128) {
     const int r = i / hd4, c = i % hd4;
     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < T) val = *reinterpret_cast<const float4*>(q + (size_t)b * q_bs + (size_t)r * q_ts + (size_t)h * HD + 4 * c);
+    if (r < T) val = *reinterpret_cast<const float4*>(q + q_b + (size_t)r * q_ts + (size_t)h * HD + 4 * c);
     *reinterpret_cast<float4*>(sQ + (size_t)r * LQ + 4 * c) = val;
   }
   for (int i = threadIdx.x; i < Sp * hd4; i += 128) {
     const int r = i / hd4, c = i % hd4;
     float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
     if (r < S) {
-      const size_t gofs = (size_t)b * kv_bs + (size_t)r * kv_ts + (size_t)h * HD + 4 * c;
+      const size_t gofs = kv_b + (size_t)r * kv_ts + (size_t)h * HD + 4 * c;
       kv = *reinterpret_cast<const float4*>(k + gofs);
       vv = *reinterpret_cast<const float4*>(v + gofs);
     }
@@ -162,8 +172,8 @@ __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __re
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
     const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
     if (t == 0 && lse) {
-      if (r0 < T) lse[(size_t)bh * T + r0] = mx0 + __logf(sum0);
-      if (r1 < T) lse[(size_t)bh * T + r1] = mx1 + __logf(sum1);
+      if (r0 < T) lse[(size_t)bh * TL + r0] = mx0 + __logf(sum0);
+      if (r1 < T) lse[(size_t)bh * TL + r1] = mx1 + __logf(sum1);
     }
     __syncwarp();  // previous tile's P reads are done
 #pragma unroll
@@ -171,8 +181,8 @@ __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __re
       if (2 * np < nt) {
         float d0[4] = {1.f, 1.f, 1.f, 1.f}, d1[4] = {1.f, 1.f, 1.f, 1.f};
         if (p_drop > 0.f) {
-          attn_drop4(seed, stream_id, (uint64_t)bh * T + r0, np, t, p_drop, inv_keep, d0);
-          attn_drop4(seed, stream_id, (uint64_t)bh * T + r1, np, t, p_drop, inv_keep, d1);
+          attn_drop4(seed, stream_id, (uint64_t)bh * TL + r0, np, t, p_drop, inv_keep, d0);
+          attn_drop4(seed, stream_id, (uint64_t)bh * TL + r1, np, t, p_drop, inv_keep, d1);
         }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -205,8 +215,8 @@ __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __re
 #pragma unroll
     for (int n = 0; n < HD / 8; ++n) {
       const int c0 = n * 8 + 2 * t;
-      if (r0 < T) *reinterpret_cast<float2*>(ctx + (size_t)b * o_bs + (size_t)r0 * o_ts + (size_t)h * HD + c0) = make_float2(o[n][0], o[n][1]);
-      if (r1 < T) *reinterpret_cast<float2*>(ctx + (size_t)b * o_bs + (size_t)r1 * o_ts + (size_t)h * HD + c0) = make_float2(o[n][2], o[n][3]);
+      if (r0 < T) *reinterpret_cast<float2*>(ctx + o_b + (size_t)r0 * o_ts + (size_t)h * HD + c0) = make_float2(o[n][0], o[n][1]);
+      if (r1 < T) *reinterpret_cast<float2*>(ctx + o_b + (size_t)r1 * o_ts + (size_t)h * HD + c0) = make_float2(o[n][2], o[n][3]);
     }
   }
 }
@@ -215,10 +225,21 @@ template <int HD, int NT_MAX>
 __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ ctx,
     const float* __restrict__ dctx, const float* __restrict__ lse, float* __restrict__ dq, float* __restrict__ dk,
-    float* __restrict__ dv, float* __restrict__ dbias_qkv, int H, int T, int S, int64_t q_bs, int64_t q_ts, int64_t kv_bs,
+    float* __restrict__ dv, float* __restrict__ dbias_qkv, int H, int T_arg, int S_arg, int64_t q_bs, int64_t q_ts, int64_t kv_bs,
     int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale, int causal, const int32_t* __restrict__ key_len, float p_drop,
-    const uint64_t* seed_dev, uint32_t stream_id) {
+    const uint64_t* seed_dev, uint32_t stream_id, const int32_t* __restrict__ cu_rows) {
   const uint64_t seed = seed_dev ? *seed_dev : 0ull;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  // dense: sequence b owns rows [b*T, (b+1)*T).  packed (cu_rows != NULL): rows [cu_rows[b], cu_rows[b+1]) — only the
+  // live positions of each caption exist; T = S = that count.  lse / dropout keep the dense pitch TL.
+  int T = T_arg, S = S_arg;
+  const int TL = T_arg;
+  size_t q_b = (size_t)b * q_bs, kv_b = (size_t)b * kv_bs, o_b = (size_t)b * o_bs;
+  if (cu_rows) {
+    const int row_lo = cu_rows[b];
+    T = S = cu_rows[b + 1] - row_lo;
+    q_b = (size_t)row_lo * q_ts; kv_b = (size_t)row_lo * kv_ts; o_b = (size_t)row_lo * o_ts;
+  }
   extern __shared__ __align__(16) float smem[];
   const int Tp = (T + 15) & ~15, Sp = (S + 15) & ~15;
   constexpr int LQ = HD + 4;
@@ -230,7 +251,6 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
   float* sdS = sdO + (size_t)Tp * LQ;       // [Tp][LS]: P, then dS * scale
   float* sPd = sdS + (size_t)Tp * LS;       // [Tp][LS]: dropout(P)
   float* sDb = sPd + (size_t)Tp * LS;       // [3][HD] bias-gradient partial sums
-  const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr int hd4 = HD / 4;
   for (int i = threadIdx.x; i < 3 * HD; i += 128) sDb[i] = 0.f;
@@ -238,8 +258,8 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
     const int r = i / hd4, c = i % hd4;
     float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), dov = qv;
     if (r < T) {
-      qv = *reinterpret_cast<const float4*>(q + (size_t)b * q_bs + (size_t)r * q_ts + (size_t)h * HD + 4 * c);
-      dov = *reinterpret_cast<const float4*>(dctx + (size_t)b * o_bs + (size_t)r * o_ts + (size_t)h * HD + 4 * c);
+      qv = *reinterpret_cast<const float4*>(q + q_b + (size_t)r * q_ts + (size_t)h * HD + 4 * c);
+      dov = *reinterpret_cast<const float4*>(dctx + o_b + (size_t)r * o_ts + (size_t)h * HD + 4 * c);
     }
     *reinterpret_cast<float4*>(sQ + (size_t)r * LQ + 4 * c) = qv;
     *reinterpret_cast<float4*>(sdO + (size_t)r * LQ + 4 * c) = dov;
@@ -248,7 +268,7 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
     const int r = i / hd4, c = i % hd4;
     float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
     if (r < S) {
-      const size_t gofs = (size_t)b * kv_bs + (size_t)r * kv_ts + (size_t)h * HD + 4 * c;
+      const size_t gofs = kv_b + (size_t)r * kv_ts + (size_t)h * HD + 4 * c;
       kv = *reinterpret_cast<const float4*>(k + gofs);
       vv = *reinterpret_cast<const float4*>(v + gofs);
     }
@@ -270,8 +290,8 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
     // D_i = dO_i . O_i over the head dim: the 4 lanes of a row group split the columns
     float D0 = 0.f, D1 = 0.f;
     {
-      const float* o0 = ctx + (size_t)b * o_bs + (size_t)r0 * o_ts + (size_t)h * HD;
-      const float* o1 = ctx + (size_t)b * o_bs + (size_t)r1 * o_ts + (size_t)h * HD;
+      const float* o0 = ctx + o_b + (size_t)r0 * o_ts + (size_t)h * HD;
+      const float* o1 = ctx + o_b + (size_t)r1 * o_ts + (size_t)h * HD;
 #pragma unroll
       for (int c = 0; c < HD / 16; ++c) {
         const int col = (c * 4 + t) * 4;
@@ -289,7 +309,7 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
       D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
       D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
     }
-    const float l0 = (r0 < T) ? lse[(size_t)bh * T + r0] : 0.f, l1 = (r1 < T) ? lse[(size_t)bh * T + r1] : 0.f;
+    const float l0 = (r0 < T) ? lse[(size_t)bh * TL + r0] : 0.f, l1 = (r1 < T) ? lse[(size_t)bh * TL + r1] : 0.f;
     const int lim0 = (r0 < T) ? min(klen, causal ? r0 + 1 + (S - T) : S) : 0;
     const int lim1 = (r1 < T) ? min(klen, causal ? r1 + 1 + (S - T) : S) : 0;
     float acc[NT_MAX][4];
@@ -313,8 +333,8 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
     for (int np = 0; np < NT_MAX / 2; ++np) {
       float d0[4] = {1.f, 1.f, 1.f, 1.f}, d1[4] = {1.f, 1.f, 1.f, 1.f};
       if (p_drop > 0.f && 2 * np < nt) {
-        attn_drop4(seed, stream_id, (uint64_t)bh * T + r0, np, t, p_drop, inv_keep, d0);
-        attn_drop4(seed, stream_id, (uint64_t)bh * T + r1, np, t, p_drop, inv_keep, d1);
+        attn_drop4(seed, stream_id, (uint64_t)bh * TL + r0, np, t, p_drop, inv_keep, d0);
+        attn_drop4(seed, stream_id, (uint64_t)bh * TL + r1, np, t, p_drop, inv_keep, d1);
       }
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -383,8 +403,8 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
 #pragma unroll
     for (int n = 0; n < HD / 8; ++n) {
       const int c0 = n * 8 + 2 * t;
-      if (r0 < T) *reinterpret_cast<float2*>(dq + (size_t)b * q_bs + (size_t)r0 * q_ts + (size_t)h * HD + c0) = make_float2(o[n][0], o[n][1]);
-      if (r1 < T) *reinterpret_cast<float2*>(dq + (size_t)b * q_bs + (size_t)r1 * q_ts + (size_t)h * HD + c0) = make_float2(o[n][2], o[n][3]);
+      if (r0 < T) *reinterpret_cast<float2*>(dq + q_b + (size_t)r0 * q_ts + (size_t)h * HD + c0) = make_float2(o[n][0], o[n][1]);
+      if (r1 < T) *reinterpret_cast<float2*>(dq + q_b + (size_t)r1 * q_ts + (size_t)h * HD + c0) = make_float2(o[n][2], o[n][3]);
       if (dbias_qkv) {  // rows >= T contribute exact zeros (dS rows are zero there)
         float c_even = o[n][0] + o[n][2], c_odd = o[n][1] + o[n][3];
 #pragma unroll
@@ -423,12 +443,12 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
     for (int n = 0; n < HD / 8; ++n) {
       const int c0 = n * 8 + 2 * t;
       if (r0 < S) {
-        const size_t gofs = (size_t)b * kv_bs + (size_t)r0 * kv_ts + (size_t)h * HD + c0;
+        const size_t gofs = kv_b + (size_t)r0 * kv_ts + (size_t)h * HD + c0;
         *reinterpret_cast<float2*>(dk + gofs) = make_float2(ok[n][0], ok[n][1]);
         *reinterpret_cast<float2*>(dv + gofs) = make_float2(ov[n][0], ov[n][1]);
       }
       if (r1 < S) {
-        const size_t gofs = (size_t)b * kv_bs + (size_t)r1 * kv_ts + (size_t)h * HD + c0;
+        const size_t gofs = kv_b + (size_t)r1 * kv_ts + (size_t)h * HD + c0;
         *reinterpret_cast<float2*>(dk + gofs) = make_float2(ok[n][2], ok[n][3]);
         *reinterpret_cast<float2*>(dv + gofs) = make_float2(ov[n][2], ov[n][3]);
       }
@@ -466,11 +486,11 @@ template <int HD, int NT>
 static int launch_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, int B, int H, int T, int S,
                       int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale,
                       int causal, const int32_t* key_len, float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
-                      cudaStream_t stream) {
+                      const int32_t* cu_rows, cudaStream_t stream) {
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(attention_tc_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set = true; }
   attention_tc_fwd_kernel<HD, NT><<<B * H, 128, attn_tc_fwd_smem(T, S, HD), stream>>>(
-      q, k, v, ctx, lse, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id);
+      q, k, v, ctx, lse, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id, cu_rows);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("attention_tc_fwd_kernel");
   return CAPDEC_OK;
@@ -480,12 +500,12 @@ static int launch_bwd(const float* q, const float* k, const float* v, const floa
                       float* dq, float* dk, float* dv, float* dbias, int B, int H, int T, int S, int64_t q_bs, int64_t q_ts,
                       int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale, int causal,
                       const int32_t* key_len, float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
-                      cudaStream_t stream) {
+                      const int32_t* cu_rows, cudaStream_t stream) {
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(attention_tc_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set = true; }
   attention_tc_bwd_kernel<HD, NT><<<B * H, 128, attn_tc_bwd_smem(T, S, HD), stream>>>(
       q, k, v, ctx, dctx, lse, dq, dk, dv, dbias, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len,
-      p_drop, seed_dev, stream_id);
+      p_drop, seed_dev, stream_id, cu_rows);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("attention_tc_bwd_kernel");
   return CAPDEC_OK;
@@ -501,14 +521,15 @@ extern "C" int capdec_attention_tc_fwd(const float* q, const float* k, const flo
                                        int H, int T, int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs,
                                        int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale, int causal,
                                        const int32_t* key_len, float p_drop, const uint64_t* seed_dev,
-                                       uint32_t stream_id, capdec_stream_t stream_) {
+                                       uint32_t stream_id, const int32_t* cu_rows, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(q && k && v && ctx, "attention_tc_fwd: null argument");
+  CAPDEC_REQUIRE(!cu_rows || (T == S && causal), "attention_tc_fwd: packed rows are for causal self-attention");
   CAPDEC_REQUIRE(B > 0 && H > 0 && T > 0 && S > 0 && T <= 128 && S <= 128, "attention_tc_fwd: T,S must be in 1..128");
   CAPDEC_REQUIRE(hd == 64 || hd == 96, "attention_tc_fwd: head_dim must be 64 or 96");
   CAPDEC_REQUIRE(q_ts % 4 == 0 && kv_ts % 4 == 0 && o_ts % 2 == 0, "attention_tc_fwd: misaligned strides");
   if (attn_tc_fwd_smem(T, S, hd) > 227 * 1024) { set_last_error("attention_tc_fwd: tile does not fit shared memory"); return CAPDEC_ERR_UNSUPPORTED; }
-#define FWD_ARGS q, k, v, ctx, lse, B, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id, stream
+#define FWD_ARGS q, k, v, ctx, lse, B, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id, cu_rows, stream
   if (hd == 64) return S <= 64 ? launch_fwd<64, 8>(FWD_ARGS) : launch_fwd<64, 16>(FWD_ARGS);
   return S <= 64 ? launch_fwd<96, 8>(FWD_ARGS) : launch_fwd<96, 16>(FWD_ARGS);
 #undef FWD_ARGS
@@ -519,14 +540,15 @@ extern "C" int capdec_attention_tc_bwd(const float* q, const float* k, const flo
                                        float* dbias_qkv, int B, int H, int T, int S, int hd, int64_t q_bs, int64_t q_ts,
                                        int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale,
                                        int causal, const int32_t* key_len, float p_drop, const uint64_t* seed_dev,
-                                       uint32_t stream_id, capdec_stream_t stream_) {
+                                       uint32_t stream_id, const int32_t* cu_rows, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(q && k && v && ctx && dctx && lse && dq && dk && dv, "attention_tc_bwd: null argument");
+  CAPDEC_REQUIRE(!cu_rows || (T == S && causal), "attention_tc_bwd: packed rows are for causal self-attention");
   CAPDEC_REQUIRE(B > 0 && H > 0 && T > 0 && S > 0 && T <= 128 && S <= 128, "attention_tc_bwd: T,S must be in 1..128");
   CAPDEC_REQUIRE(hd == 64 || hd == 96, "attention_tc_bwd: head_dim must be 64 or 96");
   CAPDEC_REQUIRE(q_ts % 4 == 0 && kv_ts % 4 == 0 && o_ts % 4 == 0, "attention_tc_bwd: misaligned strides");
   if (attn_tc_bwd_smem(T, S, hd) > 227 * 1024) { set_last_error("attention_tc_bwd: tile does not fit shared memory"); return CAPDEC_ERR_UNSUPPORTED; }
-#define BWD_ARGS q, k, v, ctx, dctx, lse, dq, dk, dv, dbias_qkv, B, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id, stream
+#define BWD_ARGS q, k, v, ctx, dctx, lse, dq, dk, dv, dbias_qkv, B, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id, cu_rows, stream
   if (hd == 64) return S <= 64 ? launch_bwd<64, 8>(BWD_ARGS) : launch_bwd<64, 16>(BWD_ARGS);
   return S <= 64 ? launch_bwd<96, 8>(BWD_ARGS) : launch_bwd<96, 16>(BWD_ARGS);
 #undef BWD_ARGS

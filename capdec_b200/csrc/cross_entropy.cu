@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(1024) compact_targets_kernel(const int64_t* __
                                                                int32_t* __restrict__ dst_of,
                                                                int64_t* __restrict__ targets_c,
                                                                int32_t* __restrict__ counts, float* __restrict__ n_valid,
-                                                               float* __restrict__ loss_sum) {
+                                                               float* __restrict__ loss_sum,
+                                                               const int32_t* __restrict__ cu) {
   __shared__ int s_warp[32];
   __shared__ int s_base;
   const int n = B * L;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(1024) compact_targets_kernel(const int64_t* __
     if (valid) {
       const int r = base + woff + wpre;
       const int b = i / L, j = i % L;
-      const int hrow = b * T + off + j;
+      const int hrow = (cu ? cu[b] : b * T) + off + j;   // packed rows: caption b starts at cu[b]
       row_src[r] = hrow;
       dst_of[hrow] = r;
       targets_c[r] = tg;
@@ -203,12 +204,13 @@ extern "C" int capdec_ce_fwd_bwd(float* logits, int64_t ld, const int64_t* targe
 
 extern "C" int capdec_compact_targets(const int64_t* targets, int B, int L, int T, int off, int64_t ignore_index,
                                       int32_t* row_src, int32_t* dst_of, int64_t* targets_c, int32_t* counts,
-                                      float* n_valid, float* loss_sum_to_zero, capdec_stream_t stream_) {
+                                      float* n_valid, float* loss_sum_to_zero, const int32_t* cu_rows,
+                                      capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(targets && row_src && dst_of && targets_c && counts && n_valid, "compact_targets: null argument");
   CAPDEC_REQUIRE(B > 0 && L > 0 && off >= 0 && off + L <= T, "compact_targets: bad shape");
   compact_targets_kernel<<<1, 1024, 0, stream>>>(targets, B, L, T, off, ignore_index, row_src, dst_of, targets_c, counts,
-                                                 n_valid, loss_sum_to_zero);
+                                                 n_valid, loss_sum_to_zero, cu_rows);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("compact_targets_kernel");
   return CAPDEC_OK;

@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
           float cs = 0.f;
 #pragma unroll 8
           for (int rr = 0; rr < 32; ++rr) {
-            if (m0 + rr < p.M)
+            if (m0 + rr < m_lim)
               cs += *reinterpret_cast<const float*>(buf0 + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
           }
           atomicAdd(&sCol[c * 32 + lane], cs);
@@ -704,12 +704,12 @@ static thread_local float* t_colsum = nullptr;
 // bias gradient of the layer below fused (HF:modeling_gpt2.py:238-243 c_fc -> gelu_new; train.py:106-118 tanh; :121 relu)
 extern "C" int capdec_gemm_tf32_mul(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
                                     float* C, int64_t ldc, int M, int N, int K, const float* mul_in, int mul_act,
-                                    float* colsum, int block_n, capdec_stream_t stream_) {
+                                    float* colsum, int block_n, const int32_t* m_limit_dev, capdec_stream_t stream_) {
   CAPDEC_REQUIRE(mul_in && mul_act >= 1 && mul_act <= 3, "gemm_mul: bad epilogue input");
   CAPDEC_REQUIRE(((uintptr_t)mul_in % 16) == 0, "gemm_mul: mul_in must be 16-byte aligned");
   t_mul_in = mul_in; t_mul_act = mul_act; t_colsum = colsum;
   int rc = capdec_gemm_tf32_ex(A, a_major, lda, B, b_major, ldb, C, ldc, M, N, K, nullptr, 0, nullptr, 0, 0, nullptr,
-                               nullptr, block_n, 1, nullptr, nullptr, stream_);
+                               nullptr, block_n, 1, m_limit_dev, nullptr, stream_);
   t_mul_in = nullptr; t_mul_act = 0; t_colsum = nullptr;
   return rc;
 }

@@ -14,10 +14,12 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
                                                          float* __restrict__ h_out, float* __restrict__ x,
                                                          float* __restrict__ stats, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, int rows, int d, float eps,
-                                                         float p_drop, const uint64_t* seed_dev, uint32_t stream_id) {
+                                                         float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
+                                                         const int32_t* __restrict__ rows_dev) {
   const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
+  if (rows_dev) rows = min(rows, __ldg(rows_dev));     // packed rows: the live row count of this step
   if (row >= rows) return;
   const int d4 = d >> 2;
   const float4* hin4 = reinterpret_cast<const float4*>(h_in) + (size_t)row * d4;
@@ -88,8 +90,24 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
                                                          float* __restrict__ dy, float* __restrict__ dgamma,
                                                          float* __restrict__ dbeta, float* __restrict__ dbias_branch,
                                                          int rows, int d, int rows_per_cta, float p_drop,
-                                                         const uint64_t* seed_dev, uint32_t stream_id) {
+                                                         const uint64_t* seed_dev, uint32_t stream_id,
+                                                         const int32_t* __restrict__ rows_dev) {
   const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
+  if (rows_dev) {  // packed rows: re-balance the static grid over the live rows of this step
+    const int rows_max = rows;
+    rows = min(rows, __ldg(rows_dev));
+    rows_per_cta = (((rows + (int)gridDim.x - 1) / (int)gridDim.x + kR - 1) / kR) * kR;
+    if (rows_per_cta < kR) rows_per_cta = kR;
+    // rows [live, next multiple of 32) are read by the K-limited weight-gradient GEMMs: they must be exact zeros
+    if (blockIdx.x == gridDim.x - 1) {
+      const int tail1 = min(rows_max, (rows + 31) & ~31);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int row = rows; row < tail1; ++row) {
+        reinterpret_cast<float4*>(dh_out)[(size_t)row * (d >> 2) + threadIdx.x] = z;
+        if (dy) reinterpret_cast<float4*>(dy)[(size_t)row * (d >> 2) + threadIdx.x] = z;
+      }
+    }
+  }
   __shared__ float s_part[2][8][2 * kR];              // [batch parity][warp][c1_0..c1_{R-1}, c2_0..c2_{R-1}]
   const int c = threadIdx.x;                          // float4 column
   const int d4 = d >> 2;
@@ -103,31 +121,31 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
   for (int rb = row0; rb < row1; rb += kR, parity ^= 1) {
     float4 g[kR], xh[kR], res[kR];
     float part[2 * kR];
-    // issue every global load of the batch up front (dx, r AND the residual gradient): 12 independent 16-byte loads per thread
+    // issue every global load of the batch up front (dx, r, the residual gradient and the row statistics): the row index
+    // is clamped instead of predicated so that nothing stops the compiler from hoisting all 12 16-byte loads
+    float4 dvv[kR], rvv[kR];
+    float mean[kR], rstd[kR];
 #pragma unroll
     for (int i = 0; i < kR; ++i) {
-      const int row = rb + i;
-      res[i] = (dh_res && row < row1) ? ld_stream(reinterpret_cast<const float4*>(dh_res) + (size_t)row * d4 + c)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      const size_t rowc = (size_t)min(rb + i, row1 - 1);
+      res[i] = dh_res ? ld_stream(reinterpret_cast<const float4*>(dh_res) + rowc * d4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dvv[i] = ld_stream(reinterpret_cast<const float4*>(dx) + rowc * d4 + c);
+      rvv[i] = ld_stream(reinterpret_cast<const float4*>(r) + rowc * d4 + c);
+      mean[i] = __ldg(stats + 2 * rowc);
+      rstd[i] = __ldg(stats + 2 * rowc + 1);
     }
 #pragma unroll
     for (int i = 0; i < kR; ++i) {
-      const int row = rb + i;
-      if (row < row1) {
-        const float4 dv = ld_stream(reinterpret_cast<const float4*>(dx) + (size_t)row * d4 + c);
-        const float4 rv = ld_stream(reinterpret_cast<const float4*>(r) + (size_t)row * d4 + c);
-        const float mean = __ldg(stats + 2 * (size_t)row), rstd = __ldg(stats + 2 * (size_t)row + 1);
-        xh[i].x = (rv.x - mean) * rstd; xh[i].y = (rv.y - mean) * rstd;
-        xh[i].z = (rv.z - mean) * rstd; xh[i].w = (rv.w - mean) * rstd;
-        dg.x += dv.x * xh[i].x; dg.y += dv.y * xh[i].y; dg.z += dv.z * xh[i].z; dg.w += dv.w * xh[i].w;
-        db.x += dv.x; db.y += dv.y; db.z += dv.z; db.w += dv.w;
-        g[i].x = dv.x * gm.x; g[i].y = dv.y * gm.y; g[i].z = dv.z * gm.z; g[i].w = dv.w * gm.w;
-        part[i] = (g[i].x + g[i].y) + (g[i].z + g[i].w);
-        part[kR + i] = (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-      } else {
-        g[i] = xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        part[i] = part[kR + i] = 0.f;
-      }
+      const bool live = rb + i < row1;
+      const float4 dv = live ? dvv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 rv = rvv[i];
+      xh[i].x = (rv.x - mean[i]) * rstd[i]; xh[i].y = (rv.y - mean[i]) * rstd[i];
+      xh[i].z = (rv.z - mean[i]) * rstd[i]; xh[i].w = (rv.w - mean[i]) * rstd[i];
+      dg.x += dv.x * xh[i].x; dg.y += dv.y * xh[i].y; dg.z += dv.z * xh[i].z; dg.w += dv.w * xh[i].w;
+      db.x += dv.x; db.y += dv.y; db.z += dv.z; db.w += dv.w;
+      g[i].x = dv.x * gm.x; g[i].y = dv.y * gm.y; g[i].z = dv.z * gm.z; g[i].w = dv.w * gm.w;
+      part[i] = (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      part[kR + i] = (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
     }
 #pragma unroll
     for (int j = 0; j < 2 * kR; ++j) part[j] = warp_sum(part[j]);
@@ -146,13 +164,12 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict
     for (int i = 0; i < kR; ++i) {
       const int row = rb + i;
       if (row >= row1) break;
-      const float rstd = __ldg(stats + 2 * (size_t)row + 1);
       const float c1 = part[i], c2 = part[kR + i];
       float4 o;
-      o.x = rstd * (g[i].x - c1 - xh[i].x * c2);
-      o.y = rstd * (g[i].y - c1 - xh[i].y * c2);
-      o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
-      o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
+      o.x = rstd[i] * (g[i].x - c1 - xh[i].x * c2);
+      o.y = rstd[i] * (g[i].y - c1 - xh[i].y * c2);
+      o.z = rstd[i] * (g[i].z - c1 - xh[i].z * c2);
+      o.w = rstd[i] * (g[i].w - c1 - xh[i].w * c2);
       o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w;
       reinterpret_cast<float4*>(dh_out)[(size_t)row * d4 + c] = o;
       if (dy || dbias_branch) {
@@ -196,7 +213,8 @@ using namespace capdec;
 
 extern "C" int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out, float* x, float* stats,
                                  const float* gamma, const float* beta, int rows, int d, float eps, float p_drop,
-                                 const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream_) {
+                                 const uint64_t* seed_dev, uint32_t stream_id, const int32_t* rows_dev,
+                                 capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(h_in && x && stats && gamma && beta && rows > 0, "add_ln_fwd: null argument");
   CAPDEC_REQUIRE(d % 128 == 0 && d <= 128 * kMaxV, "add_ln_fwd: d=%d must be a multiple of 128 and <= 1024", d);
@@ -204,7 +222,7 @@ extern "C" int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out
   const int nv = d / 128;
   const int grid = (rows + 7) / 8;
   DISPATCH_NV(nv, (add_ln_fwd_kernel<NV><<<grid, 256, 0, stream>>>(h_in, y, h_out, x, stats, gamma, beta, rows, d, eps,
-                                                                   p_drop, seed_dev, stream_id)));
+                                                                   p_drop, seed_dev, stream_id, rows_dev)));
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("add_ln_fwd_kernel");
   return CAPDEC_OK;
@@ -212,7 +230,8 @@ extern "C" int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out
 
 extern "C" int capdec_add_ln_bwd(const float* dx, const float* r, const float* stats, const float* gamma,
                                  const float* dh_res, float* dh_out, float* dy, float* dgamma, float* dbeta,
-                                 float* dbias_branch, int rows, int d, float p_drop, const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream_) {
+                                 float* dbias_branch, int rows, int d, float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
+                                 const int32_t* rows_dev, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CAPDEC_REQUIRE(dx && r && stats && gamma && dh_out && rows > 0, "add_ln_bwd: null argument");
   CAPDEC_REQUIRE(d % 128 == 0 && d <= 128 * kMaxV, "add_ln_bwd: d=%d must be a multiple of 128 and <= 1024", d);
@@ -224,7 +243,7 @@ extern "C" int capdec_add_ln_bwd(const float* dx, const float* r, const float* s
   if (rpc < kR) rpc = kR;
   ctas = (rows + rpc - 1) / rpc;
   add_ln_bwd_kernel<<<ctas, threads, 0, stream>>>(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma, dbeta, dbias_branch, rows,
-                                                  d, rpc, p_drop, seed_dev, stream_id);
+                                                  d, rpc, p_drop, seed_dev, stream_id, rows_dev);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("add_ln_bwd_kernel");
   return CAPDEC_OK;

@@ -15,6 +15,7 @@ MLP :229-243; ln_f/lm_head :628,703-706; mapper MLP train.py:106-118; Transforme
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 from typing import Optional
 
@@ -54,6 +55,8 @@ class Engine:
         self.seed = ops.make_seed(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, self.dev)
         self.arenas = {}
         self._mapper_arenas = {}
+        # packed-row execution of the fused train step (csrc/packed.cu): on unless CAPDEC_PACKED=0
+        self.packed = os.environ.get("CAPDEC_PACKED", "1") != "0" and self.P >= 1
 
     # ------------------------------------------------------------------------------------------------------------
     # parameter / gradient views
@@ -116,8 +119,12 @@ class Engine:
             raise CapdecError(f"sequence of {T} positions exceeds the single-tile attention limit (128)")
         M = B * T
         d, F = self.d, self.F
-        e = lambda *s: torch.empty(*s, device=self.dev, dtype=torch.float32)
-        a = SimpleNamespace(B=B, P=P, L=L, T=T, M=M)
+        # zero-initialised: the packed path lets GEMM tiles run over (finite) stale rows past the live row count
+        e = lambda *s: torch.zeros(*s, device=self.dev, dtype=torch.float32)
+        a = SimpleNamespace(B=B, P=P, L=L, T=T, M=M, packed=False)
+        a.cu = torch.zeros(B + 1, device=self.dev, dtype=torch.int32)       # first packed row of each caption
+        a.rows = torch.zeros(2, device=self.dev, dtype=torch.int32)         # {live rows, rounded up to 32}
+        a.row_bt = torch.zeros(M, device=self.dev, dtype=torch.int32)       # packed row -> (b << 8) | t
         a.h = [e(M, d) for _ in range(self.nl + 1)]       # residual stream entering layer l (h[nl] = input of ln_f)
         a.x1 = [e(M, d) for _ in range(self.nl)]
         a.st1 = [e(M, 2) for _ in range(self.nl)]
@@ -296,30 +303,32 @@ class Engine:
         p = self.p
         B, T, M, d, F = a.B, a.T, a.M, self.d, self.F
         _, p_attn, p_res = a.pdrop
+        R = a.rows[0:1] if a.packed else None     # live row count (device scalar) of a packed batch
+        cu = a.cu if a.packed else None
         ops.add_ln_fwd(a.h[0], None, None, a.x1[0], a.st1[0], p["gpt.transformer.h.0.ln_1.weight"],
-                       p["gpt.transformer.h.0.ln_1.bias"], eps=self.cfg.layer_norm_epsilon)
+                       p["gpt.transformer.h.0.ln_1.bias"], eps=self.cfg.layer_norm_epsilon, rows=R)
         for l in range(self.nl):
             pre = f"gpt.transformer.h.{l}."
-            ops.linear_fwd(a.x1[l], p[pre + "attn.c_attn.weight"], "conv1d", p[pre + "attn.c_attn.bias"], a.qkv[l])
+            ops.linear_fwd(a.x1[l], p[pre + "attn.c_attn.weight"], "conv1d", p[pre + "attn.c_attn.bias"], a.qkv[l], rows=R)
             q, k, v = a.qkv[l][:, :d], a.qkv[l][:, d:2 * d], a.qkv[l][:, 2 * d:]
             ops.attention_fwd(q, k, v, a.ctx[l], a.lse[l], B, self.H, T, T, self.hd, T * 3 * d, 3 * d, T * 3 * d, 3 * d,
                               T * d, d, self.hd ** -0.5, 1, key_len=key_len, p_drop=p_attn, seed=self.seed,
-                              stream_id=_site(l, 0))
-            ops.linear_fwd(a.ctx[l], p[pre + "attn.c_proj.weight"], "conv1d", p[pre + "attn.c_proj.bias"], a.y)
+                              stream_id=_site(l, 0), cu_rows=cu)
+            ops.linear_fwd(a.ctx[l], p[pre + "attn.c_proj.weight"], "conv1d", p[pre + "attn.c_proj.bias"], a.y, rows=R)
             ops.add_ln_fwd(a.h[l], a.y, a.h1[l], a.x2[l], a.st2[l], p[pre + "ln_2.weight"], p[pre + "ln_2.bias"],
-                           eps=self.cfg.layer_norm_epsilon, p_drop=p_res, seed=self.seed, stream_id=_site(l, 1))
+                           eps=self.cfg.layer_norm_epsilon, p_drop=p_res, seed=self.seed, stream_id=_site(l, 1), rows=R)
             ops.linear_fwd(a.x2[l], p[pre + "mlp.c_fc.weight"], "conv1d", p[pre + "mlp.c_fc.bias"], a.g[l],
-                           act=ops.ACT_GELU_NEW, aux=a.u[l])
-            ops.linear_fwd(a.g[l], p[pre + "mlp.c_proj.weight"], "conv1d", p[pre + "mlp.c_proj.bias"], a.y)
+                           act=ops.ACT_GELU_NEW, aux=a.u[l], rows=R)
+            ops.linear_fwd(a.g[l], p[pre + "mlp.c_proj.weight"], "conv1d", p[pre + "mlp.c_proj.bias"], a.y, rows=R)
             if l + 1 < self.nl:
                 nx = f"gpt.transformer.h.{l + 1}."
                 ops.add_ln_fwd(a.h1[l], a.y, a.h[l + 1], a.x1[l + 1], a.st1[l + 1], p[nx + "ln_1.weight"],
                                p[nx + "ln_1.bias"], eps=self.cfg.layer_norm_epsilon, p_drop=p_res, seed=self.seed,
-                               stream_id=_site(l, 2))
+                               stream_id=_site(l, 2), rows=R)
             else:
                 ops.add_ln_fwd(a.h1[l], a.y, a.h[self.nl], a.xf, a.stf, p["gpt.transformer.ln_f.weight"],
                                p["gpt.transformer.ln_f.bias"], eps=self.cfg.layer_norm_epsilon, p_drop=p_res,
-                               seed=self.seed, stream_id=_site(l, 2))
+                               seed=self.seed, stream_id=_site(l, 2), rows=R)
 
     def _trunk_bwd(self, a, dxf, train_gpt: bool, key_len=None, on_layer_done=None):
         """dxf = dL/d(ln_f output) [M, d] -> a.dh = dL/d(h[0]); GPT-2 parameter gradients accumulated if train_gpt."""
@@ -329,61 +338,72 @@ class Engine:
         gw = (lambda n: g[n]) if train_gpt else (lambda n: None)
         dy = a.dy if p_res > 0 else None     # branch-output gradient buffer (mask * dh); aliases dh when p = 0
         cur = (lambda: a.dy) if p_res > 0 else (lambda: a.dh)
+        R = a.rows[0:1] if a.packed else None
+        cu = a.cu if a.packed else None
+        if a.packed:  # attention_bwd writes live rows only; the K-limited c_attn weight gradient reads whole k-blocks
+            ops.zero_tail_rows(a.dqkv, a.rows)
         # bias gradients of attn.c_proj / mlp.c_proj / c_fc / c_attn come fused out of add_ln_bwd / act_bwd / attention_bwd
         ops.add_ln_bwd(dxf, a.h[self.nl], a.stf, p["gpt.transformer.ln_f.weight"], None, a.dh, dy,
                        gw("gpt.transformer.ln_f.weight"), gw("gpt.transformer.ln_f.bias"), p_drop=p_res, seed=self.seed,
                        stream_id=_site(self.nl - 1, 2),
-                       dbias_branch=gw(f"gpt.transformer.h.{self.nl - 1}.mlp.c_proj.bias"))
+                       dbias_branch=gw(f"gpt.transformer.h.{self.nl - 1}.mlp.c_proj.bias"), rows=R)
         for l in reversed(range(self.nl)):
             pre = f"gpt.transformer.h.{l}."
             dy2 = cur()
             # mlp.c_proj
             if train_gpt:
-                ops.linear_wgrad(a.g[l], dy2, g[pre + "mlp.c_proj.weight"], "conv1d")
+                ops.linear_wgrad(a.g[l], dy2, g[pre + "mlp.c_proj.weight"], "conv1d", rows=R)
             ops.linear_dgrad_act(dy2, p[pre + "mlp.c_proj.weight"], "conv1d", a.dF, a.u[l], ops.ACT_GELU_NEW,
-                                 dbias=gw(pre + "mlp.c_fc.bias"))
+                                 dbias=gw(pre + "mlp.c_fc.bias"), rows=R)
             if train_gpt:
-                ops.linear_wgrad(a.x2[l], a.dF, g[pre + "mlp.c_fc.weight"], "conv1d")
-            ops.linear_dgrad(a.dF, p[pre + "mlp.c_fc.weight"], "conv1d", a.dx)
+                ops.linear_wgrad(a.x2[l], a.dF, g[pre + "mlp.c_fc.weight"], "conv1d", rows=R)
+            ops.linear_dgrad(a.dF, p[pre + "mlp.c_fc.weight"], "conv1d", a.dx, rows=R)
             ops.add_ln_bwd(a.dx, a.h1[l], a.st2[l], p[pre + "ln_2.weight"], a.dh, a.dh, dy, gw(pre + "ln_2.weight"),
                            gw(pre + "ln_2.bias"), p_drop=p_res, seed=self.seed, stream_id=_site(l, 1),
-                           dbias_branch=gw(pre + "attn.c_proj.bias"))
+                           dbias_branch=gw(pre + "attn.c_proj.bias"), rows=R)
             dy1 = cur()
             # attention
             if train_gpt:
-                ops.linear_wgrad(a.ctx[l], dy1, g[pre + "attn.c_proj.weight"], "conv1d")
-            ops.linear_dgrad(dy1, p[pre + "attn.c_proj.weight"], "conv1d", a.dctx)
+                ops.linear_wgrad(a.ctx[l], dy1, g[pre + "attn.c_proj.weight"], "conv1d", rows=R)
+            ops.linear_dgrad(dy1, p[pre + "attn.c_proj.weight"], "conv1d", a.dctx, rows=R)
             q, k, v = a.qkv[l][:, :d], a.qkv[l][:, d:2 * d], a.qkv[l][:, 2 * d:]
             dq, dk, dv = a.dqkv[:, :d], a.dqkv[:, d:2 * d], a.dqkv[:, 2 * d:]
             ops.attention_bwd(q, k, v, a.ctx[l], a.dctx, a.lse[l], dq, dk, dv, B, self.H, T, T, self.hd, T * 3 * d, 3 * d,
                               T * 3 * d, 3 * d, T * d, d, self.hd ** -0.5, 1, key_len=key_len, p_drop=p_attn,
-                              seed=self.seed, stream_id=_site(l, 0), dbias_qkv=gw(pre + "attn.c_attn.bias"))
+                              seed=self.seed, stream_id=_site(l, 0), dbias_qkv=gw(pre + "attn.c_attn.bias"), cu_rows=cu)
             if train_gpt:
-                ops.linear_wgrad(a.x1[l], a.dqkv, g[pre + "attn.c_attn.weight"], "conv1d")
-            ops.linear_dgrad(a.dqkv, p[pre + "attn.c_attn.weight"], "conv1d", a.dx)
+                ops.linear_wgrad(a.x1[l], a.dqkv, g[pre + "attn.c_attn.weight"], "conv1d", rows=R)
+            ops.linear_dgrad(a.dqkv, p[pre + "attn.c_attn.weight"], "conv1d", a.dx, rows=R)
             if l > 0:
                 ops.add_ln_bwd(a.dx, a.h[l], a.st1[l], p[pre + "ln_1.weight"], a.dh, a.dh, dy, gw(pre + "ln_1.weight"),
                                gw(pre + "ln_1.bias"), p_drop=p_res, seed=self.seed, stream_id=_site(l - 1, 2),
-                               dbias_branch=gw(f"gpt.transformer.h.{l - 1}.mlp.c_proj.bias"))
+                               dbias_branch=gw(f"gpt.transformer.h.{l - 1}.mlp.c_proj.bias"), rows=R)
             else:
                 ops.add_ln_bwd(a.dx, a.h[0], a.st1[0], p[pre + "ln_1.weight"], a.dh, a.dh, None, gw(pre + "ln_1.weight"),
-                               gw(pre + "ln_1.bias"))
+                               gw(pre + "ln_1.bias"), rows=R)
             if on_layer_done is not None and train_gpt:
                 on_layer_done(l)   # every gradient of GPT-2 block l (and ln_f when l is the last block) is final now
 
     # ------------------------------------------------------------------------------------------------------------
     # fast path: loss + gradients (sum-reduced CE gradients, divided by the token count inside AdamW)
     # ------------------------------------------------------------------------------------------------------------
-    def forward_hidden(self, tokens, prefix, key_len=None):
-        """tokens int64 [B,L], prefix fp32 [B,D] (already noise-injected) -> arena with a.xf = ln_f output."""
+    def forward_hidden(self, tokens, prefix, key_len=None, packed=False):
+        """tokens int64 [B,L], prefix fp32 [B,D] (already noise-injected) -> arena with a.xf = ln_f output.
+        packed: keep only the positions that can reach the loss (csrc/packed.cu); a.xf then has a.rows[0] live rows."""
         B, L = tokens.shape
         a = self._arena(B, L)
         a.pdrop = self._drop_p()
         a.tokens, a.prefix = tokens, prefix
+        a.packed = bool(packed)
         p = self.p
         self._mapper_fwd(prefix, a.pp)
-        ops.embed_fwd(tokens, a.pp, p["gpt.transformer.wte.weight"], p["gpt.transformer.wpe.weight"], a.h[0], B, self.P, L,
-                      p_drop=a.pdrop[0], seed=self.seed, stream_id=_SITE_EMBD)
+        if a.packed:
+            ops.pack_plan(tokens, self.P, a.cu, a.rows, a.row_bt)
+            ops.embed_fwd_packed(tokens, a.pp, p["gpt.transformer.wte.weight"], p["gpt.transformer.wpe.weight"], a.h[0],
+                                 a.row_bt, a.rows, B, self.P, L, p_drop=a.pdrop[0], seed=self.seed, stream_id=_SITE_EMBD)
+        else:
+            ops.embed_fwd(tokens, a.pp, p["gpt.transformer.wte.weight"], p["gpt.transformer.wpe.weight"], a.h[0], B, self.P,
+                          L, p_drop=a.pdrop[0], seed=self.seed, stream_id=_SITE_EMBD)
         self._trunk_fwd(a, key_len)
         return a
 
@@ -391,9 +411,14 @@ class Engine:
         """Everything below ln_f: trunk, embedding scatter, mapper."""
         g = self.g
         self._trunk_bwd(a, dxf, train_gpt, key_len, on_layer_done)
-        ops.embed_bwd(a.tokens, a.dh, a.dpp, g["gpt.transformer.wte.weight"] if train_gpt else None,
-                      g["gpt.transformer.wpe.weight"] if train_gpt else None, a.B, self.P, a.L, self.V,
-                      p_drop=a.pdrop[0], seed=self.seed, stream_id=_SITE_EMBD)
+        d_wte = g["gpt.transformer.wte.weight"] if train_gpt else None
+        d_wpe = g["gpt.transformer.wpe.weight"] if train_gpt else None
+        if a.packed:
+            ops.embed_bwd_packed(a.tokens, a.dh, a.dpp, d_wte, d_wpe, a.cu, a.B, self.P, a.L, self.V, p_drop=a.pdrop[0],
+                                 seed=self.seed, stream_id=_SITE_EMBD)
+        else:
+            ops.embed_bwd(a.tokens, a.dh, a.dpp, d_wte, d_wpe, a.B, self.P, a.L, self.V, p_drop=a.pdrop[0], seed=self.seed,
+                          stream_id=_SITE_EMBD)
         self._mapper_bwd(a.prefix, a.dpp)
 
     def loss_and_grads(self, tokens, prefix, train_gpt: Optional[bool] = None, mean_reduce: bool = False,
@@ -405,7 +430,8 @@ class Engine:
             train_gpt = self.m.gpt_trainable()
         fl = self.flat
         B, L = tokens.shape
-        a = self.forward_hidden(tokens, prefix)
+        fast = ops.get_precision() == "tf32"
+        a = self.forward_hidden(tokens, prefix, packed=fast and self.packed)
         p, g = self.p, self.g
         P, T, d = self.P, a.T, self.d
         tail = fl.grads[:4]
@@ -413,10 +439,11 @@ class Engine:
         targets = tokens.reshape(-1)
         wte = p["gpt.transformer.wte.weight"]
         logits = a.logits_sel[:, : self.V]
-        if ops.get_precision() == "tf32":
+        if fast:
             # LM head + CE only over the rows whose target is not ignored: compact them on device, keep every shape
             # static and let the GEMMs / CE read the row count from a device scalar (CUDA-graph friendly).
-            ops.compact_targets(targets, B, L, T, P - 1, a.row_src, a.dst_of, a.targets_c, a.counts, n_valid, loss_sum)
+            ops.compact_targets(targets, B, L, T, P - 1, a.row_src, a.dst_of, a.targets_c, a.counts, n_valid, loss_sum,
+                                cu_rows=a.cu if a.packed else None)
             nv = a.counts[0:1]
             ops.rows_gather_idx(a.xf, a.xsel, a.row_src, a.counts)
             ops.gemm(a.xsel, 0, wte, 0, logits, B * L, self.V, d, m_limit=nv)                       # tied lm_head

@@ -101,49 +101,58 @@ def gemm(A: torch.Tensor, a_major: int, B: torch.Tensor, b_major: int, C: torch.
     _lib.check(rc, "gemm_tf32")
 
 
-def gemm_mul(A, a_major, B, b_major, C, M, N, K, mul_in, mul_act, colsum=None, block_n=0):
+def gemm_mul(A, a_major, B, b_major, C, M, N, K, mul_in, mul_act, colsum=None, block_n=0, m_limit=None):
     """C = (A . B^T) * act'(mul_in), colsum += column sums of C — dgrad + activation backward + bias gradient in one
     tcgen05 launch (1xTF32 mode)."""
     lda, ldb, ldc = _rowmajor(A, "A"), _rowmajor(B, "B"), _rowmajor(C, "C")
     if _rowmajor(mul_in, "mul_in") != ldc or tuple(mul_in.shape) != (M, N):
         raise ValueError("mul_in must have C's shape and leading dimension")
     rc = _lib.load().capdec_gemm_tf32_mul(A.data_ptr(), a_major, lda, B.data_ptr(), b_major, ldb, C.data_ptr(), ldc, M, N,
-                                          K, mul_in.data_ptr(), mul_act, _ptr(colsum), block_n, _stream())
+                                          K, mul_in.data_ptr(), mul_act, _ptr(colsum), block_n, _ptr(m_limit),
+                                          _stream())
     _lib.check(rc, "gemm_tf32_mul")
 
 
-def linear_dgrad_act(dy, W, layout, dx, act_in, act, dbias=None):
-    """dx = (dy . W^T) * act'(act_in) (+ dbias += colsum(dx)).  tf32: one fused launch; parity modes: dgrad then act_bwd."""
+def linear_dgrad_act(dy, W, layout, dx, act_in, act, dbias=None, rows=None):
+    """dx = (dy . W^T) * act'(act_in) (+ dbias += colsum(dx)).  tf32: one fused launch; parity modes: dgrad then act_bwd.
+    `rows` (everywhere below): device int32 scalar with the live row count of a packed batch (tf32 mode only)."""
     if _PRECISION == "tf32":
         M, K = dy.shape
-        gemm_mul(dy, 0, W, 0 if layout == "conv1d" else 1, dx, M, dx.shape[1], K, act_in, act, dbias)
+        gemm_mul(dy, 0, W, 0 if layout == "conv1d" else 1, dx, M, dx.shape[1], K, act_in, act, dbias, m_limit=rows)
     else:
+        _no_rows(rows)
         linear_dgrad(dy, W, layout, dx)
         act_bwd(dx, act_in, dx, act, dbias=dbias)
 
 
 # ---- layer helpers: `layout` is "conv1d" (HF Conv1D weight [in,out]) or "linear" (nn.Linear weight [out,in]) --------
-def linear_fwd(x, W, layout, bias, out, act=ACT_NONE, aux=None):
+def _no_rows(rows):
+    if rows is not None:
+        raise _lib.CapdecError("packed rows (device row limits) are implemented for the tf32 tcgen05 path only")
+
+
+def linear_fwd(x, W, layout, bias, out, act=ACT_NONE, aux=None, rows=None):
     M, K = x.shape
     N = out.shape[1]
-    gemm(x, 0, W, 1 if layout == "conv1d" else 0, out, M, N, K, bias=bias, act=act, aux=aux)
+    gemm(x, 0, W, 1 if layout == "conv1d" else 0, out, M, N, K, bias=bias, act=act, aux=aux, m_limit=rows)
 
 
-def linear_dgrad(dy, W, layout, dx, accumulate=False):
+def linear_dgrad(dy, W, layout, dx, accumulate=False, rows=None):
     M, K = dy.shape  # K = out features (reduction)
     N = dx.shape[1]
-    gemm(dy, 0, W, 0 if layout == "conv1d" else 1, dx, M, N, K, accumulate=accumulate)
+    gemm(dy, 0, W, 0 if layout == "conv1d" else 1, dx, M, N, K, accumulate=accumulate, m_limit=rows)
 
 
-def linear_wgrad(x, dy, dW, layout, dbias=None):
+def linear_wgrad(x, dy, dW, layout, dbias=None, rows=None):
     """dW += x^T dy (conv1d) / dy^T x (linear); dbias (optional) += column sums of dy via a separate pass — the engine
     normally gets bias gradients from the fused producers (add_ln_bwd / act_bwd / attention_bwd) instead."""
-    rows = x.shape[0]
+    n_rows = x.shape[0]
     if layout == "conv1d":  # dW[in,out] += x^T dy
-        gemm(x, 1, dy, 1, dW, x.shape[1], dy.shape[1], rows, accumulate=True)
+        gemm(x, 1, dy, 1, dW, x.shape[1], dy.shape[1], n_rows, accumulate=True, k_limit=rows)
     else:  # dW[out,in] += dy^T x
-        gemm(dy, 1, x, 1, dW, dy.shape[1], x.shape[1], rows, accumulate=True)
+        gemm(dy, 1, x, 1, dW, dy.shape[1], x.shape[1], n_rows, accumulate=True, k_limit=rows)
     if dbias is not None:
+        _no_rows(rows)
         colsum_acc(dy, dbias)
 
 
@@ -188,21 +197,20 @@ def embed_bwd(tokens, dh, d_prefix_proj, d_wte, d_wpe, B, P, L, vocab, p_drop=0.
     _lib.check(rc, "embed_bwd")
 
 
-def add_ln_fwd(h_in, y, h_out, x, stats, gamma, beta, eps=1e-5, p_drop=0.0, seed=None, stream_id=0):
-    rows, d = x.shape
+def add_ln_fwd(h_in, y, h_out, x, stats, gamma, beta, eps=1e-5, p_drop=0.0, seed=None, stream_id=0, rows=None):
+    n_rows, d = x.shape
     rc = _lib.load().capdec_add_ln_fwd(h_in.data_ptr(), _ptr(y), _ptr(h_out), x.data_ptr(), stats.data_ptr(),
-                                       gamma.data_ptr(), beta.data_ptr(), rows, d, eps, float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id,
-                                       _stream())
+                                       gamma.data_ptr(), beta.data_ptr(), n_rows, d, eps, float(p_drop),
+                                       _seed_ptr(seed, p_drop > 0), stream_id, _ptr(rows), _stream())
     _lib.check(rc, "add_ln_fwd")
 
 
 def add_ln_bwd(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma, dbeta, p_drop=0.0, seed=None, stream_id=0,
-               dbias_branch=None):
-    rows, d = dx.shape
+               dbias_branch=None, rows=None):
+    n_rows, d = dx.shape
     rc = _lib.load().capdec_add_ln_bwd(dx.data_ptr(), r.data_ptr(), stats.data_ptr(), gamma.data_ptr(), _ptr(dh_res),
-                                       dh_out.data_ptr(), _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(dbias_branch), rows, d,
-                                       float(p_drop),
-                                       _seed_ptr(seed, p_drop > 0), stream_id, _stream())
+                                       dh_out.data_ptr(), _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(dbias_branch), n_rows,
+                                       d, float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id, _ptr(rows), _stream())
     _lib.check(rc, "add_ln_bwd")
 
 
@@ -215,13 +223,13 @@ def _use_tc(impl):
 
 
 def attention_fwd(q, k, v, ctx, lse, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal,
-                  key_len=None, p_drop=0.0, seed=None, stream_id=0, impl=None):
-    if _use_tc(impl):
+                  key_len=None, p_drop=0.0, seed=None, stream_id=0, impl=None, cu_rows=None):
+    if _use_tc(impl) or cu_rows is not None:
         rc = _lib.load().capdec_attention_tc_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), _ptr(lse), B, H,
                                                  T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, float(scale), int(causal),
                                                  _ptr(key_len), float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id,
-                                                 _stream())
-        if rc != -3:
+                                                 _ptr(cu_rows), _stream())
+        if rc != -3 or cu_rows is not None:
             _lib.check(rc, "attention_tc_fwd")
             return
     rc = _lib.load().capdec_attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), _ptr(lse), B, H, T,
@@ -231,14 +239,14 @@ def attention_fwd(q, k, v, ctx, lse, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o
 
 
 def attention_bwd(q, k, v, ctx, dctx, lse, dq, dk, dv, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale,
-                  causal, key_len=None, p_drop=0.0, seed=None, stream_id=0, dbias_qkv=None, impl=None):
-    if _use_tc(impl):
+                  causal, key_len=None, p_drop=0.0, seed=None, stream_id=0, dbias_qkv=None, impl=None, cu_rows=None):
+    if _use_tc(impl) or cu_rows is not None:
         rc = _lib.load().capdec_attention_tc_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), dctx.data_ptr(),
                                                  lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
                                                  _ptr(dbias_qkv), B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts,
                                                  float(scale), int(causal), _ptr(key_len), float(p_drop),
-                                                 _seed_ptr(seed, p_drop > 0), stream_id, _stream())
-        if rc != -3:
+                                                 _seed_ptr(seed, p_drop > 0), stream_id, _ptr(cu_rows), _stream())
+        if rc != -3 or cu_rows is not None:
             _lib.check(rc, "attention_tc_bwd")
             return
     rc = _lib.load().capdec_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), dctx.data_ptr(),
@@ -256,11 +264,11 @@ def ce_count(targets, n_valid, loss_sum_to_zero=None, ignore_index=0):
 
 
 def compact_targets(targets, B, L, T, off, row_src, dst_of, targets_c, counts, n_valid, loss_sum_to_zero=None,
-                    ignore_index=0):
+                    ignore_index=0, cu_rows=None):
     _chk(targets, "targets", torch.int64)
     rc = _lib.load().capdec_compact_targets(targets.data_ptr(), B, L, T, off, ignore_index, row_src.data_ptr(),
                                             dst_of.data_ptr(), targets_c.data_ptr(), counts.data_ptr(),
-                                            n_valid.data_ptr(), _ptr(loss_sum_to_zero), _stream())
+                                            n_valid.data_ptr(), _ptr(loss_sum_to_zero), _ptr(cu_rows), _stream())
     _lib.check(rc, "compact_targets")
 
 
@@ -378,3 +386,32 @@ def beam_select(st, n_img, beam, P, Tmax, V, stop_token):
                                         st.hist_parent.data_ptr(), st.img_done.data_ptr(), st.ticket.data_ptr(), n_img,
                                         beam, P, Tmax, V, int(stop_token), _stream())
     _lib.check(rc, "beam_select")
+
+
+# ---- packed-row execution (packed.cu) ------------------------------------------------------------------------------
+def pack_plan(tokens, P, cu, rows, row_bt):
+    _chk(tokens, "tokens", torch.int64)
+    B, L = tokens.shape
+    _lib.check(_lib.load().capdec_pack_plan(tokens.data_ptr(), B, L, P, cu.data_ptr(), rows.data_ptr(), row_bt.data_ptr(),
+                                            _stream()), "pack_plan")
+
+
+def embed_fwd_packed(tokens, prefix_proj, wte, wpe, h, row_bt, rows, B, P, L, p_drop=0.0, seed=None, stream_id=0):
+    d = h.shape[1]
+    rc = _lib.load().capdec_embed_fwd_packed(tokens.data_ptr(), prefix_proj.data_ptr(), wte.data_ptr(), wpe.data_ptr(),
+                                             h.data_ptr(), row_bt.data_ptr(), rows.data_ptr(), B, P, L, d, wte.shape[0],
+                                             float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id, _stream())
+    _lib.check(rc, "embed_fwd_packed")
+
+
+def embed_bwd_packed(tokens, dh, d_prefix_proj, d_wte, d_wpe, cu, B, P, L, vocab, p_drop=0.0, seed=None, stream_id=0):
+    d = dh.shape[1]
+    rc = _lib.load().capdec_embed_bwd_packed(tokens.data_ptr(), dh.data_ptr(), _ptr(d_prefix_proj), _ptr(d_wte), _ptr(d_wpe),
+                                             cu.data_ptr(), B, P, L, d, vocab, float(p_drop), _seed_ptr(seed, p_drop > 0),
+                                             stream_id, _stream())
+    _lib.check(rc, "embed_bwd_packed")
+
+
+def zero_tail_rows(buf, rows):
+    _lib.check(_lib.load().capdec_zero_tail_rows(buf.data_ptr(), _rowmajor(buf, "buf"), rows.data_ptr(), _stream()),
+               "zero_tail_rows")

@@ -65,7 +65,7 @@ int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B
  * (train.py:121).  mul_in shares C's leading dimension.  1xTF32 only (the parity modes use capdec_act_bwd). */
 int capdec_gemm_tf32_mul(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb, float* C,
                          int64_t ldc, int M, int N, int K, const float* mul_in, int mul_act, float* colsum,
-                         int block_n, capdec_stream_t stream);
+                         int block_n, const int32_t* m_limit_dev, capdec_stream_t stream);
 
 /* debug/bring-up override of the UMMA shared-memory descriptor encoding for MN-major operands
  * (layout_type, LBO bytes, SBO bytes, TMA swizzle enum); pass -1 to keep the default. Not used in production. */
@@ -108,7 +108,7 @@ int capdec_embed_bwd(const int64_t* tokens, const float* dh, float* d_prefix_pro
  *      h_out receives r (may alias h_in; may be NULL when y == NULL).  rows x d, d % 128 == 0, d <= 1024. */
 int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out, float* x, float* stats, const float* gamma,
                       const float* beta, int rows, int d, float eps, float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
-                      capdec_stream_t stream);
+                      const int32_t* rows_dev, capdec_stream_t stream);
 /* bwd: dr = dh_res (running residual gradient, may be NULL = 0) + LN_bwd(dx; r, stats, gamma) -> written to dh_out
  *      (may alias dh_res); if dy != NULL: dy = dropout_mask * dr (gradient of the branch output y).
  *      dgamma/dbeta accumulated (+=) unless NULL (frozen GPT-2, train.py:276-284).
@@ -117,7 +117,10 @@ int capdec_add_ln_fwd(const float* h_in, const float* y, float* h_out, float* x,
 int capdec_add_ln_bwd(const float* dx, const float* r, const float* stats, const float* gamma, const float* dh_res,
                       float* dh_out, float* dy, float* dgamma, float* dbeta, float* dbias_branch, int rows, int d,
                       float p_drop,
-                      const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
+                      const uint64_t* seed_dev, uint32_t stream_id, const int32_t* rows_dev, capdec_stream_t stream);
+/* rows_dev (both LayerNorm entry points, may be NULL): device scalar with the live row count of a packed batch
+ * (capdec_pack_plan); rows >= *rows_dev are not touched, except that bwd zero-fills dh_out / dy up to the next multiple
+ * of 32 rows so that K-limited weight-gradient GEMMs can read whole k-blocks. */
 
 /* ---- attention core ----------------------------------------------------------------------------------------------
  * GPT-2 (HF:modeling_gpt2.py:54-72,185-191): qkv [B,T,3*H*hd] (q|k|v thirds, heads contiguous hd slices),
@@ -142,12 +145,14 @@ int capdec_attention_bwd(const float* q, const float* k, const float* v, const f
 int capdec_attention_tc_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, int B, int H, int T,
                             int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs,
                             int64_t o_ts, float scale, int causal, const int32_t* key_len, float p_drop,
-                            const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
+                            const uint64_t* seed_dev, uint32_t stream_id, const int32_t* cu_rows, capdec_stream_t stream);
 int capdec_attention_tc_bwd(const float* q, const float* k, const float* v, const float* ctx, const float* dctx,
                             const float* lse, float* dq, float* dk, float* dv, float* dbias_qkv, int B, int H, int T,
                             int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs,
                             int64_t o_ts, float scale, int causal, const int32_t* key_len, float p_drop,
-                            const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
+                            const uint64_t* seed_dev, uint32_t stream_id, const int32_t* cu_rows, capdec_stream_t stream);
+/* cu_rows (may be NULL): packed rows — caption b owns rows [cu_rows[b], cu_rows[b+1]) of q/k/v/ctx (causal
+ * self-attention, T = S = that count <= the T argument, which stays the pitch of lse and of the dropout counters). */
 
 /* ---- masked cross entropy: train.py:349-350 (nnf.cross_entropy(..., ignore_index=0), mean over targets != 0) -----
  * logits [rows, ld] (ld >= V, padded pitch), targets int64 [rows].  loss_sum/n_valid are device scalars (float);
@@ -166,12 +171,29 @@ int capdec_ce_fwd_bwd(float* logits, int64_t ld, const int64_t* targets, int row
  * *n_valid (float) and zeroes *loss_sum_to_zero.  Replaces capdec_ce_count on the compacted path. */
 int capdec_compact_targets(const int64_t* targets, int B, int L, int T, int off, int64_t ignore_index,
                            int32_t* row_src, int32_t* dst_of, int64_t* targets_c, int32_t* counts, float* n_valid,
-                           float* loss_sum_to_zero, capdec_stream_t stream);
-/* dst[r] = src[row_src[r]] for r < counts[0], zero rows up to counts[1]; dst has max_rows rows of width d */
+                           float* loss_sum_to_zero, const int32_t* cu_rows, capdec_stream_t stream);
+/* cu_rows (may be NULL): hidden rows are packed, caption b starts at row cu_rows[b] instead of b*T.
+ * dst[r] = src[row_src[r]] for r < counts[0], zero rows up to counts[1]; dst has max_rows rows of width d */
 int capdec_rows_gather_idx(const float* src, float* dst, const int32_t* row_src, const int32_t* counts, int max_rows,
                            int d, capdec_stream_t stream);
 /* dst[row] = dst_of[row] >= 0 ? src[dst_of[row]] : 0 for every one of `rows` rows */
 int capdec_rows_scatter_idx(const float* src, float* dst, const int32_t* dst_of, int rows, int d, capdec_stream_t stream);
+
+/* ---- packed-row execution: run the trunk only over the positions that can reach the loss ------------------------------
+ * Caption b (tokens [B,L], right-padded with 0, train.py:55-63) keeps positions 0 .. P + len_b - 2, len_b = 1 + index of
+ * its last non-zero token: later rows only feed ignored targets (train.py:349-350) and no live row attends to them.
+ * pack_plan: cu[B+1] (first packed row per caption), rows = {live rows, live rounded up to 32}, row_bt[r] = b<<8 | t. */
+int capdec_pack_plan(const int64_t* tokens, int B, int L, int P, int32_t* cu, int32_t* rows, int32_t* row_bt,
+                     capdec_stream_t stream);
+/* packed forms of capdec_embed_fwd / capdec_embed_bwd (train.py:253-255): h / dh have one row per live position */
+int capdec_embed_fwd_packed(const int64_t* tokens, const float* prefix_proj, const float* wte, const float* wpe, float* h,
+                            const int32_t* row_bt, const int32_t* rows, int B, int P, int L, int d, int vocab, float p_drop,
+                            const uint64_t* seed_dev, uint32_t stream_id, capdec_stream_t stream);
+int capdec_embed_bwd_packed(const int64_t* tokens, const float* dh, float* d_prefix_proj, float* d_wte, float* d_wpe,
+                            const int32_t* cu, int B, int P, int L, int d, int vocab, float p_drop, const uint64_t* seed_dev,
+                            uint32_t stream_id, capdec_stream_t stream);
+/* rows [rows[0], rows[1]) of buf [*, ld] <- 0 */
+int capdec_zero_tail_rows(float* buf, int64_t ld, const int32_t* rows, capdec_stream_t stream);
 
 /* ---- KV-cached batched beam search (replaces gpt2_prefix_eval.py:50-115 generate_beam) -----------------
  * R = n_img*beam physical rows; caches are per layer [R][Tmax][d]; `src` is the int32 [2][R][Tmax] lineage table
