@@ -39,15 +39,34 @@ def flops_per_caption(P=P_LEN, L=SEQ, d=D_MODEL, F=F_MLP, nl=N_LAYER, Dc=D_CLIP)
     return 3.0 * fwd
 
 
+FULL_LENGTH = False   # --full_length: every caption has all 40 tokens (worst case for the packed path)
+
+
 def synth_batch(B, seed):
+    """SURVEY §8d: L2-normalised Gaussian CLIP embeddings, token ids uniform in [1, V), caption length ~ U{8..40}
+    (COCO-like), right-padded with id 0 exactly as ClipCocoDataset does (train.py:55-63)."""
     import torch
     g = torch.Generator().manual_seed(seed)
     prefix = torch.randn(B, D_CLIP, generator=g)
     prefix = prefix / prefix.norm(2, -1, keepdim=True)
     tokens = torch.randint(1, V, (B, SEQ), generator=g, dtype=torch.int64)
     lens = torch.randint(8, SEQ + 1, (B,), generator=g)
-    tokens[torch.arange(SEQ)[None, :] >= lens[:, None]] = 0
+    if not FULL_LENGTH:
+        tokens[torch.arange(SEQ)[None, :] >= lens[:, None]] = 0
     return tokens, prefix
+
+
+def executed_flops(tokens, P, packed, d=D_MODEL, F=F_MLP, nl=N_LAYER, Dc=D_CLIP):
+    """FLOPs the step actually executes for this batch (3 x forward): the packed path runs the trunk on the live rows only
+    (prefix + every token that is the input of a non-ignored target); the LM head runs on the non-ignored targets."""
+    B, L = tokens.shape
+    nz = tokens != 0
+    lens = (nz * (1 + nz.new_tensor(range(L)))).max(dim=1).values          # 1 + index of the last non-zero token
+    tb = (P + (lens - 1).clamp_min(0)) if packed else lens.new_full((B,), P + L)
+    rows, sq = int(tb.sum()), int((tb * tb).sum())
+    fwd = nl * (rows * (2 * d * 3 * d + 2 * d * d + 2 * 2 * d * F) + 4 * sq * d) + 2 * int(nz.sum()) * d * V
+    fwd += B * (2 * Dc * (d * P // 2) + 2 * (d * P // 2) * (d * P))
+    return 3.0 * fwd, rows, B * (P + L)
 
 
 def peaks():
@@ -256,7 +275,10 @@ def run_gpu(args):
         e2e = captions / (ms_e2e * 1e-3)
         tf32_peak = pk["bf16"] / 2.0
         qkv_tf, qkv_ms = qkv_gemm_roofline(cb, torch)
-        step_tf = flops_per_caption(P=P_LEN) * B / (ms_dev / args.steps * 1e-3) / 1e12
+        step_tf = flops_per_caption(P=P_LEN) * B / (ms_dev / args.steps * 1e-3) / 1e12   # what the reference executes
+        packed = bool(model.engine().packed)
+        ex_flops, live_rows, dense_rows = executed_flops(host[0][0], P_LEN, packed)
+        exec_tf = ex_flops / (ms_dev / args.steps * 1e-3) / 1e12
         cpu_rate, cores, cpu_s = cpu_train_step_rate(16, 2, 1) if (world == 1 and args.workload == "c2") else (None, None, None)
         line = {
             "metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
@@ -268,6 +290,11 @@ def run_gpu(args):
                                     "c3": "C3: TransformerMapper (8 layers, P=C=40) + GPT-2-small fine-tuned, bs=256/GPU, seq_len=40, dropout 0.1 live",
                                     "c4": "C4: MLP mapper P=10 + GPT-2-small fine-tuned, bs=512/GPU, seq_len=40, dropout 0.1 live"}[args.workload],
                        "global_batch": B * world, "seq_len": SEQ, "parallelism": f"dp{world}",
+                       "captions": ("all 40 tokens long (--full_length)" if FULL_LENGTH else
+                                    "length ~ U{8..40}, right-padded with id 0 (SURVEY §8d)"),
+                       "rows": (f"packed: {live_rows} of {dense_rows} trunk rows per step are live (padding and each caption's "
+                                "final token cannot reach the loss and are skipped; CAPDEC_PACKED=0 runs every row)"
+                                if packed else f"dense: all {dense_rows} trunk rows per step"),
                        "l2": "working set per step (0.62 GB weights + 7.5 GB activations) >> 126 MB L2; 8 distinct host batches",
                        "arithmetic": "fp32 storage, TF32 tcgen05 GEMMs with fp32 TMEM accumulation, fp32 everywhere else"},
             "e2e": {"value": e2e, "unit": "captions/s", "h2d_bytes_per_step": B * SEQ * 8 + B * D_CLIP * 4,
@@ -281,7 +308,8 @@ def run_gpu(args):
                                                                 "algorithmic 164.4e6 (operands + output once)",
                          "ms_per_launch": qkv_ms,
                          "peak_source": pk["source"] + ": bf16 burst %.1f TF/s / 2 (kind::tf32 issues at half the kind::f16 rate)" % pk["bf16"],
-                         "step_algorithmic_tflops": step_tf, "step_frac_of_tf32_peak_sustained": step_tf / (pk["bf16_sustained"] / 2.0)},
+                         "step_executed_tflops": exec_tf, "step_executed_frac_of_tf32_peak_sustained": exec_tf / (pk["bf16_sustained"] / 2.0),
+                         "step_reference_equivalent_tflops": step_tf},
             "last_loss": last,
         }
         if cpu_rate is not None:
@@ -299,11 +327,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="capdec_b200", choices=["capdec_b200", "reference"])
+    ap.add_argument("--full_length", action="store_true", help="captions without padding (worst case for the packed path)")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"],
                     help="BASELINE.json config: c2 (default, the headline metric), c1 = --only_prefix bs=32, "
                          "c3 = TransformerMapper P=40 bs=256, c4 = MLP bs=512/GPU")
     args = ap.parse_args()
-    global P_LEN, BS_PER_GPU
+    global P_LEN, BS_PER_GPU, FULL_LENGTH
+    FULL_LENGTH = bool(args.full_length)
     if args.workload == "c1":
         BS_PER_GPU = 32
     elif args.workload == "c3":
