@@ -61,7 +61,8 @@ def executed_flops(tokens, P, packed, d=D_MODEL, F=F_MLP, nl=N_LAYER, Dc=D_CLIP)
     (prefix + every token that is the input of a non-ignored target); the LM head runs on the non-ignored targets."""
     B, L = tokens.shape
     nz = tokens != 0
-    lens = (nz * (1 + nz.new_tensor(range(L)))).max(dim=1).values          # 1 + index of the last non-zero token
+    import torch
+    lens = (nz.long() * torch.arange(1, L + 1)).max(dim=1).values            # 1 + index of the last non-zero token
     tb = (P + (lens - 1).clamp_min(0)) if packed else lens.new_full((B,), P + L)
     rows, sq = int(tb.sum()), int((tb * tb).sum())
     fwd = nl * (rows * (2 * d * 3 * d + 2 * d * d + 2 * 2 * d * F) + 4 * sq * d) + 2 * int(nz.sum()) * d * V
