@@ -9,9 +9,10 @@ from .model import (ClipCaptionModel, ClipCaptionPrefix, GPT2Config, GPT2LMHead,
                     noise_injection)
 from .optim import AdamW, get_linear_schedule_with_warmup
 from .trainer import Trainer
+from .data import DeviceCaptionDataset
 from .decode import BeamDecoder, generate_beam, generate_beam_ids
 from . import ops
 
 __all__ = ["ClipCaptionModel", "ClipCaptionPrefix", "GPT2Config", "GPT2LMHead", "MappingType", "MLP",
            "TransformerMapper", "noise_injection", "AdamW", "get_linear_schedule_with_warmup", "Trainer", "ops",
-           "BeamDecoder", "generate_beam", "generate_beam_ids"]
+           "DeviceCaptionDataset", "BeamDecoder", "generate_beam", "generate_beam_ids"]

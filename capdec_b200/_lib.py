@@ -28,6 +28,8 @@ SIGNATURES = {
     "capdec_gemm_tf32_mul": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p, _p],
     "capdec_gemm_debug_mn_encoding": [_i, _i, _i, _i],
     "capdec_gemm_debug_force_pair": [_i],
+    "capdec_gemm_set_row_hint": [_i],
+    "capdec_gemm_autotune": [_i],
     "capdec_gemm_fp32_simt": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p],
     "capdec_split_tf32": [_p, _p, _p, _i64, _p],
     "capdec_noise_injection": [_p, _p, _i, _i, _f, _p, _p, _i, _i, _p, _u64, _p],
@@ -64,11 +66,12 @@ SIGNATURES = {
     "capdec_embed_fwd_packed": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _u32, _p],
     "capdec_embed_bwd_packed": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _u32, _p],
     "capdec_zero_tail_rows": [_p, _i64, _p, _p],
+    "capdec_batch_gather": [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "capdec_step_clock": [_p, _p, _p, _p, _f, _i, _i, _p],
     "capdec_adamw_step": [_p, _p, _p, _p, _i64, _p, _p, _f, _f, _f, _f, _p, _i, _p],
 }
 _RESTYPES = {"capdec_last_error": C.c_char_p, "capdec_launch_count": C.c_int64, "capdec_gemm_debug_mn_encoding": None,
-             "capdec_gemm_debug_force_pair": None}
+             "capdec_gemm_debug_force_pair": None, "capdec_gemm_set_row_hint": None}
 
 
 class CapdecError(RuntimeError):

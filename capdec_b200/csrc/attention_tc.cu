@@ -10,6 +10,8 @@
 // shared memory -> O = PV.  Backward: phase A per query tile (P, dP = dO V^T, dS, dQ = dS K), phase B per key tile
 // (dK = dS^T Q, dV = P^T dO), plus the fused c_attn bias gradient (column sums of dq|dk|dv).
 // tcgen05 is reserved for the GEMMs (attention is 0.7 % of the step FLOPs; a 50x50x64 tile cannot feed a 128-row UMMA).
+#include <stdlib.h>
+
 #include "../../include/capdec_b200.h"
 #include "common.cuh"
 
@@ -20,6 +22,15 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// 16-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination without touching `g`
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* g, bool valid) {
+  const uint32_t sz = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // A fragment (16x8, row-major) of X[row0.., k0..] with row stride `ld` (floats)
@@ -93,28 +104,26 @@ __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __re
   float* sP = sV + (size_t)Sp * LV;  // [4 warps][16][LP]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr int hd4 = HD / 4;
+  // the whole head goes global -> shared with 16-byte async copies: every load of the tile is in flight at once (the
+  // register-staged loop exposed one HBM round trip per iteration); rows >= T / S are zero-filled
   for (int i = threadIdx.x; i < Tp * hd4; i += 128) {
     const int r = i / hd4, c = i % hd4;
-    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < T) val = *reinterpret_cast<const float4*>(q + q_b + (size_t)r * q_ts + (size_t)h * HD + 4 * c);
-    *reinterpret_cast<float4*>(sQ + (size_t)r * LQ + 4 * c) = val;
+    const bool ok = r < T;
+    cp_async16(sQ + (size_t)r * LQ + 4 * c, ok ? q + q_b + (size_t)r * q_ts + (size_t)h * HD + 4 * c : q, ok);
   }
   for (int i = threadIdx.x; i < Sp * hd4; i += 128) {
     const int r = i / hd4, c = i % hd4;
-    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-    if (r < S) {
-      const size_t gofs = kv_b + (size_t)r * kv_ts + (size_t)h * HD + 4 * c;
-      kv = *reinterpret_cast<const float4*>(k + gofs);
-      vv = *reinterpret_cast<const float4*>(v + gofs);
-    }
-    *reinterpret_cast<float4*>(sK + (size_t)r * LQ + 4 * c) = kv;
-    *reinterpret_cast<float4*>(sV + (size_t)r * LV + 4 * c) = vv;
+    const bool ok = r < S;
+    const size_t gofs = ok ? kv_b + (size_t)r * kv_ts + (size_t)h * HD + 4 * c : 0;
+    cp_async16(sK + (size_t)r * LQ + 4 * c, k + gofs, ok);
+    cp_async16(sV + (size_t)r * LV + 4 * c, v + gofs, ok);
   }
-  __syncthreads();
   const int klen = key_len ? min(S, (int)key_len[b]) : S;
   const int nt_all = Sp / 8;
   const float inv_keep = 1.0f / (1.0f - p_drop);
   float* myP = sP + (size_t)warp * 16 * LP;
+  cp_async_wait_all();
+  __syncthreads();
 
   for (int m0 = warp * 16; m0 < Tp; m0 += 64) {
     // key tiles that can hold an unmasked column for this query tile
@@ -473,13 +482,269 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
   }
 }
 
+// Backward, 8-warp variant (default): same arithmetic, dropout mapping and shared-memory tiles as
+// attention_tc_bwd_kernel, but TWO warps share every 16-row tile so that a 105 KB (batch, head) CTA brings 16 resident
+// warps per SM instead of 8 (profiles/r1_ncu_nongemm.md: 12 % warps active, latency-bound at 1.4 TB/s):
+//   phase A  warp (wq, hh): query tile wq, key-tile PAIRS np with (np & 1) == hh for S / P / dP / dS (so each Philox call is
+//            still made exactly once), then - after a 64-thread named barrier - half of the head-dim columns of dQ = dS K;
+//   phase B  warp (wq, hh): key tile wq, hh == 0 -> dK = dS^T Q, hh == 1 -> dV = Pd^T dO.
+// Q / K / V / dO arrive by cp.async; D_i = dO_i . O_i and the LSE rows are fetched from global memory while those copies
+// are in flight, so phase A never waits on HBM.
+template <int HD, int NT_MAX>
+__global__ void __launch_bounds__(256, 2) attention_tc_bwd8_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ ctx,
+    const float* __restrict__ dctx, const float* __restrict__ lse, float* __restrict__ dq, float* __restrict__ dk,
+    float* __restrict__ dv, float* __restrict__ dbias_qkv, int H, int T_arg, int S_arg, int64_t q_bs, int64_t q_ts, int64_t kv_bs,
+    int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale, int causal, const int32_t* __restrict__ key_len, float p_drop,
+    const uint64_t* seed_dev, uint32_t stream_id, const int32_t* __restrict__ cu_rows) {
+  const uint64_t seed = seed_dev ? *seed_dev : 0ull;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  int T = T_arg, S = S_arg;
+  const int TL = T_arg;
+  size_t q_b = (size_t)b * q_bs, kv_b = (size_t)b * kv_bs, o_b = (size_t)b * o_bs;
+  if (cu_rows) {
+    const int row_lo = cu_rows[b];
+    T = S = cu_rows[b + 1] - row_lo;
+    q_b = (size_t)row_lo * q_ts; kv_b = (size_t)row_lo * kv_ts; o_b = (size_t)row_lo * o_ts;
+  }
+  extern __shared__ __align__(16) float smem[];
+  const int Tp = (T + 15) & ~15, Sp = (S + 15) & ~15;
+  constexpr int LQ = HD + 4;
+  const int LS = Sp + 4;
+  float* sQ = smem;
+  float* sK = sQ + (size_t)Tp * LQ;
+  float* sV = sK + (size_t)Sp * LQ;
+  float* sdO = sV + (size_t)Sp * LQ;
+  float* sdS = sdO + (size_t)Tp * LQ;       // [Tp][LS]: P, then dS * scale
+  float* sPd = sdS + (size_t)Tp * LS;       // [Tp][LS]: dropout(P)
+  float* sDb = sPd + (size_t)Tp * LS;       // [3][HD] bias-gradient partial sums
+  float* sD = sDb + 3 * HD;                 // [Tp] D_i = dO_i . O_i
+  float* sL = sD + Tp;                      // [Tp] log-sum-exp of row i
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wq = warp & 3, hh = warp >> 2;
+  constexpr int hd4 = HD / 4;
+  for (int i = tid; i < Tp * hd4; i += 256) {
+    const int r = i / hd4, c = i % hd4;
+    const bool ok = r < T;
+    cp_async16(sQ + (size_t)r * LQ + 4 * c, ok ? q + q_b + (size_t)r * q_ts + (size_t)h * HD + 4 * c : q, ok);
+    cp_async16(sdO + (size_t)r * LQ + 4 * c, ok ? dctx + o_b + (size_t)r * o_ts + (size_t)h * HD + 4 * c : dctx, ok);
+  }
+  for (int i = tid; i < Sp * hd4; i += 256) {
+    const int r = i / hd4, c = i % hd4;
+    const bool ok = r < S;
+    const size_t gofs = ok ? kv_b + (size_t)r * kv_ts + (size_t)h * HD + 4 * c : 0;
+    cp_async16(sK + (size_t)r * LQ + 4 * c, k + gofs, ok);
+    cp_async16(sV + (size_t)r * LQ + 4 * c, v + gofs, ok);
+  }
+  for (int i = tid; i < 3 * HD; i += 256) sDb[i] = 0.f;
+  // D_i and LSE_i while the tile copies are in flight: 4 adjacent lanes split the head dim of one row
+  for (int idx = tid; idx < Tp * 4; idx += 256) {
+    const int row = idx >> 2, part = idx & 3;
+    float acc = 0.f;
+    if (row < T) {
+      const float* o_row = ctx + o_b + (size_t)row * o_ts + (size_t)h * HD;
+      const float* do_row = dctx + o_b + (size_t)row * o_ts + (size_t)h * HD;
+#pragma unroll
+      for (int c = 0; c < HD / 16; ++c) {
+        const int col = (c * 4 + part) * 4;
+        const float4 ov = *reinterpret_cast<const float4*>(o_row + col);
+        const float4 dv4 = *reinterpret_cast<const float4*>(do_row + col);
+        acc += ov.x * dv4.x + ov.y * dv4.y + ov.z * dv4.z + ov.w * dv4.w;
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0) {
+      sD[row] = acc;
+      sL[row] = (row < T) ? lse[(size_t)bh * TL + row] : 0.f;
+    }
+  }
+  const int klen = key_len ? min(S, (int)key_len[b]) : S;
+  const int nt_all = Sp / 8;
+  const float inv_keep = 1.0f / (1.0f - p_drop);
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ================= phase A: per query tile - P, dP, dS (to smem), dQ =================
+  constexpr int NL = NT_MAX / 2;            // key tiles owned by one warp of the pair
+  for (int m0 = wq * 16; m0 < Tp; m0 += 64) {
+    int nt = nt_all;
+    if (causal) nt = min(nt, (m0 + 15 + (S - T)) / 8 + 1);
+    nt = min(nt, (klen + 7) / 8);
+    if (nt < 1) nt = 1;
+    const int r0 = m0 + g, r1 = r0 + 8;
+    const float D0 = sD[r0], D1 = sD[r1];
+    const float l0 = sL[r0], l1 = sL[r1];
+    const int lim0 = (r0 < T) ? min(klen, causal ? r0 + 1 + (S - T) : S) : 0;
+    const int lim1 = (r1 < T) ? min(klen, causal ? r1 + 1 + (S - T) : S) : 0;
+    float acc[NL][4];
+    // local tile lt -> key tile n = 4*(lt>>1) + 2*hh + (lt&1)   (tile pair np = 2*(lt>>1) + hh)
+    // ---- S = Q K^T -> P ----
+#pragma unroll
+    for (int lt = 0; lt < NL; ++lt) { acc[lt][0] = acc[lt][1] = acc[lt][2] = acc[lt][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < HD / 8; ++kk) {
+      uint32_t a[4];
+      lda_frag(a, sQ, LQ, m0, kk * 8, g, t);
+#pragma unroll
+      for (int lt = 0; lt < NL; ++lt) {
+        const int n = 4 * (lt >> 1) + 2 * hh + (lt & 1);
+        if (n < nt) {
+          uint32_t bb[2];
+          ldb_frag_nk(bb, sK, LQ, n * 8, kk * 8, g, t);
+          mma_tf32(acc[lt], a, bb);
+        }
+      }
+    }
+#pragma unroll
+    for (int lp = 0; lp < NL / 2; ++lp) {
+      const int np = 2 * lp + hh;
+      float d0[4] = {1.f, 1.f, 1.f, 1.f}, d1[4] = {1.f, 1.f, 1.f, 1.f};
+      if (p_drop > 0.f && 2 * np < nt) {
+        attn_drop4(seed, stream_id, (uint64_t)bh * TL + r0, np, t, p_drop, inv_keep, d0);
+        attn_drop4(seed, stream_id, (uint64_t)bh * TL + r1, np, t, p_drop, inv_keep, d1);
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int lt = 2 * lp + e;
+        const int n = 2 * np + e;
+        if (n < nt_all) {   // also zero-fill the tiles this query tile never touches (phase B reads whole columns)
+          const int c0 = n * 8 + 2 * t;
+          float p00 = 0.f, p01 = 0.f, p10 = 0.f, p11 = 0.f;
+          if (n < nt) {
+            p00 = (c0 < lim0) ? __expf(acc[lt][0] * scale - l0) : 0.f;
+            p01 = (c0 + 1 < lim0) ? __expf(acc[lt][1] * scale - l0) : 0.f;
+            p10 = (c0 < lim1) ? __expf(acc[lt][2] * scale - l1) : 0.f;
+            p11 = (c0 + 1 < lim1) ? __expf(acc[lt][3] * scale - l1) : 0.f;
+          }
+          *reinterpret_cast<float2*>(sdS + (size_t)r0 * LS + c0) = make_float2(p00, p01);
+          *reinterpret_cast<float2*>(sdS + (size_t)r1 * LS + c0) = make_float2(p10, p11);
+          *reinterpret_cast<float2*>(sPd + (size_t)r0 * LS + c0) = make_float2(p00 * d0[2 * e], p01 * d0[2 * e + 1]);
+          *reinterpret_cast<float2*>(sPd + (size_t)r1 * LS + c0) = make_float2(p10 * d1[2 * e], p11 * d1[2 * e + 1]);
+        }
+      }
+    }
+    // ---- dP = dO V^T ----
+#pragma unroll
+    for (int lt = 0; lt < NL; ++lt) { acc[lt][0] = acc[lt][1] = acc[lt][2] = acc[lt][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < HD / 8; ++kk) {
+      uint32_t a[4];
+      lda_frag(a, sdO, LQ, m0, kk * 8, g, t);
+#pragma unroll
+      for (int lt = 0; lt < NL; ++lt) {
+        const int n = 4 * (lt >> 1) + 2 * hh + (lt & 1);
+        if (n < nt) {
+          uint32_t bb[2];
+          ldb_frag_nk(bb, sV, LQ, n * 8, kk * 8, g, t);
+          mma_tf32(acc[lt], a, bb);
+        }
+      }
+    }
+    // ---- dS = Pd * dP - P * D (each thread re-reads the P / Pd values it wrote), stored pre-multiplied by `scale` ----
+#pragma unroll
+    for (int lt = 0; lt < NL; ++lt) {
+      const int n = 4 * (lt >> 1) + 2 * hh + (lt & 1);
+      if (n < nt) {
+        const int c0 = n * 8 + 2 * t;
+        float2* ps0 = reinterpret_cast<float2*>(sdS + (size_t)r0 * LS + c0);
+        float2* ps1 = reinterpret_cast<float2*>(sdS + (size_t)r1 * LS + c0);
+        const float2 p0 = *ps0, p1 = *ps1;
+        const float2 pd0 = *reinterpret_cast<const float2*>(sPd + (size_t)r0 * LS + c0);
+        const float2 pd1 = *reinterpret_cast<const float2*>(sPd + (size_t)r1 * LS + c0);
+        *ps0 = make_float2((pd0.x * acc[lt][0] - p0.x * D0) * scale, (pd0.y * acc[lt][1] - p0.y * D0) * scale);
+        *ps1 = make_float2((pd1.x * acc[lt][2] - p1.x * D1) * scale, (pd1.y * acc[lt][3] - p1.y * D1) * scale);
+      }
+    }
+    named_bar_sync(1 + wq, 64);   // both warps of the tile have published their dS columns
+    // ---- dQ = dS K: this warp's half of the head-dim column tiles ----
+    constexpr int NH = HD / 16;
+    float o[NH][4];
+#pragma unroll
+    for (int n = 0; n < NH; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+    for (int kk = 0; kk < nt; ++kk) {
+      uint32_t a[4];
+      lda_frag(a, sdS, LS, m0, kk * 8, g, t);
+#pragma unroll
+      for (int n = 0; n < NH; ++n) {
+        uint32_t bb[2];
+        ldb_frag_kn(bb, sK, LQ, (hh * NH + n) * 8, kk * 8, g, t);
+        mma_tf32(o[n], a, bb);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NH; ++n) {
+      const int c0 = (hh * NH + n) * 8 + 2 * t;
+      if (r0 < T) *reinterpret_cast<float2*>(dq + q_b + (size_t)r0 * q_ts + (size_t)h * HD + c0) = make_float2(o[n][0], o[n][1]);
+      if (r1 < T) *reinterpret_cast<float2*>(dq + q_b + (size_t)r1 * q_ts + (size_t)h * HD + c0) = make_float2(o[n][2], o[n][3]);
+      if (dbias_qkv) {  // rows >= T contribute exact zeros (dS rows are zero there)
+        float c_even = o[n][0] + o[n][2], c_odd = o[n][1] + o[n][3];
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+          c_even += __shfl_xor_sync(0xffffffffu, c_even, off);
+          c_odd += __shfl_xor_sync(0xffffffffu, c_odd, off);
+        }
+        if (g == 0) { atomicAdd(&sDb[c0], c_even); atomicAdd(&sDb[c0 + 1], c_odd); }
+      }
+    }
+  }
+  __syncthreads();
+  // ================= phase B: per key tile - hh == 0: dK = dS^T Q, hh == 1: dV = Pd^T dO =================
+  {
+    const float* sA = hh ? sPd : sdS;
+    const float* sB = hh ? sdO : sQ;
+    float* outp = hh ? dv : dk;
+    float* sDbo = sDb + (hh ? 2 * HD : HD);
+    for (int j0 = wq * 16; j0 < Sp; j0 += 64) {
+      float oa[HD / 8][4];
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n) { oa[n][0] = oa[n][1] = oa[n][2] = oa[n][3] = 0.f; }
+      // queries that can see any key of this tile: i >= j0 - (S - T) under the causal mask
+      int kk0 = 0;
+      if (causal) kk0 = max(0, (j0 - (S - T))) / 8;
+      for (int kk = kk0; kk < Tp / 8; ++kk) {
+        uint32_t a[4];
+        lda_frag_t(a, sA, LS, j0, kk * 8, g, t);
+#pragma unroll
+        for (int n = 0; n < HD / 8; ++n) {
+          uint32_t bb[2];
+          ldb_frag_kn(bb, sB, LQ, n * 8, kk * 8, g, t);
+          mma_tf32(oa[n], a, bb);
+        }
+      }
+      const int r0 = j0 + g, r1 = r0 + 8;
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n) {
+        const int c0 = n * 8 + 2 * t;
+        if (r0 < S) *reinterpret_cast<float2*>(outp + kv_b + (size_t)r0 * kv_ts + (size_t)h * HD + c0) = make_float2(oa[n][0], oa[n][1]);
+        if (r1 < S) *reinterpret_cast<float2*>(outp + kv_b + (size_t)r1 * kv_ts + (size_t)h * HD + c0) = make_float2(oa[n][2], oa[n][3]);
+        if (dbias_qkv) {  // padded key rows hold exact zeros (their dS / Pd columns are zero)
+          float ce = oa[n][0] + oa[n][2], co = oa[n][1] + oa[n][3];
+#pragma unroll
+          for (int off = 4; off < 32; off <<= 1) {
+            ce += __shfl_xor_sync(0xffffffffu, ce, off);
+            co += __shfl_xor_sync(0xffffffffu, co, off);
+          }
+          if (g == 0) { atomicAdd(&sDbo[c0], ce); atomicAdd(&sDbo[c0 + 1], co); }
+        }
+      }
+    }
+  }
+  if (dbias_qkv) {
+    __syncthreads();
+    for (int i = tid; i < 3 * HD; i += 256)
+      atomicAdd(dbias_qkv + (size_t)(i / HD) * H * HD + (size_t)h * HD + (i % HD), sDb[i]);
+  }
+}
+
 size_t attn_tc_fwd_smem(int T, int S, int hd) {
   const int Tp = (T + 15) & ~15, Sp = (S + 7) & ~7;
   return ((size_t)Tp * (hd + 4) + (size_t)Sp * (hd + 4) + (size_t)Sp * (hd + 8) + (size_t)4 * 16 * (Sp + 4)) * sizeof(float);
 }
 size_t attn_tc_bwd_smem(int T, int S, int hd) {
   const int Tp = (T + 15) & ~15, Sp = (S + 15) & ~15;
-  return ((size_t)2 * Tp * (hd + 4) + (size_t)2 * Sp * (hd + 4) + (size_t)2 * Tp * (Sp + 4) + 3 * hd) * sizeof(float);
+  return ((size_t)2 * Tp * (hd + 4) + (size_t)2 * Sp * (hd + 4) + (size_t)2 * Tp * (Sp + 4) + 3 * hd + 2 * Tp) * sizeof(float);
 }
 
 template <int HD, int NT>
@@ -502,10 +767,21 @@ static int launch_bwd(const float* q, const float* k, const float* v, const floa
                       const int32_t* key_len, float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
                       const int32_t* cu_rows, cudaStream_t stream) {
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(attention_tc_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set = true; }
-  attention_tc_bwd_kernel<HD, NT><<<B * H, 128, attn_tc_bwd_smem(T, S, HD), stream>>>(
-      q, k, v, ctx, dctx, lse, dq, dk, dv, dbias, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len,
-      p_drop, seed_dev, stream_id, cu_rows);
+  if (!set) {
+    cudaFuncSetAttribute(attention_tc_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attention_tc_bwd8_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    set = true;
+  }
+  static const char* env8 = getenv("CAPDEC_ATTN_BWD8");   // bring-up switch: 0 = the 4-warp kernel
+  if (env8 && env8[0] == '0') {
+    attention_tc_bwd_kernel<HD, NT><<<B * H, 128, attn_tc_bwd_smem(T, S, HD), stream>>>(
+        q, k, v, ctx, dctx, lse, dq, dk, dv, dbias, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len,
+        p_drop, seed_dev, stream_id, cu_rows);
+  } else {
+    attention_tc_bwd8_kernel<HD, NT><<<B * H, 256, attn_tc_bwd_smem(T, S, HD), stream>>>(
+        q, k, v, ctx, dctx, lse, dq, dk, dv, dbias, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len,
+        p_drop, seed_dev, stream_id, cu_rows);
+  }
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("attention_tc_bwd_kernel");
   return CAPDEC_OK;

@@ -19,7 +19,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <vector>
 
 #include "../../include/capdec_b200.h"
 #include "common.cuh"
@@ -66,6 +68,7 @@ constexpr int kABytes = kBlockM * kBlockK * 4;  // 16 KB
 constexpr int kStagingBytes = 128 * 128;        // 128 rows x 32 fp32
 constexpr int kWarpStagingBytes = 32 * 128;     // one epilogue warp's box: 32 rows x 32 fp32 (4 per 16 KB slot)
 constexpr int kMaxStages = 8;
+constexpr int kMulDepth = 4;  // epilogue-input boxes in flight per epilogue warp (C = acc * act'(input))
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;  // columns per accumulator stage
 constexpr int kSmemLimit = 227 * 1024;
@@ -137,6 +140,21 @@ __device__ __forceinline__ void apply_act32(float (&v)[32], int act, bool exact)
   }
 }
 
+// v *= act'(u) over a 32-column register chunk, dispatch hoisted out of the element loop for the same reason: the
+// 32 independent dependency chains (MUFU.TANH + ~15 FMAs each) must interleave, the epilogue has one warp per scheduler.
+__device__ __forceinline__ void apply_mul32(float (&v)[32], const float (&u)[32], int mul_act) {
+  if (mul_act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= gelu_grad_fast(u[j]);
+  } else if (mul_act == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= 1.f - u[j] * u[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = u[j] > 0.f ? v[j] : 0.f;
+  }
+}
+
 // Tile engines (template kMode):
 //   0  one CTA per 128 x block_n tile (tcgen05 cta_group::1).
 //   1  a CTA PAIR (cluster of 2, cta_group::2) per 256 x block_n tile.  CTA r of the pair TMA-loads its own 128 A rows
@@ -162,15 +180,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.stages * kABytes;
   uint8_t* sStage = smem + p.stages * stage_bytes;  // epilogue staging: C ping-pong [+ aux ping-pong]
-  const int n_staging = (p.has_aux || p.mul_act) ? 4 : 2;
+  const int n_staging = p.mul_act ? 2 + kMulDepth : (p.has_aux ? 4 : 2);
   float* sBias = reinterpret_cast<float*>(sStage + n_staging * kStagingBytes);
   float* sCol = sBias;                              // per-tile column sums (mul epilogue; never together with a bias)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 256);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* mul_bar = tmem_empty_bar + 2;           // TMA loads of the epilogue input boxes (2 per epilogue warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mul_bar + 8);
+  uint64_t* mul_bar = tmem_empty_bar + 2;           // TMA loads of the epilogue input boxes (kMulDepth per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mul_bar + 4 * kMulDepth);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -199,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       mbar_init(&full_bar[i], kCtasPerPair);      // pair: leader's arrive.expect_tx + the peer's remote arrive
       mbar_init(&empty_bar[i], kPairsPerCluster);  // quad: both pairs' MMAs must have retired (multicast writes my smem)
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&mul_bar[i], 1);
+    for (int i = 0; i < 4 * kMulDepth; ++i) mbar_init(&mul_bar[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], kCtasPerPair * kEpiThreads);  // pair: both CTAs' epilogues report to the leader
@@ -220,11 +238,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   const int kb_lim = p.k_limit ? min(p.kb_total, (__ldg(p.k_limit) + kBlockK - 1) / kBlockK) : p.kb_total;
   const int kb_per_split = p.k_limit ? max(1, (kb_lim + p.splits - 1) / p.splits) : p.kb_per_split;  // rebalance the splits
   // cluster-level tile grid: m_tiles x n_tiles cluster tiles (each kCM x kCN*block_n), times split-K
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   const int tile0 = (int)(blockIdx.x / kCtasPerCluster);
   const int tile_step = (int)(gridDim.x / kCtasPerCluster);
   constexpr int kPairM = kPair ? 2 * kBlockM : kBlockM;                       // rows per pair tile
   constexpr int kTileM = (kQuad && kShareB) ? 2 * kPairM : kPairM;            // rows per cluster tile
+  // only the LIVE row tiles are enumerated, so that the round-robin over cluster tiles stays balanced under split-K
+  const int m_tiles = min(p.m_tiles, (m_lim + kTileM - 1) / kTileM);
+  const int total_tiles = m_tiles * p.n_tiles * p.splits;
   const int tile_n = (kQuad && !kShareB) ? 2 * p.block_n : p.block_n;         // columns per cluster tile
   // this CTA's pair tile inside the cluster tile
   const int pm_off = (kQuad && kShareB) ? (int)pair_idx * kPairM : 0;
@@ -240,8 +260,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       uint32_t phase = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int n_blk = tile % p.n_tiles;
-        const int m_blk = (tile / p.n_tiles) % p.m_tiles;
-        const int split = tile / (p.n_tiles * p.m_tiles);
+        const int m_blk = (tile / p.n_tiles) % m_tiles;
+        const int split = tile / (p.n_tiles * m_tiles);
         const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM;               // my 128 A rows
         const int n0 = n_blk * tile_n + pn_off + (kPair ? (int)half * bn_local : 0);  // my bn_local B columns
         const int kb0 = split * kb_per_split;
@@ -325,8 +345,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-        const int split = tile / (p.n_tiles * p.m_tiles);
-        const int m_blk = (tile / p.n_tiles) % p.m_tiles;
+        const int split = tile / (p.n_tiles * m_tiles);
+        const int m_blk = (tile / p.n_tiles) % m_tiles;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_lim);
         if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
@@ -372,18 +392,47 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
     const int row = q * 32 + lane;            // row of this CTA's 128-row slab owned by this thread
     const int epi_tid = threadIdx.x - 4 * 32;
     uint8_t* wst = sStage + q * (n_staging * kWarpStagingBytes);   // this warp's staging: C[0], C[1], (X[0], X[1])
-    uint64_t* my_mul_bar = mul_bar + 2 * q;
+    uint64_t* my_mul_bar = mul_bar + kMulDepth * q;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t store_idx = 0;  // running chunk counter: staging buffers alternate ACROSS tiles too
-    uint32_t mul_idx = 0;    // running count of epilogue-input chunks consumed (buffer = idx & 1, phase = (idx >> 1) & 1)
-    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+    uint32_t mul_idx = 0;    // running count of epilogue-input chunks consumed (buffer = idx % kMulDepth, phase = (idx / kMulDepth) & 1)
+    // this warp's (tile, chunk) stream: first row of the warp's 32-row box, the pair's first column, chunks to store
+    auto tile_coords = [&](int tile, int& m0w, int& n0w, int& nch) -> bool {
       const int n_blk = tile % p.n_tiles;
-      const int m_blk = (tile / p.n_tiles) % p.m_tiles;
-      const int split = tile / (p.n_tiles * p.m_tiles);
-      if (m_blk * kTileM >= m_lim || split * kb_per_split >= kb_lim) continue;
-      const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM + q * 32;   // first row of this WARP's 32-row box
-      const int n0 = n_blk * tile_n + pn_off;   // the pair's full block_n columns (each CTA stores its 128 rows x block_n)
+      const int m_blk = (tile / p.n_tiles) % m_tiles;
+      const int split = tile / (p.n_tiles * m_tiles);
+      if (m_blk * kTileM >= m_lim || split * kb_per_split >= kb_lim) return false;
+      m0w = m_blk * kTileM + pm_off + (int)half * kBlockM + q * 32;
+      n0w = n_blk * tile_n + pn_off;   // the pair's full block_n columns (each CTA stores its 128 rows x block_n)
+      nch = (p.N > n0w) ? min(p.block_n, p.N - n0w + 31) / 32 : 0;  // skip chunks (or whole tiles) past N
+      if (p.dbg & 8u) nch = 0;
+      return true;
+    };
+    // Epilogue-input prefetcher (lane 0): runs kMulDepth chunks AHEAD of the consumer over the same (tile, chunk) stream,
+    // across tile boundaries, so that the HBM latency of the 4 KB input boxes never sits on the epilogue's critical path
+    // (one-chunk-ahead prefetch left the fused GELU-backward dgrad at 315 TF/s vs 650 for the plain dgrad).
+    int la_tile = tile0 - tile_step, la_c = 0, la_nch = 0, la_m0 = 0, la_n0 = 0;
+    uint32_t mul_issued = 0;
+    auto mul_prefetch = [&]() {
+      while (la_tile < total_tiles && la_c >= la_nch) {
+        la_tile += tile_step; la_c = 0; la_nch = 0;
+        if (la_tile < total_tiles && !tile_coords(la_tile, la_m0, la_n0, la_nch)) la_nch = 0;
+      }
+      if (la_tile >= total_tiles) return;
+      const uint32_t slot = mul_issued % kMulDepth;
+      uint64_t* mb = &my_mul_bar[slot];
+      mbar_arrive_expect_tx(mb, kWarpStagingBytes);
+      tma_load_2d(wst + (2 + slot) * kWarpStagingBytes, &p.tmMul, mb, la_n0 + la_c * 32, la_m0);
+      ++mul_issued; ++la_c;
+    };
+    if (p.mul_act && lane == 0) {
+      for (int i = 0; i < kMulDepth; ++i) mul_prefetch();
+    }
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      int m0, n0, n_chunks;
+      if (!tile_coords(tile, m0, n0, n_chunks)) continue;
+      const int split = tile / (p.n_tiles * m_tiles);
       const bool use_bias = (p.bias != nullptr) && (split == 0);
       if (use_bias) {
         named_bar_sync(1, kEpiThreads);  // the warps run independently: nobody may still be reading the previous bias tile
@@ -392,17 +441,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       if (p.colsum) {
         for (int i = epi_tid; i < 256; i += kEpiThreads) sCol[i] = 0.f;
       }
-      int n_chunks = (p.N > n0) ? min(p.block_n, p.N - n0 + 31) / 32 : 0;  // skip chunks (or whole tiles) past N
-      if (p.mul_act && n_chunks > 0 && lane == 0) {  // prefetch the first epilogue-input box of this tile
-        uint64_t* mb = &my_mul_bar[mul_idx & 1];
-        mbar_arrive_expect_tx(mb, kWarpStagingBytes);
-        tma_load_2d(wst + (2 + (mul_idx & 1)) * kWarpStagingBytes, &p.tmMul, mb, n0, m0);
-      }
       mbar_wait(&tmem_full_bar[acc], acc_phase, 4);
       tc_fence_after();
       if (use_bias || p.colsum) named_bar_sync(1, kEpiThreads);  // bias tile / zeroed column sums visible to all 4 warps
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols);
-      if ((p.dbg & 8u) || n_chunks == 0) {  // nothing to store: release the accumulator right away
+      if (n_chunks == 0) {  // nothing to store (or dbg 8): release the accumulator right away
         tc_fence_before();
         if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], pair_leader); else mbar_arrive(&tmem_empty_bar[acc]);
         n_chunks = 0;
@@ -410,11 +453,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       for (int c = 0; c < n_chunks; ++c) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
-        if (p.mul_act && c + 1 < n_chunks && lane == 0) {  // next chunk's input box: its buffer was last read one chunk ago
-          uint64_t* mb = &my_mul_bar[(mul_idx + 1) & 1];
-          mbar_arrive_expect_tx(mb, kWarpStagingBytes);
-          tma_load_2d(wst + (2 + ((mul_idx + 1) & 1)) * kWarpStagingBytes, &p.tmMul, mb, n0 + (c + 1) * 32, m0);
-        }
         tmem_ld_wait();
         if (c == n_chunks - 1) {
           // all TMEM reads of this accumulator stage are done -> hand it back to the (leader's) MMA warp
@@ -426,29 +464,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
           for (int j = 0; j < 32; ++j) v[j] += sBias[c * 32 + j];
         }
         if (p.mul_act) {  // v *= act'(input box), read back from the 128B-swizzled TMA layout (row = lane)
-          mbar_wait(&my_mul_bar[mul_idx & 1], (mul_idx >> 1) & 1, 5);
-          const float4* u4 = reinterpret_cast<const float4*>(wst + (2 + (mul_idx & 1)) * kWarpStagingBytes + lane * 128);
+          const uint32_t slot = mul_idx % kMulDepth;
+          mbar_wait(&my_mul_bar[slot], (mul_idx / kMulDepth) & 1, 5);
+          const float4* u4 = reinterpret_cast<const float4*>(wst + (2 + slot) * kWarpStagingBytes + lane * 128);
           ++mul_idx;
+          float uu[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 u = u4[j ^ (lane & 7)];
-            if (p.mul_act == 1) {
-              v[4 * j] *= gelu_grad_fast(u.x); v[4 * j + 1] *= gelu_grad_fast(u.y);
-              v[4 * j + 2] *= gelu_grad_fast(u.z); v[4 * j + 3] *= gelu_grad_fast(u.w);
-            } else if (p.mul_act == 2) {
-              v[4 * j] *= 1.f - u.x * u.x; v[4 * j + 1] *= 1.f - u.y * u.y;
-              v[4 * j + 2] *= 1.f - u.z * u.z; v[4 * j + 3] *= 1.f - u.w * u.w;
-            } else {
-              v[4 * j] = u.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = u.y > 0.f ? v[4 * j + 1] : 0.f;
-              v[4 * j + 2] = u.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = u.w > 0.f ? v[4 * j + 3] : 0.f;
-            }
+            uu[4 * j] = u.x; uu[4 * j + 1] = u.y; uu[4 * j + 2] = u.z; uu[4 * j + 3] = u.w;
           }
+          apply_mul32(v, uu, p.mul_act);
         }
         const uint32_t pp = store_idx++ & 1;
         uint8_t* buf0 = wst + pp * kWarpStagingBytes;          // C box
         uint8_t* buf1 = wst + (2 + pp) * kWarpStagingBytes;    // aux (pre-activation) box
         if (lane == 0) tma_store_wait_read<1>();  // the group this lane committed two chunks ago has released buf[pp]
         __syncwarp();
+        if (p.mul_act && lane == 0) mul_prefetch();  // every lane has read the input box just consumed: refill its slot
         if (p.has_aux) {
           float4* d1 = reinterpret_cast<float4*>(buf1 + lane * 128);
 #pragma unroll
@@ -541,12 +574,14 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim
 }
 
 // 3-D view of an MN-major operand: [MN/32 slabs][K rows][32 floats]; one box = {32, 32 k-rows, nslabs} lands in shared
-// memory slab after slab (4 KB each), i.e. exactly the layout the UMMA descriptor expects.  Needs MN % 32 == 0.
+// memory slab after slab (4 KB each), i.e. exactly the layout the UMMA descriptor expects.  Needs MN % 32 == 0, or a row
+// pitch that covers the 32-rounded extent (the tied-embedding gradient: MN = V = 50257 inside a 50304-float pitch): the pad
+// columns only feed accumulator rows / columns >= M / N, which the bounds of the C tensor map clip at the store.
 static int make_map_mn3d(CUtensorMap* m, const void* ptr, uint64_t mn, uint64_t k_rows, uint64_t pitch_elems,
                          uint32_t nslabs, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return CAPDEC_ERR_CUDA;
-  cuuint64_t dims[3] = {32, k_rows, mn / 32};
+  cuuint64_t dims[3] = {32, k_rows, (mn + 31) / 32};   // a ragged last slab reads (finite or not) pad columns < pitch
   cuuint64_t strides[2] = {pitch_elems * 4, 128};
   cuuint32_t box[3] = {32, kBlockK, nslabs};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -585,28 +620,30 @@ static OperandEnc operand_encoding(bool mn_major) {
 }
 
 static int g_force_pair = -1;  // bring-up override: -1 auto, 0 never, 1 always (pairs), 2/3 force quad modes
+static thread_local int t_m_hint = 0;   // expected live rows of the next row-limited GEMMs (capdec_gemm_set_row_hint)
 
 // pick block_n and split-K for a given engine: `units` = concurrently running tile owners (SMs, pairs or quads),
 // tile_m rows and nmul*block_n columns per cluster tile
 static void choose_tiling(int M, int N, int kb_total, int accumulate, int units, int tile_m, int nmul, int min_bn,
-                          int& block_n, int& splits) {
+                          bool allow192, int& block_n, int& splits) {
   const int m_tiles = (M + tile_m - 1) / tile_m;
   auto cost = [&](int bn, int s) {
     const long tiles = (long)m_tiles * ((N + nmul * bn - 1) / (nmul * bn)) * s;
     const long waves = (tiles + units - 1) / units;
     const double kb = (double)((kb_total + s - 1) / s);
     // per-tile time ~ k-blocks x (operand bytes per k-block, the L2 feed is the limiter) + epilogue
-    const double per_kb = (bn >= 256) ? 1.0 : (bn == 128 ? 0.62 : 0.40);
+    const double per_kb = (bn >= 256) ? 1.0 : (bn == 192 ? 0.82 : (bn == 128 ? 0.62 : 0.40));
     const double epi = (bn / 256.0) * 5.0;
     return waves * (kb * per_kb + epi + 1.5);
   };
   int best_bn = block_n, best_s = splits;
   double best = 1e30;
-  const int bns[3] = {256, 128, 64};
-  for (int bi = 0; bi < 3; ++bi) {
+  const int bns[4] = {256, 192, 128, 64};
+  for (int bi = 0; bi < 4; ++bi) {
     const int bn = bns[bi];
     if (block_n > 0 && bn != block_n) continue;
     if (bn < min_bn) continue;
+    if (bn == 192 && !allow192 && block_n != 192) continue;
     const int smax = (splits > 0) ? splits : (accumulate ? 32 : 1);
     for (int s = (splits > 0 ? splits : 1); s <= smax; ++s) {
       if (s > 1 && kb_total / s < 4) break;
@@ -675,6 +712,11 @@ extern "C" int64_t capdec_launch_count(void) { return g_launches.load(); }
 
 extern "C" void capdec_gemm_debug_force_pair(int mode) { g_force_pair = mode; }  // -1 auto, 0..3 engine
 
+// Tiling hint for GEMMs launched with a device-side row limit (packed caption batches): the row count is data dependent
+// and unknown to the host, so engine / tile width / wave quantisation are chosen for `rows` (0 = the static M).  Results
+// do not depend on the hint.
+extern "C" void capdec_gemm_set_row_hint(int rows) { t_m_hint = rows > 0 ? rows : 0; }
+
 extern "C" void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, int sbo_bytes, int tma_swizzle) {
   g_mn_layout = layout_type;
   g_mn_lbo = lbo_bytes;
@@ -714,101 +756,108 @@ extern "C" int capdec_gemm_tf32_mul(const float* A, int a_major, int64_t lda, co
   return rc;
 }
 
-extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
-                                   float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
-                                   int accumulate, int precision, const float* a_lo, const float* b_lo, int block_n,
-                                   int split_k, const int32_t* m_limit_dev, const int32_t* k_limit_dev,
-                                   capdec_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CAPDEC_REQUIRE(A && B && C, "gemm: null operand");
-  CAPDEC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
-  CAPDEC_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0, "gemm: leading dims must be multiples of 4 (16 B TMA pitch): lda=%lld ldb=%lld ldc=%lld", (long long)lda, (long long)ldb, (long long)ldc);
-  CAPDEC_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0, "gemm: operands must be 16-byte aligned");
-  CAPDEC_REQUIRE(lda >= (a_major ? M : K) && ldb >= (b_major ? N : K) && ldc >= N, "gemm: leading dim smaller than extent");
-  CAPDEC_REQUIRE(precision == 0 || (a_lo && b_lo), "gemm: 3xTF32 needs a_lo and b_lo");
-  CAPDEC_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 256, "gemm: block_n must be 0/64/128/256");
-  CAPDEC_REQUIRE(act >= 0 && act <= 3, "gemm: bad act %d", act);
-  CAPDEC_REQUIRE(!aux || ((uintptr_t)aux % 16) == 0, "gemm: aux must be 16-byte aligned");
+// ---------------------------------------------------------------------------------------------------------------
+// plan (engine, tile width, split-K)  ->  launch;  measured plan selection ("autotune") on top of the heuristic
+// ---------------------------------------------------------------------------------------------------------------
+namespace capdec {
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm_tf32_kernel)");
-    attr_set = true;
-  }
+struct GemmArgs {
+  const float *A, *B; float* C;
+  int a_major, b_major; int64_t lda, ldb, ldc;
+  int M, N, K;
+  const float* bias; int act; float* aux; int accumulate, precision;
+  const float *a_lo, *b_lo;
+  const int32_t *m_limit, *k_limit;
+  const float* mul_in; int mul_act; float* colsum;
+};
+struct GemmPlan { int mode, bn, splits; };
 
-  GemmDev p;
-  memset(&p, 0, sizeof(p));
-  p.M = M; p.N = N; p.K = K;
-  p.kb_total = (K + kBlockK - 1) / kBlockK;
-  // ---- engine selection: 0 single CTA, 1 CTA pair, 2 quad sharing A (pairs side by side in N), 3 quad sharing B ----
+static inline int plan_units(int mode) { return mode >= 2 ? 33 : num_sms() / (mode == 0 ? 1 : 2); }  // quads: 132 of 148 SMs
+static inline int plan_tile_m(int mode) { return mode == 0 ? kBlockM : (mode == 3 ? 4 * kBlockM : 2 * kBlockM); }
+static inline bool plan_ok192(int mode, int b_major) { return !(mode == 3 && b_major); }
+
+// heuristic plan (also the fallback whenever nothing was measured for this problem)
+static GemmPlan heuristic_plan(const GemmArgs& a, int block_n, int split_k, int forced) {
+  const int M = a.M, N = a.N;
   int mode = ((M > kBlockM) && (N >= 128) && (block_n == 0 || block_n >= 128)) ? 1 : 0;
-  static const char* env_pair = getenv("CAPDEC_GEMM_PAIR");  // bring-up switch: 0 = cta_group::1 only, 1 = pairs only
-  static const char* env_mode = getenv("CAPDEC_GEMM_MODE");  // bring-up switch: force engine 0..3 where legal
-  int forced = g_force_pair >= 0 ? g_force_pair : (env_mode ? atoi(env_mode) : (env_pair ? atoi(env_pair) : -1));
-  int bn = block_n, splits = accumulate ? split_k : 1;
   if (forced == 0) mode = 0;
+  const int m_live = (a.m_limit && t_m_hint > 0 && t_m_hint < M) ? t_m_hint : M;
   if (mode >= 1) {
     const bool quad_ok = (M > 2 * kBlockM || N > 256);
     if (forced < 0 && quad_ok) {
       // Measured on B200 (profiles/r1_gemm_modes.md): stacking the two pairs in M and multicasting B (mode 3) wins
-      // 10-16 % whenever there are enough 256-row tiles to fill the 33 resident quads; sharing A (mode 2) loses to
-      // wave quantisation on every shape of this model, and few-row problems (wgrad, M = 768) stay on plain pairs.
-      const int mt = (M + 255) / 256;
+      // 10-16 % at the dense C2 extent (M = 12800) when B is MN-major; sharing A (mode 2) loses to wave quantisation on
+      // every shape of this model, and few-row problems (wgrad, M = 768) stay on plain pairs.
+      const int mt = (m_live + 255) / 256;
       const double waste_b = (double)(((mt + 1) / 2) * 2) / mt;
-      // ... and only when B is MN-major: there multicast halves the number of small (4 KB) TMA boxes per k-block; with a
-      // K-major B (one 16 KB box) the in-step profile shows mode 3 ~10 % SLOWER than pairs (132 vs 148 SMs, no fewer requests)
-      if (mt >= 8 && waste_b <= 1.15 && b_major) mode = 3;
+      if (mt >= 8 && waste_b <= 1.15 && a.b_major && block_n != 192) mode = 3;
     } else if (forced == 2 || forced == 3) {
       mode = forced;
     }
   }
-  const int tile_m = (mode == 0) ? kBlockM : (mode == 3 ? 4 * kBlockM : 2 * kBlockM);   // rows per cluster tile
+  GemmPlan pl;
+  pl.mode = mode;
+  pl.bn = block_n;
+  pl.splits = a.accumulate ? split_k : 1;
+  static const char* env_192 = getenv("CAPDEC_GEMM_BN192");   // bring-up switch: 0 keeps the automatic choice to 256/128/64
+  const bool allow192 = plan_ok192(mode, a.b_major) && !(env_192 && env_192[0] == '0');
+  const int kb_total = (a.K + kBlockK - 1) / kBlockK;
+  choose_tiling(m_live, N, kb_total, a.accumulate, plan_units(mode), plan_tile_m(mode), mode == 2 ? 2 : 1, mode == 0 ? 64 : 128,
+                allow192, pl.bn, pl.splits);
+  return pl;
+}
+
+static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t stream) {
+  const int M = a.M, N = a.N, K = a.K, mode = pl.mode, bn = pl.bn;
+  CAPDEC_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "gemm: bad tile width %d", bn);
+  CAPDEC_REQUIRE(mode == 0 || bn >= 128, "gemm: CTA-pair engines need block_n >= 128");
+  CAPDEC_REQUIRE(bn != 192 || plan_ok192(mode, a.b_major),
+                 "gemm: block_n=192 is not available for the B-sharing quad with an MN-major B");
+  CAPDEC_REQUIRE(pl.splits == 1 || (a.accumulate && a.act == 0 && !a.aux), "gemm: split-K needs accumulate=1, act=0, no aux");
+  GemmDev p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.kb_total = (K + kBlockK - 1) / kBlockK;
+  const int tile_m = plan_tile_m(mode);                                                 // rows per cluster tile
   const int pair_m = (mode == 0) ? kBlockM : 2 * kBlockM;                               // rows per MMA (instruction M)
   const int nmul = (mode == 2) ? 2 : 1;
   const int cluster_size = (mode == 0) ? 1 : (mode == 1 ? 2 : 4);
-  const int units = (mode >= 2) ? 33 : num_sms() / cluster_size;   // quads: 132 of the 148 SMs are schedulable in 4-clusters
-  const int min_bn = (mode == 0) ? 64 : 128;
-  choose_tiling(M, N, p.kb_total, accumulate, units, tile_m, nmul, min_bn, bn, splits);
-  CAPDEC_REQUIRE(splits == 1 || (accumulate && act == 0 && !aux), "gemm: split-K needs accumulate=1, act=0, no aux");
+  int splits = pl.splits < 1 ? 1 : pl.splits;
   p.block_n = bn;
   p.splits = splits;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // drop empty splits
   p.m_tiles = (M + tile_m - 1) / tile_m;
   p.n_tiles = (N + nmul * bn - 1) / (nmul * bn);
-  p.nseg = precision ? 3 : 1;
-  p.act = act;
-  p.has_aux = aux ? 1 : 0;
-  p.accumulate = accumulate ? 1 : 0;
-  p.a_mn = a_major ? 1 : 0;
-  p.b_mn = b_major ? 1 : 0;
-  p.bias = bias;
-  p.m_limit = m_limit_dev;
-  p.mul_act = t_mul_act;
-  p.colsum = t_colsum;
-  p.k_limit = k_limit_dev;
+  p.nseg = a.precision ? 3 : 1;
+  p.act = a.act;
+  p.has_aux = a.aux ? 1 : 0;
+  p.accumulate = a.accumulate ? 1 : 0;
+  p.a_mn = a.a_major ? 1 : 0;
+  p.b_mn = a.b_major ? 1 : 0;
+  p.bias = a.bias;
+  p.m_limit = a.m_limit;
+  p.mul_act = a.mul_act;
+  p.colsum = a.colsum;
+  p.k_limit = a.k_limit;
   static const char* env_dbg = getenv("CAPDEC_GEMM_DBG");
   p.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
 
   const int bn_local = (mode == 0) ? bn : bn / 2;
   const int b_bytes = bn_local * kBlockK * 4;
-  const int fixed = ((aux || t_mul_act) ? 4 : 2) * kStagingBytes + 256 * 4 + (2 * kMaxStages + 12) * 8 + 16 + 960 /* alignment slack */;
+  const int fixed = (a.mul_act ? 2 + kMulDepth : (a.aux ? 4 : 2)) * kStagingBytes + 256 * 4 + (2 * kMaxStages + 4 + 4 * kMulDepth) * 8 + 16 + 960 /* alignment slack */;
   int stages = (kSmemLimit - fixed) / (kABytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
   const int smem_bytes = stages * (kABytes + b_bytes) + fixed;
 
-  const OperandEnc ea = operand_encoding(a_major != 0), eb = operand_encoding(b_major != 0);
+  const OperandEnc ea = operand_encoding(a.a_major != 0), eb = operand_encoding(a.b_major != 0);
   p.adesc_hi = ea.desc_hi; p.adesc_lo16 = ea.desc_lo16; p.a_kstep = ea.kstep;
   p.bdesc_hi = eb.desc_hi; p.bdesc_lo16 = eb.desc_lo16; p.b_kstep = eb.kstep;
   // instruction descriptor: D=F32 (bits 4-5 = 1), A/B = TF32 (2) at bits 7-9 / 10-12, majors at 15/16,
   // N>>3 at bits 17-22, M>>4 at bits 24-28
-  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_major ? 1 : 0) << 15) |
-            ((uint32_t)(b_major ? 1 : 0) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(pair_m >> 4) << 24);
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.a_major ? 1 : 0) << 15) |
+            ((uint32_t)(a.b_major ? 1 : 0) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(pair_m >> 4) << 24);
 
   // TMA boxes: K-major operands move {32 fp32, rows}; a quad that shares the operand moves half the rows per CTA
   const uint32_t a_rows = (mode == 2) ? kBlockM / 2 : kBlockM;
@@ -817,33 +866,33 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
   const bool allow3d = !(env_3d && env_3d[0] == '0') && g_mn_swz < 0;
   const uint32_t a_slabs = (mode == 2) ? kBlockM / 64 : kBlockM / 32;
   const uint32_t b_slabs = (mode == 3) ? (uint32_t)bn_local / 64 : (uint32_t)bn_local / 32;
-  p.a_3d = (a_major && allow3d && (M % 32) == 0) ? 1 : 0;
-  p.b_3d = (b_major && allow3d && (N % 32) == 0) ? 1 : 0;
+  p.a_3d = (a.a_major && allow3d && ((M % 32) == 0 || a.lda >= (int64_t)((M + 31) / 32) * 32)) ? 1 : 0;
+  p.b_3d = (a.b_major && allow3d && ((N % 32) == 0 || a.ldb >= (int64_t)((N + 31) / 32) * 32)) ? 1 : 0;
   int rc;
   for (int s = 0; s < p.nseg && s < 2; ++s) {
-    const float* a = s ? a_lo : A;
-    const float* b = s ? b_lo : B;
-    if (!a_major) rc = make_map(&p.tmA[s], a, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBlockK, a_rows, ea.swz);
+    const float* pa = s ? a.a_lo : a.A;
+    const float* pb = s ? a.b_lo : a.B;
+    if (!a.a_major) rc = make_map(&p.tmA[s], pa, (uint64_t)K, (uint64_t)M, (uint64_t)a.lda, kBlockK, a_rows, ea.swz);
     else {
-      rc = p.a_3d ? make_map_mn3d(&p.tmA[s], a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, a_slabs, ea.swz) : CAPDEC_ERR_UNSUPPORTED;
-      if (rc) { p.a_3d = 0; rc = make_map(&p.tmA[s], a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, kBlockK, ea.swz); }
+      rc = p.a_3d ? make_map_mn3d(&p.tmA[s], pa, (uint64_t)M, (uint64_t)K, (uint64_t)a.lda, a_slabs, ea.swz) : CAPDEC_ERR_UNSUPPORTED;
+      if (rc) { p.a_3d = 0; rc = make_map(&p.tmA[s], pa, (uint64_t)M, (uint64_t)K, (uint64_t)a.lda, 32, kBlockK, ea.swz); }
     }
     if (rc) return rc;
-    if (!b_major) rc = make_map(&p.tmB[s], b, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBlockK, b_rows, eb.swz);
+    if (!a.b_major) rc = make_map(&p.tmB[s], pb, (uint64_t)K, (uint64_t)N, (uint64_t)a.ldb, kBlockK, b_rows, eb.swz);
     else {
-      rc = p.b_3d ? make_map_mn3d(&p.tmB[s], b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, b_slabs, eb.swz) : CAPDEC_ERR_UNSUPPORTED;
-      if (rc) { p.b_3d = 0; rc = make_map(&p.tmB[s], b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, kBlockK, eb.swz); }
+      rc = p.b_3d ? make_map_mn3d(&p.tmB[s], pb, (uint64_t)N, (uint64_t)K, (uint64_t)a.ldb, b_slabs, eb.swz) : CAPDEC_ERR_UNSUPPORTED;
+      if (rc) { p.b_3d = 0; rc = make_map(&p.tmB[s], pb, (uint64_t)N, (uint64_t)K, (uint64_t)a.ldb, 32, kBlockK, eb.swz); }
     }
     if (rc) return rc;
   }
-  rc = make_map(&p.tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);  // per-warp {32 x 32} boxes
+  rc = make_map(&p.tmC, a.C, (uint64_t)N, (uint64_t)M, (uint64_t)a.ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);  // per-warp {32 x 32} boxes
   if (rc) return rc;
-  if (aux) {
-    rc = make_map(&p.tmAux, aux, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (a.aux) {
+    rc = make_map(&p.tmAux, a.aux, (uint64_t)N, (uint64_t)M, (uint64_t)a.ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  if (t_mul_act) {
-    rc = make_map(&p.tmMul, t_mul_in, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (a.mul_act) {
+    rc = make_map(&p.tmMul, a.mul_in, (uint64_t)N, (uint64_t)M, (uint64_t)a.ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
 
@@ -864,4 +913,151 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("gemm_tf32_kernel");
   return CAPDEC_OK;
+}
+
+// ---- measured plan selection ------------------------------------------------------------------------------------
+// While tuning is enabled (capdec_gemm_autotune(1)), the first call for a problem signature times a short list of
+// candidate plans on the caller's stream with the caller's operands (so device-side row / reduction limits are the
+// real ones) and remembers the fastest; afterwards - and under CUDA-graph capture - the remembered plan is used.
+// A tuning call launches the problem several times: accumulate outputs and fused column sums are garbage afterwards,
+// so the caller runs tuning on a throw-away step (Trainer.autotune).
+struct TuneKey {
+  int v[18];
+  bool operator<(const TuneKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+static std::map<TuneKey, GemmPlan> g_tuned;
+static std::mutex g_tune_mu;
+static std::atomic<int> g_tune_on{0};
+
+static TuneKey tune_key(const GemmArgs& a, int block_n, int split_k) {
+  TuneKey k;
+  const int vals[18] = {a.M, a.N, a.K, a.a_major, a.b_major, a.accumulate, a.act, a.aux != nullptr, a.bias != nullptr,
+                        a.mul_act, a.colsum != nullptr, a.precision, block_n, split_k, a.m_limit != nullptr,
+                        a.k_limit != nullptr, (int)(a.lda % 32 == 0), (int)(a.ldb % 32 == 0)};
+  memcpy(k.v, vals, sizeof(vals));
+  return k;
+}
+
+static int tune_and_launch(const GemmArgs& a, int block_n, int split_k, const GemmPlan& base, cudaStream_t stream) {
+  std::vector<GemmPlan> cands;
+  cands.push_back(base);
+  auto add = [&](int mode, int bn) {
+    if (block_n && bn != block_n) return;
+    if (bn == 192 && !plan_ok192(mode, a.b_major)) return;
+    GemmPlan pl{mode, bn, a.accumulate ? split_k : 1};
+    int bn_fixed = bn;
+    const int m_live = (a.m_limit && t_m_hint > 0 && t_m_hint < a.M) ? t_m_hint : a.M;
+    choose_tiling(m_live, a.N, (a.K + kBlockK - 1) / kBlockK, a.accumulate, plan_units(mode), plan_tile_m(mode), 1,
+                  mode == 0 ? 64 : 128, true, bn_fixed, pl.splits);
+    pl.bn = bn;
+    for (const GemmPlan& c : cands) if (c.mode == pl.mode && c.bn == pl.bn && c.splits == pl.splits) return;
+    cands.push_back(pl);
+    if (a.accumulate && !split_k && pl.splits > 1) {   // neighbours of the heuristic split factor
+      GemmPlan lo = pl, hi = pl;
+      lo.splits = pl.splits - 1; hi.splits = pl.splits + 1;
+      cands.push_back(lo);
+      if ((a.K + kBlockK - 1) / kBlockK / hi.splits >= 4) cands.push_back(hi);
+    }
+  };
+  if (base.mode == 0) {
+    add(0, 256); add(0, 128); add(0, 64);
+  } else {
+    add(1, 256); add(1, 192); add(1, 128);
+    if (a.M > 2 * kBlockM || a.N > 256) { add(3, 256); add(3, 192); }
+  }
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaGetLastError(); return launch_plan(a, base, stream); }
+  GemmPlan best = base;
+  float best_ms = 1e30f;
+  for (const GemmPlan& c : cands) {
+    if (launch_plan(a, c, stream) != CAPDEC_OK) continue;   // warm-up (and legality check)
+    const int reps = 4;
+    cudaEventRecord(e0, stream);
+    bool ok = true;
+    for (int r = 0; r < reps && ok; ++r) ok = launch_plan(a, c, stream) == CAPDEC_OK;
+    cudaEventRecord(e1, stream);
+    if (!ok || cudaEventSynchronize(e1) != cudaSuccess) { cudaGetLastError(); continue; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best_ms) { best_ms = ms; best = c; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    g_tuned[tune_key(a, block_n, split_k)] = best;
+  }
+  static const char* env_v = getenv("CAPDEC_GEMM_TUNE_VERBOSE");
+  if (env_v && env_v[0] == '1')
+    fprintf(stderr, "capdec gemm tune: M=%d N=%d K=%d maj=%d%d acc=%d mul=%d lim=%d%d -> mode %d bn %d splits %d (%.1f us; heuristic mode %d bn %d splits %d)\n",
+            a.M, a.N, a.K, a.a_major, a.b_major, a.accumulate, a.mul_act, a.m_limit != nullptr, a.k_limit != nullptr, best.mode,
+            best.bn, best.splits, best_ms * 250.f, base.mode, base.bn, base.splits);
+  return launch_plan(a, best, stream);
+}
+
+}  // namespace capdec
+
+// 1 = measure plans for problems not seen yet (see above), 0 = stop measuring (remembered plans stay in use),
+// -1 = forget every remembered plan.  Returns the number of remembered plans.
+extern "C" int capdec_gemm_autotune(int enable) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  if (enable < 0) g_tuned.clear();
+  else g_tune_on.store(enable ? 1 : 0);
+  return (int)g_tuned.size();
+}
+
+extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
+                                   float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
+                                   int accumulate, int precision, const float* a_lo, const float* b_lo, int block_n,
+                                   int split_k, const int32_t* m_limit_dev, const int32_t* k_limit_dev,
+                                   capdec_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CAPDEC_REQUIRE(A && B && C, "gemm: null operand");
+  CAPDEC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  CAPDEC_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0, "gemm: leading dims must be multiples of 4 (16 B TMA pitch): lda=%lld ldb=%lld ldc=%lld", (long long)lda, (long long)ldb, (long long)ldc);
+  CAPDEC_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0, "gemm: operands must be 16-byte aligned");
+  CAPDEC_REQUIRE(lda >= (a_major ? M : K) && ldb >= (b_major ? N : K) && ldc >= N, "gemm: leading dim smaller than extent");
+  CAPDEC_REQUIRE(precision == 0 || (a_lo && b_lo), "gemm: 3xTF32 needs a_lo and b_lo");
+  CAPDEC_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 192 || block_n == 256, "gemm: block_n must be 0/64/128/192/256");
+  CAPDEC_REQUIRE(act >= 0 && act <= 3, "gemm: bad act %d", act);
+  CAPDEC_REQUIRE(!aux || ((uintptr_t)aux % 16) == 0, "gemm: aux must be 16-byte aligned");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm_tf32_kernel)");
+    attr_set = true;
+  }
+
+  GemmArgs a;
+  a.A = A; a.B = B; a.C = C; a.a_major = a_major ? 1 : 0; a.b_major = b_major ? 1 : 0; a.lda = lda; a.ldb = ldb; a.ldc = ldc;
+  a.M = M; a.N = N; a.K = K; a.bias = bias; a.act = act; a.aux = aux; a.accumulate = accumulate ? 1 : 0; a.precision = precision;
+  a.a_lo = a_lo; a.b_lo = b_lo; a.m_limit = m_limit_dev; a.k_limit = k_limit_dev;
+  a.mul_in = t_mul_in; a.mul_act = t_mul_act; a.colsum = t_colsum;
+
+  // ---- engine selection: 0 single CTA, 1 CTA pair, 2 quad sharing A (pairs side by side in N), 3 quad sharing B ----
+  static const char* env_pair = getenv("CAPDEC_GEMM_PAIR");  // bring-up switch: 0 = cta_group::1 only, 1 = pairs only
+  static const char* env_mode = getenv("CAPDEC_GEMM_MODE");  // bring-up switch: force engine 0..3 where legal
+  const int forced = g_force_pair >= 0 ? g_force_pair : (env_mode ? atoi(env_mode) : (env_pair ? atoi(env_pair) : -1));
+  GemmPlan pl = heuristic_plan(a, block_n, split_k, forced);
+  if (forced < 0) {
+    bool have = false;
+    {
+      std::lock_guard<std::mutex> lk(g_tune_mu);
+      if (!g_tuned.empty() || g_tune_on.load()) {
+        auto it = g_tuned.find(tune_key(a, block_n, split_k));
+        if (it != g_tuned.end()) { pl = it->second; have = true; }
+      }
+    }
+    if (!have && g_tune_on.load()) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone)
+        return tune_and_launch(a, block_n, split_k, pl, stream);
+      cudaGetLastError();
+    }
+  }
+  return launch_plan(a, pl, stream);
 }

@@ -57,6 +57,10 @@ class Engine:
         self._mapper_arenas = {}
         # packed-row execution of the fused train step (csrc/packed.cu): on unless CAPDEC_PACKED=0
         self.packed = os.environ.get("CAPDEC_PACKED", "1") != "0" and self.P >= 1
+        # expected live rows of a packed batch (trunk rows / non-ignored targets): the GEMM planner sizes its tiles for
+        # them (capdec_gemm_set_row_hint).  0 = plan for the dense extent.  `measure_row_hints` fills them in.
+        self.hint_rows = 0
+        self.hint_targets = 0
 
     # ------------------------------------------------------------------------------------------------------------
     # parameter / gradient views
@@ -298,6 +302,15 @@ class Engine:
             return float(c.embd_pdrop), float(c.attn_pdrop), float(c.resid_pdrop)
         return 0.0, 0.0, 0.0
 
+    def measure_row_hints(self, B: int, L: int) -> None:
+        """Read the live-row / target counts of the batch that last ran through arena (B, L) (one host sync; the
+        Trainer calls this once after its eager warm-up steps, before the step is captured in a CUDA graph)."""
+        a = self.arenas.get((B, self.P, L))
+        if a is None or not a.packed:
+            return
+        self.hint_rows = int(a.rows[0].item())
+        self.hint_targets = int(a.counts[0].item())
+
     def _trunk_fwd(self, a, key_len=None):
         """a.h[0] (embeddings + positions) -> a.xf = ln_f(h_L).  HF:modeling_gpt2.py:612-628."""
         p = self.p
@@ -431,7 +444,9 @@ class Engine:
         fl = self.flat
         B, L = tokens.shape
         fast = ops.get_precision() == "tf32"
-        a = self.forward_hidden(tokens, prefix, packed=fast and self.packed)
+        use_packed = fast and self.packed
+        ops.set_row_hint(self.hint_rows if use_packed else 0)
+        a = self.forward_hidden(tokens, prefix, packed=use_packed)
         p, g = self.p, self.g
         P, T, d = self.P, a.T, self.d
         tail = fl.grads[:4]
@@ -445,14 +460,19 @@ class Engine:
             ops.compact_targets(targets, B, L, T, P - 1, a.row_src, a.dst_of, a.targets_c, a.counts, n_valid, loss_sum,
                                 cu_rows=a.cu if a.packed else None)
             nv = a.counts[0:1]
+            ops.set_row_hint(self.hint_targets)
             ops.rows_gather_idx(a.xf, a.xsel, a.row_src, a.counts)
             ops.gemm(a.xsel, 0, wte, 0, logits, B * L, self.V, d, m_limit=nv)                       # tied lm_head
             ops.ce_fwd_bwd(logits, a.targets_c, self.V, loss_sum, n_valid=n_valid if mean_reduce else None, row_limit=nv)
             if train_gpt:
                 ops.gemm(logits, 1, a.xsel, 1, g["gpt.transformer.wte.weight"], self.V, d, B * L, accumulate=True,
                          k_limit=nv)
-            ops.gemm(logits, 0, wte, 1, a.dxsel, B * L, d, self.V, m_limit=nv)
+            # d(hidden) = dlogits . wte: a handful of 256-row tiles with a 50257-long reduction each -> split-K over the
+            # vocabulary (reduce-add into a zeroed buffer) so that the work spreads over every SM whatever the row count
+            a.dxsel.zero_()
+            ops.gemm(logits, 0, wte, 1, a.dxsel, B * L, d, self.V, m_limit=nv, accumulate=True)
             ops.rows_scatter_idx(a.dxsel, a.dx, a.dst_of)
+            ops.set_row_hint(self.hint_rows if use_packed else 0)
         else:
             ops.ce_count(targets, n_valid, loss_sum)
             ops.rows_gather(a.xf, a.xsel, B, T, L, P - 1)                      # hidden states of logits[:, P-1:-1]
@@ -464,7 +484,38 @@ class Engine:
             ops.rows_scatter(a.dxsel, a.dx, B, T, L, P - 1)
         # a.dx is reused as scratch inside the trunk; ln_f backward consumes it first
         self.backward_hidden(a, a.dx, train_gpt, on_layer_done=on_layer_done)
+        ops.set_row_hint(0)
         return tail
+
+    def loss_only(self, tokens, prefix, stats):
+        """Forward + masked CE of train.py:383-385 (the validation pass): no backward, no gradient buffers touched.
+        stats[0] <- number of non-ignored targets, stats[1] <- sum of their token losses (fp32 device tensor, >= 2).
+        Dropout follows the modules' train/eval flags exactly like the training path."""
+        B, L = tokens.shape
+        fast = ops.get_precision() == "tf32"
+        use_packed = fast and self.packed
+        ops.set_row_hint(self.hint_rows if use_packed else 0)
+        a = self.forward_hidden(tokens, prefix, packed=use_packed)
+        P, T, d = self.P, a.T, self.d
+        n_valid, loss_sum = stats[0:1], stats[1:2]
+        targets = tokens.reshape(-1)
+        wte = self.p["gpt.transformer.wte.weight"]
+        logits = a.logits_sel[:, : self.V]
+        if fast:
+            ops.compact_targets(targets, B, L, T, P - 1, a.row_src, a.dst_of, a.targets_c, a.counts, n_valid, loss_sum,
+                                cu_rows=a.cu if a.packed else None)
+            nv = a.counts[0:1]
+            ops.set_row_hint(self.hint_targets)
+            ops.rows_gather_idx(a.xf, a.xsel, a.row_src, a.counts)
+            ops.gemm(a.xsel, 0, wte, 0, logits, B * L, self.V, d, m_limit=nv)
+            ops.ce_fwd_bwd(logits, a.targets_c, self.V, loss_sum, write_grad=False, row_limit=nv)
+        else:
+            ops.ce_count(targets, n_valid, loss_sum)
+            ops.rows_gather(a.xf, a.xsel, B, T, L, P - 1)
+            ops.linear_fwd(a.xsel, wte, "linear", None, logits)
+            ops.ce_fwd_bwd(logits, targets, self.V, loss_sum, write_grad=False)
+        ops.set_row_hint(0)
+        return stats
 
     # ------------------------------------------------------------------------------------------------------------
     # drop-in path: full logits + autograd hook

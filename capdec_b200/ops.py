@@ -101,6 +101,16 @@ def gemm(A: torch.Tensor, a_major: int, B: torch.Tensor, b_major: int, C: torch.
     _lib.check(rc, "gemm_tf32")
 
 
+def set_row_hint(rows: int) -> None:
+    """Tiling hint for the row-limited GEMMs launched next from this thread (0 clears it); never changes results."""
+    _lib.load().capdec_gemm_set_row_hint(int(rows))
+
+
+def gemm_autotune(enable: int) -> int:
+    """1 / 0: start / stop measuring GEMM plans for unseen problems; -1: forget measured plans.  Returns their count."""
+    return int(_lib.load().capdec_gemm_autotune(int(enable)))
+
+
 def gemm_mul(A, a_major, B, b_major, C, M, N, K, mul_in, mul_act, colsum=None, block_n=0, m_limit=None):
     """C = (A . B^T) * act'(mul_in), colsum += column sums of C — dgrad + activation backward + bias gradient in one
     tcgen05 launch (1xTF32 mode)."""
@@ -415,3 +425,27 @@ def embed_bwd_packed(tokens, dh, d_prefix_proj, d_wte, d_wpe, cu, B, P, L, vocab
 def zero_tail_rows(buf, rows):
     _lib.check(_lib.load().capdec_zero_tail_rows(buf.data_ptr(), _rowmajor(buf, "buf"), rows.data_ptr(), _stream()),
                "zero_tail_rows")
+
+
+def batch_gather(tokens_all, cap2emb, table, idx, tokens, prefix, P, mask=None, normalize=False):
+    """One launch assembles a batch from the device-resident caption table (csrc/datafeed.cu; train.py:52-72)."""
+    _chk(tokens_all, "tokens_all", torch.int32)
+    _chk(cap2emb, "cap2emb", torch.int32)
+    _chk(idx, "idx", torch.int64)
+    _chk(tokens, "tokens", torch.int64)
+    _chk(prefix, "prefix")
+    if table.dtype not in (torch.float32, torch.float16) or not table.is_cuda:
+        raise TypeError("the CLIP embedding table must be a CUDA fp32 or fp16 tensor")
+    B, L = tokens.shape
+    D = table.shape[1]
+    if idx.numel() != B or tuple(prefix.shape) != (B, D) or tokens_all.shape[1] != L:
+        raise ValueError("batch_gather: shape mismatch")
+    if mask is not None and tuple(mask.shape) != (B, P + L):
+        raise ValueError("batch_gather: mask must be [B, P + L]")
+    for t in (tokens_all, cap2emb, table, idx, tokens, prefix):
+        if not t.is_contiguous():
+            raise ValueError("batch_gather expects contiguous tensors")
+    rc = _lib.load().capdec_batch_gather(tokens_all.data_ptr(), cap2emb.data_ptr(), table.data_ptr(),
+                                         int(table.dtype == torch.float16), idx.data_ptr(), tokens.data_ptr(), _ptr(mask),
+                                         prefix.data_ptr(), B, L, P, D, int(bool(normalize)), _stream())
+    _lib.check(rc, "batch_gather")

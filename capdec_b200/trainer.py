@@ -62,8 +62,10 @@ class Trainer:
             self.comm = torch.cuda.Stream(device=self.dev)
             self.buckets, self.head_bucket = self.eng.layer_grad_slices()
         self.use_graph = use_cuda_graph
-        self._g_fb = self._g_opt = None
+        self._g_fb = self._g_opt = self._g_eval = None
         self._warm = 0
+        self._eval_warm = 0
+        self.eval_stats = torch.zeros(4, device=self.dev)
         fl.grads.zero_()
 
     # ---- pieces ------------------------------------------------------------------------------------------------
@@ -94,6 +96,25 @@ class Trainer:
         ops.adamw_step(self.p_flat, self.g_flat, self.m_flat, self.v_flat, self.lr_dev, self.t_dev, self.betas[0],
                        self.betas[1], self.eps, self.wd, grad_denom=self.stats[0:1], zero_grad=True)
 
+    def autotune(self):
+        """Measure the GEMM plans (engine / tile width / split-K) of this step's problems on the batch resident in
+        `tokens_d` / `prefix_d`: one throw-away forward+backward with capdec_gemm_autotune on.  The measuring launches
+        repeat every GEMM, so the gradients of that pass are garbage: they are discarded, and the step clock / RNG seed
+        are restored.  Parameters and optimizer state are never touched.  CAPDEC_GEMM_AUTOTUNE=0 disables it."""
+        if os.environ.get("CAPDEC_GEMM_AUTOTUNE", "1") == "0" or ops.get_precision() != "tf32":
+            return 0
+        keep = [t.clone() for t in (self.eng.seed, self.step_dev, self.lr_dev, self.t_dev)]
+        ops.gemm_autotune(1)
+        try:
+            self._fwd_bwd()
+        finally:
+            n = ops.gemm_autotune(0)
+        torch.cuda.synchronize()
+        for dst, src in zip((self.eng.seed, self.step_dev, self.lr_dev, self.t_dev), keep):
+            dst.copy_(src)
+        self.eng.flat.grads.zero_()
+        return n
+
     def _capture(self, fn):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -117,6 +138,9 @@ class Trainer:
             if self.world > 1 and not self.overlap:
                 torch.distributed.all_reduce(self.reduce_buf, group=self.pg)
             self._opt()
+            if self._warm == 2:   # GEMM tile planning for the live rows seen during warm-up (one host sync, results unaffected)
+                self.eng.measure_row_hints(self.B, self.L)
+                self.autotune()
         return self.stats
 
     def step(self, tokens: torch.Tensor, prefix: torch.Tensor):
@@ -127,6 +151,48 @@ class Trainer:
         self.tokens_d.copy_(tokens, non_blocking=True)
         self.prefix_d.copy_(prefix, non_blocking=True)
         return self.step_device()
+
+    # ---- validation pass (train.py:372-389) ------------------------------------------------------------------------
+    def evaluate_device(self):
+        """Forward + masked CE on the batch resident in `tokens_d` / `prefix_d` with the model in eval mode: no noise
+        injection (train.py:382-383 feeds the raw prefix), no dropout, no gradients.  Returns the device tensor
+        [n_valid, loss_sum, ., .] (summed over ranks under data parallel)."""
+        was_training = self.model.training
+        self.model.eval()
+        try:
+            if self.use_graph and self._eval_warm >= 1:
+                if self._g_eval is None:
+                    torch.cuda.synchronize()
+                    self._g_eval = self._capture(lambda: self.eng.loss_only(self.tokens_d, self.prefix_d, self.eval_stats))
+                self._g_eval.replay()
+            else:
+                self._eval_warm += 1
+                self.eng.loss_only(self.tokens_d, self.prefix_d, self.eval_stats)
+        finally:
+            self.model.train(was_training)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.eval_stats, group=self.pg)
+        return self.eval_stats
+
+    def evaluate(self, tokens: torch.Tensor, prefix: torch.Tensor) -> float:
+        """Mean token loss of one validation batch, `nnf.cross_entropy(..., ignore_index=0)` of train.py:385."""
+        if tuple(tokens.shape) != (self.B, self.L) or prefix.shape[0] != self.B:
+            raise CapdecError(f"Trainer was built for batch {self.B} x {self.L}, got tokens {tuple(tokens.shape)}")
+        self.tokens_d.copy_(tokens, non_blocking=True)
+        self.prefix_d.copy_(prefix, non_blocking=True)
+        s = self.evaluate_device().tolist()
+        return s[1] / s[0] if s[0] > 0 else float("nan")
+
+    # ---- device-resident data feed (capdec_b200.data.DeviceCaptionDataset) -----------------------------------------
+    def step_from(self, dataset, idx: torch.Tensor):
+        """One train step on the captions `idx` (int64 CUDA tensor [B]) of a DeviceCaptionDataset: the batch is gathered
+        on the device (one launch) straight into the step's input buffers - no host work, no H2D copy."""
+        dataset.gather(idx, self.tokens_d, self.prefix_d)
+        return self.step_device()
+
+    def evaluate_from(self, dataset, idx: torch.Tensor):
+        dataset.gather(idx, self.tokens_d, self.prefix_d)
+        return self.evaluate_device()
 
     def loss(self) -> float:
         s = self.stats.tolist()

@@ -73,6 +73,19 @@ void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, int sbo_bytes
 /* tile engine selection override: -1 auto (CTA pairs / cta_group::2 whenever M > 128 and N >= 128), 0 = always one CTA
  * per 128-row tile (cta_group::1), 1 = always CTA pairs.  Used by the tests to cover both engines. */
 void capdec_gemm_debug_force_pair(int mode);
+/* Tiling hint for the GEMMs this thread launches next with a device-side row limit (m_limit_dev): the live row count
+ * of a packed caption batch is data dependent, so tile width / engine / wave quantisation are chosen for `rows`
+ * (0 clears the hint = plan for the static M).  Never changes results.  MN-major operands whose extent is not a
+ * multiple of 32 are fetched with 32-wide boxes when the row pitch covers the rounded extent: the caller guarantees
+ * that every row is readable over its full pitch (true for any pitch-allocated matrix). */
+void capdec_gemm_set_row_hint(int rows);
+/* Measured plan selection.  enable = 1: the first call for each problem signature (shape, operand majors, epilogue,
+ * limits) times a short list of (engine, tile width, split-K) plans on the caller's stream with the caller's operands
+ * and remembers the fastest; later calls - and calls under CUDA-graph capture - reuse it.  A measuring call launches
+ * the problem several times, so accumulate outputs / fused column sums of that call are garbage: run it on a
+ * throw-away step (Trainer.autotune does).  enable = 0 stops measuring (remembered plans stay in use); -1 forgets
+ * them.  Returns the number of remembered plans. */
+int capdec_gemm_autotune(int enable);
 
 /* fp32 CUDA-core GEMM with the same contract (verification kernel: exact fp32 FMA, no tensor cores). */
 int capdec_gemm_fp32_simt(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
@@ -254,6 +267,15 @@ int capdec_adamw_step(float* p, float* g, float* m, float* v, int64_t n, const f
  * correction step), *step_dev = n + 1.  One thread; exists so that the whole step is CUDA-graph replayable. */
 int capdec_step_clock(uint64_t* seed_dev, float* step_dev, float* lr_dev, float* t_dev, float base_lr,
                       int warmup_steps, int total_steps, capdec_stream_t stream);
+
+/* ---- device-resident data feed (ClipCocoDataset.pad_tokens / __getitem__, train.py:52-72; collate + H2D :327,:346) --
+ * tokens_all int32 [N, L]: captions pre-padded / truncated to L = max_seq_len with -1 in the padding; cap2emb int32 [N];
+ * table [E, D] fp32 (table_fp16 = 0) or fp16 (= 1); idx int64 [B] caption indices of this batch.
+ * tokens int64 [B, L] = max(t, 0); mask fp32 [B, P+L] = [1]*P ++ (t >= 0) (may be NULL: the fast path never needs it);
+ * prefix fp32 [B, D] = table[cap2emb[i]] (/ its L2 norm when normalize != 0; no epsilon, as train.py:71). */
+int capdec_batch_gather(const int32_t* tokens_all, const int32_t* cap2emb, const void* table, int table_fp16,
+                        const int64_t* idx, int64_t* tokens, float* mask, float* prefix, int B, int L, int P, int D,
+                        int normalize, capdec_stream_t stream);
 
 #ifdef __cplusplus
 }

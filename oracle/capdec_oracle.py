@@ -107,6 +107,44 @@ def make_batch(seed: int, B: int, L: int = 40, prefix_size: int = 512, vocab: in
     return tokens, prefix, noise
 
 
+def make_caption_table(seed: int, n: int, n_emb: int, prefix_size: int = 512, vocab: int = 50257, min_len: int = 3,
+                       max_len: int = 60, half: bool = False):
+    """Synthetic stand-in for the pickled dataset of train.py:74-103: ragged int64 token lists (ids may include 0, the
+    '!' token), a caption -> embedding index, and an un-normalised embedding table (fp32, or fp16 like CLIP's output)."""
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(min_len, max_len + 1, (n,), generator=g)
+    caps = [torch.randint(0, vocab, (int(k),), generator=g, dtype=torch.int64) for k in lens]
+    cap2emb = torch.randint(0, n_emb, (n,), generator=g).tolist()
+    table = torch.randn(n_emb, prefix_size, generator=g) * 0.7
+    return caps, cap2emb, (table.half() if half else table)
+
+
+def dataset_max_seq_len(captions_tokens) -> int:
+    """train.py:102-103."""
+    all_len = torch.tensor([len(t) for t in captions_tokens]).float()
+    return min(int(all_len.mean() + all_len.std() * 10), int(all_len.max()))
+
+
+def dataset_item(captions_tokens, caption2embedding, prefixes, item: int, max_seq_len: int, prefix_length: int,
+                 normalize_prefix: bool):
+    """ClipCocoDataset.pad_tokens + __getitem__, train.py:52-72 (without its in-place caching side effect)."""
+    tokens = captions_tokens[item]
+    padding = max_seq_len - tokens.shape[0]
+    if padding > 0:
+        tokens = torch.cat((tokens, torch.zeros(padding, dtype=torch.int64) - 1))
+    elif padding < 0:
+        tokens = tokens[:max_seq_len]
+    tokens = tokens.clone()
+    mask = tokens.ge(0)
+    tokens[~mask] = 0
+    mask = torch.cat((torch.ones(prefix_length), mask.float()), dim=0)
+    prefix = prefixes[caption2embedding[item]]
+    if normalize_prefix:
+        prefix = prefix.float()
+        prefix = prefix / prefix.norm(2, -1)
+    return tokens, mask, prefix
+
+
 def make_mask(tokens: torch.Tensor, prefix_length: int) -> torch.Tensor:
     """train.py:58-63 (mask is 0 on padding; synthetic padding == id 0)."""
     return torch.cat((torch.ones(tokens.shape[0], prefix_length), (tokens > 0).float()), dim=1)

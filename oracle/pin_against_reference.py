@@ -220,6 +220,45 @@ def pin_generate_beam():
     print("generate_beam ok", [r["ids"][0][:6] for r in recs])
 
 
+def pin_dataset():
+    """ClipCocoDataset.__getitem__ + the default collate (the reference's own class, constructed without its file /
+    tokenizer loading) vs the oracle restatement -> tests/golden/datafeed.json."""
+    ref_train = import_reference(pdrop=0.0)
+    from torch.utils.data import DataLoader
+    recs = []
+    for case, (half, norm, P) in enumerate([(False, True, 10), (True, True, 10), (False, False, 40)]):
+        caps, cap2emb, table = O.make_caption_table(seed=40 + case, n=24, n_emb=9, prefix_size=512, half=half)
+        ds = ref_train.ClipCocoDataset.__new__(ref_train.ClipCocoDataset)   # skip __init__: no pickle / tokenizer offline
+        ds.captions_tokens = [c.clone() for c in caps]
+        ds.caption2embedding = list(cap2emb)
+        ds.prefixes = table
+        ds.prefix_length = P
+        ds.normalize_prefix = norm
+        all_len = torch.tensor([len(c) for c in caps]).float()
+        ds.max_seq_len = min(int(all_len.mean() + all_len.std() * 10), int(all_len.max())) - (7 if case == 2 else 0)
+        L = ds.max_seq_len                                                  # case 2 forces truncation (train.py:56-58)
+        assert case == 2 or L == O.dataset_max_seq_len(caps)
+        idx = [3, 0, 23, 11, 7, 19]
+        batch = next(iter(DataLoader(torch.utils.data.Subset(ds, idx), batch_size=len(idx), shuffle=False)))
+        tokens, mask, prefix = batch
+        for j, it in enumerate(idx):
+            t, m, pf = O.dataset_item(caps, cap2emb, table, it, L, P, norm)
+            assert torch.equal(t, tokens[j]) and torch.equal(m, mask[j]) and torch.equal(pf, prefix[j]), (case, it)
+        # reference quirk (train.py:55-61): pad_tokens caches the padded tensor and then zeroes its padding IN PLACE, so a
+        # second visit of the same item sees no negative ids and returns mask == 1 everywhere (tokens unchanged).  The
+        # mask cannot change a consumed logit (SURVEY §8c), so the restatement keeps the first-visit semantics.
+        t2, m2, _ = ds[idx[0]]
+        assert torch.equal(t2, tokens[0]) and bool((m2 == 1).all())
+        recs.append({"table_seed": 40 + case, "n": 24, "n_emb": 9, "half": half, "normalize_prefix": norm,
+                     "prefix_length": P, "max_seq_len": L, "idx": idx, "tokens": tokens.tolist(),
+                     "mask_sum_rows": mask.sum(1).tolist(), "prefix_dtype": str(prefix.dtype).replace("torch.", ""),
+                     "prefix_row_norms": prefix.float().norm(2, -1).double().tolist(),
+                     "prefix_head": prefix[:, :6].double().tolist(), "prefix_sum": float(prefix.double().sum())})
+    (GOLD / "datafeed.json").write_text(json.dumps({"cases": recs}, indent=1))
+    print("dataset ok", [r["max_seq_len"] for r in recs])
+
+
 if __name__ == "__main__":
     main()
     pin_generate_beam()
+    pin_dataset()

@@ -544,3 +544,104 @@ def test_gemm_fused_activation_backward_and_bias_grad(ops, act, layout):
     ref = lin * d
     assert (dx.double() - ref).abs().max() < 2e-4 * max(1.0, ref.abs().max().item())
     assert (db.double() - (3.0 + ref.sum(0))).abs().max() < 2e-3 * max(1.0, ref.sum(0).abs().max().item())
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("b_major", [0, 1])
+def test_gemm_block_n_192(ops, mode, b_major):
+    """192-wide tiles (96 B columns per CTA of a pair) in every engine that supports them."""
+    from capdec_b200 import _lib
+    M, N, K = 2600, 768, 200
+    A, Al, B, Bl = make_ab(M, N, K, 0, b_major)
+    C = new_c(M, N)
+    lib = _lib.load()
+    lib.capdec_gemm_debug_force_pair(mode)
+    try:
+        if mode == 3 and b_major:
+            with pytest.raises(_lib.CapdecError):
+                ops.gemm(A, 0, B, b_major, C, M, N, K, block_n=192)
+            return
+        ops.gemm(A, 0, B, b_major, C, M, N, K, block_n=192)
+    finally:
+        lib.capdec_gemm_debug_force_pair(-1)
+    ref = trunc_tf32(Al).double() @ trunc_tf32(Bl).double().t()
+    assert (C.double() - ref).abs().max() < 1e-4 * ref.abs().max()
+
+
+@pytest.mark.parametrize("mode", [-1, 1, 3])
+def test_gemm_mn_major_ragged_extent_inside_padded_pitch(ops, mode):
+    """MN-major operands whose extent is not a multiple of 32 but whose pitch covers the rounded extent are fetched with
+    3-D boxes (the tied-embedding gradient: V = 50257 in a 50304 pitch); NaNs in the pad columns must not leak."""
+    from capdec_b200 import _lib
+    M, N, K = 5001, 777, 300
+    g = torch.Generator(device="cuda").manual_seed(11)
+    Abuf = torch.full((K, 5120), float("nan"), device="cuda")
+    Bbuf = torch.full((K, 896), float("nan"), device="cuda")
+    Abuf[:, :M] = torch.randn(K, M, device="cuda", generator=g)
+    Bbuf[:, :N] = torch.randn(K, N, device="cuda", generator=g)
+    A, B = Abuf[:, :M], Bbuf[:, :N]
+    C = torch.zeros(M, 800, device="cuda")[:, :N]
+    lib = _lib.load()
+    lib.capdec_gemm_debug_force_pair(mode)
+    try:
+        ops.gemm(A, 1, B, 1, C, M, N, K, accumulate=True)
+        ops.gemm(A, 1, B, 1, C, M, N, K, accumulate=True)
+    finally:
+        lib.capdec_gemm_debug_force_pair(-1)
+    ref = 2 * (trunc_tf32(A.t().contiguous()).double() @ trunc_tf32(B.t().contiguous()).double().t())
+    assert torch.isfinite(C).all()
+    assert (C.double() - ref).abs().max() < 1e-4 * ref.abs().max()
+
+
+@pytest.mark.parametrize("limit", [None, 8820])
+def test_gemm_fused_activation_backward_many_tiles(ops, limit):
+    """The fused act'-multiply epilogue over several tiles per CTA (its input prefetcher runs across tile boundaries),
+    with and without a device-side row limit and row hint."""
+    M, K, N = 12800, 96, 3072
+    g = torch.Generator(device="cuda").manual_seed(6)
+    dy = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    pre = torch.randn(M, N, device="cuda", generator=g)
+    dx = torch.full((M, N), 5.0, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    rows = None
+    if limit is not None:
+        rows = torch.tensor([limit], dtype=torch.int32, device="cuda")
+        ops.set_row_hint(limit)
+    try:
+        ops.linear_dgrad_act(dy, W, "conv1d", dx, pre, 1, dbias=db, rows=rows)
+    finally:
+        ops.set_row_hint(0)
+    live = M if limit is None else limit
+    lin = trunc_tf32(dy[:live]).double() @ trunc_tf32(W).double().t()
+    p64 = pre[:live].double().requires_grad_()
+    torch.nn.functional.gelu(p64, approximate="tanh").sum().backward()
+    ref = lin * p64.grad
+    assert (dx[:live].double() - ref).abs().max() < 5e-4 * max(1.0, ref.abs().max().item())
+    assert (db.double() - ref.sum(0)).abs().max() < 5e-3 * max(1.0, ref.sum(0).abs().max().item())
+    if limit is not None:
+        assert (dx[(live + 511) // 512 * 512:] == 5.0).all()
+
+
+def test_gemm_autotune_keeps_results_and_remembers_plans(ops):
+    """Measured plan selection: whatever plan wins, the product is the same; the plan is remembered per signature."""
+    ops.gemm_autotune(-1)
+    try:
+        assert ops.gemm_autotune(1) == 0
+        for (M, N, K, am, bm, acc) in [(2600, 768, 200, 0, 1, False), (768, 2304, 3200, 1, 1, True), (100, 300, 64, 0, 0, False)]:
+            A, Al, B, Bl = make_ab(M, N, K, am, bm)
+            ref = trunc_tf32(Al).double() @ trunc_tf32(Bl).double().t()
+            C = torch.zeros(M, (N + 3) // 4 * 4, device="cuda")[:, :N]
+            ops.gemm(A, am, B, bm, C, M, N, K, accumulate=acc)        # measuring call (accumulate output is garbage)
+            C.zero_()
+            ops.gemm(A, am, B, bm, C, M, N, K, accumulate=acc)        # remembered plan
+            assert (C.double() - ref).abs().max() < 1e-4 * ref.abs().max()
+        assert ops.gemm_autotune(0) == 3
+        # still served from the table after measuring stopped, and under a different hint
+        A, Al, B, Bl = make_ab(2600, 768, 200, 0, 1)
+        C = new_c(2600, 768)
+        ops.gemm(A, 0, B, 1, C, 2600, 768, 200)
+        ref = trunc_tf32(Al).double() @ trunc_tf32(Bl).double().t()
+        assert (C.double() - ref).abs().max() < 1e-4 * ref.abs().max()
+    finally:
+        assert ops.gemm_autotune(-1) == 0
