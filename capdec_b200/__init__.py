@@ -5,7 +5,7 @@ MLP, TransformerMapper, noise_injection; plus Trainer (the fused, CUDA-graph'ed 
 get_linear_schedule_with_warmup with the reference's HuggingFace semantics.  There is no CPU fallback: the CUDA
 library (capdec_b200/libcapdec_b200.so, built by `python -m capdec_b200.build`) is required.
 """
-from .model import (ClipCaptionModel, ClipCaptionPrefix, GPT2Config, GPT2LMHead, MappingType, MLP, TransformerMapper,
+from .model import (ClipCaptionModel, ClipCaptionPrefix, GPT2Config, GPT2LMHead, MappingType, MLP, TransformerEncoderDecoder, TransformerMapper,
                     noise_injection)
 from .optim import AdamW, get_linear_schedule_with_warmup
 from .trainer import Trainer
@@ -14,5 +14,5 @@ from .decode import BeamDecoder, generate_beam, generate_beam_ids
 from . import ops
 
 __all__ = ["ClipCaptionModel", "ClipCaptionPrefix", "GPT2Config", "GPT2LMHead", "MappingType", "MLP",
-           "TransformerMapper", "noise_injection", "AdamW", "get_linear_schedule_with_warmup", "Trainer", "ops",
+           "TransformerMapper", "TransformerEncoderDecoder", "noise_injection", "AdamW", "get_linear_schedule_with_warmup", "Trainer", "ops",
            "DeviceCaptionDataset", "BeamDecoder", "generate_beam", "generate_beam_ids"]

@@ -67,6 +67,7 @@ SIGNATURES = {
     "capdec_embed_bwd_packed": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _u32, _p],
     "capdec_zero_tail_rows": [_p, _i64, _p, _p],
     "capdec_batch_gather": [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "capdec_zero_fill": [_p, _i64, _p],
     "capdec_step_clock": [_p, _p, _p, _p, _f, _i, _i, _p],
     "capdec_adamw_step": [_p, _p, _p, _p, _i64, _p, _p, _f, _f, _f, _f, _p, _i, _p],
 }

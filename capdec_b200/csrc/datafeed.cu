@@ -66,3 +66,11 @@ extern "C" int capdec_batch_gather(const int32_t* tokens_all, const int32_t* cap
   CAPDEC_LAUNCH_CHECK("batch_gather_kernel");
   return CAPDEC_OK;
 }
+
+// Zero-fill of a caller-owned buffer on the caller's stream (a memset node under CUDA-graph capture): accumulate targets of
+// the split-K GEMMs are cleared through the library instead of a framework fill kernel.
+extern "C" int capdec_zero_fill(void* p, int64_t bytes, capdec_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CAPDEC_REQUIRE(p && bytes >= 0, "zero_fill: bad arguments");
+  return check_cuda(cudaMemsetAsync(p, 0, (size_t)bytes, stream), "cudaMemsetAsync");
+}

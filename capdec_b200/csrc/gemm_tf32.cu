@@ -140,6 +140,23 @@ __device__ __forceinline__ void apply_act32(float (&v)[32], int act, bool exact)
   }
 }
 
+// act == 4: gelu_new forward AND its derivative from one MUFU.TANH (v <- gelu_new(v), dv <- gelu_new'(v)).  The forward
+// c_fc epilogue has slack under its mainloop; storing the derivative instead of the pre-activation turns the fused
+// GELU-backward of the dgrad epilogue (which is NOT hidden: N = 3072, K = 768) into a plain multiply (mul_act == 4).
+__device__ __forceinline__ void gelu_fwd_and_grad32(float (&v)[32], float (&dv)[32], bool exact) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float x = v[j];
+    const float x2 = x * x;
+    const float u = k0 * (x + k1 * x * x2);
+    const float t = exact ? tanhf(u) : tanh_fast(u);
+    const float h = 0.5f * (1.0f + t);
+    v[j] = x * h;
+    dv[j] = h + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x2);
+  }
+}
+
 // v *= act'(u) over a 32-column register chunk, dispatch hoisted out of the element loop for the same reason: the
 // 32 independent dependency chains (MUFU.TANH + ~15 FMAs each) must interleave, the epilogue has one warp per scheduler.
 __device__ __forceinline__ void apply_mul32(float (&v)[32], const float (&u)[32], int mul_act) {
@@ -149,6 +166,9 @@ __device__ __forceinline__ void apply_mul32(float (&v)[32], const float (&u)[32]
   } else if (mul_act == 2) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= 1.f - u[j] * u[j];
+  } else if (mul_act == 4) {   // u already holds the derivative (forward ran with act == 4)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= u[j];
   } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = u[j] > 0.f ? v[j] : 0.f;
@@ -182,7 +202,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   uint8_t* sStage = smem + p.stages * stage_bytes;  // epilogue staging: C ping-pong [+ aux ping-pong]
   const int n_staging = p.mul_act ? 2 + kMulDepth : (p.has_aux ? 4 : 2);
   float* sBias = reinterpret_cast<float*>(sStage + n_staging * kStagingBytes);
-  float* sCol = sBias;                              // per-tile column sums (mul epilogue; never together with a bias)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 256);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
@@ -438,12 +457,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         named_bar_sync(1, kEpiThreads);  // the warps run independently: nobody may still be reading the previous bias tile
         for (int i = epi_tid; i < p.block_n; i += kEpiThreads) sBias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
       }
-      if (p.colsum) {
-        for (int i = epi_tid; i < 256; i += kEpiThreads) sCol[i] = 0.f;
-      }
       mbar_wait(&tmem_full_bar[acc], acc_phase, 4);
       tc_fence_after();
-      if (use_bias || p.colsum) named_bar_sync(1, kEpiThreads);  // bias tile / zeroed column sums visible to all 4 warps
+      if (use_bias) named_bar_sync(1, kEpiThreads);  // bias tile visible to all 4 warps
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols);
       if (n_chunks == 0) {  // nothing to store (or dbg 8): release the accumulator right away
         tc_fence_before();
@@ -482,12 +498,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         if (lane == 0) tma_store_wait_read<1>();  // the group this lane committed two chunks ago has released buf[pp]
         __syncwarp();
         if (p.mul_act && lane == 0) mul_prefetch();  // every lane has read the input box just consumed: refill its slot
-        if (p.has_aux) {
-          float4* d1 = reinterpret_cast<float4*>(buf1 + lane * 128);
+        if (p.act == 4) {      // aux <- gelu_new'(pre-activation), C <- gelu_new(pre-activation)
+          float dv[32];
+          gelu_fwd_and_grad32(v, dv, p.nseg > 1);
+          if (p.has_aux) {
+            float4* d1 = reinterpret_cast<float4*>(buf1 + lane * 128);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) d1[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) d1[j ^ (lane & 7)] = make_float4(dv[4 * j], dv[4 * j + 1], dv[4 * j + 2], dv[4 * j + 3]);
+          }
+        } else {
+          if (p.has_aux) {     // aux <- pre-activation
+            float4* d1 = reinterpret_cast<float4*>(buf1 + lane * 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d1[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.act != 0) apply_act32(v, p.act, p.nseg > 1);
         }
-        if (p.act != 0) apply_act32(v, p.act, p.nseg > 1);
         {
           float4* d0 = reinterpret_cast<float4*>(buf0 + lane * 128);
 #pragma unroll
@@ -495,14 +521,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (p.colsum) {  // bias gradient: lane = column of this chunk, summed over this warp's 32 staged rows
-          float cs = 0.f;
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            if (m0 + rr < m_lim)
-              cs += *reinterpret_cast<const float*>(buf0 + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
+        if (p.colsum) {  // bias gradient: lane = column of this chunk, summed over this warp's live staged rows and sent
+          // straight to global memory as one coalesced 128-byte reduction per chunk (no cross-warp exchange, no barrier:
+          // the four epilogue warps stay independent; shared-memory atomics + two named barriers per tile cost 20 us here)
+          const int nrows = min(32, m_lim - m0);
+          const int col = n0 + c * 32 + lane;
+          float cs0 = 0.f, cs1 = 0.f;
+          const uint8_t* colp = buf0 + ((lane & 3) << 2);
+          const int l4 = lane >> 2;
+          if (nrows >= 32) {
+#pragma unroll
+            for (int rr = 0; rr < 32; rr += 2) {
+              cs0 += *reinterpret_cast<const float*>(colp + rr * 128 + ((l4 ^ (rr & 7)) << 4));
+              cs1 += *reinterpret_cast<const float*>(colp + (rr + 1) * 128 + ((l4 ^ ((rr + 1) & 7)) << 4));
+            }
+          } else {
+            for (int rr = 0; rr < nrows; ++rr) cs0 += *reinterpret_cast<const float*>(colp + rr * 128 + ((l4 ^ (rr & 7)) << 4));
           }
-          atomicAdd(&sCol[c * 32 + lane], cs);
+          if (nrows > 0 && col < p.N) atomicAdd(p.colsum + col, cs0 + cs1);
         }
         if (lane == 0 && !(p.dbg & 4u)) {
           if (p.accumulate) tma_reduce_add_2d(&p.tmC, buf0, n0 + c * 32, m0);
@@ -510,12 +546,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
           if (p.has_aux) tma_store_2d(&p.tmAux, buf1, n0 + c * 32, m0);
           tma_store_commit();
         }
-      }
-      if (p.colsum && n_chunks > 0) {
-        named_bar_sync(1, kEpiThreads);
-        for (int i = epi_tid; i < n_chunks * 32; i += kEpiThreads)
-          if (n0 + i < p.N) atomicAdd(p.colsum + n0 + i, sCol[i]);
-        named_bar_sync(1, kEpiThreads);  // sCol is re-zeroed by other threads at the next tile
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -747,7 +777,7 @@ static thread_local float* t_colsum = nullptr;
 extern "C" int capdec_gemm_tf32_mul(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
                                     float* C, int64_t ldc, int M, int N, int K, const float* mul_in, int mul_act,
                                     float* colsum, int block_n, const int32_t* m_limit_dev, capdec_stream_t stream_) {
-  CAPDEC_REQUIRE(mul_in && mul_act >= 1 && mul_act <= 3, "gemm_mul: bad epilogue input");
+  CAPDEC_REQUIRE(mul_in && mul_act >= 1 && mul_act <= 4, "gemm_mul: bad epilogue input");
   CAPDEC_REQUIRE(((uintptr_t)mul_in % 16) == 0, "gemm_mul: mul_in must be 16-byte aligned");
   t_mul_in = mul_in; t_mul_act = mul_act; t_colsum = colsum;
   int rc = capdec_gemm_tf32_ex(A, a_major, lda, B, b_major, ldb, C, ldc, M, N, K, nullptr, 0, nullptr, 0, 0, nullptr,
@@ -1019,7 +1049,7 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
   CAPDEC_REQUIRE(lda >= (a_major ? M : K) && ldb >= (b_major ? N : K) && ldc >= N, "gemm: leading dim smaller than extent");
   CAPDEC_REQUIRE(precision == 0 || (a_lo && b_lo), "gemm: 3xTF32 needs a_lo and b_lo");
   CAPDEC_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 192 || block_n == 256, "gemm: block_n must be 0/64/128/192/256");
-  CAPDEC_REQUIRE(act >= 0 && act <= 3, "gemm: bad act %d", act);
+  CAPDEC_REQUIRE(act >= 0 && act <= 4, "gemm: bad act %d", act);
   CAPDEC_REQUIRE(!aux || ((uintptr_t)aux % 16) == 0, "gemm: aux must be 16-byte aligned");
 
   static bool attr_set = false;

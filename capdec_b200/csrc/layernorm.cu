@@ -350,15 +350,14 @@ __global__ void __launch_bounds__(256, 2) add_ln_bwd_pipe_kernel(
       }
     }
   }
-  if (dgamma) {
-    float* a = dgamma + 4 * c;
-    float* b = dbeta + 4 * c;
-    atomicAdd(a + 0, dg.x); atomicAdd(a + 1, dg.y); atomicAdd(a + 2, dg.z); atomicAdd(a + 3, dg.w);
-    atomicAdd(b + 0, db.x); atomicAdd(b + 1, db.y); atomicAdd(b + 2, db.z); atomicAdd(b + 3, db.w);
-  }
-  if (dbias_branch) {
-    float* a = dbias_branch + 4 * c;
-    atomicAdd(a + 0, dbr.x); atomicAdd(a + 1, dbr.y); atomicAdd(a + 2, dbr.z); atomicAdd(a + 3, dbr.w);
+  // ~300 CTAs finish together and reduce into the same 3 x d floats: 128-bit vector reductions quarter the number of
+  // same-address L2 atomic operations in that tail
+  if (nb > 0) {
+    if (dgamma) {
+      red_add_v4(dgamma + 4 * c, dg);
+      red_add_v4(dbeta + 4 * c, db);
+    }
+    if (dbias_branch) red_add_v4(dbias_branch + 4 * c, dbr);
   }
 }
 
@@ -406,7 +405,8 @@ extern "C" int capdec_add_ln_bwd(const float* dx, const float* r, const float* s
   const int threads = d / 4;                     // one float4 column per thread (d = 768 -> 192 threads)
   static const char* env_pipe = getenv("CAPDEC_LN_BWD_PIPE");   // bring-up switch: 0 = register-staged kernel
   const bool aligned = ((uintptr_t)dx % 16 == 0) && ((uintptr_t)r % 16 == 0) && ((uintptr_t)stats % 16 == 0) &&
-                       (!dh_res || (uintptr_t)dh_res % 16 == 0);
+                       (!dh_res || (uintptr_t)dh_res % 16 == 0) && ((uintptr_t)dgamma % 16 == 0) &&
+                       ((uintptr_t)dbeta % 16 == 0) && ((uintptr_t)dbias_branch % 16 == 0);
   if (!(env_pipe && env_pipe[0] == '0') && aligned) {
     const size_t smem = (size_t)kLnStages * ((dh_res ? 3 : 2) * (size_t)kR * d * 4 + 128);
     static bool attr_set = false;

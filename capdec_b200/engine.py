@@ -49,6 +49,7 @@ class Engine:
         self.P = model.prefix_length
         self.D = model.prefix_size
         self.is_mlp = model.mapping_type.value == "mlp"
+        self.is_encdec = model.mapping_type.value == "transformer_decoder"
         if self.d % 128 or self.hd not in (64, 96):
             raise CapdecError(f"unsupported GPT-2 geometry d={self.d} heads={self.H}")
         self._params()
@@ -61,6 +62,7 @@ class Engine:
         # them (capdec_gemm_set_row_hint).  0 = plan for the dense extent.  `measure_row_hints` fills them in.
         self.hint_rows = 0
         self.hint_targets = 0
+        self.lm_dgrad_splitk = os.environ.get("CAPDEC_LM_DGRAD_SPLITK", "1") != "0"
 
     # ------------------------------------------------------------------------------------------------------------
     # parameter / gradient views
@@ -71,7 +73,14 @@ class Engine:
         if fl.grads is None:
             fl.grads = torch.zeros_like(fl.params)
         self.g = {n: fl.grads[o: o + k].view(s) for n, (o, k, s) in fl.layout.items()}
-        if not self.is_mlp:
+        if self.is_encdec:
+            cp = self.m.clip_project
+            self.C = cp.clip_length
+            self.mH = cp.num_heads
+            self.de = cp.dim_ref
+            self.n_enc_layers = len(cp.ref_encoder.layers)
+            self.n_dec_layers = len(cp.prefix_decoder.layers)
+        elif not self.is_mlp:
             # to_queries [d,d] and to_keys_values [2d,d] are adjacent in the flat buffer -> one fused [3d,d] weight
             self.wqkv, self.gqkv = [], []
             j = 0
@@ -180,6 +189,14 @@ class Engine:
             hdim = (d * P) // 2
             a.a1 = e(B, hdim)
             a.da1 = e(B, hdim)
+        elif self.is_encdec:
+            C, de = self.C, self.de
+            a.lin = e(B, C * de)
+            mk = lambda rows, c, rows_kv: SimpleNamespace(
+                y=e(rows, c), st=e(rows, 2), q=e(rows, c), kv=e(rows_kv, 2 * c), o=e(rows, c), t=e(rows, c),
+                x1=e(rows, c), f=e(rows, 2 * c), xa=e(rows, c), xb=e(rows, c))
+            a.enc = mk(B * C, de, B * C)
+            a.dec = mk(B * P, d, B * max(C, P))
         else:
             C, S = self.C, self.C + P
             Mm = B * S
@@ -221,6 +238,8 @@ class Engine:
                            act=ops.ACT_TANH)
             ops.linear_fwd(ma.a1, p["clip_project.model.2.weight"], "linear", p["clip_project.model.2.bias"], pp)
             return
+        if self.is_encdec:
+            return self._encdec_fwd(x, pp, ma)
         d, C, P, S, Mm = self.d, self.C, self.P, ma.S, ma.Mm
         ops.linear_fwd(x, p["clip_project.linear.weight"], "linear", p["clip_project.linear.bias"], ma.lin)
         ops.mapper_concat_fwd(ma.lin, p["clip_project.prefix_const"], ma.hm[0], B, C, P)
@@ -245,7 +264,56 @@ class Engine:
                 ops.add_ln_fwd(ma.hm1[j], ma.t, ma.hm[nl], ma.scratch, ma.sscr, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
         ops.rows_gather(ma.hm[nl], pp.view(B * P, d), B, S, P, C)  # out = transformer(prefix)[:, clip_length:]
 
+    def _mapper_layer_fwd(self, pre, ws, x_in, x_out, B, Tq, c, kv_src=None, Tk=None, c_ref=None):
+        """One transformer_mapper.TransformerLayer (transformer_mapper.py:63-66): x_out = x1 + mlp(norm2(x1)),
+        x1 = x_in + project(attention(q = to_queries(norm1(x_in)), k|v = to_keys_values(kv_src))).
+        kv_src None -> norm1(x_in) (the layer's own normalised input), else a [B*Tk, c_ref] matrix."""
+        p = self.p
+        H = self.mH
+        hd = c // H
+        Mq = B * Tq
+        ops.add_ln_fwd(x_in, None, None, ws.y, ws.st, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
+        ops.gemm(ws.y, 0, p[pre + "attn.to_queries.weight"], 0, ws.q, Mq, c, c)
+        if kv_src is None:
+            kv_src, Tk, c_ref = ws.y, Tq, c
+        Mk = B * Tk
+        kv = ws.kv[:Mk]
+        ops.gemm(kv_src, 0, p[pre + "attn.to_keys_values.weight"], 0, kv, Mk, 2 * c, c_ref)
+        ops.attention_fwd(ws.q, kv[:, :c], kv[:, c:], ws.o, None, B, H, Tq, Tk, hd, Tq * c, c, Tk * 2 * c, 2 * c, Tq * c, c,
+                          hd ** -0.5, 0)
+        ops.linear_fwd(ws.o, p[pre + "attn.project.weight"], "linear", p[pre + "attn.project.bias"], ws.t)
+        ops.add_ln_fwd(x_in, ws.t, ws.x1, ws.y, ws.st, p[pre + "norm2.weight"], p[pre + "norm2.bias"])
+        ops.linear_fwd(ws.y, p[pre + "mlp.fc1.weight"], "linear", p[pre + "mlp.fc1.bias"], ws.f, act=ops.ACT_RELU)
+        ops.linear_fwd(ws.f, p[pre + "mlp.fc2.weight"], "linear", p[pre + "mlp.fc2.bias"], ws.t)
+        # last residual add: reuse the fused add + LayerNorm kernel and discard its LayerNorm output
+        ops.add_ln_fwd(ws.x1, ws.t, x_out, ws.y, ws.st, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
+
+    def _encdec_fwd(self, x, pp, ma):
+        """transformer_mapper.TransformerEncoderDecoder.forward (transformer_mapper.py:132-137), forward only."""
+        B = x.shape[0]
+        p = self.p
+        C, P, d, de = self.C, self.P, self.d, self.de
+        ops.linear_fwd(x, p["clip_project.linear.weight"], "linear", p["clip_project.linear.bias"], ma.lin)
+        cur, nxt = ma.lin.view(B * C, de), ma.enc.xa
+        for j in range(self.n_enc_layers):          # ref_encoder: plain self-attention layers over the C tokens
+            self._mapper_layer_fwd(f"clip_project.ref_encoder.layers.{j}.", ma.enc, cur, nxt, B, C, de)
+            cur, nxt = nxt, (ma.enc.xb if nxt is ma.enc.xa else ma.enc.xa)
+        ref = cur
+        h, hn = ma.dec.xa, ma.dec.xb
+        h.view(B, P, d).copy_(p["clip_project.prefix_const"].unsqueeze(0).expand(B, P, d))   # broadcast, no arithmetic
+        for j in range(self.n_dec_layers):          # even: cross-attention to ref; odd: keys/values from the raw stream
+            pre = f"clip_project.prefix_decoder.layers.{j}."
+            if j % 2 == 0:
+                self._mapper_layer_fwd(pre, ma.dec, h, hn, B, P, d, kv_src=ref, Tk=C, c_ref=de)
+            else:
+                self._mapper_layer_fwd(pre, ma.dec, h, hn, B, P, d, kv_src=h, Tk=P, c_ref=d)
+            h, hn = hn, h
+        pp.view(B * P, d).copy_(h)
+
     def _mapper_bwd(self, x, dpp):
+        if self.is_encdec:
+            raise CapdecError("the TransformerDecoder mapper (transformer_mapper.TransformerEncoderDecoder) is "
+                              "inference-only here: the reference's train.py cannot construct it (train.py:42-44)")
         B = x.shape[0]
         ma = self._mapper_arena(B)
         p, g = self.p, self.g
@@ -330,8 +398,9 @@ class Engine:
             ops.linear_fwd(a.ctx[l], p[pre + "attn.c_proj.weight"], "conv1d", p[pre + "attn.c_proj.bias"], a.y, rows=R)
             ops.add_ln_fwd(a.h[l], a.y, a.h1[l], a.x2[l], a.st2[l], p[pre + "ln_2.weight"], p[pre + "ln_2.bias"],
                            eps=self.cfg.layer_norm_epsilon, p_drop=p_res, seed=self.seed, stream_id=_site(l, 1), rows=R)
+            # tf32 mode: a.u holds gelu_new'(pre-activation) (one MUFU.TANH serves both), parity modes: the pre-activation
             ops.linear_fwd(a.x2[l], p[pre + "mlp.c_fc.weight"], "conv1d", p[pre + "mlp.c_fc.bias"], a.g[l],
-                           act=ops.ACT_GELU_NEW, aux=a.u[l], rows=R)
+                           act=ops.ACT_GELU_NEW_D if ops.get_precision() == "tf32" else ops.ACT_GELU_NEW, aux=a.u[l], rows=R)
             ops.linear_fwd(a.g[l], p[pre + "mlp.c_proj.weight"], "conv1d", p[pre + "mlp.c_proj.bias"], a.y, rows=R)
             if l + 1 < self.nl:
                 nx = f"gpt.transformer.h.{l + 1}."
@@ -366,7 +435,8 @@ class Engine:
             # mlp.c_proj
             if train_gpt:
                 ops.linear_wgrad(a.g[l], dy2, g[pre + "mlp.c_proj.weight"], "conv1d", rows=R)
-            ops.linear_dgrad_act(dy2, p[pre + "mlp.c_proj.weight"], "conv1d", a.dF, a.u[l], ops.ACT_GELU_NEW,
+            ops.linear_dgrad_act(dy2, p[pre + "mlp.c_proj.weight"], "conv1d", a.dF, a.u[l],
+                                 ops.ACT_GELU_NEW_D if ops.get_precision() == "tf32" else ops.ACT_GELU_NEW,
                                  dbias=gw(pre + "mlp.c_fc.bias"), rows=R)
             if train_gpt:
                 ops.linear_wgrad(a.x2[l], a.dF, g[pre + "mlp.c_fc.weight"], "conv1d", rows=R)
@@ -469,8 +539,11 @@ class Engine:
                          k_limit=nv)
             # d(hidden) = dlogits . wte: a handful of 256-row tiles with a 50257-long reduction each -> split-K over the
             # vocabulary (reduce-add into a zeroed buffer) so that the work spreads over every SM whatever the row count
-            a.dxsel.zero_()
-            ops.gemm(logits, 0, wte, 1, a.dxsel, B * L, d, self.V, m_limit=nv, accumulate=True)
+            # (reduce-add order is not deterministic; CAPDEC_LM_DGRAD_SPLITK=0 / eng.lm_dgrad_splitk = False restores
+            # the single-pass, bit-reproducible product)
+            if self.lm_dgrad_splitk:
+                ops.zero_fill(a.dxsel)
+            ops.gemm(logits, 0, wte, 1, a.dxsel, B * L, d, self.V, m_limit=nv, accumulate=self.lm_dgrad_splitk)
             ops.rows_scatter_idx(a.dxsel, a.dx, a.dst_of)
             ops.set_row_hint(self.hint_rows if use_packed else 0)
         else:

@@ -25,6 +25,7 @@ class MappingType(Enum):
     MLP = "mlp"
     Transformer = "transformer"
     TransformerEncoder = "transformer"  # gpt2_prefix.py spelling 'transformer_encoder' maps to the same mapper
+    TransformerDecoder = "transformer_decoder"  # gpt2_prefix.py:18 -> transformer_mapper.TransformerEncoderDecoder
 
     @classmethod
     def parse(cls, v):
@@ -35,7 +36,9 @@ class MappingType(Enum):
             return cls.MLP
         if v in ("transformer", "transformer_encoder"):
             return cls.Transformer
-        raise ValueError(f"unsupported mapping type {v!r} (TransformerDecoder mapper is out of scope, SURVEY §8f #4)")
+        if v == "transformer_decoder":
+            return cls.TransformerDecoder
+        raise ValueError(f"unsupported mapping type {v!r}")
 
 
 _noise_state = {"seed": None, "step": 0}
@@ -178,10 +181,11 @@ class MLP(nn.Module):
 
 
 class _MapperAttn(nn.Module):
-    def __init__(self, d):
+    def __init__(self, d, d_ref=None):
         super().__init__()
+        d_ref = d if d_ref is None else d_ref
         self.to_queries = nn.Linear(d, d, bias=False)        # train.py:144 (bias=False via :183,187)
-        self.to_keys_values = nn.Linear(d, 2 * d, bias=False)  # train.py:145
+        self.to_keys_values = nn.Linear(d_ref, 2 * d, bias=False)  # train.py:145 / transformer_mapper.py:30 (dim_ref)
         self.project = nn.Linear(d, d)                         # train.py:146
 
 
@@ -193,18 +197,24 @@ class _MapperMlp(nn.Module):
 
 
 class _MapperLayer(nn.Module):
-    def __init__(self, d, h):
+    def __init__(self, d, h, d_ref=None):
         super().__init__()
         self.norm1 = nn.LayerNorm(d)
-        self.attn = _MapperAttn(d)
+        self.attn = _MapperAttn(d, d_ref)
         self.norm2 = nn.LayerNorm(d)
         self.mlp = _MapperMlp(d, h)
 
 
 class _MapperTransformer(nn.Module):
-    def __init__(self, d, num_layers, mlp_ratio=2.0):
+    """Parameter holder with the layout of train.py:192-226 / transformer_mapper.py:71-108 (`enc_dec` doubles the layer
+    count and alternates cross-attention layers, whose keys/values read `d_ref` features, with self-attention ones)."""
+
+    def __init__(self, d, num_layers, mlp_ratio=2.0, d_ref=None, enc_dec=False):
         super().__init__()
-        self.layers = nn.ModuleList([_MapperLayer(d, int(d * mlp_ratio)) for _ in range(num_layers)])
+        self.enc_dec = enc_dec
+        n = num_layers * 2 if enc_dec else num_layers
+        self.layers = nn.ModuleList([
+            _MapperLayer(d, int(d * mlp_ratio), d_ref if (not enc_dec or i % 2 == 0) else None) for i in range(n)])
 
 
 class TransformerMapper(nn.Module):
@@ -217,6 +227,28 @@ class TransformerMapper(nn.Module):
         self.clip_length = clip_length
         self.transformer = _MapperTransformer(dim_embedding, num_layers)
         self.linear = nn.Linear(dim_clip, clip_length * dim_embedding)
+        self.prefix_const = nn.Parameter(torch.randn(prefix_length, dim_embedding), requires_grad=True)
+        self._owner = None
+
+    def forward(self, x):
+        return self._owner()._mapper_forward(x)
+
+
+class TransformerEncoderDecoder(nn.Module):
+    """transformer_mapper.py:130-145 (gpt2_prefix.py:167-168, MappingType.TransformerDecoder): a 512-wide encoder over
+    the CLIP embedding re-shaped to `clip_length` tokens, and a decoder whose `prefix_length` learned query tokens
+    cross-attend to it.  Inference-side mapper of predictions_runner.py:457-460; train.py cannot construct it, so only
+    its forward pass is implemented (the backward raises)."""
+
+    num_heads = 8
+    dim_ref = 512
+
+    def __init__(self, dim_clip: int, dim_embedding: int, prefix_length: int, clip_length: int, num_layers: int = 4):
+        super().__init__()
+        self.clip_length = clip_length
+        self.ref_encoder = _MapperTransformer(self.dim_ref, num_layers)
+        self.prefix_decoder = _MapperTransformer(dim_embedding, num_layers, d_ref=self.dim_ref, enc_dec=True)
+        self.linear = nn.Linear(dim_clip, clip_length * self.dim_ref)
         self.prefix_const = nn.Parameter(torch.randn(prefix_length, dim_embedding), requires_grad=True)
         self._owner = None
 
@@ -248,8 +280,9 @@ class ClipCaptionModel(nn.Module):
             self.clip_project = MLP((prefix_size, (d * prefix_length) // 2, d * prefix_length))
         else:
             if clip_length is None:
-                raise ValueError("clip_length is required for the transformer mapper")
-            self.clip_project = TransformerMapper(prefix_size, d, prefix_length, clip_length, num_layers)
+                clip_length = prefix_length           # gpt2_prefix.py:160 (train.py:272 would fail on None)
+            cls = TransformerMapper if self.mapping_type == MappingType.Transformer else TransformerEncoderDecoder
+            self.clip_project = cls(prefix_size, d, prefix_length, clip_length, num_layers)
         ref = weakref.ref(self)
         self.gpt._owner = ref
         self.clip_project._owner = ref

@@ -11,6 +11,7 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_GELU_NEW, ACT_TANH, ACT_RELU = 0, 1, 2, 3
+ACT_GELU_NEW_D = 4   # tcgen05 path only: C = gelu_new(x), aux = gelu_new'(x); backward multiplies by aux (mul_act 4)
 
 # GEMM arithmetic: "tf32" = 1xTF32 tcgen05 (perf), "tf32x3" = 3xTF32 split on tcgen05 (fp32-grade parity mode),
 # "fp32" = CUDA-core FFMA verification kernel.
@@ -449,3 +450,10 @@ def batch_gather(tokens_all, cap2emb, table, idx, tokens, prefix, P, mask=None, 
                                          int(table.dtype == torch.float16), idx.data_ptr(), tokens.data_ptr(), _ptr(mask),
                                          prefix.data_ptr(), B, L, P, D, int(bool(normalize)), _stream())
     _lib.check(rc, "batch_gather")
+
+
+def zero_fill(t: torch.Tensor) -> None:
+    """t <- 0 through the library (cudaMemsetAsync on the current stream; t must be contiguous)."""
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("zero_fill expects a contiguous CUDA tensor")
+    _lib.check(_lib.load().capdec_zero_fill(t.data_ptr(), t.numel() * t.element_size(), _stream()), "zero_fill")

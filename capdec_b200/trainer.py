@@ -81,15 +81,21 @@ class Trainer:
         eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False,
                            on_layer_done=self._reduce_layer if self.overlap else None)
         if self.overlap:
-            torch.distributed.all_reduce(self.head_bucket, group=self.pg)       # ready last: not overlappable
+            # [tail | mapper | wte | wpe] is ready last.  It goes to the SAME side stream as the per-block buckets: every
+            # collective of this communicator then sits on one branch of the captured graph, in one fixed order on every
+            # rank (collectives on two concurrent branches may replay in different orders on different ranks and deadlock)
+            self._reduce_bucket(self.head_bucket)
             torch.cuda.current_stream().wait_stream(self.comm)
 
     def _reduce_layer(self, l: int):
+        self._reduce_bucket(self.buckets[l])
+
+    def _reduce_bucket(self, bucket: torch.Tensor):
         ev = torch.cuda.Event()
         ev.record()
         self.comm.wait_event(ev)
         with torch.cuda.stream(self.comm):
-            torch.distributed.all_reduce(self.buckets[l], group=self.pg)
+            torch.distributed.all_reduce(bucket, group=self.pg)
 
     def _opt(self):
         self.stats.copy_(self.tail)
@@ -105,8 +111,13 @@ class Trainer:
             return 0
         keep = [t.clone() for t in (self.eng.seed, self.step_dev, self.lr_dev, self.t_dev)]
         ops.gemm_autotune(1)
-        try:
-            self._fwd_bwd()
+        try:   # the same launches as _fwd_bwd, but never a collective: ranks measure independently
+            pfx = self.prefix_d
+            if self.noise_variance > 0.0:
+                ops.noise_injection(self.prefix_d, self.prefix_n, self.noise_variance, offset=self.offset,
+                                    uniform_ball=self.uniform_noise, dont_norm=self.dont_norm, seed=self.eng.seed)
+                pfx = self.prefix_n
+            self.eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False)
         finally:
             n = ops.gemm_autotune(0)
         torch.cuda.synchronize()

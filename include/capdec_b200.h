@@ -40,7 +40,8 @@ int64_t capdec_launch_count(void);
  *                      1 = MN-major (A stored [K,M] / B stored [K,N], M resp. N contiguous)
  *   precision: 0 = 1xTF32 (perf mode), 1 = 3xTF32 split (fp32-grade, A/B must then be the `hi` parts and a_lo/b_lo the `lo`
  *              parts produced by capdec_split_tf32)
- *   act: 0 none, 1 gelu_new (HF:activations.py:59-66), 2 tanh (train.py:106 MLP act), 3 relu (train.py:121)
+ *   act: 0 none, 1 gelu_new (HF:activations.py:59-66), 2 tanh (train.py:106 MLP act), 3 relu (train.py:121),
+ *        4 gelu_new with aux <- gelu_new'(pre-activation) instead of the pre-activation (feeds mul_act 4 below)
  *   aux: optional second output receiving the PRE-activation (needed by backward); ld = ldc
  *   accumulate: C += result (TMA reduce-add in L2); required for split_k > 1 (wgrad over M = B*T)
  *   block_n / split_k: 0 = auto
@@ -60,7 +61,8 @@ int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B
                         const int32_t* m_limit_dev, const int32_t* k_limit_dev, capdec_stream_t stream);
 
 /* dgrad GEMM with a fused activation backward and bias gradient:  C[M,N] = (A . B^T) * act'(mul_in[M,N]),
- * colsum[n] += sum_m C[m,n] (may be NULL).  mul_act: 1 = gelu_new'(pre-activation u) (HF:activations.py:59-66),
+ * colsum[n] += sum_m C[m,n] (may be NULL).  mul_act: 4 = mul_in already holds the derivative (forward act 4),
+ * 1 = gelu_new'(pre-activation u) (HF:activations.py:59-66),
  * 2 = tanh' = 1 - a^2 with a the activated output (train.py:106), 3 = relu mask from the activated output
  * (train.py:121).  mul_in shares C's leading dimension.  1xTF32 only (the parity modes use capdec_act_bwd). */
 int capdec_gemm_tf32_mul(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb, float* C,
@@ -276,6 +278,9 @@ int capdec_step_clock(uint64_t* seed_dev, float* step_dev, float* lr_dev, float*
 int capdec_batch_gather(const int32_t* tokens_all, const int32_t* cap2emb, const void* table, int table_fp16,
                         const int64_t* idx, int64_t* tokens, float* mask, float* prefix, int B, int L, int P, int D,
                         int normalize, capdec_stream_t stream);
+
+/* zero-fill `bytes` bytes at p on `stream` (cudaMemsetAsync; a memset node under graph capture) */
+int capdec_zero_fill(void* p, int64_t bytes, capdec_stream_t stream);
 
 #ifdef __cplusplus
 }

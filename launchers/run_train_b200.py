@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Run the reference's own, unmodified `train.py` on the capdec_b200 kernels.
+
+    CAPDEC_REFERENCE_DIR=/path/to/CapDec python launchers/run_train_b200.py --data ... --noise_variance 0.016 \
+        --mapping_type mlp --only_prefix ...            # train.py's own flags, untouched (train.py:397-416)
+
+`train.py` resolves ClipCaptionModel / ClipCaptionPrefix / noise_injection / MappingType / AdamW /
+get_linear_schedule_with_warmup as module globals at call time (train.py:326-328,347,446-454), so rebinding them on the
+imported module is the whole integration: no reference file is edited.  What then runs per batch is exactly
+train.py:345-354 — `model(tokens, prefix, mask)` enters `Engine.logits_autograd`, `loss.backward()` our hand-written
+backward through one autograd.Function, `optimizer.step()` the fused HF-semantics AdamW kernel; checkpoints keep the
+reference's key layout (train.py:359-371).
+"""
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def bind(ref_dir: str):
+    import transformers
+    import capdec_b200 as cb
+    if not hasattr(transformers, "AdamW"):        # train.py:6 imports it; the class left transformers in 4.5x
+        transformers.AdamW = cb.AdamW
+    sys.path.insert(0, ref_dir)
+    import train                                   # the unmodified reference module
+    train.ClipCaptionModel = cb.ClipCaptionModel   # train.py:447-454 construct these by name
+    train.ClipCaptionPrefix = cb.ClipCaptionPrefix
+    train.noise_injection = cb.noise_injection     # train.py:347
+    train.MappingType = cb.MappingType             # train.py:446
+    train.AdamW = cb.AdamW                         # train.py:326
+    train.get_linear_schedule_with_warmup = cb.get_linear_schedule_with_warmup   # train.py:328
+    return train
+
+
+def main():
+    ref_dir = os.environ.get("CAPDEC_REFERENCE_DIR", "")
+    if not ref_dir or not (Path(ref_dir) / "train.py").exists():
+        sys.exit("set CAPDEC_REFERENCE_DIR to a checkout of DavidHuji/CapDec (the directory that holds train.py)")
+    train = bind(ref_dir)
+    return train.main()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

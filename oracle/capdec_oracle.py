@@ -259,9 +259,78 @@ def transformer_mapper(sd: Params, x, clip_length: int, num_heads: int = 8):
     return h[:, clip_length:]
 
 
+def _mapper_layer(sd: Params, p: str, x, y=None, num_heads: int = 8):
+    """transformer_mapper.TransformerLayer.forward, transformer_mapper.py:63-66 -> MultiHeadAttention :34-51 + Mlp :13-19.
+    `y` = key/value source; None -> norm1(x) (what MultiHeadAttention sees as its own `x`)."""
+    B, n, c = x.shape
+    hd = c // num_heads
+    xn = F.layer_norm(x, (c,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
+    y = xn if y is None else y
+    m = y.shape[1]
+    q = F.linear(xn, sd[p + "attn.to_queries.weight"]).reshape(B, n, num_heads, hd)
+    kv = F.linear(y, sd[p + "attn.to_keys_values.weight"]).reshape(B, m, 2, num_heads, hd)
+    k, v = kv[:, :, 0], kv[:, :, 1]
+    att = (torch.einsum("bnhd,bmhd->bnmh", q, k) * (hd ** -0.5)).softmax(dim=2)
+    o = torch.einsum("bnmh,bmhd->bnhd", att, v).reshape(B, n, c)
+    x = x + F.linear(o, sd[p + "attn.project.weight"], sd[p + "attn.project.bias"])
+    h = F.layer_norm(x, (c,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
+    h = F.relu(F.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))
+    return x + F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+
+
+def encdec_mapper(sd: Params, x, clip_length: int, num_heads: int = 8):
+    """transformer_mapper.TransformerEncoderDecoder.forward, transformer_mapper.py:132-137 (gpt2_prefix.py:167-168,
+    MappingType.TransformerDecoder): ref = ref_encoder(linear(x) as clip_length x 512 tokens);
+    prefix = prefix_decoder(prefix_const, ref) with layers alternating cross (keys/values from ref, :87-88) and 'self'
+    (:89-90 - keys/values from the UN-normalised stream x, queries from norm1(x))."""
+    B = x.shape[0]
+    pc = sd["clip_project.prefix_const"]
+    de = sd["clip_project.ref_encoder.layers.0.norm1.weight"].shape[0]
+    ref = F.linear(x, sd["clip_project.linear.weight"], sd["clip_project.linear.bias"]).view(B, clip_length, de)
+    j = 0
+    while f"clip_project.ref_encoder.layers.{j}.norm1.weight" in sd:
+        ref = _mapper_layer(sd, f"clip_project.ref_encoder.layers.{j}.", ref, None, num_heads)   # :91-92 (enc_dec False)
+        j += 1
+    h = pc.unsqueeze(0).expand(B, *pc.shape)
+    j = 0
+    while f"clip_project.prefix_decoder.layers.{j}.norm1.weight" in sd:
+        p = f"clip_project.prefix_decoder.layers.{j}."
+        h = _mapper_layer(sd, p, h, ref if j % 2 == 0 else h, num_heads)
+        j += 1
+    return h
+
+
+def make_encdec_state_dict(seed: int, prefix_length: int = 10, clip_length: int = 10, prefix_size: int = 512,
+                           num_layers: int = 2, d: int = 768, de: int = 512) -> Params:
+    """Seeded parameters with the key layout of transformer_mapper.TransformerEncoderDecoder (under `clip_project.`)."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s, std=0.02: torch.randn(*s, generator=g) * std
+    sd: Params = {"clip_project.prefix_const": rn(prefix_length, d, std=1.0),
+                  "clip_project.linear.weight": rn(clip_length * de, prefix_size, std=1.0 / math.sqrt(prefix_size)),
+                  "clip_project.linear.bias": rn(clip_length * de, std=0.02)}
+
+    def layer(p, c, c_ref):
+        hm = int(c * 2.0)
+        sd[p + "norm1.weight"] = 1.0 + rn(c, std=0.1); sd[p + "norm1.bias"] = rn(c, std=0.05)
+        sd[p + "attn.to_queries.weight"] = rn(c, c, std=1.0 / math.sqrt(c))
+        sd[p + "attn.to_keys_values.weight"] = rn(2 * c, c_ref, std=1.0 / math.sqrt(c_ref))
+        sd[p + "attn.project.weight"] = rn(c, c, std=1.0 / math.sqrt(c)); sd[p + "attn.project.bias"] = rn(c, std=0.02)
+        sd[p + "norm2.weight"] = 1.0 + rn(c, std=0.1); sd[p + "norm2.bias"] = rn(c, std=0.05)
+        sd[p + "mlp.fc1.weight"] = rn(hm, c, std=1.0 / math.sqrt(c)); sd[p + "mlp.fc1.bias"] = rn(hm, std=0.02)
+        sd[p + "mlp.fc2.weight"] = rn(c, hm, std=1.0 / math.sqrt(hm)); sd[p + "mlp.fc2.bias"] = rn(c, std=0.02)
+
+    for j in range(num_layers):
+        layer(f"clip_project.ref_encoder.layers.{j}.", de, de)
+    for j in range(2 * num_layers):
+        layer(f"clip_project.prefix_decoder.layers.{j}.", d, de if j % 2 == 0 else d)
+    return sd
+
+
 def clip_project(sd: Params, prefix, clip_length: Optional[int] = None):
     if "clip_project.model.0.weight" in sd:
         return mlp_mapper(sd, prefix)
+    if "clip_project.ref_encoder.layers.0.norm1.weight" in sd:
+        return encdec_mapper(sd, prefix, clip_length)
     return transformer_mapper(sd, prefix, clip_length)
 
 

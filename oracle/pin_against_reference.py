@@ -258,7 +258,34 @@ def pin_dataset():
     print("dataset ok", [r["max_seq_len"] for r in recs])
 
 
+def pin_encdec_mapper():
+    """transformer_mapper.TransformerEncoderDecoder (the reference's own module) vs oracle.encdec_mapper
+    -> tests/golden/encdec_mapper.json."""
+    sys.path.insert(0, str(REF))
+    import transformer_mapper as tm  # noqa
+    recs = []
+    for case, (P, C, D, nl, B) in enumerate([(10, 10, 512, 2, 3), (40, 40, 640, 1, 2), (4, 7, 512, 3, 1)]):
+        sd = O.make_encdec_state_dict(seed=60 + case, prefix_length=P, clip_length=C, prefix_size=D, num_layers=nl)
+        torch.manual_seed(0)
+        net = tm.TransformerEncoderDecoder(D, 768, P, C, nl)
+        net.load_state_dict({k[len("clip_project."):]: v for k, v in sd.items()}, strict=True)
+        x = torch.randn(B, D, generator=torch.Generator().manual_seed(70 + case))
+        x = x / x.norm(2, -1, keepdim=True)
+        with torch.no_grad():
+            ref = net(x)
+        out = O.encdec_mapper(sd, x, C)
+        assert ref.shape == out.shape == (B, P, 768)
+        assert (ref - out).abs().max() <= 1e-5 * ref.abs().max(), float((ref - out).abs().max())
+        idx = sample_idx(ref.numel(), 64, 5)
+        recs.append({"sd_seed": 60 + case, "x_seed": 70 + case, "P": P, "C": C, "D": D, "num_layers": nl, "B": B,
+                     "idx": idx.tolist(), "val": ref.flatten()[idx].double().tolist(), "absmax": float(ref.abs().max()),
+                     "norm": float(ref.double().norm()), "oracle_maxabs_diff": float((ref - out).abs().max())})
+    (GOLD / "encdec_mapper.json").write_text(json.dumps({"cases": recs}, indent=1))
+    print("encdec mapper ok", [r["oracle_maxabs_diff"] for r in recs])
+
+
 if __name__ == "__main__":
     main()
     pin_generate_beam()
     pin_dataset()
+    pin_encdec_mapper()

@@ -645,3 +645,27 @@ def test_gemm_autotune_keeps_results_and_remembers_plans(ops):
         assert (C.double() - ref).abs().max() < 1e-4 * ref.abs().max()
     finally:
         assert ops.gemm_autotune(-1) == 0
+
+
+def test_gemm_gelu_forward_with_stored_derivative_and_multiply_backward(ops):
+    """act 4: C = gelu_new(x W + b), aux = gelu_new'(x W + b) from one tanh; mul_act 4: dx = (dy W2^T) * aux."""
+    M, K, N = 700, 256, 1100
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(K, N, device="cuda", generator=g) * 0.08          # Conv1D layout [in, out]
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    out, aux = new_c(M, N), new_c(M, N)
+    ops.linear_fwd(x, W, "conv1d", b, out, act=ops.ACT_GELU_NEW_D, aux=aux)
+    pre = (trunc_tf32(x).double() @ trunc_tf32(W.t().contiguous()).double().t() + b.double()).requires_grad_()
+    ref = torch.nn.functional.gelu(pre, approximate="tanh")
+    ref.sum().backward()
+    assert (out.double() - ref).abs().max() < 2e-3          # MUFU.TANH: 2^-11 relative
+    assert (aux.double() - pre.grad).abs().max() < 2e-3
+    dy = torch.randn(M, 96, device="cuda", generator=g)
+    W2 = torch.randn(N, 96, device="cuda", generator=g) * 0.05       # Conv1D [in = N, out = 96]
+    dx = new_c(M, N)
+    db = torch.zeros(N, device="cuda")
+    ops.linear_dgrad_act(dy, W2, "conv1d", dx, aux, ops.ACT_GELU_NEW_D, dbias=db)
+    refdx = (trunc_tf32(dy).double() @ trunc_tf32(W2).double().t()) * aux.double()
+    assert (dx.double() - refdx).abs().max() < 2e-4 * max(1.0, refdx.abs().max().item())
+    assert (db.double() - refdx.sum(0)).abs().max() < 2e-3 * max(1.0, refdx.sum(0).abs().max().item())

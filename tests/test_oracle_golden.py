@@ -101,3 +101,39 @@ def test_oracle_beam_search_reproduces_the_reference_ids():
                                             c["entry_length"], case["temperature"], case["stop_token_index"])
         assert ids == case["ids"] and lens == case["seq_lengths"]
         assert max(abs(a - b) for a, b in zip(scores, case["scores"])) < 1e-5
+
+
+def test_oracle_dataset_item_reproduces_the_reference_dataset():
+    """train.py:52-72 restated (oracle.dataset_item) vs what the reference's own ClipCocoDataset + DataLoader returned
+    (tests/golden/datafeed.json): token ids exact, mask exact, prefix to fp32 round-off."""
+    rec = json.loads((GOLD / "datafeed.json").read_text())
+    for c in rec["cases"]:
+        caps, cap2emb, table = O.make_caption_table(seed=c["table_seed"], n=c["n"], n_emb=c["n_emb"], half=c["half"])
+        L, P = c["max_seq_len"], c["prefix_length"]
+        toks, masks, pfx = [], [], []
+        for it in c["idx"]:
+            t, m, p = O.dataset_item(caps, cap2emb, table, it, L, P, c["normalize_prefix"])
+            toks.append(t), masks.append(m), pfx.append(p)
+        tokens, mask, prefix = torch.stack(toks), torch.stack(masks), torch.stack(pfx)
+        assert tokens.tolist() == c["tokens"]
+        assert mask.sum(1).tolist() == c["mask_sum_rows"]
+        assert torch.equal(mask[:, P:], torch.stack([torch.arange(L) < min(len(caps[i]), L) for i in c["idx"]]).float())
+        assert str(prefix.dtype).replace("torch.", "") == c["prefix_dtype"]
+        assert prefix.float().norm(2, -1).double().tolist() == pytest.approx(c["prefix_row_norms"], rel=1e-6)
+        assert (prefix[:, :6].double() - torch.tensor(c["prefix_head"])).abs().max() < 1e-6
+        assert float(prefix.double().sum()) == pytest.approx(c["prefix_sum"], rel=1e-5, abs=1e-5)
+
+
+def test_oracle_encdec_mapper_reproduces_the_reference_module():
+    """oracle.encdec_mapper vs values recorded from transformer_mapper.TransformerEncoderDecoder itself."""
+    rec = json.loads((GOLD / "encdec_mapper.json").read_text())
+    for c in rec["cases"]:
+        sd = O.make_encdec_state_dict(seed=c["sd_seed"], prefix_length=c["P"], clip_length=c["C"], prefix_size=c["D"],
+                                      num_layers=c["num_layers"])
+        x = torch.randn(c["B"], c["D"], generator=torch.Generator().manual_seed(c["x_seed"]))
+        x = x / x.norm(2, -1, keepdim=True)
+        out = O.encdec_mapper(sd, x, c["C"])
+        assert tuple(out.shape) == (c["B"], c["P"], 768)
+        got = out.flatten()[torch.tensor(c["idx"])].double()
+        assert (got - torch.tensor(c["val"], dtype=torch.float64)).abs().max() <= 1e-5 * c["absmax"]
+        assert float(out.double().norm()) == pytest.approx(c["norm"], rel=1e-6)

@@ -62,7 +62,12 @@ def test_packed_loss_and_grads_equal_dense(mapping, only_prefix):
     model = model.to("cuda").train()
     eng = model.engine()
     assert cb.ops.get_precision() == "tf32" and eng.packed
-    for seed in (1, 2, 3):   # several batches through the same arena: stale rows of other packings must not leak in
+    # bit-reproducible activation-gradient path for the tight comparison: the split-K LM-head dgrad reduces in a
+    # non-deterministic order, and fp32 order noise becomes 2^-11 noise once the next GEMM rounds its operand to TF32
+    eng.lm_dgrad_splitk = False
+    for seed in (1, 2, 3, 4):   # several batches through the same arena: stale rows of other packings must not leak in
+        if seed == 4:
+            eng.lm_dgrad_splitk = True
         tok = _tokens(B, L, seed).cuda()
         pfx = torch.randn(B, D, generator=torch.Generator().manual_seed(seed)).cuda()
         out = {}
@@ -79,8 +84,8 @@ def test_packed_loss_and_grads_equal_dense(mapping, only_prefix):
         for k in g0:
             ref = g0[k].double()
             err = (g1[k].double() - ref).norm() / ref.norm().clamp_min(1e-30)
-            # equal up to fp32 summation order: the split-K reductions (reduce-add) are not order-deterministic
-            assert err <= 2e-4 or ref.norm() == 0, (seed, k, float(err))
+            tol = 2e-5 if not eng.lm_dgrad_splitk else 5e-3   # weight-gradient split-K order only / TF32 rounding noise
+            assert err <= tol or ref.norm() == 0, (seed, k, float(err))
             if ref.norm() == 0:
                 assert g1[k].abs().max() == 0, k
 

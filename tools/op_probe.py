@@ -142,6 +142,26 @@ def attn_probe():
         print(f"attention_bwd {name} rows={rows}: {us:.1f} us, {8 * rows * d * 4 / us / 1e6:.2f} TB/s", flush=True)
 
 
+def mul_probe():
+    """The fused dgrad x act' (+ bias-gradient column sums) epilogue, piece by piece (set CAPDEC_GEMM_DBG=4 to drop stores)."""
+    M, N, K = M_MAX, 3072, 768
+    A, B, C, u = mat(M, K), mat(N, K), torch.zeros(M, pad(N), device="cuda")[:, :N], mat(M, N)
+    col = torch.zeros(N, device="cuda")
+    lim = torch.tensor([M_LIVE], device="cuda", dtype=torch.int32)
+    ops.set_row_hint(M_LIVE)
+    flops = 2.0 * N * M_LIVE * K
+    for name, fn in {
+        "plain dgrad (no epilogue input)": lambda: ops.gemm(A, 0, B, 0, C, M, N, K, m_limit=lim),
+        "mul gelu' + colsum": lambda: ops.gemm_mul(A, 0, B, 0, C, M, N, K, u, 1, col, m_limit=lim),
+        "mul stored-derivative + colsum": lambda: ops.gemm_mul(A, 0, B, 0, C, M, N, K, u, 4, col, m_limit=lim),
+        "mul stored-derivative, no colsum": lambda: ops.gemm_mul(A, 0, B, 0, C, M, N, K, u, 4, None, m_limit=lim),
+        "mul relu mask, no colsum": lambda: ops.gemm_mul(A, 0, B, 0, C, M, N, K, u, 3, None, m_limit=lim),
+    }.items():
+        us = timeit(fn)
+        print(f"{name:36s} {us:7.1f} us  {flops / us / 1e6:5.0f} TF/s", flush=True)
+    ops.set_row_hint(0)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gemm"
-    {"gemm": gemm_sweep, "ln": ln_probe, "attn": attn_probe}[what]()
+    {"gemm": gemm_sweep, "ln": ln_probe, "attn": attn_probe, "mul": mul_probe}[what]()
