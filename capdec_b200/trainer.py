@@ -57,10 +57,22 @@ class Trainer:
             self.eng.seed.add_(7919 * (1 + torch.distributed.get_rank(process_group)))
         # data-parallel all-reduce overlapped with backward: one bucket per GPT-2 block, reduced on a side stream as
         # soon as the block's gradients are final; only [tail | mapper | wte | wpe] (ready last) stays exposed
+        # (experimental, opt-in: NCCL collectives captured on a second graph branch were seen to dead-lock on replay)
         self.overlap = (self.world > 1 and self.train_gpt and os.environ.get("CAPDEC_DP_OVERLAP", "0") == "1")
-        if self.overlap:
+        # opt-in (CAPDEC_DP_PIPELINE=1): the all-reduce is cut into chunks on a side stream and the fused AdamW of chunk k
+        # runs while chunk k+1 is still being reduced (both outside the CUDA graph: plain stream/event ordering).
+        # Validated on 2 GPUs (tests/test_dp_gpu.py passes with it) but measured equal to the plain sequence there
+        # (19.00 vs 19.01 ms/step: the all-reduce and AdamW compete for the same HBM bandwidth), so it is not the default.
+        self.pipeline = (self.world > 1 and not self.overlap and os.environ.get("CAPDEC_DP_PIPELINE", "0") == "1")
+        if self.overlap or self.pipeline:
             self.comm = torch.cuda.Stream(device=self.dev)
+        if self.overlap:
             self.buckets, self.head_bucket = self.eng.layer_grad_slices()
+        if self.pipeline:
+            n_chunks = int(os.environ.get("CAPDEC_DP_CHUNKS", "4"))
+            total = self.reduce_buf.numel()                     # 4 tail floats + trainable gradients
+            step = ((total + n_chunks - 1) // n_chunks + 1023) // 1024 * 1024
+            self.chunks = [(lo, min(total, lo + step)) for lo in range(0, total, step)]
         self.use_graph = use_cuda_graph
         self._g_fb = self._g_opt = self._g_eval = None
         self._warm = 0
@@ -126,6 +138,29 @@ class Trainer:
         self.eng.flat.grads.zero_()
         return n
 
+    def _reduce_and_opt(self):
+        """Chunked all-reduce (side stream) pipelined with the fused AdamW (main stream).  Chunk 0 carries the tail
+        [n_valid, loss_sum, ., .], so the global token count is known before the first parameter is updated."""
+        main = torch.cuda.current_stream()
+        tail = self.eng.flat.tail
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.comm.wait_event(ready)
+        for k, (lo, hi) in enumerate(self.chunks):
+            with torch.cuda.stream(self.comm):
+                torch.distributed.all_reduce(self.reduce_buf[lo:hi], group=self.pg)
+                done = torch.cuda.Event()
+                done.record(self.comm)
+            main.wait_event(done)
+            if k == 0:
+                self.stats.copy_(self.tail)
+            plo, phi = max(lo, tail) - tail, hi - tail           # the same span in parameter coordinates
+            if phi > plo:
+                ops.adamw_step(self.p_flat[plo:phi], self.g_flat[plo:phi], self.m_flat[plo:phi], self.v_flat[plo:phi],
+                               self.lr_dev, self.t_dev, self.betas[0], self.betas[1], self.eps, self.wd,
+                               grad_denom=self.stats[0:1], zero_grad=True)
+        self.comm.wait_stream(main)   # the next step's all-reduce must not start before these updates were issued
+
     def _capture(self, fn):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -140,15 +175,21 @@ class Trainer:
                 self._g_fb = self._capture(self._fwd_bwd)
                 self._g_opt = self._capture(self._opt)
             self._g_fb.replay()
-            if self.world > 1 and not self.overlap:
-                torch.distributed.all_reduce(self.reduce_buf, group=self.pg)
-            self._g_opt.replay()
+            if self.pipeline:
+                self._reduce_and_opt()
+            else:
+                if self.world > 1 and not self.overlap:
+                    torch.distributed.all_reduce(self.reduce_buf, group=self.pg)
+                self._g_opt.replay()
         else:
             self._warm += 1
             self._fwd_bwd()
-            if self.world > 1 and not self.overlap:
-                torch.distributed.all_reduce(self.reduce_buf, group=self.pg)
-            self._opt()
+            if self.pipeline:
+                self._reduce_and_opt()
+            else:
+                if self.world > 1 and not self.overlap:
+                    torch.distributed.all_reduce(self.reduce_buf, group=self.pg)
+                self._opt()
             if self._warm == 2:   # GEMM tile planning for the live rows seen during warm-up (one host sync, results unaffected)
                 self.eng.measure_row_hints(self.B, self.L)
                 self.autotune()
