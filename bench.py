@@ -305,7 +305,7 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (fused-QKV GEMM 12800x2304x768 + bias)",
                          "achieved": qkv_tf, "peak": tf32_peak, "unit": "TFLOP/s", "frac": qkv_tf / tf32_peak,
-                         "traffic": 110.5e6, "traffic_unit": "bytes/launch, dram read+write, ncu --set full (profiles/r1_ncu_qkv_pair.md); "
+                         "traffic": 108.9e6, "traffic_unit": "bytes/launch, dram read+write, ncu --set full (profiles/r1_ncu_session3.md); "
                                                                 "algorithmic 164.4e6 (operands + output once)",
                          "ms_per_launch": qkv_ms,
                          "peak_source": pk["source"] + ": bf16 burst %.1f TF/s / 2 (kind::tf32 issues at half the kind::f16 rate)" % pk["bf16"],
