@@ -63,6 +63,12 @@ class Engine:
         self.hint_rows = 0
         self.hint_targets = 0
         self.lm_dgrad_splitk = os.environ.get("CAPDEC_LM_DGRAD_SPLITK", "1") != "0"
+        # weight-gradient GEMMs of the GPT-2 blocks on a second stream (they are off the backward's critical path): their
+        # CTAs fill the SMs a dgrad GEMM leaves idle in its last, partly empty wave (18.38 -> 18.20 / 18.23 ms/step on one
+        # box, gpurun_out/s13_bench_*.log).  CAPDEC_BWD_STREAMS=0 serialises.
+        self.bwd_streams = os.environ.get("CAPDEC_BWD_STREAMS", "1") != "0"
+        self.serial_backward = False          # set while GEMM plans are being measured (Trainer.autotune)
+        self._side = None
 
     # ------------------------------------------------------------------------------------------------------------
     # parameter / gradient views
@@ -424,6 +430,33 @@ class Engine:
         cu = a.cu if a.packed else None
         if a.packed:  # attention_bwd writes live rows only; the K-limited c_attn weight gradient reads whole k-blocks
             ops.zero_tail_rows(a.dqkv, a.rows)
+        use_side = self.bwd_streams and train_gpt and not self.serial_backward
+        if use_side and self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        side = self._side
+
+        def wgrad(x, dy_, gname):
+            """dW += x^T dy_.  Two-stream mode: launched on the side stream after everything issued so far on the main
+            stream; returns the event that marks its completion (the caller waits on it before x / dy_ are overwritten)."""
+            if not train_gpt:
+                return None
+            if not use_side:
+                ops.linear_wgrad(x, dy_, g[gname], "conv1d", rows=R)
+                return None
+            ev = torch.cuda.Event()
+            ev.record()
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                ops.linear_wgrad(x, dy_, g[gname], "conv1d", rows=R)
+                done = torch.cuda.Event()
+                done.record(side)
+            return done
+
+        def wait(ev):
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
+        e_fc = e_qkv = None    # pending weight gradients that still read a.dF / a.dqkv
         # bias gradients of attn.c_proj / mlp.c_proj / c_fc / c_attn come fused out of add_ln_bwd / act_bwd / attention_bwd
         ops.add_ln_bwd(dxf, a.h[self.nl], a.stf, p["gpt.transformer.ln_f.weight"], None, a.dh, dy,
                        gw("gpt.transformer.ln_f.weight"), gw("gpt.transformer.ln_f.bias"), p_drop=p_res, seed=self.seed,
@@ -433,30 +466,30 @@ class Engine:
             pre = f"gpt.transformer.h.{l}."
             dy2 = cur()
             # mlp.c_proj
-            if train_gpt:
-                ops.linear_wgrad(a.g[l], dy2, g[pre + "mlp.c_proj.weight"], "conv1d", rows=R)
+            e_cproj = wgrad(a.g[l], dy2, pre + "mlp.c_proj.weight")
+            wait(e_fc)                                       # layer l+1's c_fc weight gradient still reads a.dF
             ops.linear_dgrad_act(dy2, p[pre + "mlp.c_proj.weight"], "conv1d", a.dF, a.u[l],
                                  ops.ACT_GELU_NEW_D if ops.get_precision() == "tf32" else ops.ACT_GELU_NEW,
                                  dbias=gw(pre + "mlp.c_fc.bias"), rows=R)
-            if train_gpt:
-                ops.linear_wgrad(a.x2[l], a.dF, g[pre + "mlp.c_fc.weight"], "conv1d", rows=R)
+            e_fc = wgrad(a.x2[l], a.dF, pre + "mlp.c_fc.weight")
             ops.linear_dgrad(a.dF, p[pre + "mlp.c_fc.weight"], "conv1d", a.dx, rows=R)
+            wait(e_cproj)                                    # the next kernel overwrites dy2
             ops.add_ln_bwd(a.dx, a.h1[l], a.st2[l], p[pre + "ln_2.weight"], a.dh, a.dh, dy, gw(pre + "ln_2.weight"),
                            gw(pre + "ln_2.bias"), p_drop=p_res, seed=self.seed, stream_id=_site(l, 1),
                            dbias_branch=gw(pre + "attn.c_proj.bias"), rows=R)
             dy1 = cur()
             # attention
-            if train_gpt:
-                ops.linear_wgrad(a.ctx[l], dy1, g[pre + "attn.c_proj.weight"], "conv1d", rows=R)
+            e_aproj = wgrad(a.ctx[l], dy1, pre + "attn.c_proj.weight")
             ops.linear_dgrad(dy1, p[pre + "attn.c_proj.weight"], "conv1d", a.dctx, rows=R)
             q, k, v = a.qkv[l][:, :d], a.qkv[l][:, d:2 * d], a.qkv[l][:, 2 * d:]
             dq, dk, dv = a.dqkv[:, :d], a.dqkv[:, d:2 * d], a.dqkv[:, 2 * d:]
+            wait(e_qkv)                                      # layer l+1's c_attn weight gradient still reads a.dqkv
             ops.attention_bwd(q, k, v, a.ctx[l], a.dctx, a.lse[l], dq, dk, dv, B, self.H, T, T, self.hd, T * 3 * d, 3 * d,
                               T * 3 * d, 3 * d, T * d, d, self.hd ** -0.5, 1, key_len=key_len, p_drop=p_attn,
                               seed=self.seed, stream_id=_site(l, 0), dbias_qkv=gw(pre + "attn.c_attn.bias"), cu_rows=cu)
-            if train_gpt:
-                ops.linear_wgrad(a.x1[l], a.dqkv, g[pre + "attn.c_attn.weight"], "conv1d", rows=R)
+            e_qkv = wgrad(a.x1[l], a.dqkv, pre + "attn.c_attn.weight")
             ops.linear_dgrad(a.dqkv, p[pre + "attn.c_attn.weight"], "conv1d", a.dx, rows=R)
+            wait(e_aproj)                                    # the next kernel overwrites dy1
             if l > 0:
                 ops.add_ln_bwd(a.dx, a.h[l], a.st1[l], p[pre + "ln_1.weight"], a.dh, a.dh, dy, gw(pre + "ln_1.weight"),
                                gw(pre + "ln_1.bias"), p_drop=p_res, seed=self.seed, stream_id=_site(l - 1, 2),
@@ -465,7 +498,10 @@ class Engine:
                 ops.add_ln_bwd(a.dx, a.h[0], a.st1[0], p[pre + "ln_1.weight"], a.dh, a.dh, None, gw(pre + "ln_1.weight"),
                                gw(pre + "ln_1.bias"), rows=R)
             if on_layer_done is not None and train_gpt:
+                if use_side:
+                    wait(e_fc), wait(e_qkv)
                 on_layer_done(l)   # every gradient of GPT-2 block l (and ln_f when l is the last block) is final now
+        wait(e_fc), wait(e_qkv)     # join the side stream
 
     # ------------------------------------------------------------------------------------------------------------
     # fast path: loss + gradients (sum-reduced CE gradients, divided by the token count inside AdamW)

@@ -123,6 +123,7 @@ class Trainer:
             return 0
         keep = [t.clone() for t in (self.eng.seed, self.step_dev, self.lr_dev, self.t_dev)]
         ops.gemm_autotune(1)
+        self.eng.serial_backward = True     # one stream while measuring: concurrent kernels would distort the timings
         try:   # the same launches as _fwd_bwd, but never a collective: ranks measure independently
             pfx = self.prefix_d
             if self.noise_variance > 0.0:
@@ -131,6 +132,7 @@ class Trainer:
                 pfx = self.prefix_n
             self.eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False)
         finally:
+            self.eng.serial_backward = False
             n = ops.gemm_autotune(0)
         torch.cuda.synchronize()
         for dst, src in zip((self.eng.seed, self.step_dev, self.lr_dev, self.t_dev), keep):
