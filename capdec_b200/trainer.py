@@ -64,6 +64,25 @@ class Trainer:
         # Validated on 2 GPUs (tests/test_dp_gpu.py passes with it) but measured equal to the plain sequence there
         # (19.00 vs 19.01 ms/step: the all-reduce and AdamW compete for the same HBM bandwidth), so it is not the default.
         self.pipeline = (self.world > 1 and not self.overlap and os.environ.get("CAPDEC_DP_PIPELINE", "0") == "1")
+        # single GPU: the fused AdamW of a GPT-2 block runs on a second stream as soon as backward has finished that block
+        # (its gradients are final and its weights are not read again this step), hidden behind the remaining backward
+        # GEMMs - AdamW is pure HBM traffic (4.4 GB/step), the GEMMs are tensor / L2 bound.  [mapper | wte | wpe] follow at
+        # the end.  Data parallel keeps reduce-then-update (the update needs the all-reduced gradient).
+        # Opt-in (CAPDEC_OPT_OVERLAP=1): validated (tests/test_model_gpu.py etc. pass with it) but measured equal to the
+        # plain sequence on this pool (17.79-17.89 vs 17.86 ms/step, gpurun_out/s15_bench_*.log) - the B200s here run
+        # against their power cap, so overlapping HBM traffic with tensor work does not shorten the step.
+        self.opt_overlap = (self.world == 1 and self.train_gpt and os.environ.get("CAPDEC_OPT_OVERLAP", "0") == "1")
+        if self.opt_overlap:
+            self.opt_stream = torch.cuda.Stream(device=self.dev)
+            lay = fl.layout
+            nl = self.eng.nl
+            first = lay["gpt.transformer.h.0.ln_1.weight"][0] - fl.tail
+            self.layer_spans = []
+            for l in range(nl):
+                a0 = lay[f"gpt.transformer.h.{l}.ln_1.weight"][0] - fl.tail
+                a1 = (lay[f"gpt.transformer.h.{l + 1}.ln_1.weight"][0] - fl.tail) if l + 1 < nl else self.n_train
+                self.layer_spans.append((a0, a1))                 # block l (+ ln_f for the last block)
+            self.head_span = (0, first)                           # mapper | wte | wpe: final only after the embedding scatter
         if self.overlap or self.pipeline:
             self.comm = torch.cuda.Stream(device=self.dev)
         if self.overlap:
@@ -90,8 +109,13 @@ class Trainer:
             pfx = self.prefix_n
         else:
             pfx = self.prefix_d                                 # train.py:28-29: variance 0 -> untouched
-        eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False,
-                           on_layer_done=self._reduce_layer if self.overlap else None)
+        hook = self._reduce_layer if self.overlap else (self._opt_layer if self.opt_overlap else None)
+        self._stats_taken = False
+        eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False, on_layer_done=hook)
+        if self.opt_overlap:
+            self._take_stats()
+            self._adamw_span(*self.head_span)
+            torch.cuda.current_stream().wait_stream(self.opt_stream)
         if self.overlap:
             # [tail | mapper | wte | wpe] is ready last.  It goes to the SAME side stream as the per-block buckets: every
             # collective of this communicator then sits on one branch of the captured graph, in one fixed order on every
@@ -109,7 +133,28 @@ class Trainer:
         with torch.cuda.stream(self.comm):
             torch.distributed.all_reduce(bucket, group=self.pg)
 
+    def _take_stats(self):
+        if not self._stats_taken:      # [n_valid, loss_sum] are final once the CE kernel ran, i.e. before backward starts
+            self.stats.copy_(self.tail)
+            self._stats_taken = True
+
+    def _adamw_span(self, lo: int, hi: int):
+        if hi > lo:
+            ops.adamw_step(self.p_flat[lo:hi], self.g_flat[lo:hi], self.m_flat[lo:hi], self.v_flat[lo:hi], self.lr_dev,
+                           self.t_dev, self.betas[0], self.betas[1], self.eps, self.wd, grad_denom=self.stats[0:1],
+                           zero_grad=True)
+
+    def _opt_layer(self, l: int):
+        self._take_stats()
+        ev = torch.cuda.Event()
+        ev.record()
+        self.opt_stream.wait_event(ev)
+        with torch.cuda.stream(self.opt_stream):
+            self._adamw_span(*self.layer_spans[l])
+
     def _opt(self):
+        if self.opt_overlap:           # the update already ran inside _fwd_bwd
+            return
         self.stats.copy_(self.tail)
         ops.adamw_step(self.p_flat, self.g_flat, self.m_flat, self.v_flat, self.lr_dev, self.t_dev, self.betas[0],
                        self.betas[1], self.eps, self.wd, grad_denom=self.stats[0:1], zero_grad=True)
@@ -175,11 +220,11 @@ class Trainer:
             if self._g_fb is None:
                 torch.cuda.synchronize()
                 self._g_fb = self._capture(self._fwd_bwd)
-                self._g_opt = self._capture(self._opt)
+                self._g_opt = None if self.opt_overlap else self._capture(self._opt)
             self._g_fb.replay()
             if self.pipeline:
                 self._reduce_and_opt()
-            else:
+            elif not self.opt_overlap:
                 if self.world > 1 and not self.overlap:
                     torch.distributed.all_reduce(self.reduce_buf, group=self.pg)
                 self._g_opt.replay()
