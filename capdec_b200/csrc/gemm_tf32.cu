@@ -1036,6 +1036,21 @@ extern "C" int capdec_gemm_autotune(int enable) {
   return (int)g_tuned.size();
 }
 
+// The heuristic plan for a problem, without launching anything (host arithmetic only; usable without a GPU, where the SM
+// count defaults to 148).  Returns engine | tile width << 8 | split-K << 20, or a negative error code.
+extern "C" int capdec_gemm_plan_query(int M, int N, int K, int b_major, int accumulate, int block_n, int split_k,
+                                      int row_limited) {
+  CAPDEC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_plan_query: bad shape M=%d N=%d K=%d", M, N, K);
+  CAPDEC_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 192 || block_n == 256, "gemm_plan_query: bad block_n");
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M; a.N = N; a.K = K; a.b_major = b_major ? 1 : 0; a.accumulate = accumulate ? 1 : 0;
+  static const int32_t dummy_limit = 0;
+  a.m_limit = row_limited ? &dummy_limit : nullptr;   // only its presence matters to the planner (never dereferenced)
+  const GemmPlan pl = heuristic_plan(a, block_n, split_k, -1);
+  return pl.mode | (pl.bn << 8) | (pl.splits << 20);
+}
+
 extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
                                    float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
                                    int accumulate, int precision, const float* a_lo, const float* b_lo, int block_n,

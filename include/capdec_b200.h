@@ -88,6 +88,10 @@ void capdec_gemm_set_row_hint(int rows);
  * throw-away step (Trainer.autotune does).  enable = 0 stops measuring (remembered plans stay in use); -1 forgets
  * them.  Returns the number of remembered plans. */
 int capdec_gemm_autotune(int enable);
+/* The heuristic plan for a problem, without launching (host arithmetic only).  row_limited != 0: plan as for a GEMM with
+ * a device-side row limit, i.e. for the rows given to capdec_gemm_set_row_hint.  Returns
+ * engine (0 single CTA, 1 CTA pair, 2/3 quads) | tile width << 8 | split-K factor << 20, or a negative error code. */
+int capdec_gemm_plan_query(int M, int N, int K, int b_major, int accumulate, int block_n, int split_k, int row_limited);
 
 /* fp32 CUDA-core GEMM with the same contract (verification kernel: exact fp32 FMA, no tensor cores). */
 int capdec_gemm_fp32_simt(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,

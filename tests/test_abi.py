@@ -50,3 +50,35 @@ def test_no_cpu_fallback():
     a = torch.zeros(4, 4)
     with pytest.raises(CapdecError):
         ops.gemm(a, 0, a, 0, a, 4, 4, 4)
+
+
+def test_gemm_planner_returns_legal_plans_on_cpu():
+    """Host-side planner (engine / tile width / split-K) over the shapes of the C1-C4 steps and some ragged ones: every
+    plan must be one the kernel accepts (pairs need >= 128 columns, 192-wide tiles never with the B-sharing quad on an
+    MN-major B, split-K only for accumulating GEMMs and never finer than 4 k-blocks)."""
+    from capdec_b200 import _lib
+    lib = _lib.load()
+    shapes = [(12800, 2304, 768), (12800, 768, 768), (12800, 3072, 768), (12800, 768, 3072), (768, 2304, 12800),
+              (3072, 768, 12800), (10240, 50257, 768), (50257, 768, 10240), (10240, 768, 50257), (256, 7680, 3840),
+              (32, 3840, 512), (1, 50257, 768), (5120, 2304, 768), (200, 300, 100), (20480, 1536, 768), (130, 120, 40)]
+    seen_modes = set()
+    for (M, N, K) in shapes:
+        for b_major in (0, 1):
+            for acc in (0, 1):
+                for hinted in (0, 1):
+                    if hinted:
+                        lib.capdec_gemm_set_row_hint(max(1, int(M * 0.69)))
+                    code = lib.capdec_gemm_plan_query(M, N, K, b_major, acc, 0, 0, hinted)
+                    lib.capdec_gemm_set_row_hint(0)
+                    assert code > 0, (M, N, K, code)
+                    mode, bn, splits = code & 0xFF, (code >> 8) & 0xFFF, code >> 20
+                    seen_modes.add(mode)
+                    assert mode in (0, 1, 2, 3) and bn in (64, 128, 192, 256) and splits >= 1, (M, N, K, mode, bn, splits)
+                    assert mode == 0 or (bn >= 128 and M > 128 and N >= 128), (M, N, K, mode, bn)
+                    assert not (bn == 192 and mode == 3 and b_major), (M, N, K)
+                    assert splits == 1 or (acc and (K + 31) // 32 // splits >= 4), (M, N, K, splits)
+    assert {0, 1, 3} <= seen_modes
+    # explicit requests are honoured
+    code = lib.capdec_gemm_plan_query(12800, 768, 3072, 0, 1, 192, 3, 0)
+    assert (code >> 8) & 0xFFF == 192 and code >> 20 == 3
+    assert lib.capdec_gemm_plan_query(0, 5, 5, 0, 0, 0, 0, 0) < 0
