@@ -415,7 +415,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
     // TMA store of a {32 cols, 32 rows} box.  No cross-warp barrier inside the chunk loop (two per tile remain, for the
     // bias tile and the column sums); staging is ping-pong per warp, gated by the warp leader's bulk-group counter.
     const int q = warp & 3;                   // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;            // row of this CTA's 128-row slab owned by this thread
     const int epi_tid = threadIdx.x - 4 * 32;
     uint8_t* wst = sStage + q * (n_staging * kWarpStagingBytes);   // this warp's staging: C[0], C[1], (X[0], X[1])
     uint64_t* my_mul_bar = mul_bar + kMulDepth * q;
@@ -775,24 +774,6 @@ extern "C" int capdec_gemm_tf32(const float* A, int a_major, int64_t lda, const 
                              a_lo, b_lo, block_n, split_k, nullptr, nullptr, stream_);
 }
 
-static thread_local const float* t_mul_in = nullptr;
-static thread_local int t_mul_act = 0;
-static thread_local float* t_colsum = nullptr;
-
-// C = (A . B^T) * act'(mul_in), colsum[n] += sum_m C[m,n]: the dgrad GEMM that feeds an activation's backward, with the
-// bias gradient of the layer below fused (HF:modeling_gpt2.py:238-243 c_fc -> gelu_new; train.py:106-118 tanh; :121 relu)
-extern "C" int capdec_gemm_tf32_mul(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
-                                    float* C, int64_t ldc, int M, int N, int K, const float* mul_in, int mul_act,
-                                    float* colsum, int block_n, const int32_t* m_limit_dev, capdec_stream_t stream_) {
-  CAPDEC_REQUIRE(mul_in && mul_act >= 1 && mul_act <= 4, "gemm_mul: bad epilogue input");
-  CAPDEC_REQUIRE(((uintptr_t)mul_in % 16) == 0, "gemm_mul: mul_in must be 16-byte aligned");
-  t_mul_in = mul_in; t_mul_act = mul_act; t_colsum = colsum;
-  int rc = capdec_gemm_tf32_ex(A, a_major, lda, B, b_major, ldb, C, ldc, M, N, K, nullptr, 0, nullptr, 0, 0, nullptr,
-                               nullptr, block_n, 1, m_limit_dev, nullptr, stream_);
-  t_mul_in = nullptr; t_mul_act = 0; t_colsum = nullptr;
-  return rc;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // plan (engine, tile width, split-K)  ->  launch;  measured plan selection ("autotune") on top of the heuristic
 // ---------------------------------------------------------------------------------------------------------------
@@ -858,7 +839,6 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   const int tile_m = plan_tile_m(mode);                                                 // rows per cluster tile
   const int pair_m = (mode == 0) ? kBlockM : 2 * kBlockM;                               // rows per MMA (instruction M)
   const int nmul = (mode == 2) ? 2 : 1;
-  const int cluster_size = (mode == 0) ? 1 : (mode == 1 ? 2 : 4);
   int splits = pl.splits < 1 ? 1 : pl.splits;
   p.block_n = bn;
   p.splits = splits;
@@ -1058,12 +1038,11 @@ extern "C" int capdec_gemm_plan_query(int M, int N, int K, int b_major, int accu
   return pl.mode | (pl.bn << 8) | (pl.splits << 20);
 }
 
-extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
-                                   float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
-                                   int accumulate, int precision, const float* a_lo, const float* b_lo, int block_n,
-                                   int split_k, const int32_t* m_limit_dev, const int32_t* k_limit_dev,
-                                   capdec_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+// common entry of capdec_gemm_tf32_ex / capdec_gemm_tf32_mul: validation, plan lookup / measurement, launch
+static int gemm_entry(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb, float* C,
+                      int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux, int accumulate, int precision,
+                      const float* a_lo, const float* b_lo, int block_n, int split_k, const int32_t* m_limit_dev,
+                      const int32_t* k_limit_dev, const float* mul_in, int mul_act, float* colsum, cudaStream_t stream) {
   CAPDEC_REQUIRE(A && B && C, "gemm: null operand");
   CAPDEC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   CAPDEC_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0, "gemm: leading dims must be multiples of 4 (16 B TMA pitch): lda=%lld ldb=%lld ldc=%lld", (long long)lda, (long long)ldb, (long long)ldc);
@@ -1088,7 +1067,7 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
   a.A = A; a.B = B; a.C = C; a.a_major = a_major ? 1 : 0; a.b_major = b_major ? 1 : 0; a.lda = lda; a.ldb = ldb; a.ldc = ldc;
   a.M = M; a.N = N; a.K = K; a.bias = bias; a.act = act; a.aux = aux; a.accumulate = accumulate ? 1 : 0; a.precision = precision;
   a.a_lo = a_lo; a.b_lo = b_lo; a.m_limit = m_limit_dev; a.k_limit = k_limit_dev;
-  a.mul_in = t_mul_in; a.mul_act = t_mul_act; a.colsum = t_colsum;
+  a.mul_in = mul_in; a.mul_act = mul_act; a.colsum = colsum;
 
   // ---- engine selection: 0 single CTA, 1 CTA pair, 2 quad sharing A (pairs side by side in N), 3 quad sharing B ----
   static const char* env_pair = getenv("CAPDEC_GEMM_PAIR");  // bring-up switch: 0 = cta_group::1 only, 1 = pairs only
@@ -1112,4 +1091,24 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
     }
   }
   return launch_plan(a, pl, stream);
+}
+
+extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
+                                   float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
+                                   int accumulate, int precision, const float* a_lo, const float* b_lo, int block_n,
+                                   int split_k, const int32_t* m_limit_dev, const int32_t* k_limit_dev,
+                                   capdec_stream_t stream_) {
+  return gemm_entry(A, a_major, lda, B, b_major, ldb, C, ldc, M, N, K, bias, act, aux, accumulate, precision, a_lo, b_lo,
+                    block_n, split_k, m_limit_dev, k_limit_dev, nullptr, 0, nullptr, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// C = (A . B^T) * act'(mul_in), colsum[n] += sum_m C[m,n]: the dgrad GEMM that feeds an activation's backward, with the
+// bias gradient of the layer below fused (HF:modeling_gpt2.py:238-243 c_fc -> gelu_new; train.py:106-118 tanh; :121 relu)
+extern "C" int capdec_gemm_tf32_mul(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
+                                    float* C, int64_t ldc, int M, int N, int K, const float* mul_in, int mul_act,
+                                    float* colsum, int block_n, const int32_t* m_limit_dev, capdec_stream_t stream_) {
+  CAPDEC_REQUIRE(mul_in && mul_act >= 1 && mul_act <= 4, "gemm_mul: bad epilogue input");
+  CAPDEC_REQUIRE(((uintptr_t)mul_in % 16) == 0, "gemm_mul: mul_in must be 16-byte aligned");
+  return gemm_entry(A, a_major, lda, B, b_major, ldb, C, ldc, M, N, K, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, block_n, 1,
+                    m_limit_dev, nullptr, mul_in, mul_act, colsum, reinterpret_cast<cudaStream_t>(stream_));
 }
