@@ -82,3 +82,14 @@ def test_gemm_planner_returns_legal_plans_on_cpu():
     code = lib.capdec_gemm_plan_query(12800, 768, 3072, 0, 1, 192, 3, 0)
     assert (code >> 8) & 0xFFF == 192 and code >> 20 == 3
     assert lib.capdec_gemm_plan_query(0, 5, 5, 0, 0, 0, 0, 0) < 0
+
+
+def test_reference_max_seq_len_rule():
+    """train.py:102-103: min(int(mean + 10 * std), max) with torch's unbiased std."""
+    from capdec_b200.data import reference_max_seq_len
+    from oracle import capdec_oracle as O
+    lens = torch.tensor([5, 9, 12, 40, 7, 7, 33])
+    caps = [torch.zeros(int(k), dtype=torch.int64) for k in lens]
+    assert reference_max_seq_len(lens) == O.dataset_max_seq_len(caps) == 40
+    tight = torch.tensor([10] * 50 + [11] * 50 + [300])
+    assert reference_max_seq_len(tight) == min(int(tight.float().mean() + tight.float().std() * 10), 300) < 300
