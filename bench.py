@@ -280,6 +280,30 @@ def run_gpu(args):
         packed = bool(model.engine().packed)
         ex_flops, live_rows, dense_rows = executed_flops(host[0][0], P_LEN, packed)
         exec_tf = ex_flops / (ms_dev / args.steps * 1e-3) / 1e12
+        # ---- worst case for the packed path: every caption 40 tokens long (SURVEY §8d "also run l = 40"), same trainer,
+        # same captured graph (row counts are device scalars), GEMM plans still the ones tuned for the mixed-length batch.
+        # Last GPU work of the run and N=1 only, so a failure here cannot take the headline numbers with it.
+        full_len = None
+        if world == 1 and not FULL_LENGTH and args.workload == "c2":
+            try:
+                gfl = torch.Generator().manual_seed(4242)
+                ft = torch.randint(1, V, (B, SEQ), generator=gfl, dtype=torch.int64).pin_memory()
+                for _ in range(3):
+                    tr.step(ft, host[0][1])
+                torch.cuda.synchronize()
+                h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                h0.record()
+                for _ in range(args.steps):
+                    tr.step_device()
+                h1.record()
+                torch.cuda.synchronize()
+                ms_full = h0.elapsed_time(h1) / args.steps
+                fx, frows, fdense = executed_flops(ft, P_LEN, packed)
+                full_len = {"value": B / (ms_full * 1e-3), "unit": "captions/s", "ms_per_step": ms_full,
+                            "rows": f"{frows} of {fdense} trunk rows live, {B * SEQ} targets",
+                            "step_executed_tflops": fx / (ms_full * 1e-3) / 1e12}
+            except Exception as ex:   # reported, never fatal
+                full_len = {"error": repr(ex)[:300]}
         cpu_rate, cores, cpu_s = cpu_train_step_rate(64, 4, 1) if (world == 1 and args.workload == "c2") else (None, None, None)
         line = {
             "metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
@@ -313,6 +337,8 @@ def run_gpu(args):
                          "step_reference_equivalent_tflops": step_tf},
             "last_loss": last,
         }
+        if full_len is not None:
+            line["full_length_captions"] = full_len
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": "captions/s", "cores": cores, "kind": "port",
                                     "sample": f"4 timed steps of 64 captions after 1 warm-up step (oracle port of train.py:345-354 incl. AdamW, torch CPU fp32, {cores} threads, {cpu_s:.2f} s/step)"}

@@ -89,6 +89,42 @@ def test_hf_adamw_and_schedule_restatement():
     assert torch.allclose(w.detach(), torch.full((3,), 1 - 0.01 * math.sqrt(0.001) / 0.1 * 0.1 / (math.sqrt(0.001) + 1e-6)), rtol=1e-5)
 
 
+def test_hf_adamw_equals_torch_adam_with_rescaled_eps():
+    """Independent pin of the one restated piece whose original class is gone (transformers.AdamW, train.py:326):
+    HF-4.24 puts eps INSIDE the bias-corrected step, p -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps), while
+    torch.optim.Adam computes p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps').  The two are the same update
+    when eps' = eps / sqrt(1-b2^t), so torch's own Adam, fed that eps every step, must reproduce the oracle."""
+    torch.manual_seed(11)
+    w0 = torch.randn(257)
+    w_hf, w_pt = torch.nn.Parameter(w0.clone()), torch.nn.Parameter(w0.clone())
+    hf = O.HFAdamW([w_hf], lr=3e-3)
+    pt = torch.optim.Adam([w_pt], lr=3e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0)
+    for t in range(1, 41):
+        g = torch.randn(257) * (10.0 ** torch.randint(-6, 1, (257,)).float())    # gradient scales across 7 decades
+        w_hf.grad, w_pt.grad = g.clone(), g.clone()
+        pt.param_groups[0]["eps"] = 1e-6 / math.sqrt(1.0 - 0.999 ** t)
+        hf.step(); pt.step()
+        assert torch.allclose(w_hf.detach(), w_pt.detach(), rtol=2e-6, atol=1e-8), t
+    # and the plain torch AdamW defaults (eps 1e-8 after the correction) are NOT the same optimizer: tiny gradients differ
+    w_a, w_b = torch.nn.Parameter(torch.ones(4)), torch.nn.Parameter(torch.ones(4))
+    a, b = O.HFAdamW([w_a], lr=1e-2), torch.optim.AdamW([w_b], lr=1e-2, weight_decay=0.0)
+    w_a.grad, w_b.grad = torch.full((4,), 1e-7), torch.full((4,), 1e-7)
+    a.step(); b.step()
+    assert (w_a - w_b).abs().max() > 1e-3
+
+
+def test_schedule_restatement_matches_the_installed_transformers():
+    """get_linear_schedule_with_warmup still exists in the installed transformers: the lr the oracle uses for optimizer
+    step k equals the lr the real scheduler has set after k scheduler.step() calls (train.py:328-330,352-353)."""
+    transformers = pytest.importorskip("transformers")
+    w = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([w], lr=2e-5)
+    sch = transformers.get_linear_schedule_with_warmup(opt, num_warmup_steps=7, num_training_steps=30)
+    for k in range(34):
+        assert opt.param_groups[0]["lr"] == pytest.approx(O.linear_warmup_lr(2e-5, k, 7, 30), rel=1e-12, abs=1e-18), k
+        opt.step(); sch.step()
+
+
 def test_oracle_beam_search_reproduces_the_reference_ids():
     """tests/golden/beam.json holds the ids the reference's own generate_beam produced (pin_generate_beam)."""
     rec = json.loads((GOLD / "beam.json").read_text())
