@@ -500,6 +500,7 @@ class Engine:
             if on_layer_done is not None and train_gpt:
                 if use_side:
                     wait(e_fc), wait(e_qkv)
+                    e_fc = e_qkv = None   # joined: a hook that cuts the CUDA graph here must not leave events behind
                 on_layer_done(l)   # every gradient of GPT-2 block l (and ln_f when l is the last block) is final now
         wait(e_fc), wait(e_qkv)     # join the side stream
 

@@ -59,6 +59,14 @@ class Trainer:
         # soon as the block's gradients are final; only [tail | mapper | wte | wpe] (ready last) stays exposed
         # (experimental, opt-in: NCCL collectives captured on a second graph branch were seen to dead-lock on replay)
         self.overlap = (self.world > 1 and self.train_gpt and os.environ.get("CAPDEC_DP_OVERLAP", "0") == "1")
+        # CAPDEC_DP_OVERLAP=2 (experimental, opt-in, NOT yet validated on hardware): the same per-block buckets, but no
+        # collective is ever captured.  The step's graph is CUT at every GPT-2 block boundary of the backward pass
+        # (13 graphs: forward + head + block 11 | block 10 | ... | block 0 | embedding scatter + mapper) and the bucket of
+        # the block a segment finished is all-reduced EAGERLY on the side stream between two segment replays, so every
+        # rank issues its collectives from host code in one fixed order and the reduction of block l travels over NVLink
+        # while blocks l-1 ... 0 are still computing.
+        self.segmented = (self.world > 1 and self.train_gpt and os.environ.get("CAPDEC_DP_OVERLAP", "0") == "2")
+        self._segs = None
         # opt-in (CAPDEC_DP_PIPELINE=1): the all-reduce is cut into chunks on a side stream and the fused AdamW of chunk k
         # runs while chunk k+1 is still being reduced (both outside the CUDA graph: plain stream/event ordering).
         # Validated on 2 GPUs (tests/test_dp_gpu.py passes with it) but measured equal to the plain sequence there
@@ -83,10 +91,12 @@ class Trainer:
                 a1 = (lay[f"gpt.transformer.h.{l + 1}.ln_1.weight"][0] - fl.tail) if l + 1 < nl else self.n_train
                 self.layer_spans.append((a0, a1))                 # block l (+ ln_f for the last block)
             self.head_span = (0, first)                           # mapper | wte | wpe: final only after the embedding scatter
-        if self.overlap or self.pipeline:
+        if self.overlap or self.pipeline or self.segmented:
             self.comm = torch.cuda.Stream(device=self.dev)
-        if self.overlap:
+        if self.overlap or self.segmented:
             self.buckets, self.head_bucket = self.eng.layer_grad_slices()
+            if not self.train_gpt or self.n_train != fl.grads.numel() - fl.tail:
+                raise CapdecError("per-block gradient buckets need every parameter trainable")
         if self.pipeline:
             n_chunks = int(os.environ.get("CAPDEC_DP_CHUNKS", "4"))
             total = self.reduce_buf.numel()                     # 4 tail floats + trainable gradients
@@ -100,7 +110,7 @@ class Trainer:
         fl.grads.zero_()
 
     # ---- pieces ------------------------------------------------------------------------------------------------
-    def _fwd_bwd(self):
+    def _fwd_bwd(self, layer_hook=None):
         eng = self.eng
         ops.step_clock(eng.seed, self.step_dev, self.lr_dev, self.t_dev, self.lr, self.warmup, self.total)
         if self.noise_variance > 0.0:
@@ -109,14 +119,18 @@ class Trainer:
             pfx = self.prefix_n
         else:
             pfx = self.prefix_d                                 # train.py:28-29: variance 0 -> untouched
-        hook = self._reduce_layer if self.overlap else (self._opt_layer if self.opt_overlap else None)
+        hook = self._reduce_layer if (self.overlap or self.segmented) else (self._opt_layer if self.opt_overlap else None)
+        if layer_hook is not None:       # segmented capture: the hook cuts the graph instead of launching a collective
+            hook = layer_hook
         self._stats_taken = False
         eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False, on_layer_done=hook)
+        if layer_hook is not None:
+            return
         if self.opt_overlap:
             self._take_stats()
             self._adamw_span(*self.head_span)
             torch.cuda.current_stream().wait_stream(self.opt_stream)
-        if self.overlap:
+        if self.overlap or self.segmented:
             # [tail | mapper | wte | wpe] is ready last.  It goes to the SAME side stream as the per-block buckets: every
             # collective of this communicator then sits on one branch of the captured graph, in one fixed order on every
             # rank (collectives on two concurrent branches may replay in different orders on different ranks and deadlock)
@@ -214,13 +228,58 @@ class Trainer:
             fn()
         return g
 
+    def _capture_segments(self):
+        """CAPDEC_DP_OVERLAP=2: capture forward+backward as a chain of graphs cut at the block boundaries of backward.
+        `Engine._trunk_bwd` calls the hook once every gradient of block l is final and its side-stream work has been
+        joined, which is exactly where one capture may end and the next begin.  No collective is captured."""
+        segs = []
+        pool = torch.cuda.graph_pool_handle()
+        cap = torch.cuda.Stream(device=self.dev)
+        cap.wait_stream(torch.cuda.current_stream())
+        cur = {}
+
+        def begin():
+            cur["g"] = torch.cuda.CUDAGraph()
+            cur["g"].capture_begin(pool=pool)
+
+        def cut(l: int):
+            cur["g"].capture_end()
+            segs.append((cur["g"], self.buckets[l]))
+            begin()
+
+        with torch.cuda.stream(cap):
+            begin()
+            self._fwd_bwd(layer_hook=cut)
+            cur["g"].capture_end()
+            segs.append((cur["g"], self.head_bucket))
+        torch.cuda.current_stream().wait_stream(cap)
+        return segs
+
+    def _replay_segments(self):
+        main = torch.cuda.current_stream()
+        for g, bucket in self._segs:
+            g.replay()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.comm.wait_event(ev)
+            with torch.cuda.stream(self.comm):
+                torch.distributed.all_reduce(bucket, group=self.pg)
+        main.wait_stream(self.comm)
+
     def step_device(self):
         """One step on the batch already resident in `tokens_d` / `prefix_d`."""
         if self.use_graph and self._warm >= 2:
-            if self._g_fb is None:
+            if self._g_fb is None and self._segs is None:
                 torch.cuda.synchronize()
-                self._g_fb = self._capture(self._fwd_bwd)
+                if self.segmented:
+                    self._segs = self._capture_segments()
+                else:
+                    self._g_fb = self._capture(self._fwd_bwd)
                 self._g_opt = None if self.opt_overlap else self._capture(self._opt)
+            if self.segmented:
+                self._replay_segments()
+                self._g_opt.replay()
+                return self.stats
             self._g_fb.replay()
             if self.pipeline:
                 self._reduce_and_opt()
@@ -234,7 +293,7 @@ class Trainer:
             if self.pipeline:
                 self._reduce_and_opt()
             else:
-                if self.world > 1 and not self.overlap:
+                if self.world > 1 and not (self.overlap or self.segmented):
                     torch.distributed.all_reduce(self.reduce_buf, group=self.pg)
                 self._opt()
             if self._warm == 2:   # GEMM tile planning for the live rows seen during warm-up (one host sync, results unaffected)
