@@ -348,6 +348,133 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# C5 (BASELINE.json config 5): batched KV-cached beam search, `--workload c5`.  Not the headline metric.
+# One step = one batch of DECODE_IMAGES synthetic CLIP embeddings -> clip_project -> beam=5 search over 67 positions with a
+# stop token that is never emitted (worst case: every beam runs all 67 steps) -> token id lists on the host.
+# ------------------------------------------------------------------------------------------------------------------
+DECODE_IMAGES, BEAM, ENTRY_LEN = 1024, 5, 67
+DECODE_METRIC = "captions/sec (beam=5 decode, entry_length=67, predictions_runner.py path)"
+DECODE_WORKLOAD = ("C5: MLP mapper P=10 + GPT-2-small (random init), beam=5, entry_length=67, stop token never emitted, "
+                   "%d images per batch per GPU")
+
+
+def cpu_decode_rate(captions: int):
+    """The oracle restatement of generate_beam (gpt2_prefix_eval.py:50-115: full re-forward of the growing sequence for
+    every new token, one image at a time) on the host cores."""
+    import torch
+    from oracle import capdec_oracle as O
+    cores = min(os.cpu_count() or 1, int(os.environ.get("CAPDEC_CPU_THREADS", "32")))
+    torch.set_num_threads(cores)
+    sd = O.make_state_dict(seed=0, mapping_type="mlp", prefix_length=P_LEN, prefix_size=D_CLIP)
+    g = torch.Generator().manual_seed(5)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for _ in range(captions):
+            e = torch.randn(1, P_LEN, D_MODEL, generator=g) * 0.1
+            O.generate_beam(sd, e, BEAM, ENTRY_LEN, 1.0, -1)
+    dt = time.perf_counter() - t0
+    return captions / dt, cores, dt / captions
+
+
+def run_decode_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n = max(1, min(args.steps, 4))        # ~6 s per caption on 32 threads: a bounded sample
+    rate, cores, s_per = cpu_decode_rate(n)
+    line = {"impl": "reference", "metric": DECODE_METRIC, "value": rate, "unit": "captions/s", "n_gpus": args.gpus,
+            "steps": n, "warmup": 0, "ms_per_step": s_per * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": DECODE_WORKLOAD % 1, "parallelism": f"dp{args.gpus}"},
+            "cpu_baseline": {"value": rate, "unit": "captions/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} captions, one at a time (oracle port of generate_beam, torch CPU fp32, {cores} threads)"},
+            "e2e": {"value": rate, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_decode(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+    torch.cuda.set_device(local)
+    if world > 1:      # images are independent: ranks decode disjoint shards, no data-path collective
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import capdec_b200 as cb
+    from capdec_b200 import _lib
+    cb.ops.set_precision("tf32")
+    torch.manual_seed(0)
+    model = cb.ClipCaptionModel(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP).to("cuda").eval()
+    n_img = DECODE_IMAGES
+    nb = 4
+    host = []
+    for i in range(nb):
+        g = torch.Generator().manual_seed(9000 + 100 * rank + i)
+        x = torch.randn(n_img, D_CLIP, generator=g)
+        host.append((x / x.norm(2, -1, keepdim=True)).pin_memory())
+    dev_x = torch.empty(n_img, D_CLIP, device="cuda")
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def decode(x):
+        embed = model.clip_project(x).view(n_img, P_LEN, -1)          # predictions_runner.py:228
+        return cb.generate_beam_ids(model, embed, BEAM, ENTRY_LEN, 1.0, -1)
+
+    c0 = _lib.launch_count()
+    dev_x.copy_(host[0]); res = decode(dev_x)
+    torch.cuda.synchronize()
+    for i in range(max(3, args.warmup)):      # the first calls allocate the K/V cache and capture the decode-step graph
+        dev_x.copy_(host[i % nb]); res = decode(dev_x)
+    sync()
+    c1 = _lib.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):               # inputs resident in HBM
+        res = decode(dev_x)
+    e1.record()
+    sync()
+    launches = _lib.launch_count() - c1
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):               # pinned host embeddings in, token id lists out (host), every step
+        dev_x.copy_(host[i % nb], non_blocking=True)
+        res = decode(dev_x)
+    f1.record()
+    sync()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([e0.elapsed_time(e1), f0.elapsed_time(f1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    if rank == 0:
+        n_tok = sum(len(b) for b in res[0][0])
+        caps = n_img * world * args.steps
+        line = {"metric": DECODE_METRIC, "value": caps / (ms_dev * 1e-3), "unit": "captions/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "config": {"workload": DECODE_WORKLOAD % n_img, "parallelism": f"dp{world}",
+                           "l2": "K/V cache 2 x 12 x 5120 x 77 x 768 x 4 B = 29 GB >> 126 MB L2; 4 distinct host batches"},
+                "e2e": {"value": caps / (ms_e2e * 1e-3), "unit": "captions/s", "h2d_bytes_per_step": n_img * D_CLIP * 4,
+                        "d2h_bytes_per_step": n_img * BEAM * (ENTRY_LEN * 8 + 8), "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "tokens_per_image_beam0": n_tok // BEAM}
+        if world == 1:
+            rate, cores, s_per = cpu_decode_rate(2)
+            line["cpu_baseline"] = {"value": rate, "unit": "captions/s", "cores": cores, "kind": "port",
+                                    "sample": f"2 captions, one at a time (oracle port of generate_beam, {cores} threads, {s_per:.1f} s each)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -355,9 +482,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="capdec_b200", choices=["capdec_b200", "reference"])
     ap.add_argument("--full_length", action="store_true", help="captions without padding (worst case for the packed path)")
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"],
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="BASELINE.json config: c2 (default, the headline metric), c1 = --only_prefix bs=32, "
-                         "c3 = TransformerMapper P=40 bs=256, c4 = MLP bs=512/GPU")
+                         "c3 = TransformerMapper P=40 bs=256, c4 = MLP bs=512/GPU, c5 = beam-5 decode (captions/s)")
     args = ap.parse_args()
     global P_LEN, BS_PER_GPU, FULL_LENGTH
     FULL_LENGTH = bool(args.full_length)
@@ -367,7 +494,9 @@ def main():
         P_LEN = 40
     elif args.workload == "c4":
         BS_PER_GPU = 512
-    if args.impl == "reference":
+    if args.workload == "c5":
+        (run_decode_reference if args.impl == "reference" else run_decode)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

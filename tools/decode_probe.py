@@ -1,5 +1,6 @@
-"""C5 probe: KV-cached batched beam search throughput (captions/s) vs the CPU restatement of the reference's
-re-forward-everything generate_beam.  Usage: python tools/decode_probe.py [n_img ...] [--cpu]"""
+"""C5 probe: KV-cached batched beam search throughput (captions/s) at several batch sizes.
+Usage: python tools/decode_probe.py [n_img ...].  The CPU baseline (the oracle restatement of the reference's
+re-forward-everything generate_beam) is timed by `python bench.py --workload c5 [--impl reference]`."""
 import json
 import sys
 import time
@@ -32,15 +33,6 @@ def main():
                "ms_per_decode_step": dt / L * 1e3, "tokens_len": len(res[0][0][0])}
         print(json.dumps(rec), flush=True)
         out.append(rec)
-    if "--cpu" in sys.argv:
-        from oracle import capdec_oracle as O  # baseline leg only
-        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-        torch.set_num_threads(32)
-        e = model.clip_project(x[:1]).view(1, P, -1).cpu()
-        t0 = time.perf_counter()
-        O.generate_beam(sd, e, 5, L, 1.0, -1)
-        dt = time.perf_counter() - t0
-        print(json.dumps({"cpu_oracle_generate_beam_s_per_caption": dt, "threads": 32}), flush=True)
 
 
 if __name__ == "__main__":
