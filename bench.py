@@ -39,6 +39,7 @@ def flops_per_caption(P=P_LEN, L=SEQ, d=D_MODEL, F=F_MLP, nl=N_LAYER, Dc=D_CLIP)
     return 3.0 * fwd
 
 
+NO_CPU = os.environ.get("CAPDEC_BENCH_NO_CPU", "0") == "1"   # profiling runs (ncu) skip the cpu_baseline leg
 FULL_LENGTH = False   # --full_length: every caption has all 40 tokens (worst case for the packed path)
 
 
@@ -304,7 +305,8 @@ def run_gpu(args):
                             "step_executed_tflops": fx / (ms_full * 1e-3) / 1e12}
             except Exception as ex:   # reported, never fatal
                 full_len = {"error": repr(ex)[:300]}
-        cpu_rate, cores, cpu_s = cpu_train_step_rate(64, 4, 1) if (world == 1 and args.workload == "c2") else (None, None, None)
+        want_cpu = world == 1 and args.workload == "c2" and not NO_CPU
+        cpu_rate, cores, cpu_s = cpu_train_step_rate(64, 4, 1) if want_cpu else (None, None, None)
         line = {
             "metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -434,6 +436,7 @@ def run_decode(args):
         dev_x.copy_(host[i % nb]); res = decode(dev_x)
     sync()
     c1 = _lib.launch_count()
+    r0 = next(iter(model.engine().__dict__["_beam_decoders"].values())).replays
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -441,7 +444,9 @@ def run_decode(args):
         res = decode(dev_x)
     e1.record()
     sync()
-    launches = _lib.launch_count() - c1
+    dec = next(iter(model.engine().__dict__["_beam_decoders"].values()))
+    r1 = dec.replays
+    launches = _lib.launch_count() - c1        # eager C-ABI launches (prefill, mapper) of the timed batches ...
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):               # pinned host embeddings in, token id lists out (host), every step
@@ -464,8 +469,9 @@ def run_decode(args):
                            "l2": "K/V cache 2 x 12 x 5120 x 77 x 768 x 4 B = 29 GB >> 126 MB L2; 4 distinct host batches"},
                 "e2e": {"value": caps / (ms_e2e * 1e-3), "unit": "captions/s", "h2d_bytes_per_step": n_img * D_CLIP * 4,
                         "d2h_bytes_per_step": n_img * BEAM * (ENTRY_LEN * 8 + 8), "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "tokens_per_image_beam0": n_tok // BEAM}
-        if world == 1:
+                "gpu_launches": int(launches + (r1 - r0) * dec.step_launches),   # ... + the kernels of the graph replays
+                "launches_per_decode_step": int(dec.step_launches), "clocks": clocks, "tokens_per_image_beam0": n_tok // BEAM}
+        if world == 1 and not NO_CPU:
             rate, cores, s_per = cpu_decode_rate(2)
             line["cpu_baseline"] = {"value": rate, "unit": "captions/s", "cores": cores, "kind": "port",
                                     "sample": f"2 captions, one at a time (oracle port of generate_beam, {cores} threads, {s_per:.1f} s each)"}

@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from ._lib import CapdecError
+from ._lib import CapdecError, launch_count as _launch_count
 
 _CHECK_EVERY = 4  # host polls the "all beams stopped" flags every few steps (gpt2_prefix_eval.py:107-108 early exit)
 
@@ -59,6 +59,8 @@ class BeamDecoder:
         self.logits0 = e(n_img, eng.Vp)
         self.use_graph = use_cuda_graph
         self._graph = None
+        self.step_launches = 0   # kernel launches inside one captured decode step
+        self.replays = 0         # graph replays so far (bench.py: launches = eager C-ABI calls + replays * step_launches)
 
     # ---- one decode step: token of selection c-1 at position P+c-1 -> selection c -----------------------------------
     def _step(self, temperature: float, stop_token: int):
@@ -121,10 +123,13 @@ class BeamDecoder:
                         n_sel += 1
                         continue
                     g = torch.cuda.CUDAGraph()
+                    c0 = _launch_count()
                     with torch.cuda.graph(g):
                         self._step(*key)
+                    self.step_launches = _launch_count() - c0   # kernels one replay of the decode-step graph launches
                     self._graph = (key, g)  # capture does not execute: fall through to the replay below
                 self._graph[1].replay()
+                self.replays += 1
             else:
                 self._step(*key)
             n_sel += 1
