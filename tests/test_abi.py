@@ -43,6 +43,41 @@ def test_header_library_and_ctypes_table_agree():
     assert lib.capdec_version() >= 100
 
 
+def test_plain_c_host_links_against_the_abi(tmp_path):
+    """The boundary is a C ABI, not a Python extension: a C99 translation unit that includes only include/capdec_b200.h
+    compiles with gcc, links against libcapdec_b200.so, takes the address of EVERY declared entry point and calls the
+    two that need no GPU (the stub a non-Python host - cgo / JNI / a C++ trainer - would start from)."""
+    from capdec_b200 import build
+    so = build.build()
+    names = sorted(declared())
+    refs = "\n".join(f"  table[{i}] = (void*)&{n};" for i, n in enumerate(names))
+    src = tmp_path / "host.c"
+    src.write_text(f"""#include <stdio.h>
+#include "capdec_b200.h"
+int main(void) {{
+  void* table[{len(names)}];
+{refs}
+  for (int i = 0; i < {len(names)}; ++i) if (!table[i]) return 2;
+  const char* err = capdec_last_error();
+  printf("%d %d %s.\\n", capdec_version(), (int)capdec_launch_count(), err ? err : "(null)");
+  /* bad arguments are rejected before any CUDA call: error code + message, no crash */
+  int rc = capdec_gemm_tf32(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+  printf("%d %s\\n", rc, capdec_last_error());
+  return rc < 0 ? 0 : 3;
+}}
+""")
+    exe = tmp_path / "host"
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(HEADER.parent), str(src), "-o", str(exe),
+                         "-L", str(so.parent), "-l:" + so.name, "-Wl,-rpath," + str(so.parent)],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    first, second = run.stdout.strip().splitlines()
+    assert first.split()[0] == "100"
+    assert second.startswith("-1 ") and "null operand" in second
+
+
 def test_no_cpu_fallback():
     """CPU tensors raise instead of silently computing somewhere else."""
     from capdec_b200 import ops
