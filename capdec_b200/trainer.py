@@ -352,6 +352,30 @@ class Trainer:
         dataset.gather(idx, self.tokens_d, self.prefix_d)
         return self.evaluate_device()
 
+    def evaluate_any(self, dataset, idx: torch.Tensor):
+        """Validation batch from a dataset whose max_seq_len (or batch size) differs from the training configuration
+        (train.py:373-385 builds a separate ClipCocoDataset for --val_pt): same eval-mode forward + masked CE, run eagerly
+        on buffers of that shape.  Falls through to the captured graph when the shapes match."""
+        B, L = int(idx.numel()), int(dataset.max_seq_len)
+        if (B, L) == (self.B, self.L):
+            return self.evaluate_from(dataset, idx)
+        bufs = self.__dict__.setdefault("_val_bufs", {})
+        if (B, L) not in bufs:
+            bufs.clear()                                   # one live validation shape: its activation arena is the big part
+            self.eng.arenas = {k: v for k, v in self.eng.arenas.items() if (k[0], k[2]) == (self.B, self.L)}
+            bufs[(B, L)] = (torch.zeros(B, L, dtype=torch.int64, device=self.dev), torch.zeros(B, self.eng.D, device=self.dev))
+        tokens, prefix = bufs[(B, L)]
+        dataset.gather(idx, tokens, prefix)
+        was_training = self.model.training
+        self.model.eval()
+        try:
+            self.eng.loss_only(tokens, prefix, self.eval_stats)
+        finally:
+            self.model.train(was_training)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.eval_stats, group=self.pg)
+        return self.eval_stats
+
     def loss(self) -> float:
         s = self.stats.tolist()
         return s[1] / s[0] if s[0] > 0 else float("nan")

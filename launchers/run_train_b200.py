@@ -10,6 +10,11 @@ imported module is the whole integration: no reference file is edited.  What the
 train.py:345-354 — `model(tokens, prefix, mask)` enters `Engine.logits_autograd`, `loss.backward()` our hand-written
 backward through one autograd.Function, `optimizer.step()` the fused HF-semantics AdamW kernel; checkpoints keep the
 reference's key layout (train.py:359-371).
+
+`--fast` (or CAPDEC_FAST=1) additionally rebinds the reference's `train()` loop (train.py:307-393) to
+`capdec_b200.fit.train`: same flags, files and epoch bookkeeping, but each batch is one `Trainer.step_from` on a
+device-resident dataset (CUDA-graph replay, no [B,T,V] logits, no per-step host sync); under
+`torchrun --nproc-per-node N` it trains data-parallel.
 """
 import os
 import sys
@@ -19,7 +24,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-def bind(ref_dir: str):
+def bind(ref_dir: str, fast: bool = False):
     import transformers
     import capdec_b200 as cb
     if not hasattr(transformers, "AdamW"):        # train.py:6 imports it; the class left transformers in 4.5x
@@ -32,6 +37,8 @@ def bind(ref_dir: str):
     train.MappingType = cb.MappingType             # train.py:446
     train.AdamW = cb.AdamW                         # train.py:326
     train.get_linear_schedule_with_warmup = cb.get_linear_schedule_with_warmup   # train.py:328
+    if fast:   # main() calls the module-global `train(dataset, model, args, ...)` (train.py:466): same signature, fast path
+        train.train = cb.fit.train
     return train
 
 
@@ -39,7 +46,16 @@ def main():
     ref_dir = os.environ.get("CAPDEC_REFERENCE_DIR", "")
     if not ref_dir or not (Path(ref_dir) / "train.py").exists():
         sys.exit("set CAPDEC_REFERENCE_DIR to a checkout of DavidHuji/CapDec (the directory that holds train.py)")
-    train = bind(ref_dir)
+    fast = os.environ.get("CAPDEC_FAST", "0") == "1"
+    if "--fast" in sys.argv:                       # our only extra flag: removed before the reference's argparse runs
+        sys.argv.remove("--fast")
+        fast = True
+    if fast and int(os.environ.get("WORLD_SIZE", "1")) > 1:   # torchrun: data parallel over the box's GPUs
+        import torch
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    train = bind(ref_dir, fast=fast)
     return train.main()
 
 

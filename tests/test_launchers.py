@@ -42,3 +42,16 @@ def test_train_launcher_keeps_the_reference_cli():
     for flag in ("--noise_variance", "--mapping_type", "--only_prefix", "--prefix_length_clip", "--uniform_noise",
                  "--dont_norm", "--add_modality_offset", "--val_pt", "--pretrain_weights"):
         assert flag in r.stdout, flag
+
+
+def test_fast_flag_rebinds_the_training_loop():
+    """`--fast`: the reference's main() keeps parsing its own flags and building its own dataset / model, but the
+    module-global `train` it calls (train.py:466) is capdec_b200.fit.train, which has the reference's signature."""
+    import inspect
+    import capdec_b200 as cb
+    train = _load("run_train_b200").bind(str(REF), fast=True)
+    assert train.train is cb.fit.train
+    ours = list(inspect.signature(cb.fit.train).parameters)[:6]
+    assert ours == ["dataset", "model", "args", "warmup_steps", "output_dir", "output_prefix"]
+    sig = inspect.signature(cb.fit.train)
+    assert sig.parameters["warmup_steps"].default == 5000 and sig.parameters["output_dir"].default == "."
