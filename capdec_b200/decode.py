@@ -184,3 +184,16 @@ def generate_beam(model, tokenizer, beam_size: int = 5, prompt=None, embed=None,
     (beams, _, _), = generate_beam_ids(model, embed.view(1, -1, embed.shape[-1]), beam_size, entry_length, temperature,
                                         stop_token_index)
     return [tokenizer.decode(ids) for ids in beams]
+
+
+def generate_beam_batch(model, tokenizer, embeds: torch.Tensor, beam_size: int = 5, entry_length: int = 67,
+                        temperature: float = 1.0, stop_token: str = "."):
+    """`generate_beam` for MANY images at once (BASELINE C5: the reference's make_preds loop, predictions_runner.py:213-233,
+    decodes one image per call): embeds [n_img, P, d] = `model.clip_project(prefix).reshape(n_img, prefix_length, -1)`.
+    Returns, per image, the list gpt2_prefix_eval.py:111-114 returns (decoded captions, best beam first); every image
+    follows the reference's per-image recurrence exactly, so entry i equals `generate_beam(..., embed=embeds[i:i+1])`."""
+    model.eval()
+    stop_token_index = tokenizer.encode(stop_token)[0]
+    embeds = embeds if embeds.dim() == 3 else embeds.view(-1, model.prefix_length, embeds.shape[-1])
+    res = generate_beam_ids(model, embeds, beam_size, entry_length, temperature, stop_token_index)
+    return [[tokenizer.decode(ids) for ids in beams] for beams, _, _ in res]

@@ -184,6 +184,9 @@ def test_generate_beam_batched_images_equal_one_at_a_time_and_api_mirror():
 
         texts = cb.generate_beam(model, Tok(), embed=embed[:1], entry_length=c["entry_length"])
         assert texts == [" ".join(str(i) for i in ids) for ids in cases[0]["ids"]]
+        # the many-images form of the same call (make_preds decodes one image per call, predictions_runner.py:213-233)
+        many = cb.generate_beam_batch(model, Tok(), embed, beam_size=c["beam_size"], entry_length=c["entry_length"])
+        assert many == [[" ".join(str(i) for i in ids) for ids in k["ids"]] for k in cases]
     finally:
         cb.ops.set_precision("tf32")
 
