@@ -10,10 +10,10 @@ from .model import (ClipCaptionModel, ClipCaptionPrefix, GPT2Config, GPT2LMHead,
 from .optim import AdamW, get_linear_schedule_with_warmup
 from .trainer import Trainer
 from .data import DeviceCaptionDataset
-from .decode import BeamDecoder, generate_beam, generate_beam_batch, generate_beam_ids
+from .decode import BeamDecoder, generate2, generate_beam, generate_beam_batch, generate_beam_ids, generate_greedy_ids
 from . import ops
 from . import fit
 
 __all__ = ["ClipCaptionModel", "ClipCaptionPrefix", "GPT2Config", "GPT2LMHead", "MappingType", "MLP",
            "TransformerMapper", "TransformerEncoderDecoder", "noise_injection", "AdamW", "get_linear_schedule_with_warmup", "Trainer", "ops",
-           "DeviceCaptionDataset", "BeamDecoder", "generate_beam", "generate_beam_batch", "generate_beam_ids", "fit"]
+           "DeviceCaptionDataset", "BeamDecoder", "generate_beam", "generate_beam_batch", "generate_beam_ids", "generate2", "generate_greedy_ids", "fit"]

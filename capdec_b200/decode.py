@@ -197,3 +197,44 @@ def generate_beam_batch(model, tokenizer, embeds: torch.Tensor, beam_size: int =
     embeds = embeds if embeds.dim() == 3 else embeds.view(-1, model.prefix_length, embeds.shape[-1])
     res = generate_beam_ids(model, embeds, beam_size, entry_length, temperature, stop_token_index)
     return [[tokenizer.decode(ids) for ids in beams] for beams, _, _ in res]
+
+
+_GREEDY_EXTRA_STOP = 764   # gpt2_prefix_eval.py:187: generate2 also stops on token id 764
+
+
+def generate_greedy_ids(model, embed: torch.Tensor, entry_length: int = 67, temperature: float = 1.0,
+                        stop_token_index: int = 13):
+    """Batched greedy decode = what gpt2_prefix_eval.generate2 (:118-198) computes: its top-p mask always keeps the best
+    logit (:169) and the next token is the ARGMAX of the masked logits (:177, the multinomial draw is commented out), so
+    `top_p` cannot change the result.  Runs the KV-cached decoder with one beam (a 1-beam search picks
+    argmax((score + log p) / len) = argmax p at every step and stops right after the stop token) and cuts each sequence
+    after the first stop token or token 764, both included, like :181-188.  embed [n_img, P, d] -> n_img id lists."""
+    res = generate_beam_ids(model, embed, 1, entry_length, temperature, stop_token_index)
+    out = []
+    for beams, _, _ in res:
+        ids = list(beams[0])
+        for k, t in enumerate(ids):
+            if t == stop_token_index or t == _GREEDY_EXTRA_STOP:
+                ids = ids[: k + 1]
+                break
+        out.append(ids)
+    return out
+
+
+def generate2(model, tokenizer, tokens=None, prompt=None, embed=None, entry_count: int = 1, entry_length: int = 67,
+              top_p: float = 0.8, temperature: float = 1.0, stop_token: str = "."):
+    """Same signature and return value as gpt2_prefix_eval.py:118-198 (one decoded caption).  `top_p` and `entry_count`
+    are accepted for compatibility: the reference's own code makes them no-ops (argmax after the mask; only
+    generated_list[0] is returned)."""
+    model.eval()
+    stop_token_index = tokenizer.encode(stop_token)[0]
+    head = []
+    if embed is None:
+        if tokens is None:
+            if prompt is None:
+                raise ValueError("generate2 needs `embed`, `tokens` or `prompt`")
+            tokens = torch.tensor(tokenizer.encode(prompt)).unsqueeze(0)          # :143-145
+        head = [int(t) for t in tokens.reshape(-1).tolist()]
+        embed = model.gpt.transformer.wte(tokens.to(model.engine().dev))           # :150
+    ids, = generate_greedy_ids(model, embed.reshape(1, -1, embed.shape[-1]), entry_length, temperature, stop_token_index)
+    return tokenizer.decode(head + ids)                                             # :189-190

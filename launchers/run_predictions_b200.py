@@ -32,6 +32,13 @@ def bind(ref_dir: str):
     import predictions_runner
     if hasattr(predictions_runner, "generate_beam"):
         predictions_runner.generate_beam = cb.generate_beam      # predictions_runner.py:232 calls it by name
+    # the non-beam branch (generate2, predictions_runner.py:234 / gpt2_prefix_eval.py:118-198) works unchanged through
+    # `model.gpt(inputs_embeds=...)`; CAPDEC_FAST_GREEDY=1 swaps in the KV-cached greedy decoder (opt-in until its GPU
+    # test, tests/test_decode_gpu.py::test_generate2_*, has been through a GPU box)
+    if os.environ.get("CAPDEC_FAST_GREEDY", "0") == "1":
+        gpt2_prefix_eval.generate2 = cb.generate2
+        if hasattr(predictions_runner, "generate2"):
+            predictions_runner.generate2 = cb.generate2
     return predictions_runner
 
 

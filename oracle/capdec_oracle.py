@@ -415,6 +415,31 @@ def generate_beam(sd: Params, embed, beam_size: int = 5, entry_length: int = 67,
     return out, scores[order].tolist(), seq_lengths[order].tolist()
 
 
+def generate2(sd: Params, embed, entry_length: int = 67, top_p: float = 0.8, temperature: float = 1.0,
+              stop_token_index: int = 13):
+    """gpt2_prefix_eval.generate2 (:118-198) for `embed` given, entry_count = 1: nucleus filtering followed by ARGMAX
+    (:176 — the multinomial draw is commented out at :177), so the top-p mask never changes the chosen token (the best
+    logit is always kept, :169) and the function is greedy decoding with a full re-forward per token; it stops after
+    emitting the stop token or token 764 (:185).  Returns the generated token ids (the reference decodes them, :189-190)."""
+    wte = sd["gpt.transformer.wte.weight"]
+    generated = embed                                                                 # [1, P, d]
+    tokens = []
+    for _ in range(entry_length):
+        logits = gpt2_forward(sd, generated)[:, -1, :] / (temperature if temperature > 0 else 1.0)      # :163-165
+        sorted_logits, sorted_indices = torch.sort(logits, descending=True)                            # :166
+        cumulative_probs = torch.cumsum(F.softmax(sorted_logits, dim=-1), dim=-1)                      # :167
+        remove = cumulative_probs > top_p
+        remove[..., 1:] = remove[..., :-1].clone()                                                     # :169-171
+        remove[..., 0] = 0
+        logits[:, sorted_indices[remove]] = -float("inf")                                             # :174-175
+        nxt = int(torch.argmax(logits, -1))                                                            # :177
+        tokens.append(nxt)
+        generated = torch.cat((generated, wte[nxt].view(1, 1, -1)), dim=1)                             # :181-186
+        if nxt == stop_token_index or nxt == 764:                                                     # :187
+            break
+    return tokens
+
+
 # --------------------------------------------------------------------------------------------------------------
 # optimizer restatement
 # --------------------------------------------------------------------------------------------------------------

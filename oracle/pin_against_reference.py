@@ -220,6 +220,47 @@ def pin_generate_beam():
     print("generate_beam ok", [r["ids"][0][:6] for r in recs])
 
 
+def pin_generate2():
+    """gpt2_prefix_eval.generate2 (the reference's own function: greedy decode behind a top-p mask) vs the oracle
+    restatement -> tests/golden/greedy.json"""
+    for name in ("clip", "pycocotools", "pycocotools.coco", "matplotlib", "matplotlib.pyplot", "skimage", "skimage.io"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["pycocotools.coco"].COCO = object
+    sys.modules["transformers"].AdamW = O.HFAdamW
+    import gpt2_prefix_eval as ev  # noqa
+    import gpt2_prefix as gp  # noqa
+    P, D = 10, 640
+    sd = O.make_state_dict(seed=1, mapping_type="mlp", prefix_length=P, prefix_size=D, weight_std=0.08)
+    torch.manual_seed(0)
+    model = gp.ClipCaptionModel(P, prefix_dim=D, mapping_type=gp.MappingType.MLP)
+    model.gpt.config._attn_implementation = "eager"
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    recs = []
+
+    def run(case, stop, temperature, entry_length=12):
+        _, prefix, _ = O.make_batch(seed=20 + case, B=1, prefix_size=D)
+        with torch.no_grad():
+            embed = model.clip_project(prefix).reshape(1, P, -1)
+            text = ev.generate2(model, _FakeTokenizer(), embed=embed, entry_length=entry_length, temperature=temperature,
+                                stop_token="." if stop == 13 else str(stop))
+            ref_ids = [int(t) for t in text.split()]
+            ids = O.generate2(sd, O.mlp_mapper(sd, prefix).view(1, P, -1), entry_length=entry_length,
+                              temperature=temperature, stop_token_index=stop)
+        assert ids == ref_ids, (ids, ref_ids)
+        recs.append({"batch_seed": 20 + case, "stop_token_index": stop, "temperature": temperature,
+                     "entry_length": entry_length, "ids": ref_ids})
+        return ref_ids
+
+    for case in range(3):
+        ids = run(case, 13, 1.0)
+        run(case, ids[3], 1.0)           # the 4th greedy token as stop token: early exit, stop token included (:181-187)
+        run(case, ids[1], 0.5)
+        run(case, 13, 0.05, entry_length=7)
+    (GOLD / "greedy.json").write_text(json.dumps({"config": dict(P=P, D=D, sd_seed=1, weight_std=0.08), "cases": recs}, indent=1))
+    print("generate2 ok", [r["ids"][:6] for r in recs])
+
+
 def pin_dataset():
     """ClipCocoDataset.__getitem__ + the default collate (the reference's own class, constructed without its file /
     tokenizer loading) vs the oracle restatement -> tests/golden/datafeed.json."""
@@ -287,5 +328,6 @@ def pin_encdec_mapper():
 if __name__ == "__main__":
     main()
     pin_generate_beam()
+    pin_generate2()
     pin_dataset()
     pin_encdec_mapper()

