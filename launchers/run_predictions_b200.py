@@ -7,7 +7,8 @@ predictions_runner.py:7 does `from gpt2_prefix import ClipCaptionModel, MappingT
 with our classes before it is imported is the binding (constructor keyword `prefix_dim`, the three mapping types of
 gpt2_prefix.py:15-18 and the checkpoint key layout are the reference's).  `gpt2_prefix_eval.generate_beam`
 (gpt2_prefix_eval.py:50-115) is rebound to the batched, KV-cached decoder with identical beam semantics
-(tests/test_decode_gpu.py pins its token ids against the reference function's own output).
+(tests/test_decode_gpu.py pins its token ids against the reference function's own output); `generate2`
+(gpt2_prefix_eval.py:118-198, greedy decoding) is rebound to the same decoder with one beam.
 """
 import os
 import sys
@@ -32,10 +33,10 @@ def bind(ref_dir: str):
     import predictions_runner
     if hasattr(predictions_runner, "generate_beam"):
         predictions_runner.generate_beam = cb.generate_beam      # predictions_runner.py:232 calls it by name
-    # the non-beam branch (generate2, predictions_runner.py:234 / gpt2_prefix_eval.py:118-198) works unchanged through
-    # `model.gpt(inputs_embeds=...)`; CAPDEC_FAST_GREEDY=1 swaps in the KV-cached greedy decoder (opt-in until its GPU
-    # test, tests/test_decode_gpu.py::test_generate2_*, has been through a GPU box)
-    if os.environ.get("CAPDEC_FAST_GREEDY", "0") == "1":
+    # the non-beam branch (generate2, predictions_runner.py:234 / gpt2_prefix_eval.py:118-198): greedy decoding on the same
+    # KV-cached decoder (ids pinned on the reference function, tests/test_decode_gpu.py::test_generate2_*);
+    # CAPDEC_FAST_GREEDY=0 keeps the reference's own generate2 running through `model.gpt(inputs_embeds=...)`
+    if os.environ.get("CAPDEC_FAST_GREEDY", "1") != "0":
         gpt2_prefix_eval.generate2 = cb.generate2
         if hasattr(predictions_runner, "generate2"):
             predictions_runner.generate2 = cb.generate2

@@ -210,8 +210,6 @@ def test_generate_beam_tf32_best_beam_score_close():
     assert agree >= len(GOLD["cases"]) // 2
 
 
-@pytest.mark.skipif(__import__("os").environ.get("CAPDEC_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="opt-in: the 1-beam (greedy) decode has not been through a GPU box yet")
 def test_generate2_greedy_matches_reference_goldens_fp32():
     """gpt2_prefix_eval.generate2 (:118-198) = greedy decoding; ids pinned on the reference's own function
     (tests/golden/greedy.json, oracle/pin_against_reference.py::pin_generate2)."""
