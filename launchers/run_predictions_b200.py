@@ -19,15 +19,44 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
+def _provide_adamw(cb):
+    """`transformers.AdamW` left the library in 4.5x; the reference imports it by name.  transformers' lazy top-level module
+    REPLACES itself in sys.modules on the first real import, so force that first and then set the name on the live module."""
+    from transformers import GPT2LMHeadModel, GPT2Tokenizer  # noqa: F401  (what the reference imports next to AdamW)
+    live = sys.modules["transformers"]
+    if not hasattr(live, "AdamW"):
+        live.AdamW = cb.AdamW
+
+
+def _reference_dataset_class(ref_dir: str):
+    """gpt2_prefix_eval.py:7 imports `ClipCocoDataset` from gpt2_prefix next to the model class.  It is the reference's own
+    data loading (out of scope here), so hand back the reference's class when its module imports (it needs `clip` etc.)."""
+    import importlib.util
+    try:
+        spec = importlib.util.spec_from_file_location("_capdec_reference_gpt2_prefix", str(Path(ref_dir) / "gpt2_prefix.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod.ClipCocoDataset
+    except Exception as e:                              # missing optional dependency of the reference: fail at USE, not import
+        err = repr(e)
+
+        class ClipCocoDataset:                          # noqa: D401 - placeholder with the reference's name
+            def __init__(self, *a, **k):
+                raise ImportError(f"the reference's gpt2_prefix.ClipCocoDataset could not be imported: {err}")
+        return ClipCocoDataset
+
+
 def bind(ref_dir: str):
     import capdec_b200 as cb
+    _provide_adamw(cb)                                 # gpt2_prefix_eval.py:2 imports transformers.AdamW
     shim = types.ModuleType("gpt2_prefix")
     shim.ClipCaptionModel = cb.ClipCaptionModel
     shim.ClipCaptionPrefix = cb.ClipCaptionPrefix
     shim.MappingType = cb.MappingType
     shim.MLP = cb.MLP
-    sys.modules["gpt2_prefix"] = shim              # predictions_runner.py:7
     sys.path.insert(0, ref_dir)
+    shim.ClipCocoDataset = _reference_dataset_class(ref_dir)     # gpt2_prefix_eval.py:7
+    sys.modules["gpt2_prefix"] = shim              # predictions_runner.py:7
     import gpt2_prefix_eval
     gpt2_prefix_eval.generate_beam = cb.generate_beam            # gpt2_prefix_eval.py:50-115
     import predictions_runner

@@ -24,11 +24,18 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
+def _provide_adamw(cb):
+    """`transformers.AdamW` left the library in 4.5x; the reference imports it by name.  transformers' lazy top-level module
+    REPLACES itself in sys.modules on the first real import, so force that first and then set the name on the live module."""
+    from transformers import GPT2LMHeadModel, GPT2Tokenizer  # noqa: F401  (what the reference imports next to AdamW)
+    live = sys.modules["transformers"]
+    if not hasattr(live, "AdamW"):
+        live.AdamW = cb.AdamW
+
+
 def bind(ref_dir: str, fast: bool = False):
-    import transformers
     import capdec_b200 as cb
-    if not hasattr(transformers, "AdamW"):        # train.py:6 imports it; the class left transformers in 4.5x
-        transformers.AdamW = cb.AdamW
+    _provide_adamw(cb)                             # train.py:6 imports transformers.AdamW
     sys.path.insert(0, ref_dir)
     import train                                   # the unmodified reference module
     train.ClipCaptionModel = cb.ClipCaptionModel   # train.py:447-454 construct these by name

@@ -55,3 +55,29 @@ def test_fast_flag_rebinds_the_training_loop():
     assert ours == ["dataset", "model", "args", "warmup_steps", "output_dir", "output_prefix"]
     sig = inspect.signature(cb.fit.train)
     assert sig.parameters["warmup_steps"].default == 5000 and sig.parameters["output_dir"].default == "."
+
+
+def test_predictions_launcher_binds_model_and_decoders():
+    """launchers/run_predictions_b200.py: predictions_runner.py imports its model from `gpt2_prefix` and its decoders from
+    `gpt2_prefix_eval` (predictions_runner.py:7,13).  After bind() the reference module resolves all of them to
+    capdec_b200 (run in a subprocess: the reference's optional imaging / CLIP dependencies are stubbed there)."""
+    code = r"""
+import sys, types, importlib.util
+for name in ("clip", "pycocotools", "pycocotools.coco", "matplotlib", "matplotlib.pyplot", "skimage", "skimage.io"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["pycocotools.coco"].COCO = object
+spec = importlib.util.spec_from_file_location("run_predictions_b200", sys.argv[1])
+m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+pr = m.bind(sys.argv[2])
+import capdec_b200 as cb, gpt2_prefix_eval as ev
+assert pr.ClipCaptionModel is cb.ClipCaptionModel and pr.MappingType is cb.MappingType
+assert pr.generate_beam is cb.generate_beam and ev.generate_beam is cb.generate_beam
+assert pr.generate2 is cb.generate2 and ev.generate2 is cb.generate2
+assert all(hasattr(pr.MappingType, n) for n in ("MLP", "TransformerEncoder", "TransformerDecoder"))    # predictions_runner.py:457-458
+assert pr.make_preds.__code__.co_filename.startswith(sys.argv[2])        # the reference's own loop, unmodified
+assert sys.modules["gpt2_prefix"].ClipCocoDataset.__name__ == "ClipCocoDataset"
+print("bound")
+"""
+    r = subprocess.run([sys.executable, "-c", code, str(ROOT / "launchers" / "run_predictions_b200.py"), str(REF)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "bound" in r.stdout, r.stderr[-3000:]
