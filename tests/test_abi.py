@@ -78,6 +78,30 @@ int main(void) {{
     assert second.startswith("-1 ") and "null operand" in second
 
 
+def test_every_entry_point_rejects_null_arguments_with_a_message():
+    """Error behaviour of the boundary: bad arguments never reach a launch or crash the host - every
+    compute entry point answers all-null / all-zero arguments with CAPDEC_ERR_INVALID (-1) and a message in
+    capdec_last_error().  Argument checks run before any CUDA call, so this needs no GPU."""
+    import ctypes as C
+    from capdec_b200 import _lib
+    lib = _lib.load()
+    not_compute = {"capdec_last_error", "capdec_version", "capdec_launch_count", "capdec_gemm_debug_mn_encoding",
+                   "capdec_gemm_debug_force_pair", "capdec_gemm_set_row_hint", "capdec_gemm_autotune", "capdec_gemm_plan_query"}
+    before = lib.capdec_launch_count()
+    checked = 0
+    for name, argtypes in _lib.SIGNATURES.items():
+        if name in not_compute:
+            continue
+        args = [None if t is C.c_void_p else (0.0 if t is C.c_float else 0) for t in argtypes]
+        rc = getattr(lib, name)(*args)
+        msg = lib.capdec_last_error()
+        assert rc == -1, (name, rc)
+        assert msg and len(msg) > 4, name
+        checked += 1
+    assert checked == len(_lib.SIGNATURES) - len(not_compute) >= 35
+    assert lib.capdec_launch_count() == before          # nothing was launched
+
+
 def test_no_cpu_fallback():
     """CPU tensors raise instead of silently computing somewhere else."""
     from capdec_b200 import ops
