@@ -76,6 +76,9 @@ CASES = {
     "mlp_prefix_only_b4": ("mlp", True, 4, 10, 10, 512, 8, False),
     "transformer_full_b2": ("transformer", False, 2, 40, 40, 512, 8, False),
     "mlp_full_d640_b3": ("mlp", False, 3, 10, 10, 640, 8, True),
+    # flag combinations beyond the BASELINE configs: --only_prefix with the transformer mapper, prefix_length != clip_length
+    "transformer_prefix_only_b2": ("transformer", True, 2, 12, 6, 640, 2, False),
+    "transformer_short_clip_b3": ("transformer", False, 3, 8, 20, 512, 3, True),
 }
 
 

@@ -10,7 +10,8 @@ import torch
 from oracle import capdec_oracle as O
 
 GOLD = Path(__file__).resolve().parent / "golden"
-CASES = ["mlp_full_b4", "mlp_prefix_only_b4", "transformer_full_b2", "mlp_full_d640_b3"]
+CASES = ["mlp_full_b4", "mlp_prefix_only_b4", "transformer_full_b2", "mlp_full_d640_b3", "transformer_prefix_only_b2",
+         "transformer_short_clip_b3"]
 
 
 def load_case(name):

@@ -16,6 +16,6 @@ if [ "$1" == "dp" ]; then
     tail -1 gpurun_out/exp_bench_dp_overlap$ov.log | cut -c1-300
   done
 else
-  (time timeout 600 python -m pytest tests/test_fit_gpu.py tests/test_decode_gpu.py -x -q 2>&1 | tail -15) > gpurun_out/exp_fit_pytest.log 2>&1
+  (time timeout 600 python -m pytest tests/test_fit_gpu.py tests/test_decode_gpu.py tests/test_model_gpu.py -x -q 2>&1 | tail -15) > gpurun_out/exp_fit_pytest.log 2>&1
   tail -4 gpurun_out/exp_fit_pytest.log
 fi
