@@ -158,7 +158,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 64          # captions per CPU step: ~2.5 s/step on 16-32 host threads, so K steps stay within minutes
+    # captions per CPU step: ~2.5 s/step on 16-32 host threads, so K steps stay within minutes (the contract test shrinks it)
+    sample = int(os.environ.get("CAPDEC_CPU_SAMPLE", "64"))
     rate, cores, s_per_step = cpu_train_step_rate(sample, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "captions/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
