@@ -213,7 +213,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import capdec_b200 as cb
     from capdec_b200 import _lib
-    cb.ops.set_precision("tf32")
+    cb.ops.set_precision(args.precision)
     torch.manual_seed(0)
     if args.workload == "c1":      # --only_prefix: GPT-2 frozen and in eval mode (train.py:276-284)
         model = cb.ClipCaptionPrefix(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP)
@@ -311,7 +311,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": {"c1": "C1: MLP mapper P=10, GPT-2 frozen (--only_prefix), bs=32, seq_len=40, noise_variance=0.016",
                                     "c2": "C2: MLP mapper P=10 + GPT-2-small fine-tuned end-to-end, bs=256/GPU, seq_len=40, "
                                           "noise_variance=0.016, dropout 0.1 live, HF-AdamW + warm-up schedule in the step",
@@ -488,6 +488,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="capdec_b200", choices=["capdec_b200", "reference"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3"],
+                    help="GEMM / attention arithmetic: tf32 = 1xTF32 (perf mode, the headline), tf32x3 = 3xTF32 fp32-grade mode")
     ap.add_argument("--full_length", action="store_true", help="captions without padding (worst case for the packed path)")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="BASELINE.json config: c2 (default, the headline metric), c1 = --only_prefix bs=32, "

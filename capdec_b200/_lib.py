@@ -26,6 +26,7 @@ SIGNATURES = {
     "capdec_gemm_tf32": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _i, _p],
     "capdec_gemm_tf32_ex": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _i, _p, _p, _p],
     "capdec_gemm_tf32_mul": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p, _p],
+    "capdec_gemm_tf32_mul_ex": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p, _i, _p],
     "capdec_gemm_debug_mn_encoding": [_i, _i, _i, _i],
     "capdec_gemm_debug_force_pair": [_i],
     "capdec_gemm_set_row_hint": [_i],
@@ -46,6 +47,10 @@ SIGNATURES = {
                                 _f, _p, _u32, _p, _p],
     "capdec_attention_tc_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
                                 _i64, _f, _i, _p, _f, _p, _u32, _p, _p],
+    "capdec_attention_tc_fwd_x3": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p,
+                                   _f, _p, _u32, _p, _p],
+    "capdec_attention_tc_bwd_x3": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
+                                   _i64, _f, _i, _p, _f, _p, _u32, _p, _p],
     "capdec_ce_count": [_p, _i64, _i64, _p, _p, _p],
     "capdec_ce_fwd_bwd": [_p, _i64, _p, _i, _i, _i64, _p, _f, _p, _i, _p, _p],
     "capdec_compact_targets": [_p, _i, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p],

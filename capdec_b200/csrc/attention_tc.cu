@@ -24,6 +24,31 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// X3 = fp32-grade arithmetic on the same tensor-core path ("tf32x3" mode): every fragment is split in registers into
+// hi = RN_tf32(x) and lo = x - hi (exact), and the product is accumulated as lo*hi + hi*lo + hi*hi (3xTF32); exp / log use
+// the accurate library functions instead of the MUFU approximations.
+__device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& lo) {
+  hi = (x + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(__uint_as_float(x) - __uint_as_float(hi));
+}
+template <bool X3>
+__device__ __forceinline__ void mma_t(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  if constexpr (!X3) {
+    mma_tf32(d, a, b);
+  } else {
+    uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) split_tf32(b[i], bh[i], bl[i]);
+    mma_tf32(d, al, bh);
+    mma_tf32(d, ah, bl);
+    mma_tf32(d, ah, bh);
+  }
+}
+template <bool X3> __device__ __forceinline__ float exp_t(float x) { return X3 ? expf(x) : __expf(x); }
+template <bool X3> __device__ __forceinline__ float log_t(float x) { return X3 ? logf(x) : __logf(x); }
+
 // 16-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination without touching `g`
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* g, bool valid) {
   const uint32_t sz = valid ? 16u : 0u;
@@ -74,7 +99,7 @@ __device__ __forceinline__ void attn_drop4(uint64_t seed, uint32_t stream_id, ui
   for (int i = 0; i < 4; ++i) s[i] = (r[i] >= thr) ? inv_keep : 0.0f;
 }
 
-template <int HD, int NT_MAX>
+template <int HD, int NT_MAX, bool X3>
 __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                const float* __restrict__ v, float* __restrict__ ctx,
                                                                float* __restrict__ lse, int H, int T_arg, int S_arg, int64_t q_bs,
@@ -143,7 +168,7 @@ __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __re
         if (n < nt) {
           uint32_t bb[2];
           ldb_frag_nk(bb, sK, LQ, n * 8, kk * 8, g, t);
-          mma_tf32(s[n], a, bb);
+          mma_t<X3>(s[n], a, bb);
         }
       }
     }
@@ -171,8 +196,8 @@ __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __re
 #pragma unroll
     for (int n = 0; n < NT_MAX; ++n) {
       if (n < nt) {
-        s[n][0] = __expf(s[n][0] - mx0); s[n][1] = __expf(s[n][1] - mx0);
-        s[n][2] = __expf(s[n][2] - mx1); s[n][3] = __expf(s[n][3] - mx1);
+        s[n][0] = exp_t<X3>(s[n][0] - mx0); s[n][1] = exp_t<X3>(s[n][1] - mx0);
+        s[n][2] = exp_t<X3>(s[n][2] - mx1); s[n][3] = exp_t<X3>(s[n][3] - mx1);
         sum0 += s[n][0] + s[n][1];
         sum1 += s[n][2] + s[n][3];
       }
@@ -181,8 +206,8 @@ __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __re
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
     const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
     if (t == 0 && lse) {
-      if (r0 < T) lse[(size_t)bh * TL + r0] = mx0 + __logf(sum0);
-      if (r1 < T) lse[(size_t)bh * TL + r1] = mx1 + __logf(sum1);
+      if (r0 < T) lse[(size_t)bh * TL + r0] = mx0 + log_t<X3>(sum0);
+      if (r1 < T) lse[(size_t)bh * TL + r1] = mx1 + log_t<X3>(sum1);
     }
     __syncwarp();  // previous tile's P reads are done
 #pragma unroll
@@ -218,7 +243,7 @@ __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __re
       for (int n = 0; n < HD / 8; ++n) {
         uint32_t bb[2];
         ldb_frag_kn(bb, sV, LV, n * 8, kk * 8, g, t);
-        mma_tf32(o[n], a, bb);
+        mma_t<X3>(o[n], a, bb);
       }
     }
 #pragma unroll
@@ -230,7 +255,7 @@ __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __re
   }
 }
 
-template <int HD, int NT_MAX>
+template <int HD, int NT_MAX, bool X3>
 __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ ctx,
     const float* __restrict__ dctx, const float* __restrict__ lse, float* __restrict__ dq, float* __restrict__ dk,
@@ -334,7 +359,7 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
         if (n < nt) {
           uint32_t bb[2];
           ldb_frag_nk(bb, sK, LQ, n * 8, kk * 8, g, t);
-          mma_tf32(acc[n], a, bb);
+          mma_t<X3>(acc[n], a, bb);
         }
       }
     }
@@ -352,10 +377,10 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
           const int c0 = n * 8 + 2 * t;
           float p00 = 0.f, p01 = 0.f, p10 = 0.f, p11 = 0.f;
           if (n < nt) {
-            p00 = (c0 < lim0) ? __expf(acc[n][0] * scale - l0) : 0.f;
-            p01 = (c0 + 1 < lim0) ? __expf(acc[n][1] * scale - l0) : 0.f;
-            p10 = (c0 < lim1) ? __expf(acc[n][2] * scale - l1) : 0.f;
-            p11 = (c0 + 1 < lim1) ? __expf(acc[n][3] * scale - l1) : 0.f;
+            p00 = (c0 < lim0) ? exp_t<X3>(acc[n][0] * scale - l0) : 0.f;
+            p01 = (c0 + 1 < lim0) ? exp_t<X3>(acc[n][1] * scale - l0) : 0.f;
+            p10 = (c0 < lim1) ? exp_t<X3>(acc[n][2] * scale - l1) : 0.f;
+            p11 = (c0 + 1 < lim1) ? exp_t<X3>(acc[n][3] * scale - l1) : 0.f;
           }
           *reinterpret_cast<float2*>(sdS + (size_t)r0 * LS + c0) = make_float2(p00, p01);
           *reinterpret_cast<float2*>(sdS + (size_t)r1 * LS + c0) = make_float2(p10, p11);
@@ -376,7 +401,7 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
         if (n < nt) {
           uint32_t bb[2];
           ldb_frag_nk(bb, sV, LQ, n * 8, kk * 8, g, t);
-          mma_tf32(acc[n], a, bb);
+          mma_t<X3>(acc[n], a, bb);
         }
       }
     }
@@ -406,7 +431,7 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
       for (int n = 0; n < HD / 8; ++n) {
         uint32_t bb[2];
         ldb_frag_kn(bb, sK, LQ, n * 8, kk * 8, g, t);
-        mma_tf32(o[n], a, bb);
+        mma_t<X3>(o[n], a, bb);
       }
     }
 #pragma unroll
@@ -443,8 +468,8 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
         uint32_t bq[2], bo[2];
         ldb_frag_kn(bq, sQ, LQ, n * 8, kk * 8, g, t);
         ldb_frag_kn(bo, sdO, LQ, n * 8, kk * 8, g, t);
-        mma_tf32(ok[n], as_, bq);
-        mma_tf32(ov[n], ap, bo);
+        mma_t<X3>(ok[n], as_, bq);
+        mma_t<X3>(ov[n], ap, bo);
       }
     }
     const int r0 = j0 + g, r1 = r0 + 8;
@@ -490,8 +515,8 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
 //   phase B  warp (wq, hh): key tile wq, hh == 0 -> dK = dS^T Q, hh == 1 -> dV = Pd^T dO.
 // Q / K / V / dO arrive by cp.async; D_i = dO_i . O_i and the LSE rows are fetched from global memory while those copies
 // are in flight, so phase A never waits on HBM.
-template <int HD, int NT_MAX>
-__global__ void __launch_bounds__(256, 2) attention_tc_bwd8_kernel(
+template <int HD, int NT_MAX, bool X3>
+__global__ void __launch_bounds__(256, X3 ? 1 : 2) attention_tc_bwd8_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ ctx,
     const float* __restrict__ dctx, const float* __restrict__ lse, float* __restrict__ dq, float* __restrict__ dk,
     float* __restrict__ dv, float* __restrict__ dbias_qkv, int H, int T_arg, int S_arg, int64_t q_bs, int64_t q_ts, int64_t kv_bs,
@@ -593,7 +618,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc_bwd8_kernel(
         if (n < nt) {
           uint32_t bb[2];
           ldb_frag_nk(bb, sK, LQ, n * 8, kk * 8, g, t);
-          mma_tf32(acc[lt], a, bb);
+          mma_t<X3>(acc[lt], a, bb);
         }
       }
     }
@@ -613,10 +638,10 @@ __global__ void __launch_bounds__(256, 2) attention_tc_bwd8_kernel(
           const int c0 = n * 8 + 2 * t;
           float p00 = 0.f, p01 = 0.f, p10 = 0.f, p11 = 0.f;
           if (n < nt) {
-            p00 = (c0 < lim0) ? __expf(acc[lt][0] * scale - l0) : 0.f;
-            p01 = (c0 + 1 < lim0) ? __expf(acc[lt][1] * scale - l0) : 0.f;
-            p10 = (c0 < lim1) ? __expf(acc[lt][2] * scale - l1) : 0.f;
-            p11 = (c0 + 1 < lim1) ? __expf(acc[lt][3] * scale - l1) : 0.f;
+            p00 = (c0 < lim0) ? exp_t<X3>(acc[lt][0] * scale - l0) : 0.f;
+            p01 = (c0 + 1 < lim0) ? exp_t<X3>(acc[lt][1] * scale - l0) : 0.f;
+            p10 = (c0 < lim1) ? exp_t<X3>(acc[lt][2] * scale - l1) : 0.f;
+            p11 = (c0 + 1 < lim1) ? exp_t<X3>(acc[lt][3] * scale - l1) : 0.f;
           }
           *reinterpret_cast<float2*>(sdS + (size_t)r0 * LS + c0) = make_float2(p00, p01);
           *reinterpret_cast<float2*>(sdS + (size_t)r1 * LS + c0) = make_float2(p10, p11);
@@ -638,7 +663,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc_bwd8_kernel(
         if (n < nt) {
           uint32_t bb[2];
           ldb_frag_nk(bb, sV, LQ, n * 8, kk * 8, g, t);
-          mma_tf32(acc[lt], a, bb);
+          mma_t<X3>(acc[lt], a, bb);
         }
       }
     }
@@ -670,7 +695,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc_bwd8_kernel(
       for (int n = 0; n < NH; ++n) {
         uint32_t bb[2];
         ldb_frag_kn(bb, sK, LQ, (hh * NH + n) * 8, kk * 8, g, t);
-        mma_tf32(o[n], a, bb);
+        mma_t<X3>(o[n], a, bb);
       }
     }
 #pragma unroll
@@ -710,7 +735,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc_bwd8_kernel(
         for (int n = 0; n < HD / 8; ++n) {
           uint32_t bb[2];
           ldb_frag_kn(bb, sB, LQ, n * 8, kk * 8, g, t);
-          mma_tf32(oa[n], a, bb);
+          mma_t<X3>(oa[n], a, bb);
         }
       }
       const int r0 = j0 + g, r1 = r0 + 8;
@@ -747,20 +772,20 @@ size_t attn_tc_bwd_smem(int T, int S, int hd) {
   return ((size_t)2 * Tp * (hd + 4) + (size_t)2 * Sp * (hd + 4) + (size_t)2 * Tp * (Sp + 4) + 3 * hd + 2 * Tp) * sizeof(float);
 }
 
-template <int HD, int NT>
+template <int HD, int NT, bool X3>
 static int launch_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, int B, int H, int T, int S,
                       int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale,
                       int causal, const int32_t* key_len, float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
                       const int32_t* cu_rows, cudaStream_t stream) {
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(attention_tc_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set = true; }
-  attention_tc_fwd_kernel<HD, NT><<<B * H, 128, attn_tc_fwd_smem(T, S, HD), stream>>>(
+  if (!set) { cudaFuncSetAttribute(attention_tc_fwd_kernel<HD, NT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set = true; }
+  attention_tc_fwd_kernel<HD, NT, X3><<<B * H, 128, attn_tc_fwd_smem(T, S, HD), stream>>>(
       q, k, v, ctx, lse, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id, cu_rows);
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("attention_tc_fwd_kernel");
   return CAPDEC_OK;
 }
-template <int HD, int NT>
+template <int HD, int NT, bool X3>
 static int launch_bwd(const float* q, const float* k, const float* v, const float* ctx, const float* dctx, const float* lse,
                       float* dq, float* dk, float* dv, float* dbias, int B, int H, int T, int S, int64_t q_bs, int64_t q_ts,
                       int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale, int causal,
@@ -768,17 +793,17 @@ static int launch_bwd(const float* q, const float* k, const float* v, const floa
                       const int32_t* cu_rows, cudaStream_t stream) {
   static bool set = false;
   if (!set) {
-    cudaFuncSetAttribute(attention_tc_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attention_tc_bwd8_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attention_tc_bwd_kernel<HD, NT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attention_tc_bwd8_kernel<HD, NT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     set = true;
   }
   static const char* env8 = getenv("CAPDEC_ATTN_BWD8");   // bring-up switch: 0 = the 4-warp kernel
   if (env8 && env8[0] == '0') {
-    attention_tc_bwd_kernel<HD, NT><<<B * H, 128, attn_tc_bwd_smem(T, S, HD), stream>>>(
+    attention_tc_bwd_kernel<HD, NT, X3><<<B * H, 128, attn_tc_bwd_smem(T, S, HD), stream>>>(
         q, k, v, ctx, dctx, lse, dq, dk, dv, dbias, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len,
         p_drop, seed_dev, stream_id, cu_rows);
   } else {
-    attention_tc_bwd8_kernel<HD, NT><<<B * H, 256, attn_tc_bwd_smem(T, S, HD), stream>>>(
+    attention_tc_bwd8_kernel<HD, NT, X3><<<B * H, 256, attn_tc_bwd_smem(T, S, HD), stream>>>(
         q, k, v, ctx, dctx, lse, dq, dk, dv, dbias, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len,
         p_drop, seed_dev, stream_id, cu_rows);
   }
@@ -793,12 +818,11 @@ using namespace capdec;
 
 // Same contract as capdec_attention_fwd / _bwd (attention.cu); returns CAPDEC_ERR_UNSUPPORTED (-3) when the shape does
 // not fit the tensor-core kernel's shared-memory budget so that the caller can use the FFMA kernel instead.
-extern "C" int capdec_attention_tc_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, int B,
-                                       int H, int T, int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs,
-                                       int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale, int causal,
-                                       const int32_t* key_len, float p_drop, const uint64_t* seed_dev,
-                                       uint32_t stream_id, const int32_t* cu_rows, capdec_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+static int attention_tc_fwd_impl(bool x3, const float* q, const float* k, const float* v, float* ctx, float* lse, int B,
+                                 int H, int T, int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs,
+                                 int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale, int causal,
+                                 const int32_t* key_len, float p_drop, const uint64_t* seed_dev,
+                                 uint32_t stream_id, const int32_t* cu_rows, cudaStream_t stream) {
   CAPDEC_REQUIRE(q && k && v && ctx, "attention_tc_fwd: null argument");
   CAPDEC_REQUIRE(!cu_rows || (T == S && causal), "attention_tc_fwd: packed rows are for causal self-attention");
   CAPDEC_REQUIRE(B > 0 && H > 0 && T > 0 && S > 0 && T <= 128 && S <= 128, "attention_tc_fwd: T,S must be in 1..128");
@@ -806,18 +830,30 @@ extern "C" int capdec_attention_tc_fwd(const float* q, const float* k, const flo
   CAPDEC_REQUIRE(q_ts % 4 == 0 && kv_ts % 4 == 0 && o_ts % 2 == 0, "attention_tc_fwd: misaligned strides");
   if (attn_tc_fwd_smem(T, S, hd) > 227 * 1024) { set_last_error("attention_tc_fwd: tile does not fit shared memory"); return CAPDEC_ERR_UNSUPPORTED; }
 #define FWD_ARGS q, k, v, ctx, lse, B, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id, cu_rows, stream
-  if (hd == 64) return S <= 64 ? launch_fwd<64, 8>(FWD_ARGS) : launch_fwd<64, 16>(FWD_ARGS);
-  return S <= 64 ? launch_fwd<96, 8>(FWD_ARGS) : launch_fwd<96, 16>(FWD_ARGS);
+  if (x3) {
+    if (hd == 64) return S <= 64 ? launch_fwd<64, 8, true>(FWD_ARGS) : launch_fwd<64, 16, true>(FWD_ARGS);
+    return S <= 64 ? launch_fwd<96, 8, true>(FWD_ARGS) : launch_fwd<96, 16, true>(FWD_ARGS);
+  }
+  if (hd == 64) return S <= 64 ? launch_fwd<64, 8, false>(FWD_ARGS) : launch_fwd<64, 16, false>(FWD_ARGS);
+  return S <= 64 ? launch_fwd<96, 8, false>(FWD_ARGS) : launch_fwd<96, 16, false>(FWD_ARGS);
 #undef FWD_ARGS
 }
+#define ATTN_FWD_PARAMS const float* q, const float* k, const float* v, float* ctx, float* lse, int B, int H, int T, int S,     \
+                        int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts,          \
+                        float scale, int causal, const int32_t* key_len, float p_drop, const uint64_t* seed_dev,               \
+                        uint32_t stream_id, const int32_t* cu_rows, capdec_stream_t stream_
+#define ATTN_FWD_FORWARD q, k, v, ctx, lse, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, \
+                         seed_dev, stream_id, cu_rows, reinterpret_cast<cudaStream_t>(stream_)
+extern "C" int capdec_attention_tc_fwd(ATTN_FWD_PARAMS) { return attention_tc_fwd_impl(false, ATTN_FWD_FORWARD); }
+// fp32-grade variant (3xTF32 split in registers, accurate exp / log): the "tf32x3" mode's attention
+extern "C" int capdec_attention_tc_fwd_x3(ATTN_FWD_PARAMS) { return attention_tc_fwd_impl(true, ATTN_FWD_FORWARD); }
 
-extern "C" int capdec_attention_tc_bwd(const float* q, const float* k, const float* v, const float* ctx,
-                                       const float* dctx, const float* lse, float* dq, float* dk, float* dv,
-                                       float* dbias_qkv, int B, int H, int T, int S, int hd, int64_t q_bs, int64_t q_ts,
-                                       int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale,
-                                       int causal, const int32_t* key_len, float p_drop, const uint64_t* seed_dev,
-                                       uint32_t stream_id, const int32_t* cu_rows, capdec_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+static int attention_tc_bwd_impl(bool x3, const float* q, const float* k, const float* v, const float* ctx,
+                                 const float* dctx, const float* lse, float* dq, float* dk, float* dv,
+                                 float* dbias_qkv, int B, int H, int T, int S, int hd, int64_t q_bs, int64_t q_ts,
+                                 int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale,
+                                 int causal, const int32_t* key_len, float p_drop, const uint64_t* seed_dev,
+                                 uint32_t stream_id, const int32_t* cu_rows, cudaStream_t stream) {
   CAPDEC_REQUIRE(q && k && v && ctx && dctx && lse && dq && dk && dv, "attention_tc_bwd: null argument");
   CAPDEC_REQUIRE(!cu_rows || (T == S && causal), "attention_tc_bwd: packed rows are for causal self-attention");
   CAPDEC_REQUIRE(B > 0 && H > 0 && T > 0 && S > 0 && T <= 128 && S <= 128, "attention_tc_bwd: T,S must be in 1..128");
@@ -825,7 +861,20 @@ extern "C" int capdec_attention_tc_bwd(const float* q, const float* k, const flo
   CAPDEC_REQUIRE(q_ts % 4 == 0 && kv_ts % 4 == 0 && o_ts % 4 == 0, "attention_tc_bwd: misaligned strides");
   if (attn_tc_bwd_smem(T, S, hd) > 227 * 1024) { set_last_error("attention_tc_bwd: tile does not fit shared memory"); return CAPDEC_ERR_UNSUPPORTED; }
 #define BWD_ARGS q, k, v, ctx, dctx, lse, dq, dk, dv, dbias_qkv, B, H, T, S, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal, key_len, p_drop, seed_dev, stream_id, cu_rows, stream
-  if (hd == 64) return S <= 64 ? launch_bwd<64, 8>(BWD_ARGS) : launch_bwd<64, 16>(BWD_ARGS);
-  return S <= 64 ? launch_bwd<96, 8>(BWD_ARGS) : launch_bwd<96, 16>(BWD_ARGS);
+  if (x3) {
+    if (hd == 64) return S <= 64 ? launch_bwd<64, 8, true>(BWD_ARGS) : launch_bwd<64, 16, true>(BWD_ARGS);
+    return S <= 64 ? launch_bwd<96, 8, true>(BWD_ARGS) : launch_bwd<96, 16, true>(BWD_ARGS);
+  }
+  if (hd == 64) return S <= 64 ? launch_bwd<64, 8, false>(BWD_ARGS) : launch_bwd<64, 16, false>(BWD_ARGS);
+  return S <= 64 ? launch_bwd<96, 8, false>(BWD_ARGS) : launch_bwd<96, 16, false>(BWD_ARGS);
 #undef BWD_ARGS
 }
+#define ATTN_BWD_PARAMS const float* q, const float* k, const float* v, const float* ctx, const float* dctx, const float* lse, \
+                        float* dq, float* dk, float* dv, float* dbias_qkv, int B, int H, int T, int S, int hd, int64_t q_bs,   \
+                        int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale, int causal,       \
+                        const int32_t* key_len, float p_drop, const uint64_t* seed_dev, uint32_t stream_id,                    \
+                        const int32_t* cu_rows, capdec_stream_t stream_
+#define ATTN_BWD_FORWARD q, k, v, ctx, dctx, lse, dq, dk, dv, dbias_qkv, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts,   \
+                         scale, causal, key_len, p_drop, seed_dev, stream_id, cu_rows, reinterpret_cast<cudaStream_t>(stream_)
+extern "C" int capdec_attention_tc_bwd(ATTN_BWD_PARAMS) { return attention_tc_bwd_impl(false, ATTN_BWD_FORWARD); }
+extern "C" int capdec_attention_tc_bwd_x3(ATTN_BWD_PARAMS) { return attention_tc_bwd_impl(true, ATTN_BWD_FORWARD); }

@@ -180,6 +180,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// cluster-scope acquire wait: the data the barrier guards was written by ANOTHER CTA of the cluster (peer converter warps)
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+      printf("capdec: mbarrier watchdog (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
 // 1-D bulk copy global -> shared (TMA engine, no tensor map): `bytes` % 16 == 0, both addresses 16-byte aligned;
 // completion is credited to `bar` as transaction bytes.
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -243,6 +268,16 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// same, with cluster-scope release: this thread's (and, after a __syncwarp, its warp's) earlier shared-memory writes are
+// visible to the CTA that acquires the barrier
+__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
 }

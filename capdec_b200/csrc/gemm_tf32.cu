@@ -13,7 +13,10 @@
 // Pipeline: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer, warp 2 = TMEM allocator,
 // warps 4-7 = epilogue (tcgen05.ld -> bias/activation -> swizzled smem -> TMA store / TMA reduce-add).
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the mainloop of tile i+1.
-// 3xTF32 ("parity") mode runs three K passes (hi*hi, lo*hi, hi*lo) into the same TMEM accumulator.
+// 3xTF32 (fp32-grade) mode, template kSplit: the fp32 operand tiles are split INSIDE the pipeline.  Four converter warps
+// turn every landed stage into hi = RN_tf32(x) (in place) and lo = x - hi (second tile, same swizzled layout - the split
+// is element-wise, so it is layout-agnostic); the issuer then runs three MMAs per k-step (lo*hi, hi*lo, hi*hi) into the
+// same TMEM accumulator.  Operands are read from HBM/L2 once, exactly as in the 1xTF32 mode; no host-side hi/lo buffers.
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -45,15 +48,22 @@ int check_cuda(cudaError_t e, const char* what) {
   set_last_error("%s: %s", what, cudaGetErrorString(e));
   return CAPDEC_ERR_CUDA;
 }
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+constexpr int kMaxDevices = 64;
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+int num_sms() {   // cached per device: a process may drive several GPUs
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cudaGetLastError();
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -63,6 +73,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;  // fp32 elements per k-block = 128 bytes = one swizzle row
 constexpr int kUmmaK = 8;    // tf32
 constexpr int kThreads = 256;
+constexpr int kSplitThreads = 384;  // 3xTF32: + warps 8..11 = operand converters (hi/lo split in shared memory)
+constexpr int kConvThreads = 128;
 constexpr int kEpiThreads = 128;
 constexpr int kABytes = kBlockM * kBlockK * 4;  // 16 KB
 constexpr int kStagingBytes = 128 * 128;        // 128 rows x 32 fp32
@@ -74,8 +86,8 @@ constexpr int kAccCols = 256;  // columns per accumulator stage
 constexpr int kSmemLimit = 227 * 1024;
 
 struct __align__(64) GemmDev {
-  CUtensorMap tmA[2];  // [0] = hi (or the operand itself), [1] = lo residual (3xTF32)
-  CUtensorMap tmB[2];
+  CUtensorMap tmA;
+  CUtensorMap tmB;
   CUtensorMap tmC;
   CUtensorMap tmAux;
   CUtensorMap tmMul;   // optional epilogue INPUT (same shape as C): C = acc * act'(mul)
@@ -83,7 +95,7 @@ struct __align__(64) GemmDev {
   int M, N, K;
   int block_n, stages;
   int m_tiles, n_tiles, splits, kb_per_split, kb_total;
-  int nseg;
+  int exact;                        // 3xTF32 mode: exact tanhf in the activation epilogues (1xTF32: MUFU.TANH)
   int act, has_aux, accumulate;
   int a_mn, b_mn;
   int a_3d, b_3d;                   // MN-major operand fetched as ONE 3-D TMA box {32, 32 k-rows, slabs} per stage
@@ -166,10 +178,15 @@ __device__ __forceinline__ void gelu_fwd_and_grad32(float (&v)[32], float (&dv)[
 
 // v *= act'(u) over a 32-column register chunk, dispatch hoisted out of the element loop for the same reason: the
 // 32 independent dependency chains (MUFU.TANH + ~15 FMAs each) must interleave, the epilogue has one warp per scheduler.
-__device__ __forceinline__ void apply_mul32(float (&v)[32], const float (&u)[32], int mul_act) {
+__device__ __forceinline__ void apply_mul32(float (&v)[32], const float (&u)[32], int mul_act, bool exact) {
   if (mul_act == 1) {
+    if (exact) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= gelu_grad_fast(u[j]);
+      for (int j = 0; j < 32; ++j) v[j] *= gelu_new_grad(u[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= gelu_grad_fast(u[j]);
+    }
   } else if (mul_act == 2) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= 1.f - u[j] * u[j];
@@ -193,11 +210,12 @@ __device__ __forceinline__ void apply_mul32(float (&v)[32], const float (&u)[32]
 //   3  a QUAD stacked in M (512 x block_n): the pairs need the same B columns; B halves are multicast instead.
 // Why: with fp32 operands these GEMMs are bound by L2->SM bandwidth (~8.3 TB/s measured: loads-only experiment in
 // profiles/r1_gemm_pipeline_experiments.md), not by the tensor pipe; FLOP per L2 byte is 43 / 64 / 87 for modes 0/1/2-3.
-template <int kMode>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_constant__ GemmDev p) {
+template <int kMode, bool kSplit>
+__global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf32_kernel(const __grid_constant__ GemmDev p) {
   constexpr bool kPair = kMode >= 1;
   constexpr bool kQuad = kMode >= 2;
   constexpr bool kShareB = kMode == 3;
+  static_assert(!(kSplit && kQuad), "the in-pipeline 3xTF32 split runs on the single-CTA and CTA-pair engines");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up (all tile buffers 1024-byte aligned for the 128B swizzle patterns); identical in every CTA of a cluster
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -206,7 +224,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   const int stage_bytes = kABytes + b_bytes;
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.stages * kABytes;
-  uint8_t* sStage = smem + p.stages * stage_bytes;  // epilogue staging: C ping-pong [+ aux ping-pong]
+  uint8_t* sAlo = smem + p.stages * stage_bytes;            // kSplit only: the lo = x - RN_tf32(x) tiles
+  uint8_t* sBlo = sAlo + p.stages * kABytes;
+  uint8_t* sStage = smem + (kSplit ? 2 : 1) * p.stages * stage_bytes;  // epilogue staging: C ping-pong [+ aux ping-pong]
   const int n_staging = p.mul_act ? 2 + kMulDepth : (p.has_aux ? 4 : 2);
   float* sBias = reinterpret_cast<float*>(sStage + n_staging * kStagingBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 256);
@@ -214,7 +234,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* mul_bar = tmem_empty_bar + 2;           // TMA loads of the epilogue input boxes (kMulDepth per epilogue warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mul_bar + 4 * kMulDepth);
+  uint64_t* conv_bar = mul_bar + 4 * kMulDepth;     // kSplit: stage converted (hi in place, lo written) in every CTA of the pair
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + kMaxStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -228,20 +249,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
   constexpr int kCtasPerCluster = kCtasPerPair * kPairsPerCluster;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&p.tmA[0]);
-    prefetch_tensormap(&p.tmB[0]);
+    prefetch_tensormap(&p.tmA);
+    prefetch_tensormap(&p.tmB);
     prefetch_tensormap(&p.tmC);
-    if (p.nseg > 1) {
-      prefetch_tensormap(&p.tmA[1]);
-      prefetch_tensormap(&p.tmB[1]);
-    }
     if (p.has_aux) prefetch_tensormap(&p.tmAux);
     if (p.mul_act) prefetch_tensormap(&p.tmMul);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&full_bar[i], kCtasPerPair);      // pair: leader's arrive.expect_tx + the peer's remote arrive
+      // 1xTF32 pair: the leader's barrier collects the leader's arrive.expect_tx + the peer's remote arrive and the bytes
+      // of both CTAs.  3xTF32: every CTA tracks its OWN loads (its converter warps wait on them locally).
+      mbar_init(&full_bar[i], kSplit ? 1 : kCtasPerPair);
       mbar_init(&empty_bar[i], kPairsPerCluster);  // quad: both pairs' MMAs must have retired (multicast writes my smem)
+      mbar_init(&conv_bar[i], kCtasPerPair * (kConvThreads / 32));  // one arrive per converter warp of each CTA
     }
     for (int i = 0; i < 4 * kMulDepth; ++i) mbar_init(&mul_bar[i], 1);
     for (int i = 0; i < 2; ++i) {
@@ -293,72 +313,72 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_lim);
         if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          const CUtensorMap* mapA = (seg == 1) ? &p.tmA[1] : &p.tmA[0];
-          const CUtensorMap* mapB = (seg == 2) ? &p.tmB[1] : &p.tmB[0];
-          for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-            const int k0 = kb * kBlockK;
-            uint8_t* a_dst = sA + stage * kABytes;
-            uint8_t* b_dst = sB + stage * b_bytes;
-            uint64_t* fb = &full_bar[stage];
-            if (p.dbg & 1u) {  // timing experiment: no loads, just hand the (stale) stage to the MMA warp
-              if constexpr (kPair) { if (leader) mbar_arrive(fb); else mbar_arrive_remote(fb, pair_leader); } else mbar_arrive(fb);
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
-              continue;
-            }
-            if constexpr (!kPair) mbar_arrive_expect_tx(fb, (uint32_t)stage_bytes);
-            auto load = [&](void* dst, const CUtensorMap* m, int x, int y) {
-              if constexpr (kPair) tma_load_2d_pair(dst, m, fb, x, y); else tma_load_2d(dst, m, fb, x, y);
-            };
-            auto load_mc = [&](void* dst, const CUtensorMap* m, int x, int y) { tma_load_2d_pair_mc(dst, m, fb, x, y, mc_mask); };
-            auto load3 = [&](void* dst, const CUtensorMap* m, int y, int z) {   // {32 floats, 32 k-rows from y, slabs from z}
-              if constexpr (kPair) tma_load_3d_pair(dst, m, fb, 0, y, z); else tma_load_3d(dst, m, fb, 0, y, z);
-            };
-            auto load3_mc = [&](void* dst, const CUtensorMap* m, int y, int z) { tma_load_3d_pair_mc(dst, m, fb, 0, y, z, mc_mask); };
-            // ---- A ----
-            if constexpr (kQuad && !kShareB) {   // my half of the shared A slab -> me + twin
-              if (!p.a_mn) load_mc(a_dst + pair_idx * (kABytes / 2), mapA, k0, m0 + (int)pair_idx * (kBlockM / 2));
-              else if (p.a_3d) load3_mc(a_dst + pair_idx * (kABytes / 2), mapA, k0, m0 / 32 + (int)pair_idx * (kBlockM / 64));
-              else {
-#pragma unroll
-                for (int i = 0; i < kBlockM / 64; ++i) {
-                  const int sl = (int)pair_idx * (kBlockM / 64) + i;
-                  load_mc(a_dst + sl * 4096, mapA, m0 + 32 * sl, k0);
-                }
-              }
-            } else {
-              if (!p.a_mn) load(a_dst, mapA, k0, m0);
-              else if (p.a_3d) load3(a_dst, mapA, k0, m0 / 32);
-              else {
-#pragma unroll
-                for (int i = 0; i < kBlockM / 32; ++i) load(a_dst + i * 4096, mapA, m0 + 32 * i, k0);
-              }
-            }
-            // ---- B ----
-            if constexpr (kQuad && kShareB) {    // my half of the shared B slab -> me + twin
-              if (!p.b_mn) load_mc(b_dst + pair_idx * (b_bytes / 2), mapB, k0, n0 + (int)pair_idx * (bn_local / 2));
-              else if (p.b_3d) load3_mc(b_dst + pair_idx * (b_bytes / 2), mapB, k0, n0 / 32 + (int)pair_idx * (bn_local / 64));
-              else {
-                const int ns = bn_local / 64;
-                for (int i = 0; i < ns; ++i) {
-                  const int sl = (int)pair_idx * ns + i;
-                  load_mc(b_dst + sl * 4096, mapB, n0 + 32 * sl, k0);
-                }
-              }
-            } else {
-              if (!p.b_mn) load(b_dst, mapB, k0, n0);
-              else if (p.b_3d) load3(b_dst, mapB, k0, n0 / 32);
-              else {
-                for (int i = 0; i < bn_local / 32; ++i) load(b_dst + i * 4096, mapB, n0 + 32 * i, k0);
-              }
-            }
-            if constexpr (kPair) {
-              if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(2 * stage_bytes));  // bytes landing in BOTH CTAs of my pair
-              else mbar_arrive_remote(fb, pair_leader);
-            }
+        const CUtensorMap* mapA = &p.tmA;
+        const CUtensorMap* mapB = &p.tmB;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          const int k0 = kb * kBlockK;
+          uint8_t* a_dst = sA + stage * kABytes;
+          uint8_t* b_dst = sB + stage * b_bytes;
+          uint64_t* fb = &full_bar[stage];
+          constexpr bool kLocalBar = !kPair || kSplit;   // the loads are credited to THIS CTA's barrier
+          if (p.dbg & 1u) {  // timing experiment: no loads, just hand the (stale) stage on
+            if constexpr (kLocalBar) mbar_arrive(fb);
+            else { if (leader) mbar_arrive(fb); else mbar_arrive_remote(fb, pair_leader); }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            continue;
           }
+          if constexpr (kLocalBar) mbar_arrive_expect_tx(fb, (uint32_t)stage_bytes);
+          auto load = [&](void* dst, const CUtensorMap* m, int x, int y) {
+            if constexpr (kLocalBar) tma_load_2d(dst, m, fb, x, y); else tma_load_2d_pair(dst, m, fb, x, y);
+          };
+          auto load_mc = [&](void* dst, const CUtensorMap* m, int x, int y) { tma_load_2d_pair_mc(dst, m, fb, x, y, mc_mask); };
+          auto load3 = [&](void* dst, const CUtensorMap* m, int y, int z) {   // {32 floats, 32 k-rows from y, slabs from z}
+            if constexpr (kLocalBar) tma_load_3d(dst, m, fb, 0, y, z); else tma_load_3d_pair(dst, m, fb, 0, y, z);
+          };
+          auto load3_mc = [&](void* dst, const CUtensorMap* m, int y, int z) { tma_load_3d_pair_mc(dst, m, fb, 0, y, z, mc_mask); };
+          // ---- A ----
+          if constexpr (kQuad && !kShareB) {   // my half of the shared A slab -> me + twin
+            if (!p.a_mn) load_mc(a_dst + pair_idx * (kABytes / 2), mapA, k0, m0 + (int)pair_idx * (kBlockM / 2));
+            else if (p.a_3d) load3_mc(a_dst + pair_idx * (kABytes / 2), mapA, k0, m0 / 32 + (int)pair_idx * (kBlockM / 64));
+            else {
+#pragma unroll
+              for (int i = 0; i < kBlockM / 64; ++i) {
+                const int sl = (int)pair_idx * (kBlockM / 64) + i;
+                load_mc(a_dst + sl * 4096, mapA, m0 + 32 * sl, k0);
+              }
+            }
+          } else {
+            if (!p.a_mn) load(a_dst, mapA, k0, m0);
+            else if (p.a_3d) load3(a_dst, mapA, k0, m0 / 32);
+            else {
+#pragma unroll
+              for (int i = 0; i < kBlockM / 32; ++i) load(a_dst + i * 4096, mapA, m0 + 32 * i, k0);
+            }
+          }
+          // ---- B ----
+          if constexpr (kQuad && kShareB) {    // my half of the shared B slab -> me + twin
+            if (!p.b_mn) load_mc(b_dst + pair_idx * (b_bytes / 2), mapB, k0, n0 + (int)pair_idx * (bn_local / 2));
+            else if (p.b_3d) load3_mc(b_dst + pair_idx * (b_bytes / 2), mapB, k0, n0 / 32 + (int)pair_idx * (bn_local / 64));
+            else {
+              const int ns = bn_local / 64;
+              for (int i = 0; i < ns; ++i) {
+                const int sl = (int)pair_idx * ns + i;
+                load_mc(b_dst + sl * 4096, mapB, n0 + 32 * sl, k0);
+              }
+            }
+          } else {
+            if (!p.b_mn) load(b_dst, mapB, k0, n0);
+            else if (p.b_3d) load3(b_dst, mapB, k0, n0 / 32);
+            else {
+              for (int i = 0; i < bn_local / 32; ++i) load(b_dst + i * 4096, mapB, n0 + 32 * i, k0);
+            }
+          }
+          if constexpr (!kLocalBar) {
+            if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(2 * stage_bytes));  // bytes landing in BOTH CTAs of my pair
+            else mbar_arrive_remote(fb, pair_leader);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -370,6 +390,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint64_t adesc_base = ((uint64_t)p.adesc_hi << 32) | (uint64_t)p.adesc_lo16;
+      const uint64_t bdesc_base = ((uint64_t)p.bdesc_hi << 32) | (uint64_t)p.bdesc_lo16;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int split = tile / (p.n_tiles * m_tiles);
         const int m_blk = (tile / p.n_tiles) % m_tiles;
@@ -380,28 +402,42 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
         uint32_t accumulate = 0;
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(&full_bar[stage], phase, 3);
-            tc_fence_after();
-            const uint32_t a_start = smem_u32(sA + stage * kABytes) >> 4;
-            const uint32_t b_start = smem_u32(sB + stage * b_bytes) >> 4;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if constexpr (kSplit) mbar_wait_cluster(&conv_bar[stage], phase, 6);   // hi/lo tiles of both CTAs are in place
+          else mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t a_start = smem_u32(sA + stage * kABytes) >> 4;
+          const uint32_t b_start = smem_u32(sB + stage * b_bytes) >> 4;
+          auto mma = [&](uint64_t adesc, uint64_t bdesc) {
+            if (!(p.dbg & 2u)) {
+              if constexpr (kPair) umma_tf32_pair(d_tmem, adesc, bdesc, p.idesc, accumulate);
+              else umma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
+            }
+            accumulate = 1;
+          };
+          if constexpr (kSplit) {
+            const uint32_t alo_start = smem_u32(sAlo + stage * kABytes) >> 4;
+            const uint32_t blo_start = smem_u32(sBlo + stage * b_bytes) >> 4;
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              const uint64_t adesc = ((uint64_t)p.adesc_hi << 32) |
-                                     (uint64_t)(p.adesc_lo16 | ((a_start + k * p.a_kstep) & 0x3FFFu));
-              const uint64_t bdesc = ((uint64_t)p.bdesc_hi << 32) |
-                                     (uint64_t)(p.bdesc_lo16 | ((b_start + k * p.b_kstep) & 0x3FFFu));
-              if (!(p.dbg & 2u)) {
-                if constexpr (kPair) umma_tf32_pair(d_tmem, adesc, bdesc, p.idesc, accumulate);
-                else umma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
-              }
-              accumulate = 1;
+              const uint64_t ah = adesc_base | (uint64_t)((a_start + k * p.a_kstep) & 0x3FFFu);
+              const uint64_t bh = bdesc_base | (uint64_t)((b_start + k * p.b_kstep) & 0x3FFFu);
+              const uint64_t al = adesc_base | (uint64_t)((alo_start + k * p.a_kstep) & 0x3FFFu);
+              const uint64_t bl = bdesc_base | (uint64_t)((blo_start + k * p.b_kstep) & 0x3FFFu);
+              mma(al, bh);   // the two cross terms first, then the leading term
+              mma(ah, bl);
+              mma(ah, bh);
             }
-            // smem slot reusable (in every CTA that writes into my pair's smem) once these MMAs retire
-            if constexpr (kPair) umma_commit_mc(&empty_bar[stage], commit_empty_mask); else umma_commit(&empty_bar[stage]);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              mma(adesc_base | (uint64_t)((a_start + k * p.a_kstep) & 0x3FFFu),
+                  bdesc_base | (uint64_t)((b_start + k * p.b_kstep) & 0x3FFFu));
+            }
           }
+          // smem slot reusable (in every CTA that writes into my pair's smem) once these MMAs retire
+          if constexpr (kPair) umma_commit_mc(&empty_bar[stage], commit_empty_mask); else umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue(s) of my pair
         if constexpr (kPair) umma_commit_mc(&tmem_full_bar[acc], commit_pair_mask); else umma_commit(&tmem_full_bar[acc]);
@@ -409,6 +445,60 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
       }
     }
     __syncwarp();
+  } else if (kSplit && warp >= 8) {
+    // ============================== 3xTF32 operand converters (4 warps, every CTA converts what IT staged) =========
+    // hi = RN_tf32(x): add half a TF32 ulp to the magnitude bits and clear the 13 low mantissa bits (= cvt.rna.tf32.f32,
+    // on the integer pipe); lo = x - hi is exact in fp32 and the tensor core keeps its leading 11 bits.  Element-wise, so
+    // the swizzled TMA layout of the tile carries over to the lo tile unchanged.
+    const int ct = threadIdx.x - kThreads;
+    int stage = 0;
+    uint32_t phase = 0;
+    auto split4 = [](float4& x, float4& lo) {
+      float* xv = reinterpret_cast<float*>(&x);
+      float* lv = reinterpret_cast<float*>(&lo);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float hi = __uint_as_float((__float_as_uint(xv[j]) + 0x1000u) & 0xFFFFE000u);
+        lv[j] = xv[j] - hi;
+        xv[j] = hi;
+      }
+    };
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      const int split = tile / (p.n_tiles * m_tiles);
+      const int m_blk = (tile / p.n_tiles) % m_tiles;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb0 + kb_per_split, kb_lim);
+      if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 7);
+        float4* a4 = reinterpret_cast<float4*>(sA + stage * kABytes);
+        float4* al4 = reinterpret_cast<float4*>(sAlo + stage * kABytes);
+        float4* b4 = reinterpret_cast<float4*>(sB + stage * b_bytes);
+        float4* bl4 = reinterpret_cast<float4*>(sBlo + stage * b_bytes);
+#pragma unroll
+        for (int i = 0; i < kABytes / 16 / kConvThreads; ++i) {
+          float4 x = a4[ct + i * kConvThreads], lo;
+          split4(x, lo);
+          a4[ct + i * kConvThreads] = x;
+          al4[ct + i * kConvThreads] = lo;
+        }
+        const int nb4 = b_bytes / 16;
+#pragma unroll 4
+        for (int i = ct; i < nb4; i += kConvThreads) {
+          float4 x = b4[i], lo;
+          split4(x, lo);
+          b4[i] = x;
+          bl4[i] = lo;
+        }
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair && !leader) mbar_arrive_remote_release(&conv_bar[stage], pair_leader);
+          else mbar_arrive(&conv_bar[stage]);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
   } else if (warp >= 4) {
     // ============================== epilogue (4 warps = this CTA's 128 TMEM lanes) ==============================
     // Every warp runs its OWN pipeline over its 32 rows: tcgen05.ld -> bias / activation -> swizzled 4 KB staging box ->
@@ -496,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
             const float4 u = u4[j ^ (lane & 7)];
             uu[4 * j] = u.x; uu[4 * j + 1] = u.y; uu[4 * j + 2] = u.z; uu[4 * j + 3] = u.w;
           }
-          apply_mul32(v, uu, p.mul_act);
+          apply_mul32(v, uu, p.mul_act, p.exact != 0);
         }
         const uint32_t pp = store_idx++ & 1;
         uint8_t* buf0 = wst + pp * kWarpStagingBytes;          // C box
@@ -506,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
         if (p.mul_act && lane == 0) mul_prefetch();  // every lane has read the input box just consumed: refill its slot
         if (p.act == 4) {      // aux <- gelu_new'(pre-activation), C <- gelu_new(pre-activation)
           float dv[32];
-          gelu_fwd_and_grad32(v, dv, p.nseg > 1);
+          gelu_fwd_and_grad32(v, dv, p.exact != 0);
           if (p.has_aux) {
             float4* d1 = reinterpret_cast<float4*>(buf1 + lane * 128);
 #pragma unroll
@@ -518,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 8; ++j) d1[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          if (p.act != 0) apply_act32(v, p.act, p.nseg > 1);
+          if (p.act != 0) apply_act32(v, p.act, p.exact != 0);
         }
         {
           float4* d0 = reinterpret_cast<float4*>(buf0 + lane * 128);
@@ -691,14 +781,15 @@ static void choose_tiling(int M, int N, int kb_total, int accumulate, int units,
   splits = best_s > 0 ? best_s : 1;
 }
 
-template <int kMode>
+template <int kMode, bool kSplit>
 static int max_clusters(int cluster_size, int smem_bytes) {
-  static int cached[4] = {0, 0, 0, 0};
-  if (cached[kMode] > 0) return cached[kMode];
+  static std::atomic<int> cached_dev[kMaxDevices];   // per instantiation and per device
+  std::atomic<int>& cached = cached_dev[current_device()];
+  if (cached.load(std::memory_order_relaxed) > 0) return cached.load(std::memory_order_relaxed);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(cluster_size * 64);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kSplit ? kSplitThreads : kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cudaLaunchAttribute attr;
   attr.id = cudaLaunchAttributeClusterDimension;
@@ -708,22 +799,22 @@ static int max_clusters(int cluster_size, int smem_bytes) {
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<kMode>, &cfg) != cudaSuccess || n <= 0) {
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<kMode, kSplit>, &cfg) != cudaSuccess || n <= 0) {
     cudaGetLastError();
     n = num_sms() / cluster_size;
   }
-  cached[kMode] = n;
+  cached.store(n, std::memory_order_relaxed);
   return n;
 }
 
-template <int kMode>
+template <int kMode, bool kSplit>
 static int launch_clustered(const GemmDev& p, int cluster_size, int total_tiles, int smem_bytes, cudaStream_t stream) {
-  const int maxc = max_clusters<kMode>(cluster_size, smem_bytes);
+  const int maxc = max_clusters<kMode, kSplit>(cluster_size, smem_bytes);
   const int nc = total_tiles < maxc ? total_tiles : maxc;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(cluster_size * nc);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kSplit ? kSplitThreads : kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr;
@@ -733,7 +824,7 @@ static int launch_clustered(const GemmDev& p, int cluster_size, int total_tiles,
   attr.val.clusterDim.z = 1;
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<kMode>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<kMode, kSplit>, p);
   if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm_tf32_kernel)");
   return CAPDEC_OK;
 }
@@ -802,7 +893,10 @@ static GemmPlan heuristic_plan(const GemmArgs& a, int block_n, int split_k, int 
   const int m_live = (a.m_limit && t_m_hint > 0 && t_m_hint < M) ? t_m_hint : M;
   if (mode >= 1) {
     const bool quad_ok = (M > 2 * kBlockM || N > 256);
-    if (forced < 0 && quad_ok) {
+    if (a.precision) {
+      // 3xTF32 is tensor-bound (three MMAs per staged byte): the operand-sharing quads have nothing to win
+      if (forced == 0) mode = 0;
+    } else if (forced < 0 && quad_ok) {
       // Measured on B200 (profiles/r1_gemm_modes.md): stacking the two pairs in M and multicasting B (mode 3) wins
       // 10-16 % at the dense C2 extent (M = 12800) when B is MN-major; sharing A (mode 2) loses to wave quantisation on
       // every shape of this model, and few-row problems (wgrad, M = 768) stay on plain pairs.
@@ -822,6 +916,18 @@ static GemmPlan heuristic_plan(const GemmArgs& a, int block_n, int split_k, int 
   const int kb_total = (a.K + kBlockK - 1) / kBlockK;
   choose_tiling(m_live, N, kb_total, a.accumulate, plan_units(mode), plan_tile_m(mode), mode == 2 ? 2 : 1, mode == 0 ? 64 : 128,
                 allow192, pl.bn, pl.splits);
+  if (a.precision) {
+    // 3xTF32: two tiles (hi, lo) per operand and stage -> the single-CTA engine fits 128 columns at most
+    if (mode == 0 && pl.bn > 128 && block_n == 0) pl.bn = 128;
+    // the tensor core adds into its fp32 accumulator with truncation, so the error of one accumulation chain grows with
+    // its length: reductions that may be split (accumulate = 1, reduce-add in L2 rounds to nearest) keep chains short
+    static const char* env_chain = getenv("CAPDEC_X3_CHAIN");
+    const int chain = env_chain ? atoi(env_chain) : 2048;
+    if (chain > 0 && a.accumulate && split_k == 0 && a.act == 0 && !a.aux) {
+      const int want = (a.K + chain - 1) / chain;
+      if (pl.splits < want) pl.splits = want;
+    }
+  }
   return pl;
 }
 
@@ -832,6 +938,8 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   CAPDEC_REQUIRE(bn != 192 || plan_ok192(mode, a.b_major),
                  "gemm: block_n=192 is not available for the B-sharing quad with an MN-major B");
   CAPDEC_REQUIRE(pl.splits == 1 || (a.accumulate && a.act == 0 && !a.aux), "gemm: split-K needs accumulate=1, act=0, no aux");
+  const bool split3 = a.precision != 0;   // 3xTF32: operands split into hi/lo inside the pipeline
+  CAPDEC_REQUIRE(!split3 || mode <= 1, "gemm: the 3xTF32 mode runs on the single-CTA and CTA-pair engines only");
   GemmDev p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
@@ -846,7 +954,7 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // drop empty splits
   p.m_tiles = (M + tile_m - 1) / tile_m;
   p.n_tiles = (N + nmul * bn - 1) / (nmul * bn);
-  p.nseg = a.precision ? 3 : 1;
+  p.exact = split3 ? 1 : 0;
   p.act = a.act;
   p.has_aux = a.aux ? 1 : 0;
   p.accumulate = a.accumulate ? 1 : 0;
@@ -862,11 +970,13 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
 
   const int bn_local = (mode == 0) ? bn : bn / 2;
   const int b_bytes = bn_local * kBlockK * 4;
-  const int fixed = (a.mul_act ? 2 + kMulDepth : (a.aux ? 4 : 2)) * kStagingBytes + 256 * 4 + (2 * kMaxStages + 4 + 4 * kMulDepth) * 8 + 16 + 960 /* alignment slack */;
-  int stages = (kSmemLimit - fixed) / (kABytes + b_bytes);
+  const int fixed = (a.mul_act ? 2 + kMulDepth : (a.aux ? 4 : 2)) * kStagingBytes + 256 * 4 + (3 * kMaxStages + 4 + 4 * kMulDepth) * 8 + 16 + 960 /* alignment slack */;
+  const int per_stage = (kABytes + b_bytes) * (split3 ? 2 : 1);   // 3xTF32 keeps a lo tile beside every operand tile
+  int stages = (kSmemLimit - fixed) / per_stage;
   if (stages > kMaxStages) stages = kMaxStages;
+  CAPDEC_REQUIRE(stages >= 2, "gemm: tile width %d leaves fewer than two pipeline stages in shared memory (3xTF32: use block_n <= 128 on the single-CTA engine)", bn);
   p.stages = stages;
-  const int smem_bytes = stages * (kABytes + b_bytes) + fixed;
+  const int smem_bytes = stages * per_stage + fixed;
 
   const OperandEnc ea = operand_encoding(a.a_major != 0), eb = operand_encoding(a.b_major != 0);
   p.adesc_hi = ea.desc_hi; p.adesc_lo16 = ea.desc_lo16; p.a_kstep = ea.kstep;
@@ -886,19 +996,19 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   p.a_3d = (a.a_major && allow3d && ((M % 32) == 0 || a.lda >= (int64_t)((M + 31) / 32) * 32)) ? 1 : 0;
   p.b_3d = (a.b_major && allow3d && ((N % 32) == 0 || a.ldb >= (int64_t)((N + 31) / 32) * 32)) ? 1 : 0;
   int rc;
-  for (int s = 0; s < p.nseg && s < 2; ++s) {
-    const float* pa = s ? a.a_lo : a.A;
-    const float* pb = s ? a.b_lo : a.B;
-    if (!a.a_major) rc = make_map(&p.tmA[s], pa, (uint64_t)K, (uint64_t)M, (uint64_t)a.lda, kBlockK, a_rows, ea.swz);
+  {
+    const float* pa = a.A;
+    const float* pb = a.B;
+    if (!a.a_major) rc = make_map(&p.tmA, pa, (uint64_t)K, (uint64_t)M, (uint64_t)a.lda, kBlockK, a_rows, ea.swz);
     else {
-      rc = p.a_3d ? make_map_mn3d(&p.tmA[s], pa, (uint64_t)M, (uint64_t)K, (uint64_t)a.lda, a_slabs, ea.swz) : CAPDEC_ERR_UNSUPPORTED;
-      if (rc) { p.a_3d = 0; rc = make_map(&p.tmA[s], pa, (uint64_t)M, (uint64_t)K, (uint64_t)a.lda, 32, kBlockK, ea.swz); }
+      rc = p.a_3d ? make_map_mn3d(&p.tmA, pa, (uint64_t)M, (uint64_t)K, (uint64_t)a.lda, a_slabs, ea.swz) : CAPDEC_ERR_UNSUPPORTED;
+      if (rc) { p.a_3d = 0; rc = make_map(&p.tmA, pa, (uint64_t)M, (uint64_t)K, (uint64_t)a.lda, 32, kBlockK, ea.swz); }
     }
     if (rc) return rc;
-    if (!a.b_major) rc = make_map(&p.tmB[s], pb, (uint64_t)K, (uint64_t)N, (uint64_t)a.ldb, kBlockK, b_rows, eb.swz);
+    if (!a.b_major) rc = make_map(&p.tmB, pb, (uint64_t)K, (uint64_t)N, (uint64_t)a.ldb, kBlockK, b_rows, eb.swz);
     else {
-      rc = p.b_3d ? make_map_mn3d(&p.tmB[s], pb, (uint64_t)N, (uint64_t)K, (uint64_t)a.ldb, b_slabs, eb.swz) : CAPDEC_ERR_UNSUPPORTED;
-      if (rc) { p.b_3d = 0; rc = make_map(&p.tmB[s], pb, (uint64_t)N, (uint64_t)K, (uint64_t)a.ldb, 32, kBlockK, eb.swz); }
+      rc = p.b_3d ? make_map_mn3d(&p.tmB, pb, (uint64_t)N, (uint64_t)K, (uint64_t)a.ldb, b_slabs, eb.swz) : CAPDEC_ERR_UNSUPPORTED;
+      if (rc) { p.b_3d = 0; rc = make_map(&p.tmB, pb, (uint64_t)N, (uint64_t)K, (uint64_t)a.ldb, 32, kBlockK, eb.swz); }
     }
     if (rc) return rc;
   }
@@ -916,15 +1026,17 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   if (mode == 0) {
     const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-    gemm_tf32_kernel<0><<<grid, kThreads, smem_bytes, stream>>>(p);
+    if (split3) gemm_tf32_kernel<0, true><<<grid, kSplitThreads, smem_bytes, stream>>>(p);
+    else gemm_tf32_kernel<0, false><<<grid, kThreads, smem_bytes, stream>>>(p);
   } else if (mode == 1) {
-    rc = launch_clustered<1>(p, 2, total_tiles, smem_bytes, stream);
+    rc = split3 ? launch_clustered<1, true>(p, 2, total_tiles, smem_bytes, stream)
+                : launch_clustered<1, false>(p, 2, total_tiles, smem_bytes, stream);
     if (rc) return rc;
   } else if (mode == 2) {
-    rc = launch_clustered<2>(p, 4, total_tiles, smem_bytes, stream);
+    rc = launch_clustered<2, false>(p, 4, total_tiles, smem_bytes, stream);
     if (rc) return rc;
   } else {
-    rc = launch_clustered<3>(p, 4, total_tiles, smem_bytes, stream);
+    rc = launch_clustered<3, false>(p, 4, total_tiles, smem_bytes, stream);
     if (rc) return rc;
   }
   g_launches.fetch_add(1);
@@ -980,7 +1092,7 @@ static int tune_and_launch(const GemmArgs& a, int block_n, int split_k, const Ge
     add(0, 256); add(0, 128); add(0, 64);
   } else {
     add(1, 256); add(1, 192); add(1, 128);
-    if (a.M > 2 * kBlockM || a.N > 256) { add(3, 256); add(3, 192); }
+    if (!a.precision && (a.M > 2 * kBlockM || a.N > 256)) { add(3, 256); add(3, 192); }
   }
   cudaEvent_t e0, e1;
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaGetLastError(); return launch_plan(a, base, stream); }
@@ -1048,19 +1160,23 @@ static int gemm_entry(const float* A, int a_major, int64_t lda, const float* B, 
   CAPDEC_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0, "gemm: leading dims must be multiples of 4 (16 B TMA pitch): lda=%lld ldb=%lld ldc=%lld", (long long)lda, (long long)ldb, (long long)ldc);
   CAPDEC_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0, "gemm: operands must be 16-byte aligned");
   CAPDEC_REQUIRE(lda >= (a_major ? M : K) && ldb >= (b_major ? N : K) && ldc >= N, "gemm: leading dim smaller than extent");
-  CAPDEC_REQUIRE(precision == 0 || (a_lo && b_lo), "gemm: 3xTF32 needs a_lo and b_lo");
+  CAPDEC_REQUIRE(precision == 0 || precision == 1, "gemm: precision must be 0 (1xTF32) or 1 (3xTF32, split in the pipeline)");
+  (void)a_lo; (void)b_lo;   // kept in the signature for ABI stability: the hi/lo split happens inside the kernel
   CAPDEC_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 192 || block_n == 256, "gemm: block_n must be 0/64/128/192/256");
   CAPDEC_REQUIRE(act >= 0 && act <= 4, "gemm: bad act %d", act);
   CAPDEC_REQUIRE(!aux || ((uintptr_t)aux % 16) == 0, "gemm: aux must be 16-byte aligned");
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  static std::atomic<bool> attr_set_dev[kMaxDevices];   // cudaFuncSetAttribute is per device
+  std::atomic<bool>& attr_set = attr_set_dev[current_device()];
+  if (!attr_set.load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm_tf32_kernel)");
-    attr_set = true;
+    attr_set.store(true, std::memory_order_release);
   }
 
   GemmArgs a;
@@ -1104,11 +1220,19 @@ extern "C" int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, con
 
 // C = (A . B^T) * act'(mul_in), colsum[n] += sum_m C[m,n]: the dgrad GEMM that feeds an activation's backward, with the
 // bias gradient of the layer below fused (HF:modeling_gpt2.py:238-243 c_fc -> gelu_new; train.py:106-118 tanh; :121 relu)
+extern "C" int capdec_gemm_tf32_mul_ex(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
+                                       float* C, int64_t ldc, int M, int N, int K, const float* mul_in, int mul_act,
+                                       float* colsum, int block_n, const int32_t* m_limit_dev, int precision,
+                                       capdec_stream_t stream_) {
+  CAPDEC_REQUIRE(mul_in && mul_act >= 1 && mul_act <= 4, "gemm_mul: bad epilogue input");
+  CAPDEC_REQUIRE(((uintptr_t)mul_in % 16) == 0, "gemm_mul: mul_in must be 16-byte aligned");
+  return gemm_entry(A, a_major, lda, B, b_major, ldb, C, ldc, M, N, K, nullptr, 0, nullptr, 0, precision, nullptr, nullptr,
+                    block_n, 1, m_limit_dev, nullptr, mul_in, mul_act, colsum, reinterpret_cast<cudaStream_t>(stream_));
+}
+
 extern "C" int capdec_gemm_tf32_mul(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb,
                                     float* C, int64_t ldc, int M, int N, int K, const float* mul_in, int mul_act,
                                     float* colsum, int block_n, const int32_t* m_limit_dev, capdec_stream_t stream_) {
-  CAPDEC_REQUIRE(mul_in && mul_act >= 1 && mul_act <= 4, "gemm_mul: bad epilogue input");
-  CAPDEC_REQUIRE(((uintptr_t)mul_in % 16) == 0, "gemm_mul: mul_in must be 16-byte aligned");
-  return gemm_entry(A, a_major, lda, B, b_major, ldb, C, ldc, M, N, K, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, block_n, 1,
-                    m_limit_dev, nullptr, mul_in, mul_act, colsum, reinterpret_cast<cudaStream_t>(stream_));
+  return capdec_gemm_tf32_mul_ex(A, a_major, lda, B, b_major, ldb, C, ldc, M, N, K, mul_in, mul_act, colsum, block_n,
+                                 m_limit_dev, 0, stream_);
 }

@@ -404,9 +404,9 @@ class Engine:
             ops.linear_fwd(a.ctx[l], p[pre + "attn.c_proj.weight"], "conv1d", p[pre + "attn.c_proj.bias"], a.y, rows=R)
             ops.add_ln_fwd(a.h[l], a.y, a.h1[l], a.x2[l], a.st2[l], p[pre + "ln_2.weight"], p[pre + "ln_2.bias"],
                            eps=self.cfg.layer_norm_epsilon, p_drop=p_res, seed=self.seed, stream_id=_site(l, 1), rows=R)
-            # tf32 mode: a.u holds gelu_new'(pre-activation) (one MUFU.TANH serves both), parity modes: the pre-activation
+            # tcgen05 modes: a.u holds gelu_new'(pre-activation) (one tanh serves both), fp32 verification mode: the pre-activation
             ops.linear_fwd(a.x2[l], p[pre + "mlp.c_fc.weight"], "conv1d", p[pre + "mlp.c_fc.bias"], a.g[l],
-                           act=ops.ACT_GELU_NEW_D if ops.get_precision() == "tf32" else ops.ACT_GELU_NEW, aux=a.u[l], rows=R)
+                           act=ops.ACT_GELU_NEW_D if ops.is_tc() else ops.ACT_GELU_NEW, aux=a.u[l], rows=R)
             ops.linear_fwd(a.g[l], p[pre + "mlp.c_proj.weight"], "conv1d", p[pre + "mlp.c_proj.bias"], a.y, rows=R)
             if l + 1 < self.nl:
                 nx = f"gpt.transformer.h.{l + 1}."
@@ -469,7 +469,7 @@ class Engine:
             e_cproj = wgrad(a.g[l], dy2, pre + "mlp.c_proj.weight")
             wait(e_fc)                                       # layer l+1's c_fc weight gradient still reads a.dF
             ops.linear_dgrad_act(dy2, p[pre + "mlp.c_proj.weight"], "conv1d", a.dF, a.u[l],
-                                 ops.ACT_GELU_NEW_D if ops.get_precision() == "tf32" else ops.ACT_GELU_NEW,
+                                 ops.ACT_GELU_NEW_D if ops.is_tc() else ops.ACT_GELU_NEW,
                                  dbias=gw(pre + "mlp.c_fc.bias"), rows=R)
             e_fc = wgrad(a.x2[l], a.dF, pre + "mlp.c_fc.weight")
             ops.linear_dgrad(a.dF, p[pre + "mlp.c_fc.weight"], "conv1d", a.dx, rows=R)
@@ -550,7 +550,7 @@ class Engine:
             train_gpt = self.m.gpt_trainable()
         fl = self.flat
         B, L = tokens.shape
-        fast = ops.get_precision() == "tf32"
+        fast = ops.is_tc()
         use_packed = fast and self.packed
         ops.set_row_hint(self.hint_rows if use_packed else 0)
         a = self.forward_hidden(tokens, prefix, packed=use_packed)
@@ -602,7 +602,7 @@ class Engine:
         stats[0] <- number of non-ignored targets, stats[1] <- sum of their token losses (fp32 device tensor, >= 2).
         Dropout follows the modules' train/eval flags exactly like the training path."""
         B, L = tokens.shape
-        fast = ops.get_precision() == "tf32"
+        fast = ops.is_tc()
         use_packed = fast and self.packed
         ops.set_row_hint(self.hint_rows if use_packed else 0)
         a = self.forward_hidden(tokens, prefix, packed=use_packed)

@@ -52,16 +52,10 @@ def _rowmajor(t: torch.Tensor, name: str) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
-def _split(t: torch.Tensor):
-    """hi/lo TF32 split of a 2-D operand into fresh zero-padded buffers with a 16-byte-aligned pitch."""
-    rows, cols = t.shape
-    ld = (cols + 3) // 4 * 4
-    src = torch.zeros(rows, ld, device=t.device, dtype=torch.float32)
-    src[:, :cols].copy_(t)
-    hi, lo = torch.empty_like(src), torch.empty_like(src)
-    _lib.check(_lib.load().capdec_split_tf32(src.data_ptr(), hi.data_ptr(), lo.data_ptr(), src.numel(), _stream()),
-               "split_tf32")
-    return hi[:, :cols], lo[:, :cols]
+def is_tc() -> bool:
+    """True in the tensor-core modes ("tf32" and the fp32-grade "tf32x3"): fused epilogues, packed rows, device row limits
+    and the mma.sync attention are available; "fp32" is the CUDA-core verification mode."""
+    return _PRECISION in ("tf32", "tf32x3")
 
 
 def gemm(A: torch.Tensor, a_major: int, B: torch.Tensor, b_major: int, C: torch.Tensor, M: int, N: int, K: int, *,
@@ -70,7 +64,7 @@ def gemm(A: torch.Tensor, a_major: int, B: torch.Tensor, b_major: int, C: torch.
          m_limit: Optional[torch.Tensor] = None, k_limit: Optional[torch.Tensor] = None) -> None:
     """C[M,N] (+)= act(A . B^T + bias).  a_major/b_major: 0 = stored [M|N, K], 1 = stored [K, M|N].
     m_limit / k_limit: optional int32 device scalars bounding the rows computed / the reduction length at run time
-    (tcgen05 path only; the fp32 / 3xTF32 parity modes compute the full static extent, which is equivalent as long as
+    (tcgen05 modes; the CUDA-core fp32 verification mode computes the full static extent, which is equivalent as long as
     the caller keeps the skipped region's contribution at zero)."""
     lib = _lib.load()
     lda, ldb, ldc = _rowmajor(A, "A"), _rowmajor(B, "B"), _rowmajor(C, "C")
@@ -89,16 +83,10 @@ def gemm(A: torch.Tensor, a_major: int, B: torch.Tensor, b_major: int, C: torch.
                                        K, _ptr(bias), act, _ptr(aux), int(accumulate), _stream())
         _lib.check(rc, "gemm_fp32_simt")
         return
-    if mode == "tf32x3":
-        ah, al = _split(A)
-        bh, bl = _split(B)
-        rc = lib.capdec_gemm_tf32(ah.data_ptr(), a_major, ah.stride(0), bh.data_ptr(), b_major, bh.stride(0),
-                                  C.data_ptr(), ldc, M, N, K, _ptr(bias), act, _ptr(aux), int(accumulate), 1,
-                                  al.data_ptr(), bl.data_ptr(), block_n, split_k, _stream())
-    else:
-        rc = lib.capdec_gemm_tf32_ex(A.data_ptr(), a_major, lda, B.data_ptr(), b_major, ldb, C.data_ptr(), ldc, M, N, K,
-                                     _ptr(bias), act, _ptr(aux), int(accumulate), 0, None, None, block_n, split_k,
-                                     _ptr(m_limit), _ptr(k_limit), _stream())
+    # "tf32x3": same kernel family, operands split into hi/lo TF32 parts inside the shared-memory pipeline
+    rc = lib.capdec_gemm_tf32_ex(A.data_ptr(), a_major, lda, B.data_ptr(), b_major, ldb, C.data_ptr(), ldc, M, N, K,
+                                 _ptr(bias), act, _ptr(aux), int(accumulate), 1 if mode == "tf32x3" else 0, None, None,
+                                 block_n, split_k, _ptr(m_limit), _ptr(k_limit), _stream())
     _lib.check(rc, "gemm_tf32")
 
 
@@ -114,20 +102,21 @@ def gemm_autotune(enable: int) -> int:
 
 def gemm_mul(A, a_major, B, b_major, C, M, N, K, mul_in, mul_act, colsum=None, block_n=0, m_limit=None):
     """C = (A . B^T) * act'(mul_in), colsum += column sums of C — dgrad + activation backward + bias gradient in one
-    tcgen05 launch (1xTF32 mode)."""
+    tcgen05 launch (1xTF32, or 3xTF32 with exact derivative arithmetic in the "tf32x3" mode)."""
     lda, ldb, ldc = _rowmajor(A, "A"), _rowmajor(B, "B"), _rowmajor(C, "C")
     if _rowmajor(mul_in, "mul_in") != ldc or tuple(mul_in.shape) != (M, N):
         raise ValueError("mul_in must have C's shape and leading dimension")
-    rc = _lib.load().capdec_gemm_tf32_mul(A.data_ptr(), a_major, lda, B.data_ptr(), b_major, ldb, C.data_ptr(), ldc, M, N,
-                                          K, mul_in.data_ptr(), mul_act, _ptr(colsum), block_n, _ptr(m_limit),
-                                          _stream())
+    rc = _lib.load().capdec_gemm_tf32_mul_ex(A.data_ptr(), a_major, lda, B.data_ptr(), b_major, ldb, C.data_ptr(), ldc, M,
+                                             N, K, mul_in.data_ptr(), mul_act, _ptr(colsum), block_n, _ptr(m_limit),
+                                             1 if _PRECISION == "tf32x3" else 0, _stream())
     _lib.check(rc, "gemm_tf32_mul")
 
 
 def linear_dgrad_act(dy, W, layout, dx, act_in, act, dbias=None, rows=None):
-    """dx = (dy . W^T) * act'(act_in) (+ dbias += colsum(dx)).  tf32: one fused launch; parity modes: dgrad then act_bwd.
-    `rows` (everywhere below): device int32 scalar with the live row count of a packed batch (tf32 mode only)."""
-    if _PRECISION == "tf32":
+    """dx = (dy . W^T) * act'(act_in) (+ dbias += colsum(dx)).  tcgen05 modes: one fused launch; fp32 verification mode:
+    dgrad then act_bwd.  `rows` (everywhere below): device int32 scalar with the live row count of a packed batch
+    (tcgen05 modes only)."""
+    if is_tc():
         M, K = dy.shape
         gemm_mul(dy, 0, W, 0 if layout == "conv1d" else 1, dx, M, dx.shape[1], K, act_in, act, dbias, m_limit=rows)
     else:
@@ -139,7 +128,7 @@ def linear_dgrad_act(dy, W, layout, dx, act_in, act, dbias=None, rows=None):
 # ---- layer helpers: `layout` is "conv1d" (HF Conv1D weight [in,out]) or "linear" (nn.Linear weight [out,in]) --------
 def _no_rows(rows):
     if rows is not None:
-        raise _lib.CapdecError("packed rows (device row limits) are implemented for the tf32 tcgen05 path only")
+        raise _lib.CapdecError("packed rows (device row limits) are implemented for the tcgen05 modes (tf32, tf32x3) only")
 
 
 def linear_fwd(x, W, layout, bias, out, act=ACT_NONE, aux=None, rows=None):
@@ -226,17 +215,19 @@ def add_ln_bwd(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma, dbeta, p_drop=0.
 
 
 def _use_tc(impl):
-    """attention implementation: 'tc' = mma.sync TF32 tensor-core kernel, 'ffma' = exact fp32 CUDA-core kernel;
-    default follows the GEMM precision mode (tf32 -> tc, fp32 / tf32x3 -> ffma)."""
+    """attention implementation: 'tc' = mma.sync tensor-core kernel (1xTF32 in the "tf32" mode, 3xTF32 split in registers
+    in the "tf32x3" mode), 'ffma' = exact fp32 CUDA-core kernel; default follows the precision mode (fp32 -> ffma)."""
     if impl is None:
-        return _PRECISION == "tf32"
+        return is_tc()
     return impl == "tc"
 
 
 def attention_fwd(q, k, v, ctx, lse, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale, causal,
                   key_len=None, p_drop=0.0, seed=None, stream_id=0, impl=None, cu_rows=None):
     if _use_tc(impl) or cu_rows is not None:
-        rc = _lib.load().capdec_attention_tc_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), _ptr(lse), B, H,
+        lib = _lib.load()
+        fn = lib.capdec_attention_tc_fwd_x3 if _PRECISION == "tf32x3" else lib.capdec_attention_tc_fwd
+        rc = fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), _ptr(lse), B, H,
                                                  T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, float(scale), int(causal),
                                                  _ptr(key_len), float(p_drop), _seed_ptr(seed, p_drop > 0), stream_id,
                                                  _ptr(cu_rows), _stream())
@@ -252,7 +243,9 @@ def attention_fwd(q, k, v, ctx, lse, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o
 def attention_bwd(q, k, v, ctx, dctx, lse, dq, dk, dv, B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts, scale,
                   causal, key_len=None, p_drop=0.0, seed=None, stream_id=0, dbias_qkv=None, impl=None, cu_rows=None):
     if _use_tc(impl) or cu_rows is not None:
-        rc = _lib.load().capdec_attention_tc_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), dctx.data_ptr(),
+        lib = _lib.load()
+        fn = lib.capdec_attention_tc_bwd_x3 if _PRECISION == "tf32x3" else lib.capdec_attention_tc_bwd
+        rc = fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), dctx.data_ptr(),
                                                  lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
                                                  _ptr(dbias_qkv), B, H, T, S, hd, q_bs, q_ts, kv_bs, kv_ts, o_bs, o_ts,
                                                  float(scale), int(causal), _ptr(key_len), float(p_drop),

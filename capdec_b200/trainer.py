@@ -178,7 +178,7 @@ class Trainer:
         `tokens_d` / `prefix_d`: one throw-away forward+backward with capdec_gemm_autotune on.  The measuring launches
         repeat every GEMM, so the gradients of that pass are garbage: they are discarded, and the step clock / RNG seed
         are restored.  Parameters and optimizer state are never touched.  CAPDEC_GEMM_AUTOTUNE=0 disables it."""
-        if os.environ.get("CAPDEC_GEMM_AUTOTUNE", "1") == "0" or ops.get_precision() != "tf32":
+        if os.environ.get("CAPDEC_GEMM_AUTOTUNE", "1") == "0" or not ops.is_tc():
             return 0
         keep = [t.clone() for t in (self.eng.seed, self.step_dev, self.lr_dev, self.t_dev)]
         ops.gemm_autotune(1)

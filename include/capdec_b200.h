@@ -38,8 +38,10 @@ int64_t capdec_launch_count(void);
  * lm_head (HF:modeling_gpt2.py:703-706) and all their autograd dgrad/wgrad products (train.py:351).
  *   a_major / b_major: 0 = K-major  (A stored [M,K] / B stored [N,K], K contiguous, leading dim = row pitch)
  *                      1 = MN-major (A stored [K,M] / B stored [K,N], M resp. N contiguous)
- *   precision: 0 = 1xTF32 (perf mode), 1 = 3xTF32 split (fp32-grade, A/B must then be the `hi` parts and a_lo/b_lo the `lo`
- *              parts produced by capdec_split_tf32)
+ *   precision: 0 = 1xTF32 (perf mode); 1 = 3xTF32 (fp32-grade): the fp32 operand tiles are split into
+ *              hi = RN_tf32(x), lo = x - hi INSIDE the kernel's shared-memory pipeline (converter warps) and every k-step
+ *              issues lo*hi + hi*lo + hi*hi into the same TMEM accumulator; operands are read from HBM once, epilogue
+ *              activations use exact tanhf.  a_lo / b_lo are ignored (kept for ABI stability; pass NULL).
  *   act: 0 none, 1 gelu_new (HF:activations.py:59-66), 2 tanh (train.py:106 MLP act), 3 relu (train.py:121),
  *        4 gelu_new with aux <- gelu_new'(pre-activation) instead of the pre-activation (feeds mul_act 4 below)
  *   aux: optional second output receiving the PRE-activation (needed by backward); ld = ldc
@@ -64,10 +66,14 @@ int capdec_gemm_tf32_ex(const float* A, int a_major, int64_t lda, const float* B
  * colsum[n] += sum_m C[m,n] (may be NULL).  mul_act: 4 = mul_in already holds the derivative (forward act 4),
  * 1 = gelu_new'(pre-activation u) (HF:activations.py:59-66),
  * 2 = tanh' = 1 - a^2 with a the activated output (train.py:106), 3 = relu mask from the activated output
- * (train.py:121).  mul_in shares C's leading dimension.  1xTF32 only (the parity modes use capdec_act_bwd). */
+ * (train.py:121).  mul_in shares C's leading dimension.  capdec_gemm_tf32_mul runs 1xTF32; the _ex form takes the
+ * `precision` of capdec_gemm_tf32 (1 = 3xTF32 with exact derivative arithmetic). */
 int capdec_gemm_tf32_mul(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb, float* C,
                          int64_t ldc, int M, int N, int K, const float* mul_in, int mul_act, float* colsum,
                          int block_n, const int32_t* m_limit_dev, capdec_stream_t stream);
+int capdec_gemm_tf32_mul_ex(const float* A, int a_major, int64_t lda, const float* B, int b_major, int64_t ldb, float* C,
+                            int64_t ldc, int M, int N, int K, const float* mul_in, int mul_act, float* colsum,
+                            int block_n, const int32_t* m_limit_dev, int precision, capdec_stream_t stream);
 
 /* debug/bring-up override of the UMMA shared-memory descriptor encoding for MN-major operands
  * (layout_type, LBO bytes, SBO bytes, TMA swizzle enum); pass -1 to keep the default. Not used in production. */
@@ -98,7 +104,8 @@ int capdec_gemm_fp32_simt(const float* A, int a_major, int64_t lda, const float*
                           float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, float* aux,
                           int accumulate, capdec_stream_t stream);
 
-/* hi = RN_tf32(x), lo = RN_tf32(x - hi) (both exact TF32 values).  n % 4 == 0. */
+/* hi = RN_tf32(x), lo = RN_tf32(x - hi) (both exact TF32 values).  n % 4 == 0.  Stand-alone restatement of the split the
+ * 3xTF32 GEMM performs in shared memory (test / analysis helper; the GEMM no longer needs pre-split operands). */
 int capdec_split_tf32(const float* x, float* hi, float* lo, int64_t n, capdec_stream_t stream);
 
 /* ---- noise injection: train.py:27-39 (+ :18-24 uniform-ball variant) ---------------------------------------------
@@ -172,6 +179,18 @@ int capdec_attention_tc_bwd(const float* q, const float* k, const float* v, cons
                             const uint64_t* seed_dev, uint32_t stream_id, const int32_t* cu_rows, capdec_stream_t stream);
 /* cu_rows (may be NULL): packed rows — caption b owns rows [cu_rows[b], cu_rows[b+1]) of q/k/v/ctx (causal
  * self-attention, T = S = that count <= the T argument, which stays the pitch of lse and of the dropout counters). */
+/* fp32-grade variants of the two above for the 3xTF32 mode: every MMA fragment is split into hi = RN_tf32(x) and
+ * lo = x - hi in registers and accumulated as lo*hi + hi*lo + hi*hi; expf / logf instead of the MUFU approximations.
+ * Same contract, same dropout mapping, packed rows included. */
+int capdec_attention_tc_fwd_x3(const float* q, const float* k, const float* v, float* ctx, float* lse, int B, int H, int T,
+                               int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs,
+                               int64_t o_ts, float scale, int causal, const int32_t* key_len, float p_drop,
+                               const uint64_t* seed_dev, uint32_t stream_id, const int32_t* cu_rows, capdec_stream_t stream);
+int capdec_attention_tc_bwd_x3(const float* q, const float* k, const float* v, const float* ctx, const float* dctx,
+                               const float* lse, float* dq, float* dk, float* dv, float* dbias_qkv, int B, int H, int T,
+                               int S, int hd, int64_t q_bs, int64_t q_ts, int64_t kv_bs, int64_t kv_ts, int64_t o_bs,
+                               int64_t o_ts, float scale, int causal, const int32_t* key_len, float p_drop,
+                               const uint64_t* seed_dev, uint32_t stream_id, const int32_t* cu_rows, capdec_stream_t stream);
 
 /* ---- masked cross entropy: train.py:349-350 (nnf.cross_entropy(..., ignore_index=0), mean over targets != 0) -----
  * logits [rows, ld] (ld >= V, padded pitch), targets int64 [rows].  loss_sum/n_valid are device scalars (float);

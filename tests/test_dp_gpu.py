@@ -78,8 +78,6 @@ def test_two_gpu_data_parallel_matches_single_gpu(tmp_path):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.skipif(os.environ.get("CAPDEC_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="opt-in: the segmented-graph overlap (CAPDEC_DP_OVERLAP=2) has not been validated on hardware yet")
 def test_two_gpu_segmented_graph_overlap_matches_single_gpu(tmp_path, monkeypatch):
     """Per-block all-reduce issued eagerly between the 13 graph segments of the step (trainer._capture_segments)."""
     monkeypatch.setenv("CAPDEC_DP_OVERLAP", "2")

@@ -1,8 +1,7 @@
 """capdec_b200.fit.train on the GPU with the real Trainer / DeviceCaptionDataset: the loop must produce exactly what the
 same sequence of Trainer.step_from calls produces by hand (same shuffling seed -> identical parameters), write the
 reference's checkpoint layout, and report the validation loss of Trainer.evaluate_any for a validation set whose
-max_seq_len differs from the training one.
-Opt-in (CAPDEC_TEST_EXPERIMENTAL=1): written after this round's GPU budget was spent, so it has not run on hardware yet."""
+max_seq_len differs from the training one."""
 import json
 import os
 from types import SimpleNamespace
@@ -10,9 +9,7 @@ from types import SimpleNamespace
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CAPDEC_TEST_EXPERIMENTAL", "0") != "1",
-                                 reason="opt-in: not yet validated on hardware")]
+pytestmark = pytest.mark.gpu
 
 from oracle import capdec_oracle as O  # noqa: E402  (fixture generator / checker only)
 

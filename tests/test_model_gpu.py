@@ -55,11 +55,8 @@ def rel_l2(a, b):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32x3", "tf32"])
-@pytest.mark.parametrize("case", ["mlp_full_b4", "mlp_prefix_only_b4", "transformer_full_b2", "mlp_full_d640_b3"] + [
-    # pinned on the reference after the round-1 GPU budget was spent: opt-in until they have been through a GPU box
-    pytest.param(n, marks=pytest.mark.skipif(__import__("os").environ.get("CAPDEC_TEST_EXPERIMENTAL", "0") != "1",
-                                             reason="opt-in: not yet run on hardware"))
-    for n in ("transformer_prefix_only_b2", "transformer_short_clip_b3")])
+@pytest.mark.parametrize("case", ["mlp_full_b4", "mlp_prefix_only_b4", "transformer_full_b2", "mlp_full_d640_b3",
+                                  "transformer_prefix_only_b2", "transformer_short_clip_b3"])
 def test_fast_path_loss_and_grads_match_oracle_and_golden(case, mode):
     import capdec_b200 as cb
     rec, c, sd, tokens, prefix, draw, model = build(case)
@@ -106,7 +103,7 @@ def test_fast_path_loss_and_grads_match_oracle_and_golden(case, mode):
         cb.ops.set_precision("tf32")
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "tf32"])
 @pytest.mark.parametrize("case", ["mlp_full_b4", "transformer_full_b2", "mlp_prefix_only_b4"])
 def test_drop_in_forward_backward_like_train_py(case, mode):
     """The reference's own lines train.py:348-351 executed against our classes: logits, loss and .grad."""
