@@ -321,28 +321,6 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
     nt = min(nt, (klen + 7) / 8);
     if (nt < 1) nt = 1;
     const int r0 = m0 + g, r1 = r0 + 8;
-    // D_i = dO_i . O_i over the head dim: the 4 lanes of a row group split the columns
-    float D0 = 0.f, D1 = 0.f;
-    {
-      const float* o0 = ctx + o_b + (size_t)r0 * o_ts + (size_t)h * HD;
-      const float* o1 = ctx + o_b + (size_t)r1 * o_ts + (size_t)h * HD;
-#pragma unroll
-      for (int c = 0; c < HD / 16; ++c) {
-        const int col = (c * 4 + t) * 4;
-        if (r0 < T) {
-          const float4 ov = *reinterpret_cast<const float4*>(o0 + col);
-          const float4 dv4 = *reinterpret_cast<const float4*>(sdO + (size_t)r0 * LQ + col);
-          D0 += ov.x * dv4.x + ov.y * dv4.y + ov.z * dv4.z + ov.w * dv4.w;
-        }
-        if (r1 < T) {
-          const float4 ov = *reinterpret_cast<const float4*>(o1 + col);
-          const float4 dv4 = *reinterpret_cast<const float4*>(sdO + (size_t)r1 * LQ + col);
-          D1 += ov.x * dv4.x + ov.y * dv4.y + ov.z * dv4.z + ov.w * dv4.w;
-        }
-      }
-      D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
-      D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
-    }
     const float l0 = (r0 < T) ? lse[(size_t)bh * TL + r0] : 0.f, l1 = (r1 < T) ? lse[(size_t)bh * TL + r1] : 0.f;
     const int lim0 = (r0 < T) ? min(klen, causal ? r0 + 1 + (S - T) : S) : 0;
     const int lim1 = (r1 < T) ? min(klen, causal ? r1 + 1 + (S - T) : S) : 0;
@@ -405,6 +383,23 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
         }
       }
     }
+    // ---- D_i = sum_j Pd_ij dP_ij: the row sum of softmax's backward exactly as autograd forms it, from the SAME P and dP
+    // that enter dS below.  (The flash-attention shortcut D_i = dO_i . O_i equals it only in exact arithmetic: with
+    // tensor-core products the two sides of dP_ij - D_i carry different rounding biases and their difference - the
+    // to_queries / c_attn query gradient - lost two digits, profiles/r2_attention_rowsum.md.)
+    float D0 = 0.f, D1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT_MAX; ++n) {
+      if (n < nt) {
+        const int c0 = n * 8 + 2 * t;
+        const float2 pd0 = *reinterpret_cast<const float2*>(sPd + (size_t)r0 * LS + c0);
+        const float2 pd1 = *reinterpret_cast<const float2*>(sPd + (size_t)r1 * LS + c0);
+        D0 += pd0.x * acc[n][0] + pd0.y * acc[n][1];
+        D1 += pd1.x * acc[n][2] + pd1.y * acc[n][3];
+      }
+    }
+    D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
+    D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
     // ---- dS = Pd * dP - P * D (each thread re-reads the P / Pd values it wrote), stored pre-multiplied by `scale` ----
 #pragma unroll
     for (int n = 0; n < NT_MAX; ++n) {
@@ -513,8 +508,8 @@ __global__ void __launch_bounds__(128) attention_tc_bwd_kernel(
 //   phase A  warp (wq, hh): query tile wq, key-tile PAIRS np with (np & 1) == hh for S / P / dP / dS (so each Philox call is
 //            still made exactly once), then - after a 64-thread named barrier - half of the head-dim columns of dQ = dS K;
 //   phase B  warp (wq, hh): key tile wq, hh == 0 -> dK = dS^T Q, hh == 1 -> dV = Pd^T dO.
-// Q / K / V / dO arrive by cp.async; D_i = dO_i . O_i and the LSE rows are fetched from global memory while those copies
-// are in flight, so phase A never waits on HBM.
+// Q / K / V / dO arrive by cp.async; the LSE rows are fetched from global memory while those copies are in flight.  `ctx`
+// is no longer read: D_i is the row sum of Pd * dP (see the 4-warp kernel), not dO_i . O_i.
 template <int HD, int NT_MAX, bool X3>
 __global__ void __launch_bounds__(256, X3 ? 1 : 2) attention_tc_bwd8_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ ctx,
@@ -543,8 +538,8 @@ __global__ void __launch_bounds__(256, X3 ? 1 : 2) attention_tc_bwd8_kernel(
   float* sdS = sdO + (size_t)Tp * LQ;       // [Tp][LS]: P, then dS * scale
   float* sPd = sdS + (size_t)Tp * LS;       // [Tp][LS]: dropout(P)
   float* sDb = sPd + (size_t)Tp * LS;       // [3][HD] bias-gradient partial sums
-  float* sD = sDb + 3 * HD;                 // [Tp] D_i = dO_i . O_i
-  float* sL = sD + Tp;                      // [Tp] log-sum-exp of row i
+  float* sD = sDb + 3 * HD;                 // [2][Tp] partial row sums of Pd * dP (one per warp of the tile's pair)
+  float* sL = sD + 2 * Tp;                  // [Tp] log-sum-exp of row i
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wq = warp & 3, hh = warp >> 2;
@@ -563,28 +558,8 @@ __global__ void __launch_bounds__(256, X3 ? 1 : 2) attention_tc_bwd8_kernel(
     cp_async16(sV + (size_t)r * LQ + 4 * c, v + gofs, ok);
   }
   for (int i = tid; i < 3 * HD; i += 256) sDb[i] = 0.f;
-  // D_i and LSE_i while the tile copies are in flight: 4 adjacent lanes split the head dim of one row
-  for (int idx = tid; idx < Tp * 4; idx += 256) {
-    const int row = idx >> 2, part = idx & 3;
-    float acc = 0.f;
-    if (row < T) {
-      const float* o_row = ctx + o_b + (size_t)row * o_ts + (size_t)h * HD;
-      const float* do_row = dctx + o_b + (size_t)row * o_ts + (size_t)h * HD;
-#pragma unroll
-      for (int c = 0; c < HD / 16; ++c) {
-        const int col = (c * 4 + part) * 4;
-        const float4 ov = *reinterpret_cast<const float4*>(o_row + col);
-        const float4 dv4 = *reinterpret_cast<const float4*>(do_row + col);
-        acc += ov.x * dv4.x + ov.y * dv4.y + ov.z * dv4.z + ov.w * dv4.w;
-      }
-    }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (part == 0) {
-      sD[row] = acc;
-      sL[row] = (row < T) ? lse[(size_t)bh * TL + row] : 0.f;
-    }
-  }
+  // LSE rows while the tile copies are in flight
+  for (int row = tid; row < Tp; row += 256) sL[row] = (row < T) ? lse[(size_t)bh * TL + row] : 0.f;
   const int klen = key_len ? min(S, (int)key_len[b]) : S;
   const int nt_all = Sp / 8;
   const float inv_keep = 1.0f / (1.0f - p_drop);
@@ -599,7 +574,6 @@ __global__ void __launch_bounds__(256, X3 ? 1 : 2) attention_tc_bwd8_kernel(
     nt = min(nt, (klen + 7) / 8);
     if (nt < 1) nt = 1;
     const int r0 = m0 + g, r1 = r0 + 8;
-    const float D0 = sD[r0], D1 = sD[r1];
     const float l0 = sL[r0], l1 = sL[r1];
     const int lim0 = (r0 < T) ? min(klen, causal ? r0 + 1 + (S - T) : S) : 0;
     const int lim1 = (r1 < T) ? min(klen, causal ? r1 + 1 + (S - T) : S) : 0;
@@ -667,6 +641,26 @@ __global__ void __launch_bounds__(256, X3 ? 1 : 2) attention_tc_bwd8_kernel(
         }
       }
     }
+    // ---- D_i = sum_j Pd_ij dP_ij over ALL key tiles of the row (see attention_tc_bwd_kernel): this warp's key tiles,
+    // then the partner warp's share through shared memory ----
+    float D0 = 0.f, D1 = 0.f;
+#pragma unroll
+    for (int lt = 0; lt < NL; ++lt) {
+      const int n = 4 * (lt >> 1) + 2 * hh + (lt & 1);
+      if (n < nt) {
+        const int c0 = n * 8 + 2 * t;
+        const float2 pd0 = *reinterpret_cast<const float2*>(sPd + (size_t)r0 * LS + c0);
+        const float2 pd1 = *reinterpret_cast<const float2*>(sPd + (size_t)r1 * LS + c0);
+        D0 += pd0.x * acc[lt][0] + pd0.y * acc[lt][1];
+        D1 += pd1.x * acc[lt][2] + pd1.y * acc[lt][3];
+      }
+    }
+    D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
+    D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
+    if (t == 0) { sD[hh * Tp + r0] = D0; sD[hh * Tp + r1] = D1; }
+    named_bar_sync(1 + wq, 64);   // both warps of the tile have published their partial row sums
+    D0 = sD[r0] + sD[Tp + r0];    // same order in both warps: bit-identical D
+    D1 = sD[r1] + sD[Tp + r1];
     // ---- dS = Pd * dP - P * D (each thread re-reads the P / Pd values it wrote), stored pre-multiplied by `scale` ----
 #pragma unroll
     for (int lt = 0; lt < NL; ++lt) {
@@ -769,7 +763,7 @@ size_t attn_tc_fwd_smem(int T, int S, int hd) {
 }
 size_t attn_tc_bwd_smem(int T, int S, int hd) {
   const int Tp = (T + 15) & ~15, Sp = (S + 15) & ~15;
-  return ((size_t)2 * Tp * (hd + 4) + (size_t)2 * Sp * (hd + 4) + (size_t)2 * Tp * (Sp + 4) + 3 * hd + 2 * Tp) * sizeof(float);
+  return ((size_t)2 * Tp * (hd + 4) + (size_t)2 * Sp * (hd + 4) + (size_t)2 * Tp * (Sp + 4) + 3 * hd + 3 * Tp) * sizeof(float);
 }
 
 template <int HD, int NT, bool X3>

@@ -636,7 +636,13 @@ class Engine:
             return None
         m = mask.reshape(mask.shape[0], -1)[:, :T] > 0
         klen = m.sum(dim=1).to(torch.int32)
-        # only right padding can be expressed as a key length (which is what ClipCocoDataset produces, train.py:55-63)
+        # only right padding can be expressed as a key length (which is what ClipCocoDataset produces, train.py:55-63);
+        # CAPDEC_CHECK_MASK=1 verifies it (one host sync per call, so it is off on the hot path)
+        if os.environ.get("CAPDEC_CHECK_MASK", "0") == "1":
+            want = torch.arange(m.shape[1], device=m.device)[None, :] < klen[:, None]
+            if not torch.equal(m, want):
+                raise CapdecError("attention mask is not right-padded: only masks of the form [1...1 0...0] "
+                                  "(ClipCocoDataset, train.py:55-63) are supported")
         return klen.contiguous()
 
     def _full_logits(self, a):
@@ -680,6 +686,13 @@ class _LogitsFn(torch.autograd.Function):
     def forward(ctx, eng: Engine, tokens, prefix, mask, *params):
         B, L = tokens.shape
         key_len = Engine._key_len(mask, eng.P + L)
+        # fresh Philox masks for every forward with dropout live (train.py:348 runs GPT-2 in train mode: p = 0.1 at 37
+        # sites); the seed this forward used is kept for ITS backward, whatever runs in between (validation, a second
+        # forward): backward regenerates the masks from it instead of storing them
+        ctx.seed = None
+        if any(p > 0.0 for p in eng._drop_p()):
+            ops.step_clock(seed=eng.seed)
+            ctx.seed = eng.seed.clone()
         a = eng.forward_hidden(tokens, prefix, key_len)
         lg = eng._full_logits(a)
         ctx.eng, ctx.arena, ctx.key_len = eng, a, key_len
@@ -698,6 +711,12 @@ class _LogitsFn(torch.autograd.Function):
         if train_gpt:
             ops.linear_wgrad(a.xf, dl, g["gpt.transformer.wte.weight"], "linear")
         ops.linear_dgrad(dl, p["gpt.transformer.wte.weight"], "linear", a.dx)
-        eng.backward_hidden(a, a.dx, train_gpt, ctx.key_len)
+        live_seed = eng.seed
+        if ctx.seed is not None:
+            eng.seed = ctx.seed            # the masks of THIS forward
+        try:
+            eng.backward_hidden(a, a.dx, train_gpt, ctx.key_len)
+        finally:
+            eng.seed = live_seed
         grads = [g[n].clone() for n in ctx.names]
         return (None, None, None, None, *grads)

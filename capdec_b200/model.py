@@ -256,6 +256,44 @@ class TransformerEncoderDecoder(nn.Module):
         return self._owner()._mapper_forward(x)
 
 
+def _pretrained_gpt2_state_dict(name: str = "gpt2"):
+    """`GPT2LMHeadModel.from_pretrained('gpt2')` exactly as the reference calls it (train.py:266, gpt2_prefix.py:162),
+    returned as a state_dict with the 4.24-era mask buffers dropped.  Raises whatever transformers raises (no local copy
+    while offline, transformers missing, ...)."""
+    from transformers import GPT2LMHeadModel   # the reference's own dependency; only its checkpoint loader is used
+    hf = GPT2LMHeadModel.from_pretrained(name)
+    sd = {k: v.detach().to(torch.float32) for k, v in hf.state_dict().items()
+          if not (k.endswith(".attn.bias") or k.endswith(".attn.masked_bias"))}
+    if "lm_head.weight" not in sd:
+        sd["lm_head.weight"] = sd["transformer.wte.weight"]
+    return sd
+
+
+_HF_MASK_BUFFERS = None
+
+
+def hf_expects_mask_buffers() -> bool:
+    """Does the INSTALLED transformers keep GPT-2's causal-mask buffers (`attn.bias`, `attn.masked_bias`) in state_dict?
+    transformers 4.24 - the reference's pin, requirments.txt:12 - does (persistent buffers), current releases do not.  The
+    reference loads checkpoints with a strict `model.load_state_dict(torch.load(...))` (predictions_runner.py:461), so
+    a checkpoint must carry exactly the keys the environment's own GPT2LMHeadModel has.  Probed once on a tiny model;
+    CAPDEC_CKPT_MASK_BUFFERS=1/0 overrides."""
+    global _HF_MASK_BUFFERS
+    import os
+    env = os.environ.get("CAPDEC_CKPT_MASK_BUFFERS")
+    if env in ("0", "1"):
+        return env == "1"
+    if _HF_MASK_BUFFERS is None:
+        try:
+            import transformers
+            tiny = transformers.GPT2LMHeadModel(transformers.GPT2Config(n_layer=1, n_embd=8, n_head=1, vocab_size=8,
+                                                                        n_positions=8))
+            _HF_MASK_BUFFERS = "transformer.h.0.attn.bias" in tiny.state_dict()
+        except Exception:
+            _HF_MASK_BUFFERS = False
+    return _HF_MASK_BUFFERS
+
+
 class _Output(SimpleNamespace):
     """Stand-in for transformers' CausalLMOutput: `.logits`, `.loss`."""
 
@@ -265,7 +303,11 @@ class ClipCaptionModel(nn.Module):
 
     def __init__(self, prefix_length: int, clip_length: Optional[int] = None, prefix_size: int = 512,
                  num_layers: int = 8, mapping_type: MappingType = MappingType.MLP, prefix_dim: Optional[int] = None,
-                 gpt_config: Optional[GPT2Config] = None):
+                 gpt_config: Optional[GPT2Config] = None, pretrained: Optional[bool] = None):
+        """`gpt_config=None` (the reference's call, train.py:262-273): GPT-2 starts from the pretrained 'gpt2' checkpoint
+        like `GPT2LMHeadModel.from_pretrained('gpt2')` (train.py:266); if that checkpoint cannot be loaded (offline, no
+        cache) the model falls back to HF-style random init AND SAYS SO on stderr.  Passing a `gpt_config` (tests, the
+        synthetic benchmark) or `pretrained=False` asks for a randomly initialised GPT-2 of that architecture explicitly."""
         super().__init__()
         import weakref
         if prefix_dim is not None:
@@ -273,7 +315,20 @@ class ClipCaptionModel(nn.Module):
         self.prefix_length = prefix_length
         self.prefix_size = prefix_size
         self.mapping_type = MappingType.parse(mapping_type)
+        if pretrained is None:
+            pretrained = gpt_config is None and __import__("os").environ.get("CAPDEC_GPT2_PRETRAINED", "1") != "0"
         self.gpt = GPT2LMHead(gpt_config)
+        self.gpt_init = "random (HF-style init, requested)"
+        if pretrained:
+            try:
+                self.gpt.load_state_dict(_pretrained_gpt2_state_dict("gpt2"), strict=True)
+                self.gpt_init = "pretrained 'gpt2' (GPT2LMHeadModel.from_pretrained)"
+            except Exception as ex:   # offline box / empty cache: keep running, but never silently
+                import sys
+                self.gpt_init = "random (HF-style init): pretrained 'gpt2' unavailable"
+                print(f"capdec_b200: WARNING - GPT2LMHeadModel.from_pretrained('gpt2') failed ({type(ex).__name__}: "
+                      f"{str(ex)[:160]}); GPT-2 starts from RANDOM weights. Load a checkpoint (--pretrain_weights / "
+                      f"load_state_dict) or make the 'gpt2' files available to train the reference's model.", file=sys.stderr)
         self.gpt_embedding_size = self.gpt.transformer.wte.weight.shape[1]
         d = self.gpt_embedding_size
         if self.mapping_type == MappingType.MLP:
@@ -375,14 +430,28 @@ class ClipCaptionModel(nn.Module):
               if not (k.endswith(".attn.bias") or k.endswith(".attn.masked_bias"))}
         return super().load_state_dict(sd, strict=strict, **kw)
 
-    def state_dict_hf424(self):
-        """state_dict plus the causal-mask buffers an unmodified transformers-4.24 strict loader expects."""
-        sd = self.state_dict()
-        n_pos = self.gpt.config.n_positions
-        for i in range(self.gpt.config.n_layer):
-            sd[f"gpt.transformer.h.{i}.attn.bias"] = torch.tril(torch.ones(n_pos, n_pos, dtype=torch.uint8)).view(1, 1, n_pos, n_pos)
-            sd[f"gpt.transformer.h.{i}.attn.masked_bias"] = torch.tensor(-1e4)
+    def state_dict(self, *args, **kw):
+        """The reference's checkpoint layout (train.py:359-371).  When the installed transformers keeps GPT-2's causal-mask
+        buffers in its state_dict (4.24, the reference's pin), they are emitted too, so that `torch.save(model.state_dict())`
+        - in the reference's own train() or in capdec_b200.fit.train - loads with strict=True in that environment."""
+        sd = super().state_dict(*args, **kw)
+        if hf_expects_mask_buffers():
+            self._add_mask_buffers(sd, kw.get("prefix", args[1] if len(args) > 1 else ""))
         return sd
+
+    def _add_mask_buffers(self, sd, prefix=""):
+        n_pos = self.gpt.config.n_positions
+        tril = torch.tril(torch.ones(n_pos, n_pos, dtype=torch.uint8)).view(1, 1, n_pos, n_pos)
+        for i in range(self.gpt.config.n_layer):
+            sd[f"{prefix}gpt.transformer.h.{i}.attn.bias"] = tril       # shared storage: HF never writes to it
+            sd[f"{prefix}gpt.transformer.h.{i}.attn.masked_bias"] = torch.tensor(-1e4)
+        return sd
+
+    def state_dict_hf424(self):
+        """state_dict plus the causal-mask buffers an unmodified transformers-4.24 strict loader expects, whatever
+        transformers is installed here."""
+        sd = nn.Module.state_dict(self)
+        return self._add_mask_buffers(sd)
 
 
 class ClipCaptionPrefix(ClipCaptionModel):

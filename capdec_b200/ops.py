@@ -4,6 +4,7 @@ pointers of caller-owned tensors to a hand-written sm_100a kernel on torch's cur
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -217,6 +218,8 @@ def add_ln_bwd(dx, r, stats, gamma, dh_res, dh_out, dy, dgamma, dbeta, p_drop=0.
 def _use_tc(impl):
     """attention implementation: 'tc' = mma.sync tensor-core kernel (1xTF32 in the "tf32" mode, 3xTF32 split in registers
     in the "tf32x3" mode), 'ffma' = exact fp32 CUDA-core kernel; default follows the precision mode (fp32 -> ffma)."""
+    if impl is None:
+        impl = os.environ.get("CAPDEC_ATTN_IMPL")   # bring-up / bisection switch: "ffma" or "tc" for every un-packed call
     if impl is None:
         return is_tc()
     return impl == "tc"

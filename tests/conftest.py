@@ -4,6 +4,10 @@ from pathlib import Path
 
 import pytest
 
+# the test-suite builds seeded random-weight models; no attempt to fetch the pretrained 'gpt2' checkpoint (there is no
+# network here or on the GPU box).  tests/test_pretrained_cpu.py switches it back on around a fake `from_pretrained`.
+os.environ.setdefault("CAPDEC_GPT2_PRETRAINED", "0")
+
 ROOT = Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))

@@ -81,3 +81,31 @@ print("bound")
     r = subprocess.run([sys.executable, "-c", code, str(ROOT / "launchers" / "run_predictions_b200.py"), str(REF)],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "bound" in r.stdout, r.stderr[-3000:]
+
+
+def test_checkpoint_loads_strictly_into_the_reference_class(tmp_path):
+    """A checkpoint written from our class (`torch.save(model.state_dict())`, as train.py:359-371 and capdec_b200.fit.train
+    do) loads with the reference's strict `model.load_state_dict(torch.load(...))` (train.py:457, predictions_runner.py:461)
+    into the reference's OWN ClipCaptionModel built on the installed transformers, and the weights arrive bit-exactly.
+    Run in a subprocess (the reference module needs the AdamW / from_pretrained / device shims of SURVEY §8c)."""
+    code = r"""
+import sys, torch, transformers
+sys.path.insert(0, sys.argv[3])
+import capdec_b200 as cb
+ours = cb.ClipCaptionModel(10, prefix_size=512, mapping_type=cb.MappingType.MLP, gpt_config=cb.GPT2Config())
+torch.save(ours.state_dict(), sys.argv[2])
+transformers.GPT2LMHeadModel.from_pretrained = staticmethod(lambda name, *a, **k: transformers.GPT2LMHeadModel(transformers.GPT2Config()))  # shim 2
+sys.path.insert(0, sys.argv[1])
+from transformers import GPT2Tokenizer, get_linear_schedule_with_warmup     # resolve the lazy attributes first
+sys.modules["transformers"].AdamW = torch.optim.AdamW        # shim 1 (the import at train.py:6): set right before the import
+import train
+ref = train.ClipCaptionModel(10, prefix_size=512, mapping_type=train.MappingType.MLP)
+ref.load_state_dict(torch.load(sys.argv[2], map_location="cpu"))            # strict, like the reference
+rsd = ref.state_dict()
+for k, v in ours.state_dict().items():
+    assert torch.equal(rsd[k], v), k
+print("strict-ok", len(rsd))
+"""
+    r = subprocess.run([sys.executable, "-c", code, str(REF), str(tmp_path / "ck.pt"), str(ROOT)], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "strict-ok" in r.stdout, r.stderr[-3000:]

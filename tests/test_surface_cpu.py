@@ -42,6 +42,27 @@ def test_state_dict_names_and_shapes_equal_the_reference_layout(kw):
         model.load_state_dict(old)
 
 
+def test_state_dict_follows_the_installed_transformers_mask_buffers(monkeypatch):
+    """transformers 4.24 (the reference's pin) keeps `attn.bias` / `attn.masked_bias` in GPT-2's state_dict and the
+    reference loads strictly: `state_dict()` emits them exactly when the environment's own GPT2LMHeadModel has them."""
+    import capdec_b200 as cb
+    m = cb.ClipCaptionModel(10, prefix_size=512)
+    monkeypatch.setenv("CAPDEC_CKPT_MASK_BUFFERS", "0")
+    plain = m.state_dict()
+    assert len(plain) == 153
+    monkeypatch.setenv("CAPDEC_CKPT_MASK_BUFFERS", "1")
+    old = m.state_dict()
+    assert len(old) == 153 + 24
+    assert old["gpt.transformer.h.11.attn.bias"].shape == (1, 1, 1024, 1024) and old["gpt.transformer.h.11.attn.bias"].dtype == torch.uint8
+    assert old["gpt.transformer.h.0.attn.bias"][0, 0, 5, :8].tolist() == [1, 1, 1, 1, 1, 1, 0, 0]      # causal (lower-triangular)
+    assert float(old["gpt.transformer.h.0.attn.masked_bias"]) == -1e4
+    m.load_state_dict(old)                                        # and accepted back (strict)
+    monkeypatch.delenv("CAPDEC_CKPT_MASK_BUFFERS")
+    import transformers
+    tiny = transformers.GPT2LMHeadModel(transformers.GPT2Config(n_layer=1, n_embd=8, n_head=1, vocab_size=8, n_positions=8))
+    assert cb.model.hf_expects_mask_buffers() == ("transformer.h.0.attn.bias" in tiny.state_dict())
+
+
 def test_prefix_only_model_trains_the_mapper_alone():
     """ClipCaptionPrefix (train.py:276-284): parameters() yields clip_project only; train() leaves GPT-2 in eval mode."""
     import capdec_b200 as cb
