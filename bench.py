@@ -120,56 +120,151 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of train.py:345-354 on the host cores (the reference is Python + torch; it cannot travel)
+# CPU arm: the reference's OWN classes (baseline/_ref/train.py, placed there unmodified by tools/install_ref.sh) running
+# train.py:345-354 on the host cores; the oracle port only when baseline/_ref is absent.
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_train_step_rate(sample_captions: int, steps: int, warmup: int):
+WORKLOADS = {
+    "c1": "C1: MLP mapper P=10, GPT-2 frozen (--only_prefix), bs=32, seq_len=40, noise_variance=0.016",
+    "c2": "C2: MLP mapper P=10 + GPT-2-small fine-tuned end-to-end, bs=256/GPU, seq_len=40, noise_variance=0.016, "
+          "dropout 0.1 live, HF-AdamW + warm-up schedule in the step",
+    "c3": "C3: TransformerMapper (8 layers, P=C=40) + GPT-2-small fine-tuned, bs=256/GPU, seq_len=40, dropout 0.1 live",
+    "c4": "C4: MLP mapper P=10 + GPT-2-small fine-tuned, bs=512/GPU, seq_len=40, dropout 0.1 live",
+}
+
+
+def bench_config(workload: str, world: int, extra=None):
+    """The `config` object both arms print (same keys, same strings: the driver compares them)."""
+    cfg = {"workload": WORKLOADS[workload], "global_batch": BS_PER_GPU * world, "seq_len": SEQ, "parallelism": f"dp{world}",
+           "captions": ("all 40 tokens long (--full_length)" if FULL_LENGTH else
+                        "length ~ U{8..40}, right-padded with id 0 (SURVEY §8d)")}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def cpu_threads():
     import torch
-    from oracle import capdec_oracle as O
     cores = min(os.cpu_count() or 1, int(os.environ.get("CAPDEC_CPU_THREADS", "32")))  # >32 threads oversubscribe this size
     torch.set_num_threads(cores)
-    sd = O.make_state_dict(seed=0, mapping_type="mlp", prefix_length=P_LEN, prefix_size=D_CLIP)
-    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "gpt.lm_head.weight"}
-    opt = O.HFAdamW(list(params.values()), lr=2e-5)
-    tokens, prefix = synth_batch(sample_captions, seed=7)
+    return cores
+
+
+def load_reference_train():
+    """Import the reference's train.py from baseline/_ref with the three environment shims of SURVEY §8c (none of them
+    touches a reference file): transformers >= 4.5x no longer exports AdamW (the HF-4.24 class is restated in the
+    oracle), `from_pretrained('gpt2')` has no network here (random init of the same architecture; transformers' stock
+    attention path), and the module-global `device` is cuda:0 (set to cpu).  Returns None when baseline/_ref is absent."""
+    ref_dir = ROOT / "baseline" / "_ref"
+    if not (ref_dir / "train.py").exists():
+        return None
+    import torch
+    from transformers import GPT2Config, GPT2LMHeadModel
+    from oracle import capdec_oracle as O
+    GPT2LMHeadModel.from_pretrained = staticmethod(lambda name, *a, **k: GPT2LMHeadModel(GPT2Config()))
+    sys.path.insert(0, str(ref_dir))
+    sys.modules.pop("train", None)
+    from transformers import GPT2Tokenizer, get_linear_schedule_with_warmup  # noqa: F401  (resolve the lazy attributes first)
+    sys.modules["transformers"].AdamW = O.HFAdamW      # must be set right before the import (train.py:6)
+    import train as ref_train
+    ref_train.device = torch.device("cpu")             # train.py:15 (used by noise_injection, :36)
+    return ref_train
+
+
+def make_cpu_stepper(workload: str, batch: int):
+    """-> (step(i) -> loss, kind, description).  kind "reference": the reference's classes and the literal statements of
+    train.py:345-354; kind "port": the oracle restatement of the same step."""
+    import torch
+    from torch.nn import functional as nnf
+    tokens, prefix = synth_batch(batch, seed=7)
+    only_prefix = workload == "c1"
+    transformer = workload == "c3"
+    ref = load_reference_train()
+    if ref is not None:
+        torch.manual_seed(0)
+        cls = ref.ClipCaptionPrefix if only_prefix else ref.ClipCaptionModel
+        if transformer:
+            model = cls(P_LEN, clip_length=40, prefix_size=D_CLIP, num_layers=8, mapping_type=ref.MappingType.Transformer)
+        else:
+            model = cls(P_LEN, prefix_size=D_CLIP, mapping_type=ref.MappingType.MLP)
+        model.train()
+        optimizer = ref.AdamW(model.parameters(), lr=2e-5)                                          # train.py:326
+        scheduler = ref.get_linear_schedule_with_warmup(optimizer, num_warmup_steps=5000, num_training_steps=100000)
+        mask = torch.cat((torch.ones(batch, P_LEN), (tokens > 0).float()), dim=1)                  # train.py:60-63
+        prefix_length = P_LEN
+
+        def step(_i):
+            # train.py:345-354, statement for statement (tokens / mask / prefix are already on the "device")
+            model.zero_grad()
+            pfx = ref.noise_injection(prefix, NOISE_VAR, modality_offset=None, uniform_noise=False, dont_norm=False)
+            outputs = model(tokens, pfx, mask)
+            logits = outputs.logits[:, prefix_length - 1: -1]
+            loss = nnf.cross_entropy(logits.reshape(-1, logits.shape[-1]), tokens.flatten(), ignore_index=0)
+            loss.backward()
+            optimizer.step()
+            scheduler.step()
+            optimizer.zero_grad()
+            return loss.item()
+
+        return step, "reference", "reference classes from baseline/_ref/train.py (unmodified) executing train.py:345-354 incl. HF-AdamW + schedule"
+    from oracle import capdec_oracle as O
+    sd = O.make_state_dict(seed=0, mapping_type="transformer" if transformer else "mlp", prefix_length=P_LEN,
+                           clip_length=40 if transformer else 10, prefix_size=D_CLIP)
+    train_keys = [k for k in sd if k != "gpt.lm_head.weight" and (not only_prefix or k.startswith("clip_project"))]
+    params = {k: (v.clone().requires_grad_(True) if k in train_keys else v.clone()) for k, v in sd.items() if k != "gpt.lm_head.weight"}
+    opt = O.HFAdamW([params[k] for k in train_keys], lr=2e-5)
     mask = O.make_mask(tokens, P_LEN)
 
-    def one(step):
+    def step(i):
         for g in opt.param_groups:
-            g["lr"] = O.linear_warmup_lr(2e-5, step, 5000, 100000)
+            g["lr"] = O.linear_warmup_lr(2e-5, i, 5000, 100000)
         opt.zero_grad()
         full = dict(params); full["gpt.lm_head.weight"] = full["gpt.transformer.wte.weight"]
         pfx = O.noise_injection(prefix, NOISE_VAR)
-        logits = O.clipcap_forward(full, tokens, pfx, mask, P_LEN, None, p_drop=0.1)
+        logits = O.clipcap_forward(full, tokens, pfx, mask, P_LEN, 40 if transformer else None, p_drop=0.0 if only_prefix else 0.1)
         loss = O.caption_loss(logits, tokens, P_LEN)
         loss.backward()
         opt.step()
         return float(loss.detach())
 
+    return step, "port", "oracle port of train.py:345-354 incl. HF-AdamW + schedule (baseline/_ref absent)"
+
+
+def cpu_train_step_rate(workload: str, batch: int, steps: int, warmup: int, budget_s: float = 0.0):
+    """Captions/s of the CPU arm.  budget_s > 0 bounds the timed region: after the warm-up steps have shown what a step
+    costs, at most floor(budget_s / step time) (>= 1) of the `steps` requested are timed."""
+    cores = cpu_threads()
+    step, kind, what = make_cpu_stepper(workload, batch)
+    t_w = time.perf_counter()
     for s in range(warmup):
-        one(s)
+        step(s)
+    per = (time.perf_counter() - t_w) / max(1, warmup)
+    n = steps
+    if budget_s > 0 and warmup > 0:
+        n = max(1, min(steps, int(budget_s / max(per, 1e-3))))
     t0 = time.perf_counter()
-    for s in range(steps):
-        one(warmup + s)
+    for s in range(n):
+        step(warmup + s)
     dt = time.perf_counter() - t0
-    return sample_captions * steps / dt, cores, dt / steps
+    return dict(rate=batch * n / dt, cores=cores, s_per_step=dt / n, steps=n, kind=kind, what=what, batch=batch)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # captions per CPU step: ~2.5 s/step on 16-32 host threads, so K steps stay within minutes (the contract test shrinks it)
-    sample = int(os.environ.get("CAPDEC_CPU_SAMPLE", "64"))
-    rate, cores, s_per_step = cpu_train_step_rate(sample, args.steps, args.warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "captions/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+    # the same configuration as our arm: one step = the per-GPU batch of BS_PER_GPU captions (~10 s on 32 host threads at
+    # bs 256), so the timed steps are bounded to a few minutes of CPU work; CAPDEC_CPU_SAMPLE shrinks the batch (contract test)
+    batch = int(os.environ.get("CAPDEC_CPU_SAMPLE", str(BS_PER_GPU)))
+    r = cpu_train_step_rate(args.workload, batch, args.steps, max(1, min(args.warmup, 1)),
+                            budget_s=float(os.environ.get("CAPDEC_CPU_BUDGET_S", "150")))
+    sample = (f"{r['steps']} timed steps of {r['batch']} captions after 1 warm-up step ({r['what']}; torch CPU fp32, "
+              f"{r['cores']} threads, {r['s_per_step']:.2f} s/step)")
+    line = {"impl": "reference", "metric": METRIC, "value": r["rate"], "unit": "captions/s", "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": 1, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: MLP mapper P=10 + GPT-2-small fine-tuned, seq_len=40, noise_variance=0.016, dropout 0.1",
-                       "global_batch": BS_PER_GPU * args.gpus, "parallelism": f"dp{args.gpus}"},
-            "cpu_baseline": {"value": rate, "unit": "captions/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} timed steps of {sample} captions each (oracle port of train.py:345-354, "
-                                       f"torch CPU fp32, {cores} threads)"},
-            "e2e": {"value": rate, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": bench_config(args.workload, args.gpus),
+            "cpu_baseline": {"value": r["rate"], "unit": "captions/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
+            "e2e": {"value": r["rate"], "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -215,12 +310,14 @@ def run_gpu(args):
     from capdec_b200 import _lib
     cb.ops.set_precision(args.precision)
     torch.manual_seed(0)
+    gcfg = cb.GPT2Config()         # explicit architecture = HF-style random init (no checkpoint files on the box), p_drop 0.1
     if args.workload == "c1":      # --only_prefix: GPT-2 frozen and in eval mode (train.py:276-284)
-        model = cb.ClipCaptionPrefix(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP)
+        model = cb.ClipCaptionPrefix(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP, gpt_config=gcfg)
     elif args.workload == "c3":    # --mapping_type transformer, prefix_length = prefix_length_clip = 40, 8 layers
-        model = cb.ClipCaptionModel(P_LEN, clip_length=40, prefix_size=D_CLIP, num_layers=8, mapping_type=cb.MappingType.Transformer)
+        model = cb.ClipCaptionModel(P_LEN, clip_length=40, prefix_size=D_CLIP, num_layers=8,
+                                    mapping_type=cb.MappingType.Transformer, gpt_config=gcfg)
     else:
-        model = cb.ClipCaptionModel(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP)   # HF-style random init
+        model = cb.ClipCaptionModel(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP, gpt_config=gcfg)
     model = model.to("cuda").train()                                                           # dropout p=0.1 live
     B = BS_PER_GPU
     tr = cb.Trainer(model, batch_size=B, seq_len=SEQ, lr=2e-5, warmup_steps=5000, total_steps=100000,
@@ -307,24 +404,19 @@ def run_gpu(args):
             except Exception as ex:   # reported, never fatal
                 full_len = {"error": repr(ex)[:300]}
         want_cpu = world == 1 and args.workload == "c2" and not NO_CPU
-        cpu_rate, cores, cpu_s = cpu_train_step_rate(64, 4, 1) if want_cpu else (None, None, None)
+        cpu = cpu_train_step_rate(args.workload, BS_PER_GPU, 2, 1) if want_cpu else None   # ~30 s of host work
         line = {
             "metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": {"c1": "C1: MLP mapper P=10, GPT-2 frozen (--only_prefix), bs=32, seq_len=40, noise_variance=0.016",
-                                    "c2": "C2: MLP mapper P=10 + GPT-2-small fine-tuned end-to-end, bs=256/GPU, seq_len=40, "
-                                          "noise_variance=0.016, dropout 0.1 live, HF-AdamW + warm-up schedule in the step",
-                                    "c3": "C3: TransformerMapper (8 layers, P=C=40) + GPT-2-small fine-tuned, bs=256/GPU, seq_len=40, dropout 0.1 live",
-                                    "c4": "C4: MLP mapper P=10 + GPT-2-small fine-tuned, bs=512/GPU, seq_len=40, dropout 0.1 live"}[args.workload],
-                       "global_batch": B * world, "seq_len": SEQ, "parallelism": f"dp{world}",
-                       "captions": ("all 40 tokens long (--full_length)" if FULL_LENGTH else
-                                    "length ~ U{8..40}, right-padded with id 0 (SURVEY §8d)"),
-                       "rows": (f"packed: {live_rows} of {dense_rows} trunk rows per step are live (padding and each caption's "
-                                "final token cannot reach the loss and are skipped; CAPDEC_PACKED=0 runs every row)"
-                                if packed else f"dense: all {dense_rows} trunk rows per step"),
-                       "l2": "working set per step (0.62 GB weights + 7.5 GB activations) >> 126 MB L2; 8 distinct host batches",
-                       "arithmetic": "fp32 storage, TF32 tcgen05 GEMMs with fp32 TMEM accumulation, fp32 everywhere else"},
+            "config": bench_config(args.workload, world, {
+                "rows": (f"packed: {live_rows} of {dense_rows} trunk rows per step are live (padding and each caption's "
+                         "final token cannot reach the loss and are skipped; CAPDEC_PACKED=0 runs every row)"
+                         if packed else f"dense: all {dense_rows} trunk rows per step"),
+                "l2": "working set per step (0.62 GB weights + 7.5 GB activations) >> 126 MB L2; 8 distinct host batches",
+                "arithmetic": ("fp32 storage, 3xTF32 tcgen05 GEMMs (hi/lo split in the pipeline) + 3xTF32 attention, fp32 elsewhere"
+                               if args.precision == "tf32x3" else
+                               "fp32 storage, TF32 tcgen05 GEMMs with fp32 TMEM accumulation, fp32 everywhere else")}),
             "e2e": {"value": e2e, "unit": "captions/s", "h2d_bytes_per_step": B * SEQ * 8 + B * D_CLIP * 4,
                     "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_per_step * args.steps),
@@ -342,9 +434,10 @@ def run_gpu(args):
         }
         if full_len is not None:
             line["full_length_captions"] = full_len
-        if cpu_rate is not None:
-            line["cpu_baseline"] = {"value": cpu_rate, "unit": "captions/s", "cores": cores, "kind": "port",
-                                    "sample": f"4 timed steps of 64 captions after 1 warm-up step (oracle port of train.py:345-354 incl. AdamW, torch CPU fp32, {cores} threads, {cpu_s:.2f} s/step)"}
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu["rate"], "unit": "captions/s", "cores": cpu["cores"], "kind": cpu["kind"],
+                                    "sample": f"{cpu['steps']} timed steps of {cpu['batch']} captions after 1 warm-up step "
+                                              f"({cpu['what']}; torch CPU fp32, {cpu['cores']} threads, {cpu['s_per_step']:.2f} s/step)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -411,7 +504,8 @@ def run_decode(args):
     from capdec_b200 import _lib
     cb.ops.set_precision("tf32")
     torch.manual_seed(0)
-    model = cb.ClipCaptionModel(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP).to("cuda").eval()
+    model = cb.ClipCaptionModel(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP,
+                                gpt_config=cb.GPT2Config()).to("cuda").eval()
     n_img = DECODE_IMAGES
     nb = 4
     host = []
