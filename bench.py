@@ -293,6 +293,44 @@ def qkv_gemm_roofline(cb, torch, iters=48):
     return 2.0 * M * N * K / (ms * 1e-3) / 1e12, ms
 
 
+def fp32_grade_leg(cb, torch, args, host, B, make_model):
+    """The same step in the fp32-grade arithmetic mode ("tf32x3": 3xTF32 tcgen05 GEMMs with the hi/lo split inside the
+    pipeline, 3xTF32 attention, exact tanh/exp) - the mode that meets the fp32 tolerances of tests/test_scale_parity_gpu.py:
+    its throughput, and the relative error of its loss against the CPU oracle (checker only) on the same weights / batch
+    (eval mode: no dropout, no noise - the oracle cannot reproduce Philox draws)."""
+    from oracle import capdec_oracle as O   # checker
+    cb.ops.set_precision("tf32x3")
+    try:
+        torch.manual_seed(0)
+        model = make_model().to("cuda").train()
+        tr = cb.Trainer(model, batch_size=B, seq_len=SEQ, lr=2e-5, warmup_steps=5000, total_steps=100000,
+                        noise_variance=NOISE_VAR, use_cuda_graph=True)
+        for i in range(max(3, args.warmup)):
+            tr.step(*host[i % len(host)])
+        tr.step(*host[0])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            tr.step_device()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        tokens, prefix = host[0]
+        loss_gpu = tr.evaluate(tokens, prefix)
+        sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items() if not k.endswith((".attn.bias", ".attn.masked_bias"))}
+        cpu_threads()
+        with torch.no_grad():
+            logits = O.clipcap_forward(sd, tokens, prefix, O.make_mask(tokens, P_LEN), P_LEN, 40 if args.workload == "c3" else None)
+            loss_ref = float(O.caption_loss(logits, tokens, P_LEN))
+        return {"value": B / (ms * 1e-3), "unit": "captions/s", "ms_per_step": ms, "dtype": "tf32x3",
+                "loss_rel_vs_oracle": abs(loss_gpu - loss_ref) / abs(loss_ref), "loss": loss_gpu, "loss_oracle": loss_ref,
+                "loss_check": f"eval-mode forward loss of one {B}-caption batch after the timed steps vs the CPU oracle on the same weights",
+                "tolerances": "tests/test_scale_parity_gpu.py: loss rel <= 2e-6, per-tensor grad rel-L2 <= 1e-4 (well-conditioned tensors) at C1/C2/C3 scale"}
+    finally:
+        cb.ops.set_precision(args.precision)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -310,15 +348,16 @@ def run_gpu(args):
     from capdec_b200 import _lib
     cb.ops.set_precision(args.precision)
     torch.manual_seed(0)
-    gcfg = cb.GPT2Config()         # explicit architecture = HF-style random init (no checkpoint files on the box), p_drop 0.1
-    if args.workload == "c1":      # --only_prefix: GPT-2 frozen and in eval mode (train.py:276-284)
-        model = cb.ClipCaptionPrefix(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP, gpt_config=gcfg)
-    elif args.workload == "c3":    # --mapping_type transformer, prefix_length = prefix_length_clip = 40, 8 layers
-        model = cb.ClipCaptionModel(P_LEN, clip_length=40, prefix_size=D_CLIP, num_layers=8,
-                                    mapping_type=cb.MappingType.Transformer, gpt_config=gcfg)
-    else:
-        model = cb.ClipCaptionModel(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP, gpt_config=gcfg)
-    model = model.to("cuda").train()                                                           # dropout p=0.1 live
+    def make_model():
+        gcfg = cb.GPT2Config()     # explicit architecture = HF-style random init (no checkpoint files on the box), p_drop 0.1
+        if args.workload == "c1":      # --only_prefix: GPT-2 frozen and in eval mode (train.py:276-284)
+            return cb.ClipCaptionPrefix(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP, gpt_config=gcfg)
+        if args.workload == "c3":      # --mapping_type transformer, prefix_length = prefix_length_clip = 40, 8 layers
+            return cb.ClipCaptionModel(P_LEN, clip_length=40, prefix_size=D_CLIP, num_layers=8,
+                                       mapping_type=cb.MappingType.Transformer, gpt_config=gcfg)
+        return cb.ClipCaptionModel(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP, gpt_config=gcfg)
+
+    model = make_model().to("cuda").train()                                                    # dropout p=0.1 live
     B = BS_PER_GPU
     tr = cb.Trainer(model, batch_size=B, seq_len=SEQ, lr=2e-5, warmup_steps=5000, total_steps=100000,
                     noise_variance=NOISE_VAR, use_cuda_graph=True)
@@ -403,6 +442,13 @@ def run_gpu(args):
                             "step_executed_tflops": fx / (ms_full * 1e-3) / 1e12}
             except Exception as ex:   # reported, never fatal
                 full_len = {"error": repr(ex)[:300]}
+        # ---- the fp32-grade arithmetic mode of the same step (N=1, default run only; never fatal) ----
+        fp32_grade = None
+        if world == 1 and args.precision == "tf32" and not FULL_LENGTH and os.environ.get("CAPDEC_BENCH_NO_X3", "0") != "1":
+            try:
+                fp32_grade = fp32_grade_leg(cb, torch, args, host, B, make_model)
+            except Exception as ex:
+                fp32_grade = {"error": repr(ex)[:300]}
         want_cpu = world == 1 and args.workload == "c2" and not NO_CPU
         cpu = cpu_train_step_rate(args.workload, BS_PER_GPU, 2, 1) if want_cpu else None   # ~30 s of host work
         line = {
@@ -434,6 +480,8 @@ def run_gpu(args):
         }
         if full_len is not None:
             line["full_length_captions"] = full_len
+        if fp32_grade is not None:
+            line["fp32_grade"] = fp32_grade
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu["rate"], "unit": "captions/s", "cores": cpu["cores"], "kind": cpu["kind"],
                                     "sample": f"{cpu['steps']} timed steps of {cpu['batch']} captions after 1 warm-up step "
