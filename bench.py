@@ -331,6 +331,41 @@ def fp32_grade_leg(cb, torch, args, host, B, make_model):
         cb.ops.set_precision(args.precision)
 
 
+def decode_leg(cb, torch, precision, steps=3, n_img=None):
+    """BASELINE config C5 as an extra key of the default line: batched beam-5 decode (predictions_runner.py path) in the
+    arithmetic mode whose token ids are IDENTICAL to the reference's generate_beam on every pinned case
+    (tests/test_decode_gpu.py: "tf32x3"); `python bench.py --workload c5 [--precision ...]` is the full C5 benchmark."""
+    n_img = n_img or DECODE_IMAGES
+    keep = cb.ops.get_precision()
+    cb.ops.set_precision(precision)
+    try:
+        torch.manual_seed(0)
+        model = cb.ClipCaptionModel(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP,
+                                    gpt_config=cb.GPT2Config()).to("cuda").eval()
+        g = torch.Generator().manual_seed(9000)
+        x = torch.randn(n_img, D_CLIP, generator=g)
+        x = (x / x.norm(2, -1, keepdim=True)).cuda()
+
+        def decode():
+            embed = model.clip_project(x).view(n_img, P_LEN, -1)
+            return cb.generate_beam_ids(model, embed, BEAM, ENTRY_LEN, 1.0, -1)
+
+        for _ in range(3):
+            decode()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            decode()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": n_img / (ms * 1e-3), "unit": "captions/s", "mode": precision, "ms_per_batch": ms,
+                "workload": DECODE_WORKLOAD % n_img, "ids": "identical to the reference's generate_beam on the pinned cases in this mode"}
+    finally:
+        cb.ops.set_precision(keep)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -449,6 +484,14 @@ def run_gpu(args):
                 fp32_grade = fp32_grade_leg(cb, torch, args, host, B, make_model)
             except Exception as ex:
                 fp32_grade = {"error": repr(ex)[:300]}
+        c5 = None
+        if fp32_grade is not None and args.workload == "c2":
+            try:
+                del tr, model            # free the train step's arena before the K/V cache (29 GB) is allocated
+                torch.cuda.empty_cache()
+                c5 = decode_leg(cb, torch, "tf32x3")
+            except Exception as ex:
+                c5 = {"error": repr(ex)[:300]}
         want_cpu = world == 1 and args.workload == "c2" and not NO_CPU
         cpu = cpu_train_step_rate(args.workload, BS_PER_GPU, 2, 1) if want_cpu else None   # ~30 s of host work
         line = {
@@ -482,6 +525,8 @@ def run_gpu(args):
             line["full_length_captions"] = full_len
         if fp32_grade is not None:
             line["fp32_grade"] = fp32_grade
+        if c5 is not None:
+            line["c5"] = c5
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu["rate"], "unit": "captions/s", "cores": cpu["cores"], "kind": cpu["kind"],
                                     "sample": f"{cpu['steps']} timed steps of {cpu['batch']} captions after 1 warm-up step "
@@ -550,7 +595,7 @@ def run_decode(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import capdec_b200 as cb
     from capdec_b200 import _lib
-    cb.ops.set_precision("tf32")
+    cb.ops.set_precision(args.precision)   # tf32x3: ids identical to the reference's; tf32: approximate (labelled in dtype)
     torch.manual_seed(0)
     model = cb.ClipCaptionModel(P_LEN, prefix_size=D_CLIP, mapping_type=cb.MappingType.MLP,
                                 gpt_config=cb.GPT2Config()).to("cuda").eval()
@@ -607,7 +652,7 @@ def run_decode(args):
         caps = n_img * world * args.steps
         line = {"metric": DECODE_METRIC, "value": caps / (ms_dev * 1e-3), "unit": "captions/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": DECODE_WORKLOAD % n_img, "parallelism": f"dp{world}",
                            "l2": "K/V cache 2 x 12 x 5120 x 77 x 768 x 4 B = 29 GB >> 126 MB L2; 4 distinct host batches"},
                 "e2e": {"value": caps / (ms_e2e * 1e-3), "unit": "captions/s", "h2d_bytes_per_step": n_img * D_CLIP * 4,

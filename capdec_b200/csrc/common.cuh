@@ -281,6 +281,15 @@ __device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32
       "r"(cta)
       : "memory");
 }
+// 32-bit store into the shared memory of CTA `cta` of the cluster (same offset as `p` in this CTA)
+__device__ __forceinline__ void st_shared_remote_u32(const void* p, uint32_t cta, uint32_t v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.u32 [ra], %2;\n\t}" ::"r"(smem_u32(p)),
+      "r"(cta), "r"(v)
+      : "memory");
+}
 // TMA load issued by either CTA of a pair; the transaction bytes are credited to the LEADER CTA's barrier
 // (peer bit of the barrier address cleared), data lands in the issuing CTA's shared memory.
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {

@@ -81,9 +81,15 @@ constexpr int kStagingBytes = 128 * 128;        // 128 rows x 32 fp32
 constexpr int kWarpStagingBytes = 32 * 128;     // one epilogue warp's box: 32 rows x 32 fp32 (4 per 16 KB slot)
 constexpr int kMaxStages = 8;
 constexpr int kMulDepth = 4;  // epilogue-input boxes in flight per epilogue warp (C = acc * act'(input))
+constexpr int kSchedDepth = 4;  // tile ids the cluster's scheduler thread may run ahead of the slowest role
+constexpr int kSchedSlots = 1024;  // launch slots of the device-side tile counters (one per GEMM launch in flight)
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;  // columns per accumulator stage
 constexpr int kSmemLimit = 227 * 1024;
+
+// device-side tile counters of the dynamic scheduler: one 128-byte line per launch slot, {next tile, clusters done, pad...}
+// zero at module load; every launch leaves its slot zeroed again (see the scheduler thread)
+__device__ int g_sched_slots[32 * kSchedSlots];
 
 struct __align__(64) GemmDev {
   CUtensorMap tmA;
@@ -107,6 +113,7 @@ struct __align__(64) GemmDev {
   int mul_act;                      // 0 none; 1 gelu_new'(pre-activation), 2 tanh' = 1 - a^2 (activated a), 3 relu' (activated a)
   const int* m_limit;               // optional device scalar: rows >= *m_limit are not computed (whole tiles skipped)
   const int* k_limit;               // optional device scalar: reduction stops at *k_limit (rounded up to a k-block)
+  int* sched;                       // dynamic tile scheduler: {next tile, clusters done} of this launch (NULL = static round-robin)
   uint32_t dbg;                     // bring-up switches (CAPDEC_GEMM_DBG): 1 skip TMA loads, 2 skip MMA, 4 skip stores, 8 skip epilogue
 };
 
@@ -235,7 +242,10 @@ __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf3
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* mul_bar = tmem_empty_bar + 2;           // TMA loads of the epilogue input boxes (kMulDepth per epilogue warp)
   uint64_t* conv_bar = mul_bar + 4 * kMulDepth;     // kSplit: stage converted (hi in place, lo written) in every CTA of the pair
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + kMaxStages);
+  uint64_t* sched_full = conv_bar + kMaxStages;     // tile id of ring slot i published (by the cluster's scheduler thread)
+  uint64_t* sched_empty = sched_full + kSchedDepth; // ring slot i read by every role of every CTA of the cluster (rank-0 CTA's copy)
+  int* sched_tile = reinterpret_cast<int*>(sched_empty + kSchedDepth);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_tile + kSchedDepth);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -264,6 +274,12 @@ __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf3
       mbar_init(&conv_bar[i], kCtasPerPair * (kConvThreads / 32));  // one arrive per converter warp of each CTA
     }
     for (int i = 0; i < 4 * kMulDepth; ++i) mbar_init(&mul_bar[i], 1);
+    for (int i = 0; i < kSchedDepth; ++i) {
+      mbar_init(&sched_full[i], 1);
+      // readers of a tile id per cluster: every CTA's producer thread + 4 epilogue warps (+ 4 converter warps), and the
+      // MMA thread of every pair leader
+      mbar_init(&sched_empty[i], kCtasPerCluster * (1 + 4 + (kSplit ? kConvThreads / 32 : 0)) + kPairsPerCluster);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], kCtasPerPair * kEpiThreads);  // pair: both CTAs' epilogues report to the leader
@@ -299,12 +315,75 @@ __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf3
   const uint16_t commit_empty_mask = kQuad ? (uint16_t)0xF : (uint16_t)0x3;
   const uint16_t commit_pair_mask = (uint16_t)(0x3u << (2 * pair_idx));
 
-  if (warp == 0) {
+  // ---- tile order ------------------------------------------------------------------------------------------------
+  // static (p.sched == NULL): cluster c takes tiles c, c + #clusters, ... ; dynamic: the scheduler thread of the cluster
+  // (warp 3 of its rank-0 CTA) draws tile ids from a device-wide counter and publishes them, kSchedDepth ahead at most, to
+  // a small ring in EVERY CTA of the cluster; each role walks the ring at its own pace.  Dynamic order keeps the kernel
+  // efficient when it does not own the whole GPU (a collective or the optimizer running beside it): a CTA that starts late
+  // simply draws fewer tiles, instead of serialising its fixed share of the problem behind everybody else.
+  const bool dyn = p.sched != nullptr;
+  auto next_tile_thread = [&](int& tile, uint32_t& cit) -> bool {      // for a single-thread role
+    if (!dyn) { tile = (cit == 0) ? tile0 : tile + tile_step; ++cit; return tile < total_tiles; }
+    const int slot = (int)(cit % kSchedDepth);
+    mbar_wait_cluster(&sched_full[slot], (cit / kSchedDepth) & 1, 9);
+    tile = *reinterpret_cast<volatile int*>(&sched_tile[slot]);
+    if constexpr (kPair) mbar_arrive_remote_release(&sched_empty[slot], 0); else mbar_arrive(&sched_empty[slot]);
+    ++cit;
+    return tile >= 0;
+  };
+  auto next_tile_warp = [&](int& tile, uint32_t& cit) -> bool {        // for a whole warp (converged)
+    if (!dyn) { tile = (cit == 0) ? tile0 : tile + tile_step; ++cit; return tile < total_tiles; }
+    const int slot = (int)(cit % kSchedDepth);
+    mbar_wait_cluster(&sched_full[slot], (cit / kSchedDepth) & 1, 10);
+    tile = *reinterpret_cast<volatile int*>(&sched_tile[slot]);
+    __syncwarp();                                                       // every lane holds the id before the slot is released
+    if (lane == 0) {
+      if constexpr (kPair) mbar_arrive_remote_release(&sched_empty[slot], 0); else mbar_arrive(&sched_empty[slot]);
+    }
+    ++cit;
+    return tile >= 0;
+  };
+
+  if (warp == 3) {
+    // ============================== tile scheduler (one thread per cluster) ========================================
+    if (dyn && lane == 0 && cta_rank == 0) {
+      for (uint32_t it = 0;; ++it) {
+        const int slot = (int)(it % kSchedDepth);
+        mbar_wait_cluster(&sched_empty[slot], ((it / kSchedDepth) & 1) ^ 1, 8);
+        int tile = atomicAdd(p.sched, 1);
+        if (tile >= total_tiles) tile = -1;
+#pragma unroll
+        for (uint32_t c = 0; c < (uint32_t)kCtasPerCluster; ++c) {
+          if constexpr (kPair) {
+            st_shared_remote_u32(&sched_tile[slot], c, (uint32_t)tile);
+            mbar_arrive_remote_release(&sched_full[slot], c);
+          } else {
+            sched_tile[slot] = tile;
+            mbar_arrive(&sched_full[slot]);
+          }
+        }
+        if (tile < 0) {
+          // the last cluster to run dry re-arms the counters for the next launch that uses this slot (a CUDA-graph
+          // replay launches with the same slot); every other cluster has made its final draw before counting itself done
+          __threadfence();
+          const int done = atomicAdd(p.sched + 1, 1);
+          if (done == (int)(gridDim.x / kCtasPerCluster) - 1) {
+            atomicExch(p.sched, 0);
+            atomicExch(p.sched + 1, 0);
+          }
+          break;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 0) {
     // ============================== TMA producer (every CTA feeds its own smem, and its twin's when multicasting) ====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      int tile = 0;
+      uint32_t cit = 0;
+      while (next_tile_thread(tile, cit)) {
         const int n_blk = tile % p.n_tiles;
         const int m_blk = (tile / p.n_tiles) % m_tiles;
         const int split = tile / (p.n_tiles * m_tiles);
@@ -392,7 +471,9 @@ __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf3
       uint32_t acc_phase = 0;
       const uint64_t adesc_base = ((uint64_t)p.adesc_hi << 32) | (uint64_t)p.adesc_lo16;
       const uint64_t bdesc_base = ((uint64_t)p.bdesc_hi << 32) | (uint64_t)p.bdesc_lo16;
-      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      int tile = 0;
+      uint32_t cit = 0;
+      while (next_tile_thread(tile, cit)) {
         const int split = tile / (p.n_tiles * m_tiles);
         const int m_blk = (tile / p.n_tiles) % m_tiles;
         const int kb0 = split * kb_per_split;
@@ -463,7 +544,9 @@ __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf3
         xv[j] = hi;
       }
     };
-    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+    int tile = 0;
+    uint32_t cit = 0;
+    while (next_tile_warp(tile, cit)) {
       const int split = tile / (p.n_tiles * m_tiles);
       const int m_blk = (tile / p.n_tiles) % m_tiles;
       const int kb0 = split * kb_per_split;
@@ -524,29 +607,29 @@ __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf3
       if (p.dbg & 8u) nch = 0;
       return true;
     };
-    // Epilogue-input prefetcher (lane 0): runs kMulDepth chunks AHEAD of the consumer over the same (tile, chunk) stream,
-    // across tile boundaries, so that the HBM latency of the 4 KB input boxes never sits on the epilogue's critical path
-    // (one-chunk-ahead prefetch left the fused GELU-backward dgrad at 315 TF/s vs 650 for the plain dgrad).
-    int la_tile = tile0 - tile_step, la_c = 0, la_nch = 0, la_m0 = 0, la_n0 = 0;
+    // Epilogue-input prefetcher (lane 0): runs kMulDepth chunks AHEAD of the consumer inside a tile; the first kMulDepth
+    // boxes of a tile are requested as soon as its id is known, i.e. while the tile's MMAs are still running, so that the
+    // HBM latency of the 4 KB input boxes never sits on the epilogue's critical path (one-chunk-ahead prefetch left the
+    // fused GELU-backward dgrad at 315 TF/s vs 650 for the plain dgrad).
+    int la_c = 0, la_nch = 0, la_m0 = 0, la_n0 = 0;
     uint32_t mul_issued = 0;
     auto mul_prefetch = [&]() {
-      while (la_tile < total_tiles && la_c >= la_nch) {
-        la_tile += tile_step; la_c = 0; la_nch = 0;
-        if (la_tile < total_tiles && !tile_coords(la_tile, la_m0, la_n0, la_nch)) la_nch = 0;
-      }
-      if (la_tile >= total_tiles) return;
+      if (la_c >= la_nch) return;
       const uint32_t slot = mul_issued % kMulDepth;
       uint64_t* mb = &my_mul_bar[slot];
       mbar_arrive_expect_tx(mb, kWarpStagingBytes);
       tma_load_2d(wst + (2 + slot) * kWarpStagingBytes, &p.tmMul, mb, la_n0 + la_c * 32, la_m0);
       ++mul_issued; ++la_c;
     };
-    if (p.mul_act && lane == 0) {
-      for (int i = 0; i < kMulDepth; ++i) mul_prefetch();
-    }
-    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+    int tile = 0;
+    uint32_t cit = 0;
+    while (next_tile_warp(tile, cit)) {
       int m0, n0, n_chunks;
       if (!tile_coords(tile, m0, n0, n_chunks)) continue;
+      if (p.mul_act && lane == 0) {   // every box of the previous tile has been consumed: all kMulDepth slots are free
+        la_c = 0; la_nch = n_chunks; la_m0 = m0; la_n0 = n0;
+        for (int i = 0; i < kMulDepth; ++i) mul_prefetch();
+      }
       const int split = tile / (p.n_tiles * m_tiles);
       const bool use_bias = (p.bias != nullptr) && (split == 0);
       if (use_bias) {
@@ -967,10 +1050,28 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   p.k_limit = a.k_limit;
   static const char* env_dbg = getenv("CAPDEC_GEMM_DBG");
   p.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
+  static const char* env_sched = getenv("CAPDEC_GEMM_SCHED");   // "static" = fixed round-robin tile order (bring-up / A-B)
+  if (!(env_sched && env_sched[0] == 's')) {
+    static std::atomic<int*> base_dev[kMaxDevices];
+    static std::atomic<unsigned> next_slot{0};
+    const int dev = current_device();
+    int* base = base_dev[dev].load(std::memory_order_acquire);
+    if (!base) {
+      void* sym = nullptr;
+      cudaError_t e = cudaGetSymbolAddress(&sym, g_sched_slots);
+      if (e != cudaSuccess) return check_cuda(e, "cudaGetSymbolAddress(g_sched_slots)");
+      base = static_cast<int*>(sym);
+      base_dev[dev].store(base, std::memory_order_release);
+    }
+    // one slot per launch; a slot is reused 1024 launches later (or by the replay of the CUDA graph that captured it), long
+    // after the launch that owned it has re-armed it
+    p.sched = base + 32 * (next_slot.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
+  }
 
   const int bn_local = (mode == 0) ? bn : bn / 2;
   const int b_bytes = bn_local * kBlockK * 4;
-  const int fixed = (a.mul_act ? 2 + kMulDepth : (a.aux ? 4 : 2)) * kStagingBytes + 256 * 4 + (3 * kMaxStages + 4 + 4 * kMulDepth) * 8 + 16 + 960 /* alignment slack */;
+  const int fixed = (a.mul_act ? 2 + kMulDepth : (a.aux ? 4 : 2)) * kStagingBytes + 256 * 4 +
+                    (3 * kMaxStages + 4 + 4 * kMulDepth + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 16 + 960 /* alignment slack */;
   const int per_stage = (kABytes + b_bytes) * (split3 ? 2 : 1);   // 3xTF32 keeps a lo tile beside every operand tile
   int stages = (kSmemLimit - fixed) / per_stage;
   if (stages > kMaxStages) stages = kMaxStages;

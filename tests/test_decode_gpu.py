@@ -147,10 +147,13 @@ def _beam_model(mode):
     return model.to("cuda").eval(), c
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("graph", [False, True])
-def test_generate_beam_matches_reference_goldens_fp32(graph):
+def test_generate_beam_matches_reference_goldens(graph, mode):
+    """Token ids IDENTICAL to the reference's generate_beam (gpt2_prefix_eval.py:50-115) on all pinned cases, in the
+    CUDA-core fp32 mode and in the tensor-core fp32-grade mode (3xTF32 tcgen05 GEMMs)."""
     import capdec_b200 as cb
-    model, c = _beam_model("fp32")
+    model, c = _beam_model(mode)
     try:
         for case in GOLD["cases"]:
             _, prefix, _ = O.make_batch(seed=case["batch_seed"], B=1, prefix_size=c["D"])
@@ -210,13 +213,15 @@ def test_generate_beam_tf32_best_beam_score_close():
     assert agree >= len(GOLD["cases"]) // 2
 
 
-def test_generate2_greedy_matches_reference_goldens_fp32():
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_generate2_greedy_matches_reference_goldens(mode):
     """gpt2_prefix_eval.generate2 (:118-198) = greedy decoding; ids pinned on the reference's own function
-    (tests/golden/greedy.json, oracle/pin_against_reference.py::pin_generate2)."""
+    (tests/golden/greedy.json, oracle/pin_against_reference.py::pin_generate2); identical in the CUDA-core fp32 mode and in
+    the tensor-core fp32-grade mode."""
     import json
     import capdec_b200 as cb
     rec = json.loads((Path(__file__).resolve().parent / "golden" / "greedy.json").read_text())
-    model, c = _beam_model("fp32")
+    model, c = _beam_model(mode)
     try:
         class Tok:
             def __init__(self, stop):

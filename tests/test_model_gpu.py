@@ -3,8 +3,10 @@ bit-exactly to the reference's own classes, tests/golden) on identical seeded we
 
 Stated tolerances (SURVEY §8c budget; measured values are appended to gpurun_out/parity_report.jsonl):
   fp32   (CUDA-core GEMMs)        loss rel <= 3e-6, logits max-abs <= 1e-4 * max|logit|, per-tensor grad rel-L2 <= 3e-4
-  tf32x3 (3xTF32 on tcgen05)      loss rel <= 2e-5, logits rel-L2 <= 1e-4,               per-tensor grad rel-L2 <= 3e-3
-  tf32   (1xTF32 on tcgen05,perf) loss rel <= 2e-4, logits rel-L2 <= 5e-3,               per-tensor grad rel-L2 <= 5e-2
+  tf32x3 (3xTF32 on tcgen05)      loss rel <= 2e-6, logits rel-L2 <= 2e-5,               per-tensor grad rel-L2 <= 2e-4 (5e-3)
+  tf32   (1xTF32 on tcgen05,perf) loss rel <= 2e-4, logits rel-L2 <= 5e-3,               per-tensor grad rel-L2 <= 2e-2 (5e-2)
+In brackets: the bound for the ILL-CONDITIONED gradients of the TransformerMapper (tests/golden/conditioning.json: tensors on
+which fp32 rounding alone moves the reference algorithm by more than 1e-5, 10x the median; see tests/test_scale_parity_gpu.py).
 """
 import json
 import os
@@ -19,9 +21,11 @@ from oracle import capdec_oracle as O  # noqa: E402  (checker only)
 
 ROOT = Path(__file__).resolve().parent.parent
 GOLD = ROOT / "tests" / "golden"
-TOL = {"fp32": dict(loss=3e-6, logits_abs=1e-4, logits_l2=2e-5, grad=3e-4),
-       "tf32x3": dict(loss=2e-5, logits_abs=1e-3, logits_l2=1e-4, grad=3e-3),
-       "tf32": dict(loss=2e-4, logits_abs=5e-2, logits_l2=5e-3, grad=5e-2)}
+TOL = {"fp32": dict(loss=3e-6, logits_abs=1e-4, logits_l2=2e-5, grad=3e-4, grad_ill=3e-4),
+       "tf32x3": dict(loss=2e-6, logits_abs=2e-4, logits_l2=2e-5, grad=2e-4, grad_ill=5e-3),
+       "tf32": dict(loss=2e-4, logits_abs=5e-2, logits_l2=5e-3, grad=2e-2, grad_ill=5e-2)}
+_COND = json.loads((GOLD / "conditioning.json").read_text())["c3"]["fp32_vs_fp64_rel_l2"]
+ILL = {k for k, v in _COND.items() if v > 1e-5}      # TransformerMapper tensors only (none of the MLP / GPT-2 names)
 
 
 def report(rec):
@@ -85,17 +89,24 @@ def test_fast_path_loss_and_grads_match_oracle_and_golden(case, mode):
         o_loss, o_logits, o_grads = O.loss_and_grads(sd, tokens, pfx_ref, O.make_mask(tokens, P), P, c["C"], trainable)
         assert abs(loss - float(o_loss)) <= tol["loss"] * abs(float(o_loss))
         g = eng.grad_views()
-        worst, worst_name = 0.0, None
+        transformer = c["mapping_type"] != "mlp"
+        worst, worst_name, worst_ill, worst_ill_name = 0.0, None, 0.0, None
         for k, og in o_grads.items():
             r = rel_l2(g[k].cpu(), og)
-            if r > worst:
+            ill = transformer and k in ILL
+            if ill and r > worst_ill:
+                worst_ill, worst_ill_name = r, k
+            if not ill and r > worst:
                 worst, worst_name = r, k
             gr = rec["grads"][k]
             vals = g[k].flatten()[torch.tensor(gr["idx"], device="cuda")].cpu().double()
-            assert (vals - torch.tensor(gr["val"], dtype=torch.float64)).abs().max() <= 3 * tol["grad"] * gr["norm"] + 1e-9, k
+            t_k = tol["grad_ill"] if ill else tol["grad"]
+            assert (vals - torch.tensor(gr["val"], dtype=torch.float64)).abs().max() <= 3 * t_k * gr["norm"] + 1e-9, k
         report(dict(test="fast_path", case=case, mode=mode, loss=loss, loss_ref=rec["loss"],
-                    loss_rel=abs(loss - rec["loss"]) / abs(rec["loss"]), worst_grad_rel_l2=worst, worst_grad=worst_name))
+                    loss_rel=abs(loss - rec["loss"]) / abs(rec["loss"]), worst_grad_rel_l2=worst, worst_grad=worst_name,
+                    worst_ill_conditioned_rel_l2=worst_ill, worst_ill_conditioned=worst_ill_name))
         assert worst <= tol["grad"], (worst_name, worst)
+        assert worst_ill <= tol["grad_ill"], (worst_ill_name, worst_ill)
         if c["only_prefix"]:  # frozen GPT-2: no gradient may have been written (train.py:276-284)
             fl = eng.flat
             assert fl.grads[fl.tail + fl.n_mapper:].abs().max().item() == 0.0
@@ -136,7 +147,8 @@ def test_drop_in_forward_backward_like_train_py(case, mode):
         worst = 0.0
         for k, gr in rec["grads"].items():
             assert named[k].grad is not None, k
-            assert abs(named[k].grad.double().norm().item() - gr["norm"]) <= 2 * tol["grad"] * gr["norm"] + 1e-9, k
+            t_k = tol["grad_ill"] if (c["mapping_type"] != "mlp" and k in ILL) else tol["grad"]
+            assert abs(named[k].grad.double().norm().item() - gr["norm"]) <= 2 * t_k * gr["norm"] + 1e-9, k
             vals = named[k].grad.flatten()[torch.tensor(gr["idx"], device="cuda")].cpu().double()
             worst = max(worst, ((vals - torch.tensor(gr["val"], dtype=torch.float64)).abs().max() / gr["norm"]).item())
         report(dict(test="drop_in", case=case, mode=mode, logits_rel_l2=l2, loss=loss.item(), loss_ref=rec["loss"],
