@@ -271,6 +271,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "r"(cta)
       : "memory");
 }
+// same; `after` is a value the arrive must not overtake (it is an operand of the instruction sequence, so the load that
+// produced it has returned before the arrive is issued)
+__device__ __forceinline__ void mbar_arrive_remote_after(uint64_t* bar, uint32_t cta, uint32_t after) {
+  asm volatile(
+      "{\n\t.reg .b32 ra, rz;\n\t"
+      "and.b32 rz, %2, 0;\n\t"
+      "add.u32 ra, %0, rz;\n\t"
+      "mapa.shared::cluster.u32 ra, ra, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta), "r"(after)
+      : "memory");
+}
 // same, with cluster-scope release: this thread's (and, after a __syncwarp, its warp's) earlier shared-memory writes are
 // visible to the CTA that acquires the barrier
 __device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t cta) {

@@ -327,7 +327,9 @@ __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf3
     const int slot = (int)(cit % kSchedDepth);
     mbar_wait_cluster(&sched_full[slot], (cit / kSchedDepth) & 1, 9);
     tile = *reinterpret_cast<volatile int*>(&sched_tile[slot]);
-    if constexpr (kPair) mbar_arrive_remote_release(&sched_empty[slot], 0); else mbar_arrive(&sched_empty[slot]);
+    // plain arrive, issued only once the id sits in a register (operand dependency): a cluster-scope RELEASE here made the
+    // role wait for all of its outstanding memory traffic at every tile and cost 4-6 % per GEMM (profiles/r2_gemm_scheduler.md)
+    if constexpr (kPair) mbar_arrive_remote_after(&sched_empty[slot], 0, (uint32_t)tile); else mbar_arrive(&sched_empty[slot]);
     ++cit;
     return tile >= 0;
   };
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf3
     tile = *reinterpret_cast<volatile int*>(&sched_tile[slot]);
     __syncwarp();                                                       // every lane holds the id before the slot is released
     if (lane == 0) {
-      if constexpr (kPair) mbar_arrive_remote_release(&sched_empty[slot], 0); else mbar_arrive(&sched_empty[slot]);
+      if constexpr (kPair) mbar_arrive_remote_after(&sched_empty[slot], 0, (uint32_t)tile); else mbar_arrive(&sched_empty[slot]);
     }
     ++cit;
     return tile >= 0;
@@ -576,7 +578,9 @@ __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf3
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
         __syncwarp();
         if (lane == 0) {
-          if (kPair && !leader) mbar_arrive_remote_release(&conv_bar[stage], pair_leader);
+          // (plain arrive: the tensor core reads this CTA's tiles through the async proxy, which the fence above has
+          // ordered after the conversion; a cluster-scope release would stall the warp on all of its outstanding traffic)
+          if (kPair && !leader) mbar_arrive_remote(&conv_bar[stage], pair_leader);
           else mbar_arrive(&conv_bar[stage]);
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }

@@ -175,15 +175,20 @@ def generate_beam(model, tokenizer, beam_size: int = 5, prompt=None, embed=None,
     """Same signature and return value as gpt2_prefix_eval.py:50-52 (list of decoded captions, best first)."""
     model.eval()
     stop_token_index = tokenizer.encode(stop_token)[0]
+    head = []
     if embed is None:
         if prompt is None:
             raise ValueError("generate_beam needs `embed` or `prompt`")
         dev = model.engine().dev
-        ids = torch.tensor(tokenizer.encode(prompt), device=dev).unsqueeze(0)  # :65-68
+        head = [int(t) for t in tokenizer.encode(prompt)]
+        ids = torch.tensor(head, device=dev).unsqueeze(0)  # :65-68
         embed = model.gpt.transformer.wte(ids)
     (beams, _, _), = generate_beam_ids(model, embed.view(1, -1, embed.shape[-1]), beam_size, entry_length, temperature,
                                         stop_token_index)
-    return [tokenizer.decode(ids) for ids in beams]
+    # prompt path of the reference (:82-88, :111-112): `tokens` starts as the prompt ids, the generated ids are appended,
+    # and each beam is cut to `seq_length` tokens, a count that starts at 1 and only counts GENERATED tokens - so the
+    # decoded text is the first `seq_length` ids of prompt + generated.  Reproduced as is.  (embed path: head is empty.)
+    return [tokenizer.decode((head + ids)[: len(ids)]) for ids in beams]
 
 
 def generate_beam_batch(model, tokenizer, embeds: torch.Tensor, beam_size: int = 5, entry_length: int = 67,

@@ -223,6 +223,32 @@ def pin_generate_beam():
     print("generate_beam ok", [r["ids"][0][:6] for r in recs])
 
 
+def pin_generate_beam_prompt():
+    """The PROMPT path of gpt2_prefix_eval.generate_beam (:65-68, :82-88, :111-112: the prompt ids stay in `tokens` and each
+    beam is cut to `seq_length` ids, a count of generated tokens only) -> tests/golden/beam_prompt.json (decoded texts)."""
+    for name in ("clip", "pycocotools", "pycocotools.coco", "matplotlib", "matplotlib.pyplot", "skimage", "skimage.io"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["pycocotools.coco"].COCO = object
+    sys.modules["transformers"].AdamW = O.HFAdamW
+    import gpt2_prefix_eval as ev  # noqa
+    import gpt2_prefix as gp  # noqa
+    P, D = 10, 640
+    sd = O.make_state_dict(seed=1, mapping_type="mlp", prefix_length=P, prefix_size=D, weight_std=0.08)
+    torch.manual_seed(0)
+    model = gp.ClipCaptionModel(P, prefix_dim=D, mapping_type=gp.MappingType.MLP)
+    model.gpt.config._attn_implementation = "eager"
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    recs = []
+    for prompt, temperature in (("capdec", 1.0), ("a b", 0.7), ("x", 1.0)):       # _FakeTokenizer: one id per character
+        with torch.no_grad():
+            texts = ev.generate_beam(model, _FakeTokenizer(), prompt=prompt, entry_length=12, temperature=temperature)
+        recs.append({"prompt": prompt, "temperature": temperature, "texts": texts})
+    (GOLD / "beam_prompt.json").write_text(json.dumps({"config": dict(P=P, D=D, sd_seed=1, weight_std=0.08, entry_length=12,
+                                                                        beam_size=5), "cases": recs}, indent=1))
+    print("generate_beam (prompt) ok", [r["texts"][0] for r in recs])
+
+
 def pin_generate2():
     """gpt2_prefix_eval.generate2 (the reference's own function: greedy decode behind a top-p mask) vs the oracle
     restatement -> tests/golden/greedy.json"""
@@ -331,6 +357,7 @@ def pin_encdec_mapper():
 if __name__ == "__main__":
     main()
     pin_generate_beam()
+    pin_generate_beam_prompt()
     pin_generate2()
     pin_dataset()
     pin_encdec_mapper()

@@ -249,3 +249,29 @@ def test_generate2_greedy_matches_reference_goldens(mode):
         assert out == [k["ids"] for k in cases]
     finally:
         cb.ops.set_precision("tf32")
+
+
+def test_generate_beam_prompt_path_matches_reference_goldens():
+    """`generate_beam(prompt=...)` (gpt2_prefix_eval.py:65-68): the prompt ids stay in front and every beam is cut to its
+    generated-token count, exactly as the reference's own function returns it (tests/golden/beam_prompt.json,
+    oracle/pin_against_reference.py::pin_generate_beam_prompt)."""
+    import json
+    import capdec_b200 as cb
+    rec = json.loads((Path(__file__).resolve().parent / "golden" / "beam_prompt.json").read_text())
+    model, c = _beam_model("fp32")
+    try:
+        class Tok:      # the pin script's tokenizer: one id per character, '.' -> 13
+            def encode(self, text):
+                if text == ".":
+                    return [13]
+                return [int(text)] if text.isdigit() else [ord(ch) % 50257 for ch in text]
+
+            def decode(self, ids):
+                return " ".join(str(int(i)) for i in ids)
+
+        for case in rec["cases"]:
+            texts = cb.generate_beam(model, Tok(), prompt=case["prompt"], entry_length=rec["config"]["entry_length"],
+                                     temperature=case["temperature"])
+            assert texts == case["texts"], case["prompt"]
+    finally:
+        cb.ops.set_precision("tf32")

@@ -3,10 +3,10 @@ bit-exactly to the reference's own classes, tests/golden) on identical seeded we
 
 Stated tolerances (SURVEY §8c budget; measured values are appended to gpurun_out/parity_report.jsonl):
   fp32   (CUDA-core GEMMs)        loss rel <= 3e-6, logits max-abs <= 1e-4 * max|logit|, per-tensor grad rel-L2 <= 3e-4
-  tf32x3 (3xTF32 on tcgen05)      loss rel <= 2e-6, logits rel-L2 <= 2e-5,               per-tensor grad rel-L2 <= 2e-4 (5e-3)
+  tf32x3 (3xTF32 on tcgen05)      loss rel <= 2e-6, logits rel-L2 <= 5e-5,               per-tensor grad rel-L2 <= 2e-4 (5e-3)
   tf32   (1xTF32 on tcgen05,perf) loss rel <= 2e-4, logits rel-L2 <= 5e-3,               per-tensor grad rel-L2 <= 2e-2 (5e-2)
 In brackets: the bound for the ILL-CONDITIONED gradients of the TransformerMapper (tests/golden/conditioning.json: tensors on
-which fp32 rounding alone moves the reference algorithm by more than 1e-5, 10x the median; see tests/test_scale_parity_gpu.py).
+which fp32 rounding alone moves the reference algorithm by more than 3e-6, 3x the median; see tests/test_scale_parity_gpu.py).
 """
 import json
 import os
@@ -22,10 +22,10 @@ from oracle import capdec_oracle as O  # noqa: E402  (checker only)
 ROOT = Path(__file__).resolve().parent.parent
 GOLD = ROOT / "tests" / "golden"
 TOL = {"fp32": dict(loss=3e-6, logits_abs=1e-4, logits_l2=2e-5, grad=3e-4, grad_ill=3e-4),
-       "tf32x3": dict(loss=2e-6, logits_abs=2e-4, logits_l2=2e-5, grad=2e-4, grad_ill=5e-3),
+       "tf32x3": dict(loss=2e-6, logits_abs=5e-4, logits_l2=5e-5, grad=2e-4, grad_ill=5e-3),
        "tf32": dict(loss=2e-4, logits_abs=5e-2, logits_l2=5e-3, grad=2e-2, grad_ill=5e-2)}
 _COND = json.loads((GOLD / "conditioning.json").read_text())["c3"]["fp32_vs_fp64_rel_l2"]
-ILL = {k for k, v in _COND.items() if v > 1e-5}      # TransformerMapper tensors only (none of the MLP / GPT-2 names)
+ILL = {k for k, v in _COND.items() if v > 3e-6}      # TransformerMapper tensors only (none of the MLP / GPT-2 names)
 
 
 def report(rec):

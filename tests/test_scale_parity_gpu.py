@@ -11,12 +11,12 @@ Dropout is off (p = 0; the oracle cannot reproduce Philox masks).
 Stated tolerances (SURVEY §8c): "tf32" (1xTF32, the perf mode) loss rel <= 2e-4, per-tensor grad rel-L2 <= 2e-2;
 "tf32x3" (3xTF32, the fp32-grade mode) loss rel <= 2e-6, per-tensor grad rel-L2 <= 1e-4.
 These hold for every WELL-CONDITIONED gradient.  tests/golden/conditioning.json (tests/golden/make_conditioning.py) holds,
-per tensor, what fp32 rounding alone does to the reference algorithm (oracle fp32 vs fp64): ~1e-6 for every tensor of C1 /
-C2, but up to 3e-4 - 300x the median - for 45 tensors of C3's TransformerMapper (layers 0-1: ReLU gates of mlp.fc1 flip
-under 1e-7 perturbations and the near-uniform softmax of a randomly initialised mapper amplifies the change; the reference
-itself on another BLAS differs by that much).  Tensors whose fp32-vs-fp64 error exceeds 1e-5 are held to the
-ill-conditioned bound instead: 5e-2 ("tf32"), 5e-3 ("tf32x3").  Measured values: gpurun_out/parity_report.jsonl ->
-profiles/r2_parity_report.md.
+per tensor, what fp32 rounding alone does to the reference algorithm (oracle fp32 vs fp64): 0.8-1.2e-6 for every tensor of
+C1 / C2 and for all 148 GPT-2 tensors of C3, but 3e-6 ... 3e-4 (up to 300x the median) for 97 of the 99 tensors of C3's
+randomly initialised TransformerMapper: ReLU gates of mlp.fc1 flip under 1e-7 perturbations and the near-uniform softmax
+amplifies the change; the reference itself on another BLAS differs by that much.  Tensors whose fp32-vs-fp64 error exceeds
+3e-6 (3x the median) are held to the ill-conditioned bound instead: 5e-2 ("tf32"), 5e-3 ("tf32x3").  Measured values:
+gpurun_out/parity_report.jsonl -> profiles/r2_parity_report.md.
 """
 import json
 import os
@@ -31,7 +31,7 @@ from oracle import capdec_oracle as O  # noqa: E402  (checker only)
 
 ROOT = Path(__file__).resolve().parent.parent
 TOL = {"tf32": dict(loss=2e-4, grad=2e-2, grad_ill=5e-2), "tf32x3": dict(loss=2e-6, grad=1e-4, grad_ill=5e-3)}
-ILL_CONDITIONED_ABOVE = 1e-5      # fp32-vs-fp64 rel-L2 of the reference algorithm itself (median over tensors: 1e-6)
+ILL_CONDITIONED_ABOVE = 3e-6      # fp32-vs-fp64 rel-L2 of the reference algorithm itself (median over tensors: 1e-6)
 COND = json.loads((ROOT / "tests" / "golden" / "conditioning.json").read_text())
 CASES = {
     "c1": dict(B=32, P=10, C=10, mapping="mlp", only_prefix=True, noise=0.016),

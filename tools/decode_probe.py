@@ -16,7 +16,7 @@ def main():
     sizes = [int(a) for a in sys.argv[1:] if a.isdigit()] or [1, 64, 256]
     P, D, L = 10, 512, 67
     torch.manual_seed(0)
-    model = cb.ClipCaptionModel(P, prefix_size=D, mapping_type=cb.MappingType.MLP).to("cuda").eval()
+    model = cb.ClipCaptionModel(P, prefix_size=D, mapping_type=cb.MappingType.MLP, gpt_config=cb.GPT2Config()).to("cuda").eval()
     out = []
     for n_img in sizes:
         x = torch.randn(n_img, D, device="cuda")

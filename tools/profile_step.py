@@ -50,9 +50,10 @@ def main():
     torch.manual_seed(0)
     if a.mapping == "mlp":
         cls = cb.ClipCaptionPrefix if a.only_prefix else cb.ClipCaptionModel
-        model = cls(10, prefix_size=512)
+        model = cls(10, prefix_size=512, gpt_config=cb.GPT2Config())
     else:
-        model = cb.ClipCaptionModel(40, clip_length=40, prefix_size=512, mapping_type=cb.MappingType.Transformer)
+        model = cb.ClipCaptionModel(40, clip_length=40, prefix_size=512, mapping_type=cb.MappingType.Transformer,
+                                    gpt_config=cb.GPT2Config())
     model = model.to("cuda").train()
     tr = cb.Trainer(model, batch_size=a.bs, seq_len=40, noise_variance=0.016, use_cuda_graph=False)
     tok, pfx = bench.synth_batch(a.bs, 1)
