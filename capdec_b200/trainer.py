@@ -82,6 +82,7 @@ class Trainer:
         self.opt_overlap = (self.world == 1 and self.train_gpt and os.environ.get("CAPDEC_OPT_OVERLAP", "0") == "1")
         if self.opt_overlap:
             self.opt_stream = torch.cuda.Stream(device=self.dev)
+        if self.train_gpt:     # parameter spans (in trainable-parameter coordinates) in the order backward finishes them
             lay = fl.layout
             nl = self.eng.nl
             first = lay["gpt.transformer.h.0.ln_1.weight"][0] - fl.tail
@@ -244,26 +245,36 @@ class Trainer:
 
         def cut(l: int):
             cur["g"].capture_end()
-            segs.append((cur["g"], self.buckets[l]))
+            segs.append((cur["g"], self.buckets[l], self.layer_spans[l]))
             begin()
 
         with torch.cuda.stream(cap):
             begin()
             self._fwd_bwd(layer_hook=cut)
             cur["g"].capture_end()
-            segs.append((cur["g"], self.head_bucket))
+            segs.append((cur["g"], self.head_bucket, self.head_span))
         torch.cuda.current_stream().wait_stream(cap)
         return segs
 
     def _replay_segments(self):
+        """Segment replays on the main stream; on the side stream, per finished segment: all-reduce of that block's
+        gradient bucket, then the fused AdamW of the same parameters - both run while the main stream is already replaying
+        the backward of the blocks below.  The global token count the update divides by is all-reduced first (the CE
+        kernel finishes before the first cut), so no update waits for the head bucket.  Exposed at the end of the step:
+        the all-reduce + update of [mapper | wte | wpe], which the embedding scatter completes last."""
         main = torch.cuda.current_stream()
-        for g, bucket in self._segs:
+        self.comm.wait_stream(main)          # the previous step's forward has read the parameters the updates will overwrite
+        for i, (g, bucket, (lo, hi)) in enumerate(self._segs):
             g.replay()
             ev = torch.cuda.Event()
             ev.record(main)
             self.comm.wait_event(ev)
             with torch.cuda.stream(self.comm):
+                if i == 0:               # [n_valid, loss_sum] of this rank are final -> global counts
+                    self.stats.copy_(self.tail)
+                    torch.distributed.all_reduce(self.stats, group=self.pg)
                 torch.distributed.all_reduce(bucket, group=self.pg)
+                self._adamw_span(lo, hi)
         main.wait_stream(self.comm)
 
     def step_device(self):
@@ -275,10 +286,9 @@ class Trainer:
                     self._segs = self._capture_segments()
                 else:
                     self._g_fb = self._capture(self._fwd_bwd)
-                self._g_opt = None if self.opt_overlap else self._capture(self._opt)
+                self._g_opt = None if (self.opt_overlap or self.segmented) else self._capture(self._opt)
             if self.segmented:
-                self._replay_segments()
-                self._g_opt.replay()
+                self._replay_segments()      # reduces AND updates bucket by bucket
                 return self.stats
             self._g_fb.replay()
             if self.pipeline:
