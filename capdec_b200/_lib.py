@@ -30,6 +30,7 @@ SIGNATURES = {
     "capdec_gemm_debug_mn_encoding": [_i, _i, _i, _i],
     "capdec_gemm_debug_force_pair": [_i],
     "capdec_gemm_set_row_hint": [_i],
+    "capdec_gemm_set_schedule": [_i],
     "capdec_gemm_autotune": [_i],
     "capdec_gemm_plan_query": [_i, _i, _i, _i, _i, _i, _i, _i],
     "capdec_gemm_fp32_simt": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p],

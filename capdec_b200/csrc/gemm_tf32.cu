@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf3
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_lim);
         if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
+        if (p.dbg & 64u) continue;   // timing experiment: raw tcgen05.mma issue rate, no stage handshake at all
         const CUtensorMap* mapA = &p.tmA;
         const CUtensorMap* mapB = &p.tmB;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -486,7 +487,8 @@ __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf3
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
         uint32_t accumulate = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
-          if constexpr (kSplit) mbar_wait_cluster(&conv_bar[stage], phase, 6);   // hi/lo tiles of both CTAs are in place
+          if (p.dbg & 64u) {}                                                     // (experiment: no wait)
+          else if constexpr (kSplit) mbar_wait_cluster(&conv_bar[stage], phase, 6);   // hi/lo tiles of both CTAs are in place
           else mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
           const uint32_t a_start = smem_u32(sA + stage * kABytes) >> 4;
@@ -832,6 +834,9 @@ static OperandEnc operand_encoding(bool mn_major) {
   return e;
 }
 
+// tile order of the persistent kernels: 0 = static round-robin (default: fastest while a GEMM owns the GPU, which is the
+// single-GPU step), 1 = dynamic (device-wide tile counter: robust when collectives / the optimizer share the SMs)
+static std::atomic<int> g_sched_dynamic{0};
 static int g_force_pair = -1;  // bring-up override: -1 auto, 0 never, 1 always (pairs), 2/3 force quad modes
 static thread_local int t_m_hint = 0;   // expected live rows of the next row-limited GEMMs (capdec_gemm_set_row_hint)
 
@@ -925,6 +930,7 @@ extern "C" int capdec_version(void) { return 100; }
 extern "C" int64_t capdec_launch_count(void) { return g_launches.load(); }
 
 extern "C" void capdec_gemm_debug_force_pair(int mode) { g_force_pair = mode; }  // -1 auto, 0..3 engine
+extern "C" int capdec_gemm_set_schedule(int dynamic) { return g_sched_dynamic.exchange(dynamic ? 1 : 0); }
 
 // Tiling hint for GEMMs launched with a device-side row limit (packed caption batches): the row count is data dependent
 // and unknown to the host, so engine / tile width / wave quantisation are chosen for `rows` (0 = the static M).  Results
@@ -1054,8 +1060,9 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   p.k_limit = a.k_limit;
   static const char* env_dbg = getenv("CAPDEC_GEMM_DBG");
   p.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
-  static const char* env_sched = getenv("CAPDEC_GEMM_SCHED");   // "static" = fixed round-robin tile order (bring-up / A-B)
-  if (!(env_sched && env_sched[0] == 's')) {
+  static const char* env_sched = getenv("CAPDEC_GEMM_SCHED");   // "dynamic" / "static": overrides capdec_gemm_set_schedule
+  const bool dynamic = env_sched ? env_sched[0] == 'd' : g_sched_dynamic.load(std::memory_order_relaxed) != 0;
+  if (dynamic) {
     static std::atomic<int*> base_dev[kMaxDevices];
     static std::atomic<unsigned> next_slot{0};
     const int dev = current_device();

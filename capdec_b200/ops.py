@@ -96,6 +96,12 @@ def set_row_hint(rows: int) -> None:
     _lib.load().capdec_gemm_set_row_hint(int(rows))
 
 
+def gemm_set_schedule(dynamic: bool) -> bool:
+    """Tile order of the persistent GEMM kernels launched from now on: dynamic (device-wide tile counter) or static
+    round-robin (default).  Returns the previous setting.  See capdec_gemm_set_schedule."""
+    return bool(_lib.load().capdec_gemm_set_schedule(int(bool(dynamic))))
+
+
 def gemm_autotune(enable: int) -> int:
     """1 / 0: start / stop measuring GEMM plans for unseen problems; -1: forget measured plans.  Returns their count."""
     return int(_lib.load().capdec_gemm_autotune(int(enable)))

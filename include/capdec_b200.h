@@ -81,6 +81,14 @@ void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, int sbo_bytes
 /* tile engine selection override: -1 auto (CTA pairs / cta_group::2 whenever M > 128 and N >= 128), 0 = always one CTA
  * per 128-row tile (cta_group::1), 1 = always CTA pairs.  Used by the tests to cover both engines. */
 void capdec_gemm_debug_force_pair(int mode);
+/* Tile order of the persistent GEMM kernels launched from now on (process-wide; returns the previous setting).
+ * 0 = static: cluster c takes tiles c, c + #clusters, ... - the fastest order while a GEMM owns the whole GPU (default).
+ * 1 = dynamic: one scheduler thread per cluster draws tile ids from a device-wide counter and publishes them to a ring in
+ *     every CTA of the cluster; a cluster that shares its SMs with a collective or another kernel simply draws fewer tiles
+ *     (used by the data-parallel Trainer while gradient buckets are all-reduced beside the backward pass).
+ * Results do not depend on the order (split-K reduce-add order is not deterministic in either).  Environment override:
+ * CAPDEC_GEMM_SCHED=static|dynamic. */
+int capdec_gemm_set_schedule(int dynamic);
 /* Tiling hint for the GEMMs this thread launches next with a device-side row limit (m_limit_dev): the live row count
  * of a packed caption batch is data dependent, so tile width / engine / wave quantisation are chosen for `rows`
  * (0 clears the hint = plan for the static M).  Never changes results.  MN-major operands whose extent is not a
