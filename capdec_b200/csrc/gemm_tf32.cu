@@ -85,7 +85,7 @@ constexpr int kSchedDepth = 4;  // tile ids the cluster's scheduler thread may r
 constexpr int kSchedSlots = 1024;  // launch slots of the device-side tile counters (one per GEMM launch in flight)
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;  // columns per accumulator stage
-constexpr int kSmemLimit = 227 * 1024;
+constexpr int kSmemLimit = 226 * 1024;  // of 228 KB per SM: 1 KB is reserved per CTA, and > 1 KB stays free for a co-resident CTA
 
 // device-side tile counters of the dynamic scheduler: one 128-byte line per launch slot, {next tile, clusters done, pad...}
 // zero at module load; every launch leaves its slot zeroed again (see the scheduler thread)
@@ -217,15 +217,24 @@ __device__ __forceinline__ void apply_mul32(float (&v)[32], const float (&u)[32]
 //   3  a QUAD stacked in M (512 x block_n): the pairs need the same B columns; B halves are multicast instead.
 // Why: with fp32 operands these GEMMs are bound by L2->SM bandwidth (~8.3 TB/s measured: loads-only experiment in
 // profiles/r1_gemm_pipeline_experiments.md), not by the tensor pipe; FLOP per L2 byte is 43 / 64 / 87 for modes 0/1/2-3.
+// Register / shared-memory budget: every variant is compiled for <= 168 registers per thread (the bound of the 384-thread
+// 3xTF32 variant; no spills) and leaves > 1 KB of the SM's shared memory free, so that a GEMM CTA does not lock the SM:
+// a small streaming kernel (the fused AdamW on its side stream) can be co-resident and use the HBM bandwidth the
+// tensor-bound GEMM leaves idle.  At 244 registers x 256 threads + 227 KB nothing else could ever share the SM.
 template <int kMode, bool kSplit>
-__global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, 1) gemm_tf32_kernel(const __grid_constant__ GemmDev p) {
+__global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __grid_constant__ GemmDev p) {
   constexpr bool kPair = kMode >= 1;
   constexpr bool kQuad = kMode >= 2;
   constexpr bool kShareB = kMode == 3;
   static_assert(!(kSplit && kQuad), "the in-pipeline 3xTF32 split runs on the single-CTA and CTA-pair engines");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up (all tile buffers 1024-byte aligned for the 128B swizzle patterns); identical in every CTA of a cluster
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (the __align__(1024) on the dynamic array places it on a 1024-byte boundary of the CTA's shared window: no slack bytes)
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("capdec gemm: dynamic shared memory is not 1024-byte aligned (%u)\n", smem_u32(smem_raw));
+    __trap();
+  }
   const int bn_local = kPair ? p.block_n / 2 : p.block_n;  // B columns this CTA stages
   const int b_bytes = bn_local * kBlockK * 4;
   const int stage_bytes = kABytes + b_bytes;
@@ -1082,7 +1091,7 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   const int bn_local = (mode == 0) ? bn : bn / 2;
   const int b_bytes = bn_local * kBlockK * 4;
   const int fixed = (a.mul_act ? 2 + kMulDepth : (a.aux ? 4 : 2)) * kStagingBytes + 256 * 4 +
-                    (3 * kMaxStages + 4 + 4 * kMulDepth + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 16 + 960 /* alignment slack */;
+                    (3 * kMaxStages + 4 + 4 * kMulDepth + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 32;
   const int per_stage = (kABytes + b_bytes) * (split3 ? 2 : 1);   // 3xTF32 keeps a lo tile beside every operand tile
   int stages = (kSmemLimit - fixed) / per_stage;
   if (stages > kMaxStages) stages = kMaxStages;

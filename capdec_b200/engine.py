@@ -67,6 +67,11 @@ class Engine:
         # CTAs fill the SMs a dgrad GEMM leaves idle in its last, partly empty wave (18.38 -> 18.20 / 18.23 ms/step on one
         # box, gpurun_out/s13_bench_*.log).  CAPDEC_BWD_STREAMS=0 serialises.
         self.bwd_streams = os.environ.get("CAPDEC_BWD_STREAMS", "1") != "0"
+        # N = 768 GEMMs with a linear epilogue (attn / mlp c_proj forward, the three plain dgrads): 105-150 tiles of 256 x 256
+        # on 74 CTA pairs are 1.4-2.03 waves that run as 2-3 (profiles/r2_gemm_waves.md: the raw tcgen05 issue rate of
+        # fc_proj is 586 TF/s against 763 for fc for this reason alone).  Their outputs are zeroed and accumulated instead
+        # (TMA reduce-add), which lets the planner split the reduction in two and fill the last wave.  tcgen05 modes only.
+        self.splitk_linear = os.environ.get("CAPDEC_SPLITK_LINEAR", "1") != "0"
         self.serial_backward = False          # set while GEMM plans are being measured (Trainer.autotune)
         self._side = None
 
@@ -401,13 +406,20 @@ class Engine:
             ops.attention_fwd(q, k, v, a.ctx[l], a.lse[l], B, self.H, T, T, self.hd, T * 3 * d, 3 * d, T * 3 * d, 3 * d,
                               T * d, d, self.hd ** -0.5, 1, key_len=key_len, p_drop=p_attn, seed=self.seed,
                               stream_id=_site(l, 0), cu_rows=cu)
-            ops.linear_fwd(a.ctx[l], p[pre + "attn.c_proj.weight"], "conv1d", p[pre + "attn.c_proj.bias"], a.y, rows=R)
+            sk = self.splitk_linear and ops.is_tc()
+            if sk:
+                ops.zero_fill(a.y)
+            ops.linear_fwd(a.ctx[l], p[pre + "attn.c_proj.weight"], "conv1d", p[pre + "attn.c_proj.bias"], a.y, rows=R,
+                           accumulate=sk)
             ops.add_ln_fwd(a.h[l], a.y, a.h1[l], a.x2[l], a.st2[l], p[pre + "ln_2.weight"], p[pre + "ln_2.bias"],
                            eps=self.cfg.layer_norm_epsilon, p_drop=p_res, seed=self.seed, stream_id=_site(l, 1), rows=R)
             # tcgen05 modes: a.u holds gelu_new'(pre-activation) (one tanh serves both), fp32 verification mode: the pre-activation
             ops.linear_fwd(a.x2[l], p[pre + "mlp.c_fc.weight"], "conv1d", p[pre + "mlp.c_fc.bias"], a.g[l],
                            act=ops.ACT_GELU_NEW_D if ops.is_tc() else ops.ACT_GELU_NEW, aux=a.u[l], rows=R)
-            ops.linear_fwd(a.g[l], p[pre + "mlp.c_proj.weight"], "conv1d", p[pre + "mlp.c_proj.bias"], a.y, rows=R)
+            if sk:
+                ops.zero_fill(a.y)
+            ops.linear_fwd(a.g[l], p[pre + "mlp.c_proj.weight"], "conv1d", p[pre + "mlp.c_proj.bias"], a.y, rows=R,
+                           accumulate=sk)
             if l + 1 < self.nl:
                 nx = f"gpt.transformer.h.{l + 1}."
                 ops.add_ln_fwd(a.h1[l], a.y, a.h[l + 1], a.x1[l + 1], a.st1[l + 1], p[nx + "ln_1.weight"],
@@ -430,6 +442,7 @@ class Engine:
         cu = a.cu if a.packed else None
         if a.packed:  # attention_bwd writes live rows only; the K-limited c_attn weight gradient reads whole k-blocks
             ops.zero_tail_rows(a.dqkv, a.rows)
+        sk = self.splitk_linear and ops.is_tc()
         use_side = self.bwd_streams and train_gpt and not self.serial_backward
         if use_side and self._side is None:
             self._side = torch.cuda.Stream(device=self.dev)
@@ -472,7 +485,9 @@ class Engine:
                                  ops.ACT_GELU_NEW_D if ops.is_tc() else ops.ACT_GELU_NEW,
                                  dbias=gw(pre + "mlp.c_fc.bias"), rows=R)
             e_fc = wgrad(a.x2[l], a.dF, pre + "mlp.c_fc.weight")
-            ops.linear_dgrad(a.dF, p[pre + "mlp.c_fc.weight"], "conv1d", a.dx, rows=R)
+            if sk:
+                ops.zero_fill(a.dx)
+            ops.linear_dgrad(a.dF, p[pre + "mlp.c_fc.weight"], "conv1d", a.dx, rows=R, accumulate=sk)
             wait(e_cproj)                                    # the next kernel overwrites dy2
             ops.add_ln_bwd(a.dx, a.h1[l], a.st2[l], p[pre + "ln_2.weight"], a.dh, a.dh, dy, gw(pre + "ln_2.weight"),
                            gw(pre + "ln_2.bias"), p_drop=p_res, seed=self.seed, stream_id=_site(l, 1),
@@ -480,7 +495,9 @@ class Engine:
             dy1 = cur()
             # attention
             e_aproj = wgrad(a.ctx[l], dy1, pre + "attn.c_proj.weight")
-            ops.linear_dgrad(dy1, p[pre + "attn.c_proj.weight"], "conv1d", a.dctx, rows=R)
+            if sk:
+                ops.zero_fill(a.dctx)
+            ops.linear_dgrad(dy1, p[pre + "attn.c_proj.weight"], "conv1d", a.dctx, rows=R, accumulate=sk)
             q, k, v = a.qkv[l][:, :d], a.qkv[l][:, d:2 * d], a.qkv[l][:, 2 * d:]
             dq, dk, dv = a.dqkv[:, :d], a.dqkv[:, d:2 * d], a.dqkv[:, 2 * d:]
             wait(e_qkv)                                      # layer l+1's c_attn weight gradient still reads a.dqkv
@@ -488,7 +505,9 @@ class Engine:
                               T * 3 * d, 3 * d, T * d, d, self.hd ** -0.5, 1, key_len=key_len, p_drop=p_attn,
                               seed=self.seed, stream_id=_site(l, 0), dbias_qkv=gw(pre + "attn.c_attn.bias"), cu_rows=cu)
             e_qkv = wgrad(a.x1[l], a.dqkv, pre + "attn.c_attn.weight")
-            ops.linear_dgrad(a.dqkv, p[pre + "attn.c_attn.weight"], "conv1d", a.dx, rows=R)
+            if sk:
+                ops.zero_fill(a.dx)
+            ops.linear_dgrad(a.dqkv, p[pre + "attn.c_attn.weight"], "conv1d", a.dx, rows=R, accumulate=sk)
             wait(e_aproj)                                    # the next kernel overwrites dy1
             if l > 0:
                 ops.add_ln_bwd(a.dx, a.h[l], a.st1[l], p[pre + "ln_1.weight"], a.dh, a.dh, dy, gw(pre + "ln_1.weight"),

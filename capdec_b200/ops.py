@@ -138,10 +138,13 @@ def _no_rows(rows):
         raise _lib.CapdecError("packed rows (device row limits) are implemented for the tcgen05 modes (tf32, tf32x3) only")
 
 
-def linear_fwd(x, W, layout, bias, out, act=ACT_NONE, aux=None, rows=None):
+def linear_fwd(x, W, layout, bias, out, act=ACT_NONE, aux=None, rows=None, accumulate=False):
+    """accumulate=True: out += x W (+ bias once) through TMA reduce-add - the caller has zeroed `out`; lets the planner
+    split the reduction (split-K) when the tile count quantises badly onto the SMs (the N = 768 problems)."""
     M, K = x.shape
     N = out.shape[1]
-    gemm(x, 0, W, 1 if layout == "conv1d" else 0, out, M, N, K, bias=bias, act=act, aux=aux, m_limit=rows)
+    gemm(x, 0, W, 1 if layout == "conv1d" else 0, out, M, N, K, bias=bias, act=act, aux=aux, m_limit=rows,
+         accumulate=accumulate)
 
 
 def linear_dgrad(dy, W, layout, dx, accumulate=False, rows=None):
