@@ -71,7 +71,9 @@ class Engine:
         # on 74 CTA pairs are 1.4-2.03 waves that run as 2-3 (profiles/r2_gemm_waves.md: the raw tcgen05 issue rate of
         # fc_proj is 586 TF/s against 763 for fc for this reason alone).  Their outputs are zeroed and accumulated instead
         # (TMA reduce-add), which lets the planner split the reduction in two and fill the last wave.  tcgen05 modes only.
-        self.splitk_linear = os.environ.get("CAPDEC_SPLITK_LINEAR", "1") != "0"
+        # Measured (profiles/r2_gemm_waves.md): the mlp c_proj forward gains 14 us, but reduce-add (a read-modify-write in L2)
+        # and the 39 MB memset cost the other four as much: 16.82-16.95 ms/step with it, 16.86-16.94 without.  Opt-in.
+        self.splitk_linear = os.environ.get("CAPDEC_SPLITK_LINEAR", "0") == "1"
         self.serial_backward = False          # set while GEMM plans are being measured (Trainer.autotune)
         self._side = None
 
