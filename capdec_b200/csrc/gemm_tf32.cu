@@ -94,6 +94,7 @@ __device__ int g_sched_slots[32 * kSchedSlots];
 struct __align__(64) GemmDev {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmBh;    // B with half the box rows / slabs: the half-width tiles of the last, partly filled wave
   CUtensorMap tmC;
   CUtensorMap tmAux;
   CUtensorMap tmMul;   // optional epilogue INPUT (same shape as C): C = acc * act'(mul)
@@ -106,6 +107,8 @@ struct __align__(64) GemmDev {
   int a_mn, b_mn;
   int a_3d, b_3d;                   // MN-major operand fetched as ONE 3-D TMA box {32, 32 k-rows, slabs} per stage
   uint32_t idesc;
+  uint32_t idesc_h;                 // instruction descriptor of a half-width tile (N = block_n / 2)
+  int tail_ok;                      // half-width tail tiles allowed for this launch (engine, tile width, no split-K)
   uint32_t adesc_hi, bdesc_hi;      // upper 32 bits of the smem descriptors (SBO, version, layout)
   uint32_t adesc_lo16, bdesc_lo16;  // LBO field (bits 16..29 of the low word), pre-shifted
   uint32_t a_kstep, b_kstep;        // start-address increment per UMMA_K step, in 16-byte units
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tmA);
     prefetch_tensormap(&p.tmB);
+    if (p.tail_ok) prefetch_tensormap(&p.tmBh);
     prefetch_tensormap(&p.tmC);
     if (p.has_aux) prefetch_tensormap(&p.tmAux);
     if (p.mul_act) prefetch_tensormap(&p.tmMul);
@@ -315,7 +319,22 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
   constexpr int kTileM = (kQuad && kShareB) ? 2 * kPairM : kPairM;            // rows per cluster tile
   // only the LIVE row tiles are enumerated, so that the round-robin over cluster tiles stays balanced under split-K
   const int m_tiles = min(p.m_tiles, (m_lim + kTileM - 1) / kTileM);
-  const int total_tiles = m_tiles * p.n_tiles * p.splits;
+  // Wave quantisation: `base` tiles on `tile_step` clusters run floor(base / tile_step) full waves plus a tail of R tiles
+  // that keeps only R clusters busy.  When 0 < 2R <= tile_step the tail tiles are cut in two along N (tile ids
+  // F + 2r, F + 2r + 1 = the halves of tile F + r): twice as many clusters share the last wave, which then lasts about
+  // 0.6 of a tile time.  Everything is derived from the LIVE row count, identically in every role of every CTA.
+  const int base_tiles = m_tiles * p.n_tiles * p.splits;
+  int tail_first = base_tiles;                 // first tile id that denotes a half tile
+  if (!kQuad && p.tail_ok) {
+    const int full = (base_tiles / tile_step) * tile_step, rest = base_tiles - full;
+    if (full > 0 && rest > 0 && 2 * rest <= tile_step) tail_first = full;
+  }
+  const int total_tiles = base_tiles + (base_tiles - tail_first);
+  // tile id -> linear (m, n, split) index, tile width and column offset inside the full-width tile
+  auto decode = [&](int tile, int& lin, int& bn_t, int& n_off) {
+    if (tile < tail_first) { lin = tile; bn_t = p.block_n; n_off = 0; }
+    else { const int j = tile - tail_first; lin = tail_first + (j >> 1); bn_t = p.block_n >> 1; n_off = (j & 1) * bn_t; }
+  };
   const int tile_n = (kQuad && !kShareB) ? 2 * p.block_n : p.block_n;         // columns per cluster tile
   // this CTA's pair tile inside the cluster tile
   const int pm_off = (kQuad && kShareB) ? (int)pair_idx * kPairM : 0;
@@ -395,17 +414,22 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
       int tile = 0;
       uint32_t cit = 0;
       while (next_tile_thread(tile, cit)) {
-        const int n_blk = tile % p.n_tiles;
-        const int m_blk = (tile / p.n_tiles) % m_tiles;
-        const int split = tile / (p.n_tiles * m_tiles);
+        int lin, bn_t, n_off;
+        decode(tile, lin, bn_t, n_off);
+        const bool half_tile = bn_t != p.block_n;
+        const int bnl_t = kPair ? bn_t / 2 : bn_t;                                  // B columns this CTA stages for this tile
+        const int n_blk = lin % p.n_tiles;
+        const int m_blk = (lin / p.n_tiles) % m_tiles;
+        const int split = lin / (p.n_tiles * m_tiles);
         const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM;               // my 128 A rows
-        const int n0 = n_blk * tile_n + pn_off + (kPair ? (int)half * bn_local : 0);  // my bn_local B columns
+        const int n0 = n_blk * tile_n + pn_off + n_off + (kPair ? (int)half * bnl_t : 0);  // my B columns
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_lim);
         if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
         if (p.dbg & 64u) continue;   // timing experiment: raw tcgen05.mma issue rate, no stage handshake at all
         const CUtensorMap* mapA = &p.tmA;
-        const CUtensorMap* mapB = &p.tmB;
+        const CUtensorMap* mapB = half_tile ? &p.tmBh : &p.tmB;
+        const uint32_t tx_bytes = (uint32_t)(kABytes + bnl_t * kBlockK * 4);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           const int k0 = kb * kBlockK;
@@ -419,7 +443,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
             continue;
           }
-          if constexpr (kLocalBar) mbar_arrive_expect_tx(fb, (uint32_t)stage_bytes);
+          if constexpr (kLocalBar) mbar_arrive_expect_tx(fb, tx_bytes);
           auto load = [&](void* dst, const CUtensorMap* m, int x, int y) {
             if constexpr (kLocalBar) tma_load_2d(dst, m, fb, x, y); else tma_load_2d_pair(dst, m, fb, x, y);
           };
@@ -462,11 +486,11 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
             if (!p.b_mn) load(b_dst, mapB, k0, n0);
             else if (p.b_3d) load3(b_dst, mapB, k0, n0 / 32);
             else {
-              for (int i = 0; i < bn_local / 32; ++i) load(b_dst + i * 4096, mapB, n0 + 32 * i, k0);
+              for (int i = 0; i < bnl_t / 32; ++i) load(b_dst + i * 4096, &p.tmB, n0 + 32 * i, k0);   // 32-wide slab boxes
             }
           }
           if constexpr (!kLocalBar) {
-            if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(2 * stage_bytes));  // bytes landing in BOTH CTAs of my pair
+            if (leader) mbar_arrive_expect_tx(fb, 2u * tx_bytes);  // bytes landing in BOTH CTAs of my pair
             else mbar_arrive_remote(fb, pair_leader);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -486,8 +510,11 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
       int tile = 0;
       uint32_t cit = 0;
       while (next_tile_thread(tile, cit)) {
-        const int split = tile / (p.n_tiles * m_tiles);
-        const int m_blk = (tile / p.n_tiles) % m_tiles;
+        int lin, bn_t, n_off;
+        decode(tile, lin, bn_t, n_off);
+        const uint32_t idesc = (bn_t != p.block_n) ? p.idesc_h : p.idesc;
+        const int split = lin / (p.n_tiles * m_tiles);
+        const int m_blk = (lin / p.n_tiles) % m_tiles;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_lim);
         if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
@@ -504,8 +531,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
           const uint32_t b_start = smem_u32(sB + stage * b_bytes) >> 4;
           auto mma = [&](uint64_t adesc, uint64_t bdesc) {
             if (!(p.dbg & 2u)) {
-              if constexpr (kPair) umma_tf32_pair(d_tmem, adesc, bdesc, p.idesc, accumulate);
-              else umma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
+              if constexpr (kPair) umma_tf32_pair(d_tmem, adesc, bdesc, idesc, accumulate);
+              else umma_tf32(d_tmem, adesc, bdesc, idesc, accumulate);
             }
             accumulate = 1;
           };
@@ -560,8 +587,10 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     int tile = 0;
     uint32_t cit = 0;
     while (next_tile_warp(tile, cit)) {
-      const int split = tile / (p.n_tiles * m_tiles);
-      const int m_blk = (tile / p.n_tiles) % m_tiles;
+      int lin, bn_t, n_off;
+      decode(tile, lin, bn_t, n_off);
+      const int split = lin / (p.n_tiles * m_tiles);
+      const int m_blk = (lin / p.n_tiles) % m_tiles;
       const int kb0 = split * kb_per_split;
       const int kb1 = min(kb0 + kb_per_split, kb_lim);
       if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
@@ -578,7 +607,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
           a4[ct + i * kConvThreads] = x;
           al4[ct + i * kConvThreads] = lo;
         }
-        const int nb4 = b_bytes / 16;
+        const int nb4 = (kPair ? bn_t / 2 : bn_t) * kBlockK * 4 / 16;   // a half tile stages half the B rows
 #pragma unroll 4
         for (int i = ct; i < nb4; i += kConvThreads) {
           float4 x = b4[i], lo;
@@ -611,14 +640,16 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     uint32_t store_idx = 0;  // running chunk counter: staging buffers alternate ACROSS tiles too
     uint32_t mul_idx = 0;    // running count of epilogue-input chunks consumed (buffer = idx % kMulDepth, phase = (idx / kMulDepth) & 1)
     // this warp's (tile, chunk) stream: first row of the warp's 32-row box, the pair's first column, chunks to store
-    auto tile_coords = [&](int tile, int& m0w, int& n0w, int& nch) -> bool {
-      const int n_blk = tile % p.n_tiles;
-      const int m_blk = (tile / p.n_tiles) % m_tiles;
-      const int split = tile / (p.n_tiles * m_tiles);
+    auto tile_coords = [&](int tile, int& m0w, int& n0w, int& nch, int& bn_t, int& split) -> bool {
+      int lin, n_off;
+      decode(tile, lin, bn_t, n_off);
+      const int n_blk = lin % p.n_tiles;
+      const int m_blk = (lin / p.n_tiles) % m_tiles;
+      split = lin / (p.n_tiles * m_tiles);
       if (m_blk * kTileM >= m_lim || split * kb_per_split >= kb_lim) return false;
       m0w = m_blk * kTileM + pm_off + (int)half * kBlockM + q * 32;
-      n0w = n_blk * tile_n + pn_off;   // the pair's full block_n columns (each CTA stores its 128 rows x block_n)
-      nch = (p.N > n0w) ? min(p.block_n, p.N - n0w + 31) / 32 : 0;  // skip chunks (or whole tiles) past N
+      n0w = n_blk * tile_n + pn_off + n_off;   // the tile's columns (each CTA stores its 128 rows x bn_t)
+      nch = (p.N > n0w) ? min(bn_t, p.N - n0w + 31) / 32 : 0;  // skip chunks (or whole tiles) past N
       if (p.dbg & 8u) nch = 0;
       return true;
     };
@@ -639,17 +670,16 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     int tile = 0;
     uint32_t cit = 0;
     while (next_tile_warp(tile, cit)) {
-      int m0, n0, n_chunks;
-      if (!tile_coords(tile, m0, n0, n_chunks)) continue;
+      int m0, n0, n_chunks, bn_t, split;
+      if (!tile_coords(tile, m0, n0, n_chunks, bn_t, split)) continue;
       if (p.mul_act && lane == 0) {   // every box of the previous tile has been consumed: all kMulDepth slots are free
         la_c = 0; la_nch = n_chunks; la_m0 = m0; la_n0 = n0;
         for (int i = 0; i < kMulDepth; ++i) mul_prefetch();
       }
-      const int split = tile / (p.n_tiles * m_tiles);
       const bool use_bias = (p.bias != nullptr) && (split == 0);
       if (use_bias) {
         named_bar_sync(1, kEpiThreads);  // the warps run independently: nobody may still be reading the previous bias tile
-        for (int i = epi_tid; i < p.block_n; i += kEpiThreads) sBias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
+        for (int i = epi_tid; i < bn_t; i += kEpiThreads) sBias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase, 4);
       tc_fence_after();
@@ -1132,6 +1162,17 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
       if (rc) { p.b_3d = 0; rc = make_map(&p.tmB, pb, (uint64_t)N, (uint64_t)K, (uint64_t)a.ldb, 32, kBlockK, eb.swz); }
     }
     if (rc) return rc;
+    // half-width tail tiles (see the kernel): single-CTA / CTA-pair engines, no split-K, and a tile width whose half still
+    // is a whole number of 32-column slabs per CTA
+    static const char* env_tail = getenv("CAPDEC_GEMM_TAIL");   // "0" disables (bring-up / A-B)
+    p.tail_ok = (mode <= 1 && p.splits == 1 && (bn_local / 2) % 32 == 0 && !(env_tail && env_tail[0] == '0')) ? 1 : 0;
+    if (p.tail_ok) {
+      if (!a.b_major) rc = make_map(&p.tmBh, pb, (uint64_t)K, (uint64_t)N, (uint64_t)a.ldb, kBlockK, b_rows / 2, eb.swz);
+      else if (p.b_3d) rc = make_map_mn3d(&p.tmBh, pb, (uint64_t)N, (uint64_t)K, (uint64_t)a.ldb, b_slabs / 2, eb.swz);
+      else p.tmBh = p.tmB;                      // 32-wide slab boxes: the same map serves both widths
+      if (rc) return rc;
+      p.idesc_h = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)((bn / 2) >> 3) << 17);
+    }
   }
   rc = make_map(&p.tmC, a.C, (uint64_t)N, (uint64_t)M, (uint64_t)a.ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);  // per-warp {32 x 32} boxes
   if (rc) return rc;

@@ -669,3 +669,39 @@ def test_gemm_gelu_forward_with_stored_derivative_and_multiply_backward(ops):
     refdx = (trunc_tf32(dy).double() @ trunc_tf32(W2).double().t()) * aux.double()
     assert (dx.double() - refdx).abs().max() < 2e-4 * max(1.0, refdx.abs().max().item())
     assert (db.double() - refdx.sum(0)).abs().max() < 2e-3 * max(1.0, refdx.sum(0).abs().max().item())
+
+
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("bn", [256, 128])
+def test_gemm_half_width_tail_tiles(ops, pair, a_major, b_major, bn):
+    """A tile count that leaves a small last wave (here: full waves + <= 1/2 wave) is finished with half-width tiles
+    (csrc/gemm_tf32.cu `decode`): same numbers as the full-width schedule (CAPDEC_GEMM_TAIL=0 is compiled out here, so the
+    reference is the truncated fp64 product), incl. bias + gelu_new + second output, N tail, and a device row limit."""
+    from capdec_b200 import _lib
+    lib = _lib.load()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    units = sms // 2 if pair else sms
+    tile_m = 256 if pair else 128
+    n_tiles = 5
+    m_tiles = (units + 6 + n_tiles - 1) // n_tiles + 1          # base tiles = units + a handful -> tail of a few tiles
+    M, N, K = m_tiles * tile_m - 37, n_tiles * bn - 19, 160
+    A, Al, B, Bl = make_ab(M, N, K, a_major, b_major, seed=5)
+    bias = torch.randn(N, device="cuda")
+    C, aux = new_c(M, N), new_c(M, N)
+    lib.capdec_gemm_debug_force_pair(pair)
+    try:
+        ops.gemm(A, a_major, B, b_major, C, M, N, K, bias=bias, act=1, aux=aux, block_n=bn)
+        pre = trunc_tf32(Al).double() @ trunc_tf32(Bl).double().t() + bias.double()
+        assert (aux.double() - pre).abs().max() < 1e-3
+        assert (C.double() - torch.nn.functional.gelu(pre, approximate="tanh")).abs().max() < 2e-3
+        # device row limit: only whole live tiles are computed, the rest of C stays untouched
+        live = M - 3 * tile_m - 5
+        lim = torch.tensor([live], device="cuda", dtype=torch.int32)
+        C2 = new_c(M, N)
+        ops.gemm(A, a_major, B, b_major, C2, M, N, K, bias=bias, block_n=bn, m_limit=lim)
+        assert (C2[:live].double() - pre[:live]).abs().max() < 1e-3
+        done = (live + tile_m - 1) // tile_m * tile_m
+        assert torch.isnan(C2[done:]).all()
+    finally:
+        lib.capdec_gemm_debug_force_pair(-1)
