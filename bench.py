@@ -449,6 +449,11 @@ def run_gpu(args):
         e2e = captions / (ms_e2e * 1e-3)
         tf32_peak = pk["bf16"] / 2.0
         qkv_tf, qkv_ms = qkv_gemm_roofline(cb, torch)
+        traffic = {"bytes": None, "source": "no ncu capture committed"}
+        tp = ROOT / "profiles" / "qkv_traffic.json"      # written from the latest `ncu --set full` capture of this kernel
+        if tp.exists():
+            tj = json.loads(tp.read_text())
+            traffic = {"bytes": tj["dram_bytes_read"] + tj["dram_bytes_write"], "source": tj["source"]}
         step_tf = flops_per_caption(P=P_LEN) * B / (ms_dev / args.steps * 1e-3) / 1e12   # what the reference executes
         packed = bool(model.engine().packed)
         ex_flops, live_rows, dense_rows = executed_flops(host[0][0], P_LEN, packed)
@@ -513,8 +518,9 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (fused-QKV GEMM 12800x2304x768 + bias)",
                          "achieved": qkv_tf, "peak": tf32_peak, "unit": "TFLOP/s", "frac": qkv_tf / tf32_peak,
-                         "traffic": 108.9e6, "traffic_unit": "bytes/launch, dram read+write, ncu --set full (profiles/r1_ncu_session3.md); "
-                                                                "algorithmic 164.4e6 (operands + output once)",
+                         "traffic": traffic["bytes"], "traffic_source": traffic["source"],
+                         "traffic_unit": "bytes/launch, dram__bytes_read.sum + dram__bytes_write.sum of this kernel in one ncu --set full "
+                                         "capture (not measured in this run: ncu cannot wrap a timed run); algorithmic 164.4e6",
                          "ms_per_launch": qkv_ms,
                          "peak_source": pk["source"] + ": bf16 burst %.1f TF/s / 2 (kind::tf32 issues at half the kind::f16 rate)" % pk["bf16"],
                          "step_executed_tflops": exec_tf, "step_executed_frac_of_tf32_peak_sustained": exec_tf / (pk["bf16_sustained"] / 2.0),

@@ -11,9 +11,10 @@ from .optim import AdamW, get_linear_schedule_with_warmup
 from .trainer import Trainer
 from .data import DeviceCaptionDataset
 from .decode import BeamDecoder, generate2, generate_beam, generate_beam_batch, generate_beam_ids, generate_greedy_ids
+from .bridger import ModalityBridger, get_map_to_text_space_using_modality_bridger
 from . import ops
 from . import fit
 
-__all__ = ["ClipCaptionModel", "ClipCaptionPrefix", "GPT2Config", "GPT2LMHead", "MappingType", "MLP",
+__all__ = ["ModalityBridger", "get_map_to_text_space_using_modality_bridger", "ClipCaptionModel", "ClipCaptionPrefix", "GPT2Config", "GPT2LMHead", "MappingType", "MLP",
            "TransformerMapper", "TransformerEncoderDecoder", "noise_injection", "AdamW", "get_linear_schedule_with_warmup", "Trainer", "ops",
            "DeviceCaptionDataset", "BeamDecoder", "generate_beam", "generate_beam_batch", "generate_beam_ids", "generate2", "generate_greedy_ids", "fit"]

@@ -277,58 +277,150 @@ class Engine:
                 ops.add_ln_fwd(ma.hm1[j], ma.t, ma.hm[nl], ma.scratch, ma.sscr, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
         ops.rows_gather(ma.hm[nl], pp.view(B * P, d), B, S, P, C)  # out = transformer(prefix)[:, clip_length:]
 
-    def _mapper_layer_fwd(self, pre, ws, x_in, x_out, B, Tq, c, kv_src=None, Tk=None, c_ref=None):
+    def _mapper_layer_fwd(self, pre, ws, x_in, x_out, B, Tq, c, kv_src=None, Tk=None, c_ref=None, sv=None):
         """One transformer_mapper.TransformerLayer (transformer_mapper.py:63-66): x_out = x1 + mlp(norm2(x1)),
         x1 = x_in + project(attention(q = to_queries(norm1(x_in)), k|v = to_keys_values(kv_src))).
-        kv_src None -> norm1(x_in) (the layer's own normalised input), else a [B*Tk, c_ref] matrix."""
+        kv_src None -> norm1(x_in) (the layer's own normalised input), else a [B*Tk, c_ref] matrix.
+        sv: per-layer buffers that keep what backward needs (training); None -> the shared scratch `ws` (inference)."""
         p = self.p
         H = self.mH
         hd = c // H
         Mq = B * Tq
-        ops.add_ln_fwd(x_in, None, None, ws.y, ws.st, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
-        ops.gemm(ws.y, 0, p[pre + "attn.to_queries.weight"], 0, ws.q, Mq, c, c)
-        if kv_src is None:
-            kv_src, Tk, c_ref = ws.y, Tq, c
+        k_ = sv if sv is not None else ws              # where y1 / st1 / q / kv / o / x1 / f live
+        y2, st2 = (sv.y2, sv.st2) if sv is not None else (ws.y, ws.st)
+        ops.add_ln_fwd(x_in, None, None, k_.y, k_.st, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
+        ops.gemm(k_.y, 0, p[pre + "attn.to_queries.weight"], 0, k_.q, Mq, c, c)
+        self_norm = kv_src is None
+        if self_norm:
+            kv_src, Tk, c_ref = k_.y, Tq, c
         Mk = B * Tk
-        kv = ws.kv[:Mk]
+        kv = k_.kv[:Mk]
         ops.gemm(kv_src, 0, p[pre + "attn.to_keys_values.weight"], 0, kv, Mk, 2 * c, c_ref)
-        ops.attention_fwd(ws.q, kv[:, :c], kv[:, c:], ws.o, None, B, H, Tq, Tk, hd, Tq * c, c, Tk * 2 * c, 2 * c, Tq * c, c,
-                          hd ** -0.5, 0)
-        ops.linear_fwd(ws.o, p[pre + "attn.project.weight"], "linear", p[pre + "attn.project.bias"], ws.t)
-        ops.add_ln_fwd(x_in, ws.t, ws.x1, ws.y, ws.st, p[pre + "norm2.weight"], p[pre + "norm2.bias"])
-        ops.linear_fwd(ws.y, p[pre + "mlp.fc1.weight"], "linear", p[pre + "mlp.fc1.bias"], ws.f, act=ops.ACT_RELU)
-        ops.linear_fwd(ws.f, p[pre + "mlp.fc2.weight"], "linear", p[pre + "mlp.fc2.bias"], ws.t)
+        ops.attention_fwd(k_.q, kv[:, :c], kv[:, c:], k_.o, sv.lse if sv is not None else None, B, H, Tq, Tk, hd, Tq * c, c,
+                          Tk * 2 * c, 2 * c, Tq * c, c, hd ** -0.5, 0)
+        ops.linear_fwd(k_.o, p[pre + "attn.project.weight"], "linear", p[pre + "attn.project.bias"], ws.t)
+        ops.add_ln_fwd(x_in, ws.t, k_.x1, y2, st2, p[pre + "norm2.weight"], p[pre + "norm2.bias"])
+        ops.linear_fwd(y2, p[pre + "mlp.fc1.weight"], "linear", p[pre + "mlp.fc1.bias"], k_.f, act=ops.ACT_RELU)
+        ops.linear_fwd(k_.f, p[pre + "mlp.fc2.weight"], "linear", p[pre + "mlp.fc2.bias"], ws.t)
         # last residual add: reuse the fused add + LayerNorm kernel and discard its LayerNorm output
-        ops.add_ln_fwd(ws.x1, ws.t, x_out, ws.y, ws.st, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
+        ops.add_ln_fwd(k_.x1, ws.t, x_out, ws.y, ws.st, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
+        if sv is not None:
+            sv.x_in, sv.kv_src, sv.Tk, sv.c_ref, sv.self_norm = x_in, kv_src, Tk, c_ref, self_norm
+
+    def _encdec_train_buffers(self, ma, B):
+        """Per-layer activations of the TransformerDecoder mapper kept for backward, plus gradient scratch."""
+        if getattr(ma, "sv_enc", None) is not None:
+            return
+        C, P, d, de = self.C, self.P, self.d, self.de
+        e = lambda *s: torch.empty(*s, device=self.dev, dtype=torch.float32)
+
+        def mk(rows, c, rows_kv, T):
+            return SimpleNamespace(y=e(rows, c), st=e(rows, 2), q=e(rows, c), kv=e(rows_kv, 2 * c), o=e(rows, c), x1=e(rows, c),
+                                   y2=e(rows, c), st2=e(rows, 2), f=e(rows, 2 * c), lse=e(B * self.mH * T), x_out=e(rows, c))
+        ma.sv_enc = [mk(B * C, de, B * C, C) for _ in range(self.n_enc_layers)]
+        ma.sv_dec = [mk(B * P, d, B * max(C, P), P) for _ in range(self.n_dec_layers)]
+        ma.h0 = e(B * P, d)
+        n = B * max(C, P) * max(d, de)
+        ma.g = SimpleNamespace(cur=e(n), t=e(n), f=e(2 * n), q=e(n), kv=e(2 * n), o=e(n), ref=e(B * C, de), lin=e(B, C * de))
 
     def _encdec_fwd(self, x, pp, ma):
-        """transformer_mapper.TransformerEncoderDecoder.forward (transformer_mapper.py:132-137), forward only."""
+        """transformer_mapper.TransformerEncoderDecoder.forward (transformer_mapper.py:132-137).  Inference reuses one set
+        of scratch buffers; with the mapper in train mode every layer keeps its activations for `_encdec_bwd`."""
         B = x.shape[0]
         p = self.p
         C, P, d, de = self.C, self.P, self.d, self.de
+        train = bool(self.m.clip_project.training)
+        if train:
+            self._encdec_train_buffers(ma, B)
         ops.linear_fwd(x, p["clip_project.linear.weight"], "linear", p["clip_project.linear.bias"], ma.lin)
-        cur, nxt = ma.lin.view(B * C, de), ma.enc.xa
+        cur = ma.lin.view(B * C, de)
         for j in range(self.n_enc_layers):          # ref_encoder: plain self-attention layers over the C tokens
-            self._mapper_layer_fwd(f"clip_project.ref_encoder.layers.{j}.", ma.enc, cur, nxt, B, C, de)
-            cur, nxt = nxt, (ma.enc.xb if nxt is ma.enc.xa else ma.enc.xa)
+            sv = ma.sv_enc[j] if train else None
+            nxt = sv.x_out if train else (ma.enc.xb if cur is ma.enc.xa else ma.enc.xa)
+            self._mapper_layer_fwd(f"clip_project.ref_encoder.layers.{j}.", ma.enc, cur, nxt, B, C, de, sv=sv)
+            cur = nxt
         ref = cur
-        h, hn = ma.dec.xa, ma.dec.xb
+        h = ma.h0 if train else ma.dec.xa
         h.view(B, P, d).copy_(p["clip_project.prefix_const"].unsqueeze(0).expand(B, P, d))   # broadcast, no arithmetic
         for j in range(self.n_dec_layers):          # even: cross-attention to ref; odd: keys/values from the raw stream
             pre = f"clip_project.prefix_decoder.layers.{j}."
+            sv = ma.sv_dec[j] if train else None
+            hn = sv.x_out if train else (ma.dec.xb if h is ma.dec.xa else ma.dec.xa)
             if j % 2 == 0:
-                self._mapper_layer_fwd(pre, ma.dec, h, hn, B, P, d, kv_src=ref, Tk=C, c_ref=de)
+                self._mapper_layer_fwd(pre, ma.dec, h, hn, B, P, d, kv_src=ref, Tk=C, c_ref=de, sv=sv)
             else:
-                self._mapper_layer_fwd(pre, ma.dec, h, hn, B, P, d, kv_src=h, Tk=P, c_ref=d)
-            h, hn = hn, h
+                self._mapper_layer_fwd(pre, ma.dec, h, hn, B, P, d, kv_src=h, Tk=P, c_ref=d, sv=sv)
+            h = hn
         pp.view(B * P, d).copy_(h)
+        ma.trained_fwd = train
+
+    def _mapper_layer_bwd(self, pre, sv, dcur, gs, B, Tq, c, dref=None):
+        """Backward of one TransformerLayer.  dcur [B*Tq, c]: gradient of the layer output on entry, of the layer input
+        on exit.  Cross layers add the gradient of their key/value source into `dref`; layers whose keys/values come from
+        the un-normalised stream add it into dcur; self layers into the gradient of norm1's output."""
+        p, g = self.p, self.g
+        H = self.mH
+        hd = c // H
+        Mq, Tk = B * Tq, sv.Tk
+        Mk = B * Tk
+        view = lambda t, rows, cols: t[: rows * cols].view(rows, cols)
+        dt, df, dq, do = view(gs.t, Mq, c), view(gs.f, Mq, 2 * c), view(gs.q, Mq, c), view(gs.o, Mq, c)
+        dkv = view(gs.kv, Mk, 2 * c)
+        # ---- x_out = x1 + fc2(relu(fc1(norm2(x1)))) ----
+        ops.linear_wgrad(sv.f, dcur, g[pre + "mlp.fc2.weight"], "linear", g[pre + "mlp.fc2.bias"])
+        ops.linear_dgrad_act(dcur, p[pre + "mlp.fc2.weight"], "linear", df, sv.f, ops.ACT_RELU, dbias=g[pre + "mlp.fc1.bias"])
+        ops.linear_wgrad(sv.y2, df, g[pre + "mlp.fc1.weight"], "linear")
+        ops.linear_dgrad(df, p[pre + "mlp.fc1.weight"], "linear", dt)
+        ops.add_ln_bwd(dt, sv.x1, sv.st2, p[pre + "norm2.weight"], dcur, dcur, None, g[pre + "norm2.weight"],
+                       g[pre + "norm2.bias"], dbias_branch=g[pre + "attn.project.bias"])
+        # ---- x1 = x_in + project(attention(...)) : dcur is d(x1) now ----
+        ops.linear_wgrad(sv.o, dcur, g[pre + "attn.project.weight"], "linear")
+        ops.linear_dgrad(dcur, p[pre + "attn.project.weight"], "linear", do)
+        kv = sv.kv[:Mk]
+        ops.attention_bwd(sv.q, kv[:, :c], kv[:, c:], sv.o, do, sv.lse, dq, dkv[:, :c], dkv[:, c:], B, H, Tq, Tk, hd, Tq * c, c,
+                          Tk * 2 * c, 2 * c, Tq * c, c, hd ** -0.5, 0)
+        ops.linear_wgrad(sv.y, dq, g[pre + "attn.to_queries.weight"], "linear")
+        ops.linear_dgrad(dq, p[pre + "attn.to_queries.weight"], "linear", dt)                # d(norm1 output) from the queries
+        ops.linear_wgrad(sv.kv_src, dkv, g[pre + "attn.to_keys_values.weight"], "linear")
+        wkv = p[pre + "attn.to_keys_values.weight"]
+        if sv.self_norm:                       # keys/values from norm1(x_in) as well
+            ops.linear_dgrad(dkv, wkv, "linear", dt, accumulate=True)
+        elif dref is not None:                 # cross-attention: keys/values from the encoder output
+            ops.linear_dgrad(dkv, wkv, "linear", dref, accumulate=True)
+        else:                                  # keys/values from the un-normalised stream entering this layer
+            ops.linear_dgrad(dkv, wkv, "linear", dcur, accumulate=True)
+        ops.add_ln_bwd(dt, sv.x_in, sv.st, p[pre + "norm1.weight"], dcur, dcur, None, g[pre + "norm1.weight"],
+                       g[pre + "norm1.bias"])
+
+    def _encdec_bwd(self, x, dpp, ma):
+        """Backward of TransformerEncoderDecoder (what autograd derives from transformer_mapper.py:132-137 when
+        gpt2_prefix.py:219-243 trains a MappingType.TransformerDecoder model)."""
+        if not getattr(ma, "trained_fwd", False):
+            raise CapdecError("TransformerDecoder mapper: backward needs a forward pass run in train mode")
+        B = x.shape[0]
+        g = self.g
+        C, P, d, de = self.C, self.P, self.d, self.de
+        gs = ma.g
+        dcur = gs.cur[: B * P * d].view(B * P, d)
+        dcur.copy_(dpp.view(B * P, d))
+        dref = gs.ref
+        ops.zero_fill(dref)
+        for j in reversed(range(self.n_dec_layers)):
+            self._mapper_layer_bwd(f"clip_project.prefix_decoder.layers.{j}.", ma.sv_dec[j], dcur, gs, B, P, d,
+                                   dref=dref if j % 2 == 0 else None)
+        ops.colsum_acc(dcur.view(B, P * d), g["clip_project.prefix_const"].view(-1))       # prefix_const is broadcast over B
+        dcur = gs.cur[: B * C * de].view(B * C, de)
+        dcur.copy_(dref)
+        for j in reversed(range(self.n_enc_layers)):
+            self._mapper_layer_bwd(f"clip_project.ref_encoder.layers.{j}.", ma.sv_enc[j], dcur, gs, B, C, de)
+        gs.lin.view(B * C, de).copy_(dcur)
+        ops.linear_wgrad(x, gs.lin, g["clip_project.linear.weight"], "linear", g["clip_project.linear.bias"])
 
     def _mapper_bwd(self, x, dpp):
-        if self.is_encdec:
-            raise CapdecError("the TransformerDecoder mapper (transformer_mapper.TransformerEncoderDecoder) is "
-                              "inference-only here: the reference's train.py cannot construct it (train.py:42-44)")
         B = x.shape[0]
         ma = self._mapper_arena(B)
+        if self.is_encdec:
+            return self._encdec_bwd(x, dpp, ma)
         p, g = self.p, self.g
         if self.is_mlp:
             w2, w1 = "clip_project.model.2.", "clip_project.model.0."

@@ -237,8 +237,8 @@ class TransformerMapper(nn.Module):
 class TransformerEncoderDecoder(nn.Module):
     """transformer_mapper.py:130-145 (gpt2_prefix.py:167-168, MappingType.TransformerDecoder): a 512-wide encoder over
     the CLIP embedding re-shaped to `clip_length` tokens, and a decoder whose `prefix_length` learned query tokens
-    cross-attend to it.  Inference-side mapper of predictions_runner.py:457-460; train.py cannot construct it, so only
-    its forward pass is implemented (the backward raises)."""
+    cross-attend to it.  Inference-side mapper of predictions_runner.py:457-460; train.py cannot construct it, but
+    gpt2_prefix.py:219-243 trains it, so forward AND backward run on the kernels (Engine._encdec_fwd / _encdec_bwd)."""
 
     num_heads = 8
     dim_ref = 512

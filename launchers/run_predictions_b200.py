@@ -57,6 +57,15 @@ def bind(ref_dir: str):
     sys.path.insert(0, ref_dir)
     shim.ClipCocoDataset = _reference_dataset_class(ref_dir)     # gpt2_prefix_eval.py:7
     sys.modules["gpt2_prefix"] = shim              # predictions_runner.py:7
+    # --modality_bridger (predictions_runner.py:182-184): `from others.supervised_embedding_bridger import
+    # get_map_to_text_space_using_modality_bridger` resolves to the 8-GEMM stack on our kernels (same weights file)
+    others = sys.modules.setdefault("others", types.ModuleType("others"))
+    if not hasattr(others, "__path__"):
+        others.__path__ = [str(Path(ref_dir) / "others")]
+    bridger = types.ModuleType("others.supervised_embedding_bridger")
+    bridger.get_map_to_text_space_using_modality_bridger = cb.get_map_to_text_space_using_modality_bridger
+    bridger.MLP = cb.ModalityBridger
+    sys.modules["others.supervised_embedding_bridger"] = bridger
     import gpt2_prefix_eval
     gpt2_prefix_eval.generate_beam = cb.generate_beam            # gpt2_prefix_eval.py:50-115
     import predictions_runner

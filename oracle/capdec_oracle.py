@@ -326,6 +326,27 @@ def make_encdec_state_dict(seed: int, prefix_length: int = 10, clip_length: int 
     return sd
 
 
+def make_bridger_state_dict(seed: int, dim: int = 640, num_layers: int = 8, dtype=torch.float32) -> Params:
+    """Seeded weights in the layout of others/weights_modality_mapper.pt (`layers.{i}.weight [dim,dim]`, `.bias [dim]`):
+    near-identity matrices plus noise, so that the ReLU stack neither dies nor explodes."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for i in range(num_layers):
+        sd[f"layers.{i}.weight"] = (torch.eye(dim) + 0.05 * torch.randn(dim, dim, generator=g)).to(dtype)
+        sd[f"layers.{i}.bias"] = (0.02 * torch.randn(dim, generator=g)).to(dtype)
+    return sd
+
+
+def modality_bridger(sd: Params, x, num_layers: int = 8):
+    """others/supervised_embedding_bridger.py:103-108: x <- relu(layer_i(x)) for every layer but the last, which is linear
+    (used by predictions_runner.py:225-227 before clip_project)."""
+    for i in range(num_layers):
+        x = F.linear(x, sd[f"layers.{i}.weight"], sd[f"layers.{i}.bias"])
+        if i < num_layers - 1:
+            x = F.relu(x)
+    return x
+
+
 def clip_project(sd: Params, prefix, clip_length: Optional[int] = None):
     if "clip_project.model.0.weight" in sd:
         return mlp_mapper(sd, prefix)

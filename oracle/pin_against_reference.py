@@ -249,6 +249,34 @@ def pin_generate_beam_prompt():
     print("generate_beam (prompt) ok", [r["texts"][0] for r in recs])
 
 
+def pin_modality_bridger():
+    """others/supervised_embedding_bridger.MLP (the reference's own class; `wandb` stubbed) vs the oracle restatement, on
+    seeded weights and on the reference's trained weights file -> tests/golden/bridger.json"""
+    import importlib.util
+    sys.modules.setdefault("wandb", types.ModuleType("wandb"))
+    spec = importlib.util.spec_from_file_location("_ref_bridger", str(REF / "others" / "supervised_embedding_bridger.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    recs = []
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(5, 640, generator=g)
+    x = x / x.norm(2, -1, keepdim=True)
+    for name, sd in (("seeded", O.make_bridger_state_dict(seed=9)),
+                     ("trained", torch.load(REF / "others" / "weights_modality_mapper.pt", map_location="cpu"))):
+        ref = mod.MLP(640, 640, 640, 8)
+        ref.load_state_dict(sd, strict=True)
+        ref.eval()
+        with torch.no_grad():
+            y_ref = ref(x)
+        y = O.modality_bridger(sd, x)
+        assert torch.equal(y, y_ref), (name, (y - y_ref).abs().max())
+        if name == "seeded":
+            recs.append({"weights": "make_bridger_state_dict(seed=9)", "x_seed": 77, "y_row0": y_ref[0, :16].double().tolist(),
+                         "y_norms": y_ref.norm(2, -1).double().tolist(), "y_sum": float(y_ref.double().sum())})
+    (GOLD / "bridger.json").write_text(json.dumps({"cases": recs}, indent=1))
+    print("modality bridger ok (oracle == reference MLP bit for bit on seeded and on the trained weights)")
+
+
 def pin_generate2():
     """gpt2_prefix_eval.generate2 (the reference's own function: greedy decode behind a top-p mask) vs the oracle
     restatement -> tests/golden/greedy.json"""
@@ -358,6 +386,7 @@ if __name__ == "__main__":
     main()
     pin_generate_beam()
     pin_generate_beam_prompt()
+    pin_modality_bridger()
     pin_generate2()
     pin_dataset()
     pin_encdec_mapper()

@@ -76,6 +76,8 @@ assert pr.generate2 is cb.generate2 and ev.generate2 is cb.generate2
 assert all(hasattr(pr.MappingType, n) for n in ("MLP", "TransformerEncoder", "TransformerDecoder"))    # predictions_runner.py:457-458
 assert pr.make_preds.__code__.co_filename.startswith(sys.argv[2])        # the reference's own loop, unmodified
 assert sys.modules["gpt2_prefix"].ClipCocoDataset.__name__ == "ClipCocoDataset"
+from others.supervised_embedding_bridger import get_map_to_text_space_using_modality_bridger as g    # predictions_runner.py:183
+assert g is cb.get_map_to_text_space_using_modality_bridger
 print("bound")
 """
     r = subprocess.run([sys.executable, "-c", code, str(ROOT / "launchers" / "run_predictions_b200.py"), str(REF)],
