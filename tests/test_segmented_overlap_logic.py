@@ -1,8 +1,9 @@
 """CPU dry run of the segmented-graph data-parallel overlap (Trainer._capture_segments / _replay_segments,
 CAPDEC_DP_OVERLAP=2): torch.cuda's graph / stream / event objects and the engine are replaced by recording fakes, so this
-checks the HOST ordering logic only — one capture per backward block boundary, the bucket of block l reduced right after
-the segment that finished block l, [tail | mapper | wte | wpe] last, no collective inside any capture, every collective
-on the side stream after an event on the main stream.  The numerical check runs on 2 GPUs (tests/test_dp_gpu.py)."""
+checks the HOST ordering logic only — one capture per backward block boundary, the global token count all-reduced first,
+the bucket of block l reduced AND its parameters updated right after the segment that finished block l,
+[tail | mapper | wte | wpe] last, no collective inside any capture, every collective on the side stream after an event on
+the main stream.  The numerical check runs on 2 GPUs (tests/test_dp_gpu.py, which passes on hardware)."""
 import contextlib
 
 import torch
@@ -103,11 +104,17 @@ def test_segment_capture_and_replay_order(monkeypatch):
     tr.train_gpt, tr.overlap, tr.segmented, tr.opt_overlap, tr.pg = True, False, True, False, None
     tr.buckets = [torch.tensor([float(l)]) for l in range(12)]      # bucket tag = layer index
     tr.head_bucket = torch.tensor([99.0])
+    tr.layer_spans = [(100 + l, 101 + l) for l in range(12)]        # parameter span tag = 100 + layer index
+    tr.head_span = (199, 200)
+    tr.tail = torch.tensor([-7.0, 0.0, 0.0, 0.0])                   # [n_valid, loss_sum, ., .]: tag -7
+    tr.stats = torch.zeros(4)
     tr.comm = FakeStream("comm")
+    monkeypatch.setattr(T.Trainer, "_adamw_span", lambda self, lo, hi: LOG.append(("adamw", lo, CUR[-1].name)))
 
     segs = tr._capture_segments()
     assert len(segs) == 13
-    assert [int(b[0]) for _, b in segs] == [11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 99]
+    assert [int(b[0]) for _, b, _ in segs] == [11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 99]
+    assert [sp[0] for _, _, sp in segs] == [111, 110, 109, 108, 107, 106, 105, 104, 103, 102, 101, 100, 199]
     # captures are strictly sequential, each closed before the next opens, and no collective happened while capturing
     caps = [e for e in LOG if e[0] in ("begin", "end")]
     assert caps == [x for i in range(1, 14) for x in (("begin", i), ("end", i))]
@@ -120,11 +127,15 @@ def test_segment_capture_and_replay_order(monkeypatch):
     LOG.clear()
     tr._segs = segs
     tr._replay_segments()
-    order = [e for e in LOG if e[0] in ("replay", "all_reduce")]
+    order = [e for e in LOG if e[0] in ("replay", "all_reduce", "adamw")]
     expect = []
-    for (g, b) in segs:
-        expect += [("replay", g.id), ("all_reduce", int(b[0]), "comm", False)]
+    for i, (g, b, sp) in enumerate(segs):
+        expect += [("replay", g.id)]
+        if i == 0:
+            expect += [("all_reduce", -7, "comm", False)]           # the global token count, before any update
+        expect += [("all_reduce", int(b[0]), "comm", False), ("adamw", sp[0], "comm")]
     assert order == expect
     # every collective waits for an event recorded on the main stream after its segment; main joins the side stream last
     assert LOG.count(("wait_event", "comm", "main")) == 13
+    assert LOG[0] == ("wait_stream", "comm", "main")                # updates must not overtake the previous step's forward
     assert LOG[-1] == ("wait_stream", "main", "comm")

@@ -16,7 +16,7 @@ sys.path.insert(0, str(ROOT))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=12)
     a = ap.parse_args()
     import torch
     from torch.profiler import profile, ProfilerActivity
@@ -50,8 +50,9 @@ def main():
     starts = [i for i, k in enumerate(ks) if "step_clock" in k[2]]
     print(f"# r2 — kernel timeline of the CUDA-graph'ed C2 step (CUPTI via torch.profiler; {len(ks)} kernel records, "
           f"{len(starts)} steps; un-profiled step time {ms_plain:.3f} ms)\n")
-    print("| step | span ms | busy (union) ms | idle gaps ms | two kernels overlapping ms | sum of kernel durations ms | kernels |")
-    print("|---|---:|---:|---:|---:|---:|---:|")
+    print("| step | span ms | busy (union) ms | idle gaps ms | two kernels overlapping ms | sum of kernel durations ms | kernels | "
+          "gap to the next step's first kernel ms |")
+    print("|---|---:|---:|---:|---:|---:|---:|---:|")
     per_name = collections.Counter()
     for si, s in enumerate(starts):
         e = starts[si + 1] if si + 1 < len(starts) else len(ks)
@@ -73,7 +74,8 @@ def main():
                     busy += en - cur_end
                     cur_end = en
         span = t1 - t0
-        print(f"| {si} | {span / 1e3:.3f} | {busy / 1e3:.3f} | {(span - busy) / 1e3:.3f} | {overlap / 1e3:.3f} | {total / 1e3:.3f} | {len(seg)} |")
+        nxt = (ks[e][0] - t1) / 1e3 if e < len(ks) else float("nan")
+        print(f"| {si} | {span / 1e3:.3f} | {busy / 1e3:.3f} | {(span - busy) / 1e3:.3f} | {overlap / 1e3:.3f} | {total / 1e3:.3f} | {len(seg)} | {nxt:.3f} |")
     print("\n| kernel | us per step (sum of durations) |\n|---|---:|")
     for n, v in per_name.most_common(12):
         print(f"| `{n}` | {v:.1f} |")
