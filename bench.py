@@ -40,6 +40,7 @@ def flops_per_caption(P=P_LEN, L=SEQ, d=D_MODEL, F=F_MLP, nl=N_LAYER, Dc=D_CLIP)
 
 
 NO_CPU = os.environ.get("CAPDEC_BENCH_NO_CPU", "0") == "1"   # profiling runs (ncu) skip the cpu_baseline leg
+E2E_SYNC_LOSS = os.environ.get("CAPDEC_BENCH_SYNC_LOSS", "0") == "1"   # e2e leg: block on every step's loss (loss.item())
 FULL_LENGTH = False   # --full_length: every caption has all 40 tokens (worst case for the packed path)
 
 
@@ -433,7 +434,11 @@ def run_gpu(args):
     last = 0.0
     for i in range(args.steps):
         tr.step(*host[i % nb])
-        last = tr.loss()                      # D2H of the step's (n_valid, loss_sum) + sync, like loss.item() (train.py:355)
+        if E2E_SYNC_LOSS:
+            last = tr.loss()                  # D2H of the step's (n_valid, loss_sum) + sync, like loss.item() (train.py:355)
+        else:
+            tr.loss_lagged()                  # D2H of THIS step's (n_valid, loss_sum) enqueued; blocks on the previous step's only
+    last = tr.loss()                          # the last step's loss on the host: inside the timed region
     f1.record()
     sync()
     ms_e2e = f0.elapsed_time(f1)
@@ -456,6 +461,7 @@ def run_gpu(args):
             traffic = {"bytes": tj["dram_bytes_read"] + tj["dram_bytes_write"], "source": tj["source"]}
         step_tf = flops_per_caption(P=P_LEN) * B / (ms_dev / args.steps * 1e-3) / 1e12   # what the reference executes
         packed = bool(model.engine().packed)
+        tr_peer, tr_sharded = bool(getattr(tr, "peer", False)), bool(getattr(tr, "sharded", False))
         ex_flops, live_rows, dense_rows = executed_flops(host[0][0], P_LEN, packed)
         exec_tf = ex_flops / (ms_dev / args.steps * 1e-3) / 1e12
         # ---- worst case for the packed path: every caption 40 tokens long (SURVEY §8d "also run l = 40"), same trainer,
@@ -507,12 +513,20 @@ def run_gpu(args):
                 "rows": (f"packed: {live_rows} of {dense_rows} trunk rows per step are live (padding and each caption's "
                          "final token cannot reach the loss and are skipped; CAPDEC_PACKED=0 runs every row)"
                          if packed else f"dense: all {dense_rows} trunk rows per step"),
+                **({"dp_update": ("one kernel per rank over NVLink peer memory: loads its 1/N slice of every rank's gradients, "
+                                  "HF-AdamW, stores the new parameters into every rank's buffer (csrc/peer.cu)" if tr_peer else
+                                  ("NCCL reduce-scatter + AdamW on 1/N + NCCL all-gather" if tr_sharded else "NCCL all-reduce + full AdamW"))}
+                   if world > 1 else {}),
                 "l2": "working set per step (0.62 GB weights + 7.5 GB activations) >> 126 MB L2; 8 distinct host batches",
                 "arithmetic": ("fp32 storage, 3xTF32 tcgen05 GEMMs (hi/lo split in the pipeline) + 3xTF32 attention, fp32 elsewhere"
                                if args.precision == "tf32x3" else
                                "fp32 storage, TF32 tcgen05 GEMMs with fp32 TMEM accumulation, fp32 everywhere else")}),
             "e2e": {"value": e2e, "unit": "captions/s", "h2d_bytes_per_step": B * SEQ * 8 + B * D_CLIP * 4,
-                    "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps,
+                    "loss_read": ("synchronous tr.loss() after every step" if E2E_SYNC_LOSS else
+                                  "every step's (n_valid, loss_sum) copied to pinned host memory; the host waits for the copy of "
+                                  "step i-1 while step i runs (Trainer.loss_lagged), the last step's loss is read inside the timed "
+                                  "region; CAPDEC_BENCH_SYNC_LOSS=1 blocks on every step like loss.item()")},
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
             "clocks": clocks,

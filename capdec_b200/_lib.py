@@ -77,6 +77,10 @@ SIGNATURES = {
     "capdec_zero_fill": [_p, _i64, _p],
     "capdec_step_clock": [_p, _p, _p, _p, _f, _i, _i, _p],
     "capdec_adamw_step": [_p, _p, _p, _p, _i64, _p, _p, _f, _f, _f, _f, _p, _i, _p],
+    "capdec_peer_export": [_p, _p, _p],
+    "capdec_peer_open": [_p, _i64, _p],
+    "capdec_peer_close": [_p, _i64],
+    "capdec_adamw_peer_step": [_p, _p, _i, _i, _i64, _i64, _p, _p, _p, _p, _f, _f, _f, _f, _p, _p],
 }
 _RESTYPES = {"capdec_last_error": C.c_char_p, "capdec_launch_count": C.c_int64, "capdec_gemm_debug_mn_encoding": None,
              "capdec_gemm_debug_force_pair": None, "capdec_gemm_set_row_hint": None}

@@ -360,6 +360,40 @@ def adamw_step(p, g, m, v, lr_dev, t_dev, beta1=0.9, beta2=0.999, eps=1e-6, weig
     _lib.check(rc, "adamw_step")
 
 
+# ---- data-parallel update over NVLink peer memory (peer.cu) ------------------------------------------------------
+def peer_export(t: torch.Tensor):
+    """(64-byte CUDA-IPC handle, byte offset) of tensor `t`'s first element, for another process of this node."""
+    h = ctypes.create_string_buffer(64)
+    off = ctypes.c_int64(0)
+    rc = _lib.load().capdec_peer_export(t.data_ptr(), ctypes.cast(h, ctypes.c_void_p), ctypes.byref(off))
+    _lib.check(rc, "peer_export")
+    return bytes(h.raw), int(off.value)
+
+
+def peer_open(handle: bytes, offset: int) -> int:
+    """Map a buffer exported by another process; returns the device address of its first element."""
+    out = ctypes.c_void_p(0)
+    rc = _lib.load().capdec_peer_open(ctypes.c_char_p(handle), int(offset), ctypes.byref(out))
+    _lib.check(rc, "peer_open")
+    return int(out.value)
+
+
+def peer_close(ptr: int, offset: int) -> None:
+    _lib.check(_lib.load().capdec_peer_close(ptr, int(offset)), "peer_close")
+
+
+def adamw_peer_step(g_ptrs, p_ptrs, rank, lo, n, m, v, lr_dev, t_dev, beta1=0.9, beta2=0.999, eps=1e-6,
+                    weight_decay=0.0, grad_denom=None):
+    """Fused reduce-scatter + HF-AdamW + all-gather over peer memory: `g_ptrs` / `p_ptrs` = device addresses of every
+    rank's gradient / parameter buffer (ints, rank order); this rank updates elements [lo, lo + n)."""
+    world = len(g_ptrs)
+    arr = ctypes.c_void_p * world
+    rc = _lib.load().capdec_adamw_peer_step(arr(*g_ptrs), arr(*p_ptrs), world, rank, int(lo), int(n), m.data_ptr(),
+                                            v.data_ptr(), lr_dev.data_ptr(), t_dev.data_ptr(), beta1, beta2, eps,
+                                            weight_decay, _ptr(grad_denom), _stream())
+    _lib.check(rc, "adamw_peer_step")
+
+
 # ---- KV-cached beam search (decode.cu) ---------------------------------------------------------------------------
 def beam_init(st, n_img, beam, P, Tmax):
     rc = _lib.load().capdec_beam_init(st.step.data_ptr(), st.scores.data_ptr(), st.seq_len.data_ptr(),

@@ -116,6 +116,12 @@ class Trainer:
             sh = self.n_train // self.world
             self.shard = (rank * sh, (rank + 1) * sh)
             self.m_flat, self.v_flat = torch.zeros(sh, device=self.dev), torch.zeros(sh, device=self.dev)
+        # ... and by default the three steps are ONE kernel over NVLink peer memory (csrc/peer.cu): the owner of a slice
+        # loads that slice of every rank's gradient buffer, updates, and stores the new parameters into every rank's
+        # parameter buffer.  CAPDEC_DP_PEER=0 (or peers that cannot map each other's memory) keeps the NCCL sequence.
+        self.peer = False
+        if self.sharded and os.environ.get("CAPDEC_DP_PEER", "1") != "0" and self.world <= 8:
+            self.peer = self._peer_setup()
         self.use_graph = use_cuda_graph
         self._g_fb = self._g_opt = self._g_eval = None
         self._warm = 0
@@ -194,6 +200,58 @@ class Trainer:
             ops.zero_fill(self.g_flat[:lo])
         if hi < self.n_train:
             ops.zero_fill(self.g_flat[hi:])
+
+    def _peer_setup(self) -> bool:
+        """Exchange CUDA-IPC handles of the flat gradient / parameter buffers and map every peer's (one process per GPU,
+        one node).  Collective: every rank learns whether ALL ranks succeeded, so that all take the same path."""
+        dist = torch.distributed
+        rank = dist.get_rank(self.pg)
+        try:
+            mine = (ops.peer_export(self.g_flat), ops.peer_export(self.p_flat))
+        except CapdecError as e:
+            mine = str(e)
+        table = [None] * self.world
+        dist.all_gather_object(table, mine, group=self.pg)
+        g_ptrs, p_ptrs, opened, err = [], [], [], None
+        if any(isinstance(x, str) for x in table):
+            err = next(x for x in table if isinstance(x, str))
+        else:
+            try:
+                for r, ((gh, goff), (ph, poff)) in enumerate(table):
+                    if r == rank:
+                        g_ptrs.append(self.g_flat.data_ptr()); p_ptrs.append(self.p_flat.data_ptr())
+                        continue
+                    gp = ops.peer_open(gh, goff); opened.append((gp, goff))
+                    pp = ops.peer_open(ph, poff); opened.append((pp, poff))
+                    g_ptrs.append(gp); p_ptrs.append(pp)
+            except CapdecError as e:
+                err = str(e)
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err, group=self.pg)
+        bad = [x for x in oks if x is not None]
+        if bad:
+            for ptr, off in opened:
+                ops.peer_close(ptr, off)
+            if rank == 0:
+                print(f"capdec_b200: peer-memory optimizer step unavailable ({bad[0]}); using NCCL reduce-scatter / all-gather",
+                      flush=True)
+            return False
+        self.g_ptrs, self.p_ptrs, self._peer_opened, self.rank = g_ptrs, p_ptrs, opened, rank
+        self.fence = torch.zeros(4, device=self.dev)
+        return True
+
+    def _peer_opt(self):
+        """Sharded update in one kernel over peer memory.  The all-reduce of the global counts completes on a rank only
+        after every rank has entered it, i.e. after every rank's backward pass (stream order): all gradients are final when
+        the kernel starts.  The second 16-byte all-reduce is the matching fence at the other end: once it completes, every
+        rank's kernel has finished - all new parameters have landed here, and nobody reads this rank's gradients any more."""
+        lo, hi = self.shard
+        self.stats.copy_(self.tail)
+        torch.distributed.all_reduce(self.stats, group=self.pg)
+        ops.adamw_peer_step(self.g_ptrs, self.p_ptrs, self.rank, lo, hi - lo, self.m_flat, self.v_flat, self.lr_dev,
+                            self.t_dev, self.betas[0], self.betas[1], self.eps, self.wd, grad_denom=self.stats[0:1])
+        torch.distributed.all_reduce(self.fence, group=self.pg)
+        ops.zero_fill(self.g_flat)
 
     def _opt(self):
         if self.opt_overlap:           # the update already ran inside _fwd_bwd
@@ -319,7 +377,9 @@ class Trainer:
                 self._replay_segments()      # reduces AND updates bucket by bucket
                 return self.stats
             self._g_fb.replay()
-            if self.sharded:
+            if self.peer:
+                self._peer_opt()
+            elif self.sharded:
                 self._reduce_scatter_opt()
             elif self.pipeline:
                 self._reduce_and_opt()
@@ -330,7 +390,9 @@ class Trainer:
         else:
             self._warm += 1
             self._fwd_bwd()
-            if self.sharded:
+            if self.peer:
+                self._peer_opt()
+            elif self.sharded:
                 self._reduce_scatter_opt()
             elif self.pipeline:
                 self._reduce_and_opt()
@@ -420,4 +482,23 @@ class Trainer:
 
     def loss(self) -> float:
         s = self.stats.tolist()
+        return s[1] / s[0] if s[0] > 0 else float("nan")
+
+    def loss_lagged(self) -> Optional[float]:
+        """Per-step loss logging without stalling the device: enqueues the D2H copy of THIS step's [n_valid, loss_sum] into
+        pinned memory and returns the mean token loss of the PREVIOUS step (None after the first step), waiting only for
+        that earlier copy.  The host stays one step ahead of the GPU, so graph launches and collectives of step i+1 are
+        issued while step i still computes; `loss()` after the last step reads the final value."""
+        if not hasattr(self, "_lag"):
+            self._lag = {"buf": [torch.zeros(4, pin_memory=True) for _ in range(2)],
+                         "ev": [torch.cuda.Event() for _ in range(2)], "n": 0}
+        lag = self._lag
+        cur = lag["n"] & 1
+        lag["buf"][cur].copy_(self.stats, non_blocking=True)
+        lag["ev"][cur].record()
+        lag["n"] += 1
+        if lag["n"] == 1:
+            return None
+        lag["ev"][cur ^ 1].synchronize()
+        s = lag["buf"][cur ^ 1].tolist()
         return s[1] / s[0] if s[0] > 0 else float("nan")

@@ -45,18 +45,20 @@ def _worker(rank, world, port, out_dir):
     dist.all_gather(gathered, flat)
     if rank == 0:
         torch.save({"losses": losses, "identical": all(torch.equal(gathered[0], g) for g in gathered[1:]),
-                    "params": flat.cpu()}, os.path.join(out_dir, "dp.pt"))
+                    "params": flat.cpu(), "peer": tr.peer, "sharded": tr.sharded}, os.path.join(out_dir, "dp.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def _check_against_single_gpu(tmp_path):
+def _check_against_single_gpu(tmp_path, expect_peer=None):
     import torch.multiprocessing as mp
     import capdec_b200 as cb
     from oracle import capdec_oracle as O
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     got = torch.load(os.path.join(str(tmp_path), "dp.pt"))
     assert got["identical"], "ranks diverged"
+    if expect_peer is not None:
+        assert got["peer"] == expect_peer, "the data-parallel update did not take the expected path"
     sd = O.make_state_dict(seed=1)
     tokens, prefix, _ = O.make_batch(seed=2, B=8)
     tokens[0, 10:] = 0
@@ -74,7 +76,15 @@ def _check_against_single_gpu(tmp_path):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_two_gpu_data_parallel_matches_single_gpu(tmp_path):
-    _check_against_single_gpu(tmp_path)
+    """Default path: the sharded update as ONE kernel over NVLink peer memory (csrc/peer.cu)."""
+    _check_against_single_gpu(tmp_path, expect_peer=True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_two_gpu_nccl_sharded_update_matches_single_gpu(tmp_path, monkeypatch):
+    """CAPDEC_DP_PEER=0: NCCL reduce-scatter -> AdamW on the slice -> NCCL all-gather."""
+    monkeypatch.setenv("CAPDEC_DP_PEER", "0")
+    _check_against_single_gpu(tmp_path, expect_peer=False)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")

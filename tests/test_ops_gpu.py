@@ -443,6 +443,40 @@ def test_adamw_matches_hf_semantics(ops):
     assert (p.double() - pr).abs().max() < 2e-6
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_adamw_peer_step_is_reduce_scatter_update_all_gather(ops, world):
+    """csrc/peer.cu on ONE GPU: the 'ranks' are separate local buffers (the kernel only sees pointers).  Every owner's
+    launch must equal capdec_adamw_step on the rank-order sum of the gradients, restricted to its slice, and leave the
+    same new parameters in EVERY rank's buffer; gradients are not modified (the caller clears them after its fence)."""
+    n = 4 * 3 * world * 37
+    torch.manual_seed(3)
+    p0 = torch.randn(n, device="cuda")
+    gs = [torch.randn(n, device="cuda") for _ in range(world)]
+    ps = [p0.clone() for _ in range(world)]
+    lr_dev, t_dev = torch.full((1,), 1e-3, device="cuda"), torch.full((1,), 2.0, device="cuda")
+    denom = torch.full((1,), 7.0, device="cuda")
+    b1, b2, eps, wd = 0.9, 0.999, 1e-6, 0.01
+    sh = n // world
+    m0, v0 = torch.rand(n, device="cuda") * 0.1, torch.rand(n, device="cuda") * 0.01
+    # reference: plain fused AdamW on the summed gradient
+    gsum = gs[0].clone()
+    for r in range(1, world):
+        gsum += gs[r]
+    pr, mr, vr = p0.clone(), m0.clone(), v0.clone()
+    ops.adamw_step(pr, gsum, mr, vr, lr_dev, t_dev, b1, b2, eps, wd, grad_denom=denom, zero_grad=False)
+    g_before = [g.clone() for g in gs]
+    for owner in range(world):
+        lo = owner * sh
+        m, v = m0[lo:lo + sh].clone(), v0[lo:lo + sh].clone()
+        ops.adamw_peer_step([g.data_ptr() for g in gs], [q.data_ptr() for q in ps], owner, lo, sh, m, v, lr_dev, t_dev,
+                            b1, b2, eps, wd, grad_denom=denom)
+        assert torch.equal(m, mr[lo:lo + sh]) and torch.equal(v, vr[lo:lo + sh])
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert torch.equal(ps[r], pr), f"replica {r} differs from the single-buffer update"
+        assert torch.equal(gs[r], g_before[r])
+
+
 def test_step_clock_schedule_and_seed(ops):
     seed = ops.make_seed(5)
     step, lr, t = (torch.zeros(1, device="cuda") for _ in range(3))
