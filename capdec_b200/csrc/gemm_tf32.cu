@@ -117,6 +117,7 @@ struct __align__(64) GemmDev {
   const int* m_limit;               // optional device scalar: rows >= *m_limit are not computed (whole tiles skipped)
   const int* k_limit;               // optional device scalar: reduction stops at *k_limit (rounded up to a k-block)
   int* sched;                       // dynamic tile scheduler: {next tile, clusters done} of this launch (NULL = static round-robin)
+  int raster;                       // tile order inside a wave: 0 = n fastest (neighbouring clusters share A rows), 1 = m fastest (share B columns)
   uint32_t dbg;                     // bring-up switches (CAPDEC_GEMM_DBG): 1 skip TMA loads, 2 skip MMA, 4 skip stores, 8 skip epilogue
 };
 
@@ -335,6 +336,13 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     if (tile < tail_first) { lin = tile; bn_t = p.block_n; n_off = 0; }
     else { const int j = tile - tail_first; lin = tail_first + (j >> 1); bn_t = p.block_n >> 1; n_off = (j & 1) * bn_t; }
   };
+  // linear index -> (row tile, column tile, reduction split)
+  auto tile_mn = [&](int lin, int& m_blk, int& n_blk, int& split) {
+    split = lin / (p.n_tiles * m_tiles);
+    const int r = lin - split * (p.n_tiles * m_tiles);
+    if (p.raster) { m_blk = r % m_tiles; n_blk = r / m_tiles; }
+    else { n_blk = r % p.n_tiles; m_blk = r / p.n_tiles; }
+  };
   const int tile_n = (kQuad && !kShareB) ? 2 * p.block_n : p.block_n;         // columns per cluster tile
   // this CTA's pair tile inside the cluster tile
   const int pm_off = (kQuad && kShareB) ? (int)pair_idx * kPairM : 0;
@@ -418,9 +426,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
         decode(tile, lin, bn_t, n_off);
         const bool half_tile = bn_t != p.block_n;
         const int bnl_t = kPair ? bn_t / 2 : bn_t;                                  // B columns this CTA stages for this tile
-        const int n_blk = lin % p.n_tiles;
-        const int m_blk = (lin / p.n_tiles) % m_tiles;
-        const int split = lin / (p.n_tiles * m_tiles);
+        int m_blk, n_blk, split;
+        tile_mn(lin, m_blk, n_blk, split);
         const int m0 = m_blk * kTileM + pm_off + (int)half * kBlockM;               // my 128 A rows
         const int n0 = n_blk * tile_n + pn_off + n_off + (kPair ? (int)half * bnl_t : 0);  // my B columns
         const int kb0 = split * kb_per_split;
@@ -513,8 +520,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
         int lin, bn_t, n_off;
         decode(tile, lin, bn_t, n_off);
         const uint32_t idesc = (bn_t != p.block_n) ? p.idesc_h : p.idesc;
-        const int split = lin / (p.n_tiles * m_tiles);
-        const int m_blk = (lin / p.n_tiles) % m_tiles;
+        int m_blk, n_blk, split;
+        tile_mn(lin, m_blk, n_blk, split);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_lim);
         if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
@@ -589,8 +596,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     while (next_tile_warp(tile, cit)) {
       int lin, bn_t, n_off;
       decode(tile, lin, bn_t, n_off);
-      const int split = lin / (p.n_tiles * m_tiles);
-      const int m_blk = (lin / p.n_tiles) % m_tiles;
+      int m_blk, n_blk, split;
+      tile_mn(lin, m_blk, n_blk, split);
       const int kb0 = split * kb_per_split;
       const int kb1 = min(kb0 + kb_per_split, kb_lim);
       if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
@@ -643,9 +650,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     auto tile_coords = [&](int tile, int& m0w, int& n0w, int& nch, int& bn_t, int& split) -> bool {
       int lin, n_off;
       decode(tile, lin, bn_t, n_off);
-      const int n_blk = lin % p.n_tiles;
-      const int m_blk = (lin / p.n_tiles) % m_tiles;
-      split = lin / (p.n_tiles * m_tiles);
+      int m_blk, n_blk;
+      tile_mn(lin, m_blk, n_blk, split);
       if (m_blk * kTileM >= m_lim || split * kb_per_split >= kb_lim) return false;
       m0w = m_blk * kTileM + pm_off + (int)half * kBlockM + q * 32;
       n0w = n_blk * tile_n + pn_off + n_off;   // the tile's columns (each CTA stores its 128 rows x bn_t)
@@ -803,6 +809,14 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// L2 promotion of every tensor map (CAPDEC_GEMM_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B; bring-up / A-B switch)
+static CUtensorMapL2promotion l2_promotion() {
+  static const char* env = getenv("CAPDEC_GEMM_L2PROMO");
+  const int v = env ? atoi(env) : 3;
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+       : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
 // 2-D fp32 tensor map: dim0 = contiguous extent, dim1 = rows with pitch `pitch_elems`.
 static int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t pitch_elems,
                     uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz) {
@@ -816,8 +830,7 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d): ptr=%p dims=(%llu,%llu) pitch=%llu box=(%u,%u) swz=%d", (int)r,
                    ptr, (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)pitch_elems, box0,
@@ -840,8 +853,7 @@ static int make_map_mn3d(CUtensorMap* m, const void* ptr, uint64_t mn, uint64_t 
   cuuint32_t box[3] = {32, kBlockK, nslabs};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? CAPDEC_OK : CAPDEC_ERR_UNSUPPORTED;
 }
 
@@ -1097,6 +1109,8 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   p.mul_act = a.mul_act;
   p.colsum = a.colsum;
   p.k_limit = a.k_limit;
+  static const char* env_raster = getenv("CAPDEC_GEMM_RASTER");   // bring-up / A-B switch: tile order inside a wave
+  p.raster = env_raster ? atoi(env_raster) : 0;
   static const char* env_dbg = getenv("CAPDEC_GEMM_DBG");
   p.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
   static const char* env_sched = getenv("CAPDEC_GEMM_SCHED");   // "dynamic" / "static": overrides capdec_gemm_set_schedule
