@@ -29,6 +29,7 @@ SIGNATURES = {
     "capdec_gemm_tf32_mul_ex": [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i, _p, _i, _p, _i, _p, _i, _p],
     "capdec_gemm_debug_mn_encoding": [_i, _i, _i, _i],
     "capdec_gemm_debug_force_pair": [_i],
+    "capdec_gemm_debug_trace": [_p],
     "capdec_gemm_set_row_hint": [_i],
     "capdec_gemm_set_schedule": [_i],
     "capdec_gemm_autotune": [_i],
@@ -83,7 +84,7 @@ SIGNATURES = {
     "capdec_adamw_peer_step": [_p, _p, _i, _i, _i64, _i64, _p, _p, _p, _p, _f, _f, _f, _f, _p, _p],
 }
 _RESTYPES = {"capdec_last_error": C.c_char_p, "capdec_launch_count": C.c_int64, "capdec_gemm_debug_mn_encoding": None,
-             "capdec_gemm_debug_force_pair": None, "capdec_gemm_set_row_hint": None}
+             "capdec_gemm_debug_force_pair": None, "capdec_gemm_debug_trace": None, "capdec_gemm_set_row_hint": None}
 
 
 class CapdecError(RuntimeError):

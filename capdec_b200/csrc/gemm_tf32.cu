@@ -117,9 +117,21 @@ struct __align__(64) GemmDev {
   const int* m_limit;               // optional device scalar: rows >= *m_limit are not computed (whole tiles skipped)
   const int* k_limit;               // optional device scalar: reduction stops at *k_limit (rounded up to a k-block)
   int* sched;                       // dynamic tile scheduler: {next tile, clusters done} of this launch (NULL = static round-robin)
+  float* c_ptr;                     // C / aux and their pitch for the LSU store path of the epilogue (lsu_store != 0)
+  float* aux_ptr;
+  long long ldc;
+  int lsu_store;                    // epilogue stores with coalesced st.global from the staging box instead of TMA stores
+  long long* trace;                 // bring-up: cycle stamps of CTA 0's roles (capdec_gemm_debug_trace), NULL = off
+  int c_depth;                      // epilogue staging boxes per warp and output (2..4): TMA stores in flight before the warp must wait
   int raster;                       // tile order inside a wave: 0 = n fastest (neighbouring clusters share A rows), 1 = m fastest (share B columns)
-  uint32_t dbg;                     // bring-up switches (CAPDEC_GEMM_DBG): 1 skip TMA loads, 2 skip MMA, 4 skip stores, 8 skip epilogue
+  uint32_t dbg;                     // bring-up switches (CAPDEC_GEMM_DBG): 1 skip TMA loads, 2 skip MMA, 4 skip stores, 8 skip epilogue, 16 no proxy fence, 32 no staging writes, 64 no stage handshake, 128 no TMEM reads
 };
+
+// cycle stamp of CTA 0 into trace[role * 64 + idx]: role 0 = CTA, 1 = producer, 2 = MMA issuer, 3 = epilogue warp 4
+#define CAPDEC_TRACE(role, idx)                                                                                      \
+  do {                                                                                                               \
+    if (p.trace && blockIdx.x == 0 && (idx) < 64) p.trace[(role) * 64 + (idx)] = clock64();                          \
+  } while (0)
 
 __device__ __forceinline__ float tanh_fast(float x) {  // MUFU.TANH, max rel. error 2^-11: same grade as a TF32 operand
   float y;
@@ -225,7 +237,14 @@ __device__ __forceinline__ void apply_mul32(float (&v)[32], const float (&u)[32]
 // 3xTF32 variant; no spills) and leaves > 1 KB of the SM's shared memory free, so that a GEMM CTA does not lock the SM:
 // a small streaming kernel (the fused AdamW on its side stream) can be co-resident and use the HBM bandwidth the
 // tensor-bound GEMM leaves idle.  At 244 registers x 256 threads + 227 KB nothing else could ever share the SM.
-template <int kMode, bool kSplit>
+// kEpi: the epilogue variant the instantiation is compiled for - 0 = any (run-time switches), 1 = plain: bias (+ accumulate)
+// only, 2 = gelu_new forward with its derivative as second output (c_fc forward), 3 = multiply by a stored derivative (+ the
+// bias-gradient column sums; the dgrad that feeds c_fc's backward).  1-3 cover every GEMM launch of the GPT-2 trunk's train
+// step.  They get their own instantiations because the general
+// epilogue's per-chunk code is ~5000 instructions (every activation / derivative variant unrolled 32x) of which the plain
+// path executes ~150, scattered: its instruction-cache misses cost ~1000 clocks per 32-column chunk, i.e. most of the
+// epilogue's time and of each launch's un-overlapped tail (profiles/r2_gemm_timeline.md).
+template <int kMode, bool kSplit, int kEpi>
 __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __grid_constant__ GemmDev p) {
   constexpr bool kPair = kMode >= 1;
   constexpr bool kQuad = kMode >= 2;
@@ -247,7 +266,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
   uint8_t* sAlo = smem + p.stages * stage_bytes;            // kSplit only: the lo = x - RN_tf32(x) tiles
   uint8_t* sBlo = sAlo + p.stages * kABytes;
   uint8_t* sStage = smem + (kSplit ? 2 : 1) * p.stages * stage_bytes;  // epilogue staging: C ping-pong [+ aux ping-pong]
-  const int n_staging = p.mul_act ? 2 + kMulDepth : (p.has_aux ? 4 : 2);
+  const int c_depth = p.c_depth;
+  const int n_staging = c_depth + (p.mul_act ? kMulDepth : (p.has_aux ? c_depth : 0));
   float* sBias = reinterpret_cast<float*>(sStage + n_staging * kStagingBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 256);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -271,6 +291,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
   constexpr int kPairsPerCluster = kQuad ? 2 : 1;
   constexpr int kCtasPerCluster = kCtasPerPair * kPairsPerCluster;
 
+  if (threadIdx.x == 0) CAPDEC_TRACE(0, 0);
+  if (threadIdx.x == 32) CAPDEC_TRACE(0, 6);   // a second warp's entry
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tmA);
     prefetch_tensormap(&p.tmB);
@@ -305,9 +327,11 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     else { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
+  if (threadIdx.x == 32) CAPDEC_TRACE(0, 7);   // barriers initialised, about to join the opening cluster sync
   if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) CAPDEC_TRACE(0, 1);   // set-up done (barriers, TMEM, cluster sync)
 
   // data-dependent extents (LM head over the non-ignored caption tokens only): every role skips the same tiles
   const int m_lim = p.m_limit ? __ldg(p.m_limit) : p.M;
@@ -337,11 +361,22 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     else { const int j = tile - tail_first; lin = tail_first + (j >> 1); bn_t = p.block_n >> 1; n_off = (j & 1) * bn_t; }
   };
   // linear index -> (row tile, column tile, reduction split)
+  // (integer division through a float reciprocal + correction: exact for the < 2^22 tile ids here, and a fraction of the
+  // ~150-clock cost of a hardware-sequenced 32-bit division - three of them sat on every role's path at every tile boundary)
+  const int mn_tiles = p.n_tiles * m_tiles;
+  const float rcp_mn = __frcp_rn((float)mn_tiles), rcp_n = __frcp_rn((float)p.n_tiles), rcp_m = __frcp_rn((float)m_tiles);
+  auto fdiv = [](int x, int d, float rcp) {
+    int q = __float2int_rz(__int2float_rz(x) * rcp);
+    const int r = x - q * d;
+    if (r < 0) --q;
+    else if (r >= d) ++q;
+    return q;
+  };
   auto tile_mn = [&](int lin, int& m_blk, int& n_blk, int& split) {
-    split = lin / (p.n_tiles * m_tiles);
-    const int r = lin - split * (p.n_tiles * m_tiles);
-    if (p.raster) { m_blk = r % m_tiles; n_blk = r / m_tiles; }
-    else { n_blk = r % p.n_tiles; m_blk = r / p.n_tiles; }
+    split = (p.splits > 1) ? fdiv(lin, mn_tiles, rcp_mn) : 0;
+    const int r = lin - split * mn_tiles;
+    if (p.raster) { n_blk = fdiv(r, m_tiles, rcp_m); m_blk = r - n_blk * m_tiles; }
+    else { m_blk = fdiv(r, p.n_tiles, rcp_n); n_blk = r - m_blk * p.n_tiles; }
   };
   const int tile_n = (kQuad && !kShareB) ? 2 * p.block_n : p.block_n;         // columns per cluster tile
   // this CTA's pair tile inside the cluster tile
@@ -416,14 +451,20 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     __syncwarp();
   } else if (warp == 0) {
     // ============================== TMA producer (every CTA feeds its own smem, and its twin's when multicasting) ====
-    if (lane == 0) {
+    // The WHOLE warp walks the loop converged and one elected lane issues: inside `if (lane == 0)` the compiler cannot
+    // know that a single lane is active, moves every operand of the (uniform-datapath) TMA instructions through R2UR and
+    // wraps each in an ELECT / BRA.U.ANY loop - 580 clk per k-block of dependent issue latency, which made this thread, not
+    // L2 or the tensor pipe, the limiter of the mainloop (profiles/r2_gemm_timeline.md).
+    {
+      if (lane == 0) CAPDEC_TRACE(0, 4);   // producer enters its role
       int stage = 0;
       uint32_t phase = 0;
       int tile = 0;
       uint32_t cit = 0;
-      while (next_tile_thread(tile, cit)) {
+      while (next_tile_warp(tile, cit)) {
         int lin, bn_t, n_off;
         decode(tile, lin, bn_t, n_off);
+        if (cit == 1 && lane == 0) CAPDEC_TRACE(0, 5);   // first tile id decoded
         const bool half_tile = bn_t != p.block_n;
         const int bnl_t = kPair ? bn_t / 2 : bn_t;                                  // B columns this CTA stages for this tile
         int m_blk, n_blk, split;
@@ -437,8 +478,10 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
         const CUtensorMap* mapA = &p.tmA;
         const CUtensorMap* mapB = half_tile ? &p.tmBh : &p.tmB;
         const uint32_t tx_bytes = (uint32_t)(kABytes + bnl_t * kBlockK * 4);
+        if (lane == 0) CAPDEC_TRACE(1, (int)cit - 1);   // producer starts tile #cit-1
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          if (elect_one()) {
           const int k0 = kb * kBlockK;
           uint8_t* a_dst = sA + stage * kABytes;
           uint8_t* b_dst = sB + stage * b_bytes;
@@ -447,9 +490,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
           if (p.dbg & 1u) {  // timing experiment: no loads, just hand the (stale) stage on
             if constexpr (kLocalBar) mbar_arrive(fb);
             else { if (leader) mbar_arrive(fb); else mbar_arrive_remote(fb, pair_leader); }
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-            continue;
-          }
+          } else {
           if constexpr (kLocalBar) mbar_arrive_expect_tx(fb, tx_bytes);
           auto load = [&](void* dst, const CUtensorMap* m, int x, int y) {
             if constexpr (kLocalBar) tma_load_2d(dst, m, fb, x, y); else tma_load_2d_pair(dst, m, fb, x, y);
@@ -500,6 +541,10 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
             if (leader) mbar_arrive_expect_tx(fb, 2u * tx_bytes);  // bytes landing in BOTH CTAs of my pair
             else mbar_arrive_remote(fb, pair_leader);
           }
+          if (cit == 1 && kb - kb0 < 8) CAPDEC_TRACE(0, 8 + (kb - kb0));   // the first k-blocks requested
+          }   // loads
+          }   // elected lane
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -507,7 +552,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     __syncwarp();
   } else if (warp == 1) {
     // ============================== MMA issuer (one thread of each pair's leader CTA) ==============================
-    if (lane == 0 && leader) {
+    if (leader) {   // whole warp, converged; one elected lane issues (see the producer)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -516,7 +561,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
       const uint64_t bdesc_base = ((uint64_t)p.bdesc_hi << 32) | (uint64_t)p.bdesc_lo16;
       int tile = 0;
       uint32_t cit = 0;
-      while (next_tile_thread(tile, cit)) {
+      while (next_tile_warp(tile, cit)) {
         int lin, bn_t, n_off;
         decode(tile, lin, bn_t, n_off);
         const uint32_t idesc = (bn_t != p.block_n) ? p.idesc_h : p.idesc;
@@ -527,13 +572,16 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
         if (m_blk * kTileM >= m_lim || kb0 >= kb1) continue;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 2);
         tc_fence_after();
+        if (lane == 0) CAPDEC_TRACE(2, 2 * ((int)cit - 1));       // accumulator free, tile's first k-block may be issued
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
-        uint32_t accumulate = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
+          uint32_t accumulate = (kb != kb0) ? 1u : 0u;   // (per k-block, in every lane: whichever lane is elected sees it)
           if (p.dbg & 64u) {}                                                     // (experiment: no wait)
           else if constexpr (kSplit) mbar_wait_cluster(&conv_bar[stage], phase, 6);   // hi/lo tiles of both CTAs are in place
           else mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
+          if (cit == 1 && kb - kb0 < 8 && lane == 0) CAPDEC_TRACE(0, 16 + (kb - kb0));  // the first k-blocks landed (seen by the MMA issuer)
+          if (elect_one()) {
           const uint32_t a_start = smem_u32(sA + stage * kABytes) >> 4;
           const uint32_t b_start = smem_u32(sB + stage * b_bytes) >> 4;
           auto mma = [&](uint64_t adesc, uint64_t bdesc) {
@@ -565,10 +613,16 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
           }
           // smem slot reusable (in every CTA that writes into my pair's smem) once these MMAs retire
           if constexpr (kPair) umma_commit_mc(&empty_bar[stage], commit_empty_mask); else umma_commit(&empty_bar[stage]);
+          }   // elected lane
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue(s) of my pair
-        if constexpr (kPair) umma_commit_mc(&tmem_full_bar[acc], commit_pair_mask); else umma_commit(&tmem_full_bar[acc]);
+        if (elect_one()) {
+          if constexpr (kPair) umma_commit_mc(&tmem_full_bar[acc], commit_pair_mask); else umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
+        if (lane == 0) CAPDEC_TRACE(2, 2 * ((int)cit - 1) + 1);   // tile's last k-block issued
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -640,6 +694,11 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     // bias tile and the column sums); staging is ping-pong per warp, gated by the warp leader's bulk-group counter.
     const int q = warp & 3;                   // TMEM lane quadrant this warp may access
     const int epi_tid = threadIdx.x - 4 * 32;
+    const int e_act = kEpi == 0 ? p.act : (kEpi == 2 ? 4 : 0);
+    const int e_mul = kEpi == 0 ? p.mul_act : (kEpi == 3 ? 4 : 0);
+    const bool e_aux = kEpi == 0 ? (p.has_aux != 0) : (kEpi == 2);
+    float* const e_colsum = (kEpi == 0 || kEpi == 3) ? p.colsum : nullptr;
+    const bool e_lsu = kEpi == 0 ? (p.lsu_store != 0) : false;
     uint8_t* wst = sStage + q * (n_staging * kWarpStagingBytes);   // this warp's staging: C[0], C[1], (X[0], X[1])
     uint64_t* my_mul_bar = mul_bar + kMulDepth * q;
     int acc = 0;
@@ -670,7 +729,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
       const uint32_t slot = mul_issued % kMulDepth;
       uint64_t* mb = &my_mul_bar[slot];
       mbar_arrive_expect_tx(mb, kWarpStagingBytes);
-      tma_load_2d(wst + (2 + slot) * kWarpStagingBytes, &p.tmMul, mb, la_n0 + la_c * 32, la_m0);
+      tma_load_2d(wst + (c_depth + slot) * kWarpStagingBytes, &p.tmMul, mb, la_n0 + la_c * 32, la_m0);
       ++mul_issued; ++la_c;
     };
     int tile = 0;
@@ -678,7 +737,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     while (next_tile_warp(tile, cit)) {
       int m0, n0, n_chunks, bn_t, split;
       if (!tile_coords(tile, m0, n0, n_chunks, bn_t, split)) continue;
-      if (p.mul_act && lane == 0) {   // every box of the previous tile has been consumed: all kMulDepth slots are free
+      if (e_mul && lane == 0) {   // every box of the previous tile has been consumed: all kMulDepth slots are free
         la_c = 0; la_nch = n_chunks; la_m0 = m0; la_n0 = n0;
         for (int i = 0; i < kMulDepth; ++i) mul_prefetch();
       }
@@ -689,6 +748,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase, 4);
       tc_fence_after();
+      if (q == 0 && lane == 0) CAPDEC_TRACE(3, 3 * ((int)cit - 1));       // accumulator complete
       if (use_bias) named_bar_sync(1, kEpiThreads);  // bias tile visible to all 4 warps
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols);
       if (n_chunks == 0) {  // nothing to store (or dbg 8): release the accumulator right away
@@ -696,23 +756,23 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
         if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], pair_leader); else mbar_arrive(&tmem_empty_bar[acc]);
         n_chunks = 0;
       }
-      for (int c = 0; c < n_chunks; ++c) {
-        float v[32];
-        tmem_ld32(t_row + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
-        if (c == n_chunks - 1) {
-          // all TMEM reads of this accumulator stage are done -> hand it back to the (leader's) MMA warp
-          tc_fence_before();
-          if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], pair_leader); else mbar_arrive(&tmem_empty_bar[acc]);
-        }
+      // One 32-column chunk: bias / fused multiply / activation -> swizzled staging box -> TMA store.  The staging boxes
+      // rotate c_depth deep (per warp), so up to c_depth - 1 stores are still being read by the TMA engine - which also
+      // serves the mainloop's loads and answers late - while the warp fills the next box.
+      auto process = [&](float (&v)[32], int c) {
+        if (q == 0 && lane == 0) CAPDEC_TRACE(3, 32 + 4 * c);        // chunk c: accumulator columns in registers
         if (use_bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(sBias + c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += sBias[c * 32 + j];
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j];
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+          }
         }
-        if (p.mul_act) {  // v *= act'(input box), read back from the 128B-swizzled TMA layout (row = lane)
+        if (e_mul) {  // v *= act'(input box), read back from the 128B-swizzled TMA layout (row = lane)
           const uint32_t slot = mul_idx % kMulDepth;
           mbar_wait(&my_mul_bar[slot], (mul_idx / kMulDepth) & 1, 5);
-          const float4* u4 = reinterpret_cast<const float4*>(wst + (2 + slot) * kWarpStagingBytes + lane * 128);
+          const float4* u4 = reinterpret_cast<const float4*>(wst + (c_depth + slot) * kWarpStagingBytes + lane * 128);
           ++mul_idx;
           float uu[32];
 #pragma unroll
@@ -720,38 +780,46 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
             const float4 u = u4[j ^ (lane & 7)];
             uu[4 * j] = u.x; uu[4 * j + 1] = u.y; uu[4 * j + 2] = u.z; uu[4 * j + 3] = u.w;
           }
-          apply_mul32(v, uu, p.mul_act, p.exact != 0);
+          apply_mul32(v, uu, e_mul, p.exact != 0);
         }
-        const uint32_t pp = store_idx++ & 1;
-        uint8_t* buf0 = wst + pp * kWarpStagingBytes;          // C box
-        uint8_t* buf1 = wst + (2 + pp) * kWarpStagingBytes;    // aux (pre-activation) box
-        if (lane == 0) tma_store_wait_read<1>();  // the group this lane committed two chunks ago has released buf[pp]
+        const uint32_t pp = store_idx++ % (uint32_t)c_depth;
+        uint8_t* buf0 = wst + pp * kWarpStagingBytes;                // C box
+        uint8_t* buf1 = wst + (c_depth + pp) * kWarpStagingBytes;    // aux (pre-activation / derivative) box
+        // (elect.sync names the same leader for the same member mask every time: the lane that waits here is the lane that
+        // committed the bulk groups below; `if (lane == 0)` would wrap each TMA instruction in an ELECT / BRA.U.ANY loop)
+        if (!e_lsu && elect_one()) {  // the group this lane committed c_depth chunks ago has released buf[pp]
+          if (c_depth == 2) tma_store_wait_read<1>();
+          else if (c_depth == 3) tma_store_wait_read<2>();
+          else tma_store_wait_read<3>();
+        }
         __syncwarp();
-        if (p.mul_act && lane == 0) mul_prefetch();  // every lane has read the input box just consumed: refill its slot
-        if (p.act == 4) {      // aux <- gelu_new'(pre-activation), C <- gelu_new(pre-activation)
+        if (e_mul && lane == 0) mul_prefetch();  // every lane has read the input box just consumed: refill its slot
+        if (e_act == 4) {      // aux <- gelu_new'(pre-activation), C <- gelu_new(pre-activation)
           float dv[32];
           gelu_fwd_and_grad32(v, dv, p.exact != 0);
-          if (p.has_aux) {
+          if (e_aux) {
             float4* d1 = reinterpret_cast<float4*>(buf1 + lane * 128);
 #pragma unroll
             for (int j = 0; j < 8; ++j) d1[j ^ (lane & 7)] = make_float4(dv[4 * j], dv[4 * j + 1], dv[4 * j + 2], dv[4 * j + 3]);
           }
         } else {
-          if (p.has_aux) {     // aux <- pre-activation
+          if (e_aux) {     // aux <- pre-activation
             float4* d1 = reinterpret_cast<float4*>(buf1 + lane * 128);
 #pragma unroll
             for (int j = 0; j < 8; ++j) d1[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          if (p.act != 0) apply_act32(v, p.act, p.exact != 0);
+          if (e_act != 0) apply_act32(v, e_act, p.exact != 0);
         }
-        {
+        if (!(p.dbg & 32u)) {
           float4* d0 = reinterpret_cast<float4*>(buf0 + lane * 128);
 #pragma unroll
           for (int j = 0; j < 8; ++j) d0[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        fence_proxy_async_smem();
+        if (q == 0 && lane == 0) CAPDEC_TRACE(3, 32 + 4 * c + 1);    // staged
+        if (!e_lsu && !(p.dbg & 16u)) fence_proxy_async_smem();
         __syncwarp();
-        if (p.colsum) {  // bias gradient: lane = column of this chunk, summed over this warp's live staged rows and sent
+        if (q == 0 && lane == 0) CAPDEC_TRACE(3, 32 + 4 * c + 2);    // fenced
+        if (e_colsum) {  // bias gradient: lane = column of this chunk, summed over this warp's live staged rows and sent
           // straight to global memory as one coalesced 128-byte reduction per chunk (no cross-warp exchange, no barrier:
           // the four epilogue warps stay independent; shared-memory atomics + two named barriers per tile cost 20 us here)
           const int nrows = min(32, m_lim - m0);
@@ -768,22 +836,73 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
           } else {
             for (int rr = 0; rr < nrows; ++rr) cs0 += *reinterpret_cast<const float*>(colp + rr * 128 + ((l4 ^ (rr & 7)) << 4));
           }
-          if (nrows > 0 && col < p.N) atomicAdd(p.colsum + col, cs0 + cs1);
+          if (nrows > 0 && col < p.N) atomicAdd(e_colsum + col, cs0 + cs1);
         }
-        if (lane == 0 && !(p.dbg & 4u)) {
-          if (p.accumulate) tma_reduce_add_2d(&p.tmC, buf0, n0 + c * 32, m0);
-          else tma_store_2d(&p.tmC, buf0, n0 + c * 32, m0);
-          if (p.has_aux) tma_store_2d(&p.tmAux, buf1, n0 + c * 32, m0);
-          tma_store_commit();
+        if (e_lsu) {
+          // experiment (off by default, see launch_plan): the staging box is read back row-wise - 8 lanes cover one 128-byte
+          // row, a warp instruction four rows - and stored with coalesced 16-byte st.global instead of a TMA store
+          if (!(p.dbg & 4u)) {
+            const int chunk = lane & 7, rsub = lane >> 3;
+            const int col = n0 + c * 32 + chunk * 4;
+            if (col < p.N) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int row = 4 * i + rsub;
+                if (m0 + row < p.M) {
+                  const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
+                  const size_t g = (size_t)(m0 + row) * (size_t)p.ldc + (size_t)col;
+                  st_stream(reinterpret_cast<float4*>(p.c_ptr + g), *reinterpret_cast<const float4*>(buf0 + off));
+                  if (e_aux) st_stream(reinterpret_cast<float4*>(p.aux_ptr + g), *reinterpret_cast<const float4*>(buf1 + off));
+                }
+              }
+            }
+          }
+        } else if (!(p.dbg & 4u)) {
+          if (elect_one()) {
+            if (p.accumulate) tma_reduce_add_2d(&p.tmC, buf0, n0 + c * 32, m0);
+            else tma_store_2d(&p.tmC, buf0, n0 + c * 32, m0);
+            if (e_aux) tma_store_2d(&p.tmAux, buf1, n0 + c * 32, m0);
+            tma_store_commit();
+          }
+        }
+        if (q == 0 && lane == 0) CAPDEC_TRACE(3, 32 + 4 * c + 3);    // store issued
+      };
+      auto release_acc = [&]() {   // all TMEM reads of this accumulator stage are done -> hand it back to the (leader's) MMA warp
+        if (q == 0 && lane == 0) CAPDEC_TRACE(3, 3 * ((int)cit - 1) + 1);
+        tc_fence_before();
+        if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[acc], pair_leader); else mbar_arrive(&tmem_empty_bar[acc]);
+      };
+      // TMEM reads run one chunk AHEAD of the arithmetic: the load of chunk c + 1 is in flight while chunk c is processed
+      float va[32], vb[32];
+      const bool no_tmem = (p.dbg & 128u) != 0;   // timing experiment: the epilogue without its TMEM reads
+      if (no_tmem) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { va[j] = 0.f; vb[j] = 0.f; }
+      }
+      if (n_chunks > 0 && !no_tmem) tmem_ld32(t_row, va);
+      for (int c = 0; c < n_chunks; c += 2) {
+        if (!no_tmem) tmem_ld_wait_for(va);
+        if (c + 1 < n_chunks) { if (!no_tmem) tmem_ld32(t_row + (uint32_t)((c + 1) * 32), vb); }
+        else release_acc();
+        process(va, c);
+        if (c + 1 < n_chunks) {
+          if (!no_tmem) tmem_ld_wait_for(vb);
+          if (c + 2 < n_chunks) { if (!no_tmem) tmem_ld32(t_row + (uint32_t)((c + 2) * 32), va); }
+          else release_acc();
+          process(vb, c + 1);
         }
       }
+      if (q == 0 && lane == 0) CAPDEC_TRACE(3, 3 * ((int)cit - 1) + 2);   // tile's last chunk handed to the TMA engine
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    __syncwarp();
+    if (elect_one()) tma_store_wait_all<0>();
+    if (q == 0 && lane == 0) CAPDEC_TRACE(0, 2);   // every store of this warp has reached global memory
   }
 
   tc_fence_before();
   if constexpr (kPair) cluster_sync_all(); else __syncthreads();  // nobody exits while a peer may still touch its smem/barriers
+  if (threadIdx.x == 0) CAPDEC_TRACE(0, 3);     // after the closing cluster sync
   if (warp == 2) {
     tc_fence_after();
     if constexpr (kPair) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
@@ -888,6 +1007,7 @@ static OperandEnc operand_encoding(bool mn_major) {
 // tile order of the persistent kernels: 0 = static round-robin (default: fastest while a GEMM owns the GPU, which is the
 // single-GPU step), 1 = dynamic (device-wide tile counter: robust when collectives / the optimizer share the SMs)
 static std::atomic<int> g_sched_dynamic{0};
+static long long* g_trace = nullptr;   // capdec_gemm_debug_trace
 static int g_force_pair = -1;  // bring-up override: -1 auto, 0 never, 1 always (pairs), 2/3 force quad modes
 static thread_local int t_m_hint = 0;   // expected live rows of the next row-limited GEMMs (capdec_gemm_set_row_hint)
 
@@ -924,7 +1044,7 @@ static void choose_tiling(int M, int N, int kb_total, int accumulate, int units,
   splits = best_s > 0 ? best_s : 1;
 }
 
-template <int kMode, bool kSplit>
+template <int kMode, bool kSplit, int kEpi>
 static int max_clusters(int cluster_size, int smem_bytes) {
   static std::atomic<int> cached_dev[kMaxDevices];   // per instantiation and per device
   std::atomic<int>& cached = cached_dev[current_device()];
@@ -942,7 +1062,7 @@ static int max_clusters(int cluster_size, int smem_bytes) {
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<kMode, kSplit>, &cfg) != cudaSuccess || n <= 0) {
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<kMode, kSplit, kEpi>, &cfg) != cudaSuccess || n <= 0) {
     cudaGetLastError();
     n = num_sms() / cluster_size;
   }
@@ -950,9 +1070,9 @@ static int max_clusters(int cluster_size, int smem_bytes) {
   return n;
 }
 
-template <int kMode, bool kSplit>
+template <int kMode, bool kSplit, int kEpi>
 static int launch_clustered(const GemmDev& p, int cluster_size, int total_tiles, int smem_bytes, cudaStream_t stream) {
-  const int maxc = max_clusters<kMode, kSplit>(cluster_size, smem_bytes);
+  const int maxc = max_clusters<kMode, kSplit, kEpi>(cluster_size, smem_bytes);
   const int nc = total_tiles < maxc ? total_tiles : maxc;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -967,7 +1087,7 @@ static int launch_clustered(const GemmDev& p, int cluster_size, int total_tiles,
   attr.val.clusterDim.z = 1;
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<kMode, kSplit>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<kMode, kSplit, kEpi>, p);
   if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm_tf32_kernel)");
   return CAPDEC_OK;
 }
@@ -981,6 +1101,11 @@ extern "C" int capdec_version(void) { return 100; }
 extern "C" int64_t capdec_launch_count(void) { return g_launches.load(); }
 
 extern "C" void capdec_gemm_debug_force_pair(int mode) { g_force_pair = mode; }  // -1 auto, 0..3 engine
+// bring-up: every following GEMM launch writes cycle stamps (clock64 of CTA 0's SM) of its roles into trace[4][64]
+// (int64, device memory; NULL = off): [0] CTA: entry, set-up done, stores drained, closing sync; [1] producer: start of its
+// i-th tile; [2] MMA issuer: 2i = accumulator free, 2i+1 = tile's last k-block issued; [3] epilogue warp 4: 3i = accumulator
+// complete, 3i+1 = last TMEM read, 3i+2 = last chunk handed to the TMA engine
+extern "C" void capdec_gemm_debug_trace(void* trace_dev) { g_trace = static_cast<long long*>(trace_dev); }
 extern "C" int capdec_gemm_set_schedule(int dynamic) { return g_sched_dynamic.exchange(dynamic ? 1 : 0); }
 
 // Tiling hint for GEMMs launched with a device-side row limit (packed caption batches): the row count is data dependent
@@ -1109,6 +1234,13 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   p.mul_act = a.mul_act;
   p.colsum = a.colsum;
   p.k_limit = a.k_limit;
+  p.trace = g_trace;
+  // "1": plain outputs leave through coalesced st.global from the staging box instead of TMA stores.  Measured SLOWER
+  // (qkv 96 vs 80 us: the epilogue warps stall on the store queue while the TMA engine keeps its stores asynchronous), so
+  // this stays an A-B switch (profiles/r2_gemm_timeline.md)
+  static const char* env_lsu = getenv("CAPDEC_GEMM_LSU_STORE");
+  p.c_ptr = a.C; p.aux_ptr = a.aux; p.ldc = (long long)a.ldc;
+  p.lsu_store = (!a.accumulate && (N % 4) == 0 && env_lsu && env_lsu[0] == '1') ? 1 : 0;
   static const char* env_raster = getenv("CAPDEC_GEMM_RASTER");   // bring-up / A-B switch: tile order inside a wave
   p.raster = env_raster ? atoi(env_raster) : 0;
   static const char* env_dbg = getenv("CAPDEC_GEMM_DBG");
@@ -1134,11 +1266,26 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
 
   const int bn_local = (mode == 0) ? bn : bn / 2;
   const int b_bytes = bn_local * kBlockK * 4;
-  const int fixed = (a.mul_act ? 2 + kMulDepth : (a.aux ? 4 : 2)) * kStagingBytes + 256 * 4 +
-                    (3 * kMaxStages + 4 + 4 * kMulDepth + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 32;
   const int per_stage = (kABytes + b_bytes) * (split3 ? 2 : 1);   // 3xTF32 keeps a lo tile beside every operand tile
+  // Shared-memory split between pipeline stages and epilogue staging.  Measured (profiles/r2_gemm_epilogue.md): four
+  // stages feed the tensor core as well as six, while the epilogue - whose TMA stores queue behind the mainloop's loads in
+  // the SM's one TMA engine - needs more than two staging boxes per warp to keep storing.  So: the deepest staging (<= 4
+  // boxes per warp and output) that still leaves four stages.
+  static const char* env_depth = getenv("CAPDEC_GEMM_CDEPTH");   // bring-up / A-B switch: force 2..4
+  auto fixed_for = [&](int depth) {
+    return (depth + (a.mul_act ? kMulDepth : (a.aux ? depth : 0))) * kStagingBytes + 256 * 4 +
+           (3 * kMaxStages + 4 + 4 * kMulDepth + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 32;
+  };
+  int c_depth = 2;
+  for (int d = 4; d > 2; --d)
+    if ((kSmemLimit - fixed_for(d)) / per_stage >= 4) { c_depth = d; break; }
+  if (env_depth && atoi(env_depth) >= 2 && atoi(env_depth) <= 4) c_depth = atoi(env_depth);
+  p.c_depth = c_depth;
+  const int fixed = fixed_for(c_depth);
   int stages = (kSmemLimit - fixed) / per_stage;
   if (stages > kMaxStages) stages = kMaxStages;
+  static const char* env_stages = getenv("CAPDEC_GEMM_STAGES");   // bring-up / A-B switch: cap the pipeline depth
+  if (env_stages && atoi(env_stages) >= 2 && atoi(env_stages) < stages) stages = atoi(env_stages);
   CAPDEC_REQUIRE(stages >= 2, "gemm: tile width %d leaves fewer than two pipeline stages in shared memory (3xTF32: use block_n <= 128 on the single-CTA engine)", bn);
   p.stages = stages;
   const int smem_bytes = stages * per_stage + fixed;
@@ -1200,21 +1347,43 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   }
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  // epilogue variant (see the kernel's kEpi): 1 plain, 2 gelu forward + derivative output, 3 multiply by a stored derivative
+  int epi = 0;
+  if (!p.lsu_store) {
+    if (a.act == 0 && !a.aux && !a.mul_act && !a.colsum) epi = 1;
+    else if (!split3 && a.act == 4 && a.aux && !a.mul_act && !a.colsum) epi = 2;
+    else if (!split3 && a.mul_act == 4 && a.act == 0 && !a.aux) epi = 3;
+  }
+#define CAPDEC_GEMM_LAUNCH0(SPLIT, EPI, THREADS) gemm_tf32_kernel<0, SPLIT, EPI><<<grid, THREADS, smem_bytes, stream>>>(p)
+#define CAPDEC_GEMM_BY_EPI(MODE, CS)                                                                   \
+  (epi == 1 ? launch_clustered<MODE, false, 1>(p, CS, total_tiles, smem_bytes, stream)                 \
+   : epi == 2 ? launch_clustered<MODE, false, 2>(p, CS, total_tiles, smem_bytes, stream)               \
+   : epi == 3 ? launch_clustered<MODE, false, 3>(p, CS, total_tiles, smem_bytes, stream)               \
+              : launch_clustered<MODE, false, 0>(p, CS, total_tiles, smem_bytes, stream))
   if (mode == 0) {
     const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-    if (split3) gemm_tf32_kernel<0, true><<<grid, kSplitThreads, smem_bytes, stream>>>(p);
-    else gemm_tf32_kernel<0, false><<<grid, kThreads, smem_bytes, stream>>>(p);
+    if (split3) {
+      if (epi == 1) CAPDEC_GEMM_LAUNCH0(true, 1, kSplitThreads); else CAPDEC_GEMM_LAUNCH0(true, 0, kSplitThreads);
+    } else {
+      if (epi == 1) CAPDEC_GEMM_LAUNCH0(false, 1, kThreads);
+      else if (epi == 2) CAPDEC_GEMM_LAUNCH0(false, 2, kThreads);
+      else if (epi == 3) CAPDEC_GEMM_LAUNCH0(false, 3, kThreads);
+      else CAPDEC_GEMM_LAUNCH0(false, 0, kThreads);
+    }
   } else if (mode == 1) {
-    rc = split3 ? launch_clustered<1, true>(p, 2, total_tiles, smem_bytes, stream)
-                : launch_clustered<1, false>(p, 2, total_tiles, smem_bytes, stream);
+    if (split3) rc = epi == 1 ? launch_clustered<1, true, 1>(p, 2, total_tiles, smem_bytes, stream)
+                              : launch_clustered<1, true, 0>(p, 2, total_tiles, smem_bytes, stream);
+    else rc = CAPDEC_GEMM_BY_EPI(1, 2);
     if (rc) return rc;
   } else if (mode == 2) {
-    rc = launch_clustered<2, false>(p, 4, total_tiles, smem_bytes, stream);
+    rc = CAPDEC_GEMM_BY_EPI(2, 4);
     if (rc) return rc;
   } else {
-    rc = launch_clustered<3, false>(p, 4, total_tiles, smem_bytes, stream);
+    rc = CAPDEC_GEMM_BY_EPI(3, 4);
     if (rc) return rc;
   }
+#undef CAPDEC_GEMM_LAUNCH0
+#undef CAPDEC_GEMM_BY_EPI
   g_launches.fetch_add(1);
   CAPDEC_LAUNCH_CHECK("gemm_tf32_kernel");
   return CAPDEC_OK;
@@ -1345,12 +1514,14 @@ static int gemm_entry(const float* A, int a_major, int64_t lda, const float* B, 
   static std::atomic<bool> attr_set_dev[kMaxDevices];   // cudaFuncSetAttribute is per device
   std::atomic<bool>& attr_set = attr_set_dev[current_device()];
   if (!attr_set.load(std::memory_order_acquire)) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t e = cudaSuccess;
+    auto opt_in = [&](const void* fn) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit); };
+#define CAPDEC_OPT_IN4(MODE) opt_in((const void*)gemm_tf32_kernel<MODE, false, 0>); opt_in((const void*)gemm_tf32_kernel<MODE, false, 1>); \
+                             opt_in((const void*)gemm_tf32_kernel<MODE, false, 2>); opt_in((const void*)gemm_tf32_kernel<MODE, false, 3>)
+    CAPDEC_OPT_IN4(0); CAPDEC_OPT_IN4(1); CAPDEC_OPT_IN4(2); CAPDEC_OPT_IN4(3);
+#undef CAPDEC_OPT_IN4
+    opt_in((const void*)gemm_tf32_kernel<0, true, 0>); opt_in((const void*)gemm_tf32_kernel<0, true, 1>);
+    opt_in((const void*)gemm_tf32_kernel<1, true, 0>); opt_in((const void*)gemm_tf32_kernel<1, true, 1>);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm_tf32_kernel)");
     attr_set.store(true, std::memory_order_release);
   }

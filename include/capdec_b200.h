@@ -81,6 +81,8 @@ void capdec_gemm_debug_mn_encoding(int layout_type, int lbo_bytes, int sbo_bytes
 /* tile engine selection override: -1 auto (CTA pairs / cta_group::2 whenever M > 128 and N >= 128), 0 = always one CTA
  * per 128-row tile (cta_group::1), 1 = always CTA pairs.  Used by the tests to cover both engines. */
 void capdec_gemm_debug_force_pair(int mode);
+/* bring-up: following GEMM launches write clock64 stamps of CTA 0's roles into trace_dev (int64 [4][64], device; NULL = off) */
+void capdec_gemm_debug_trace(void* trace_dev);
 /* Tile order of the persistent GEMM kernels launched from now on (process-wide; returns the previous setting).
  * 0 = static: cluster c takes tiles c, c + #clusters, ... - the fastest order while a GEMM owns the whole GPU (default).
  * 1 = dynamic: one scheduler thread per cluster draws tile ids from a device-wide counter and publishes them to a ring in

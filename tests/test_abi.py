@@ -86,7 +86,7 @@ def test_every_entry_point_rejects_null_arguments_with_a_message():
     from capdec_b200 import _lib
     lib = _lib.load()
     not_compute = {"capdec_last_error", "capdec_version", "capdec_launch_count", "capdec_gemm_debug_mn_encoding",
-                   "capdec_gemm_debug_force_pair", "capdec_gemm_set_row_hint", "capdec_gemm_autotune", "capdec_gemm_plan_query",
+                   "capdec_gemm_debug_force_pair", "capdec_gemm_debug_trace", "capdec_gemm_set_row_hint", "capdec_gemm_autotune", "capdec_gemm_plan_query",
                    "capdec_gemm_set_schedule"}
     before = lib.capdec_launch_count()
     checked = 0
