@@ -326,12 +326,9 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     if constexpr (kPair) { tmem_alloc_pair(tmem_slot, kTmemCols); tmem_relinquish_pair(); }
     else { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   }
-  tc_fence_before();
-  if (threadIdx.x == 32) CAPDEC_TRACE(0, 7);   // barriers initialised, about to join the opening cluster sync
-  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) CAPDEC_TRACE(0, 1);   // set-up done (barriers, TMEM, cluster sync)
+  // (the opening cluster sync comes AFTER the scalar set-up below: the device-side row / reduction limits are global loads,
+  // and their latency - like the reciprocals and tile counts derived from them - now overlaps the barrier initialisation and
+  // the TMEM allocation of warps 1 and 2 instead of following them)
 
   // data-dependent extents (LM head over the non-ignored caption tokens only): every role skips the same tiles
   const int m_lim = p.m_limit ? __ldg(p.m_limit) : p.M;
@@ -416,6 +413,13 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
     ++cit;
     return tile >= 0;
   };
+
+  tc_fence_before();
+  if (threadIdx.x == 32) CAPDEC_TRACE(0, 7);   // barriers initialised, about to join the opening cluster sync
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) CAPDEC_TRACE(0, 1);   // set-up done (barriers, TMEM, cluster sync)
 
   if (warp == 3) {
     // ============================== tile scheduler (one thread per cluster) ========================================
@@ -896,7 +900,9 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     __syncwarp();
-    if (elect_one()) tma_store_wait_all<0>();
+    // the staging boxes must have been READ before this CTA's shared memory goes away; the writes themselves are complete
+    // (and visible) at grid completion like any other store
+    if (elect_one()) tma_store_wait_read<0>();
     if (q == 0 && lane == 0) CAPDEC_TRACE(0, 2);   // every store of this warp has reached global memory
   }
 
