@@ -462,6 +462,7 @@ def run_gpu(args):
         step_tf = flops_per_caption(P=P_LEN) * B / (ms_dev / args.steps * 1e-3) / 1e12   # what the reference executes
         packed = bool(model.engine().packed)
         tr_peer, tr_sharded = bool(getattr(tr, "peer", False)), bool(getattr(tr, "sharded", False))
+        tr_push = bool(getattr(tr, "push", False))
         ex_flops, live_rows, dense_rows = executed_flops(host[0][0], P_LEN, packed)
         exec_tf = ex_flops / (ms_dev / args.steps * 1e-3) / 1e12
         # ---- worst case for the packed path: every caption 40 tokens long (SURVEY §8d "also run l = 40"), same trainer,
@@ -513,8 +514,12 @@ def run_gpu(args):
                 "rows": (f"packed: {live_rows} of {dense_rows} trunk rows per step are live (padding and each caption's "
                          "final token cannot reach the loss and are skipped; CAPDEC_PACKED=0 runs every row)"
                          if packed else f"dense: all {dense_rows} trunk rows per step"),
-                **({"dp_update": ("one kernel per rank over NVLink peer memory: loads its 1/N slice of every rank's gradients, "
-                                  "HF-AdamW, stores the new parameters into every rank's buffer (csrc/peer.cu)" if tr_peer else
+                **({"dp_update": (("copy engines push every finished gradient bucket into the owners' staging areas during the "
+                                   "backward pass (memcpy nodes in the step graph); then one kernel per rank: sums the N "
+                                   "contributions of its 1/N slice from local HBM, HF-AdamW, stores the new parameters into every "
+                                   "rank's buffer over NVLink (csrc/peer.cu)" if tr_push else
+                                   "one kernel per rank over NVLink peer memory: loads its 1/N slice of every rank's gradients, "
+                                   "HF-AdamW, stores the new parameters into every rank's buffer (csrc/peer.cu)") if tr_peer else
                                   ("NCCL reduce-scatter + AdamW on 1/N + NCCL all-gather" if tr_sharded else "NCCL all-reduce + full AdamW"))}
                    if world > 1 else {}),
                 "l2": "working set per step (0.62 GB weights + 7.5 GB activations) >> 126 MB L2; 8 distinct host batches",

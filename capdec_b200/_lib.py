@@ -81,6 +81,7 @@ SIGNATURES = {
     "capdec_peer_export": [_p, _p, _p],
     "capdec_peer_open": [_p, _i64, _p],
     "capdec_peer_close": [_p, _i64],
+    "capdec_copy_async": [_p, _p, _i64, _p],
     "capdec_adamw_peer_step": [_p, _p, _i, _i, _i64, _i64, _p, _p, _p, _p, _f, _f, _f, _f, _p, _p],
 }
 _RESTYPES = {"capdec_last_error": C.c_char_p, "capdec_launch_count": C.c_int64, "capdec_gemm_debug_mn_encoding": None,

@@ -1,12 +1,15 @@
 // capdec_b200 — data-parallel optimizer step over NVLink peer memory (train.py:352-354 under N ranks).
 //
 // ONE kernel per step and rank replaces  ncclReduceScatter -> AdamW(1/N slice) -> ncclAllGather :
-//   every rank owns the parameters [lo, lo + n) of the flat buffer.  Its kernel LOADS the gradients of that slice from the
-//   gradient buffers of ALL ranks (peer pointers, NVLink reads; summed in rank order, so the result does not depend on
-//   who owns the slice), runs the HF-AdamW update with the moments it alone keeps, and STORES the new parameters into the
-//   parameter buffers of ALL ranks (NVLink writes).  Reads and writes travel in opposite directions of the links at the
-//   same time, and no byte is staged: (N-1)/N of the flat buffer in, (N-1)/N out per rank, against twice that, one after
-//   the other, for reduce-scatter + all-gather.  The cross-rank ordering (all gradients final before, all parameters
+//   every rank owns the parameters [lo, lo + n) of the flat buffer.  Its kernel LOADS the gradients of that slice as every
+//   rank computed them (summed in rank order, so the result does not depend on who owns the slice), runs the HF-AdamW
+//   update with the moments it alone keeps, and STORES the new parameters into the parameter buffers of ALL ranks (NVLink
+//   writes).  Where the gradients are read from is the caller's choice (g_slices): straight from the peers' gradient
+//   buffers (NVLink reads: measured 365 GB/s per direction at N = 2, loads over the link are latency-bound), or - the
+//   default of capdec_b200/trainer.py - from a local staging area into which every rank's COPY ENGINES pushed its share of
+//   each gradient bucket while the backward pass was still running (capdec_copy_async under CUDA-graph capture = a memcpy
+//   node; no SM is involved, so unlike an NCCL kernel the transfer takes nothing from the persistent GEMM CTAs).  Then the
+//   only exposed NVLink traffic of a step is the parameter all-gather.  The cross-rank ordering (all gradients final before, all parameters
 //   landed after) is two 16-byte NCCL all-reduces issued by the host code around the launch (capdec_b200/trainer.py); the
 //   first of them is the global token count the update divides by, which the step needs anyway.
 // The peer pointers come from CUDA IPC (one process per GPU): capdec_peer_export / capdec_peer_open below.
@@ -20,8 +23,8 @@ namespace capdec {
 constexpr int kMaxPeers = 8;   // one NVSwitch domain of this node
 
 struct PeerSet {
-  const float4* g[kMaxPeers];  // gradient buffers of rank 0..world-1 (element 0 = first trainable parameter)
-  float4* p[kMaxPeers];        // parameter buffers, same coordinates
+  const float4* g[kMaxPeers];  // where the gradients of THIS rank's slice, as computed by rank 0..world-1, can be read
+  float4* p[kMaxPeers];        // parameter buffers of rank 0..world-1 (element 0 = first trainable parameter)
 };
 
 // weak 128-bit load that never allocates in L1: peer lines are L1-cacheable but bypass the local L2, and the same
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerSet ps, int r
     const int64_t e = lo4 + i;
     float4 gr[kWorld];
 #pragma unroll
-    for (int r = 0; r < kWorld; ++r) gr[r] = ld_peer(ps.g[r] + e);   // kWorld independent loads in flight per thread
+    for (int r = 0; r < kWorld; ++r) gr[r] = ld_peer(ps.g[r] + i);   // kWorld independent loads in flight per thread
     float4 pp = ps.p[rank][e], mm = m[i], vv = v[i];
     float4 gg = gr[0];
 #pragma unroll
@@ -125,21 +128,28 @@ extern "C" int capdec_peer_close(void* ptr, int64_t offset) {
   return check_cuda(cudaIpcCloseMemHandle(static_cast<char*>(ptr) - offset), "cudaIpcCloseMemHandle");
 }
 
-extern "C" int capdec_adamw_peer_step(void* const* g_peers, void* const* p_peers, int world, int rank, int64_t lo,
+extern "C" int capdec_copy_async(void* dst, const void* src, int64_t bytes, capdec_stream_t stream_) {
+  CAPDEC_REQUIRE(dst && src && bytes >= 0, "copy_async: bad arguments");
+  if (bytes == 0) return CAPDEC_OK;
+  return check_cuda(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(stream_)),
+                    "cudaMemcpyAsync");
+}
+
+extern "C" int capdec_adamw_peer_step(void* const* g_slices, void* const* p_peers, int world, int rank, int64_t lo,
                                       int64_t n, float* m, float* v, const float* lr_dev, const float* t_dev,
                                       float beta1, float beta2, float eps, float weight_decay,
                                       const float* grad_denom_dev, capdec_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CAPDEC_REQUIRE(g_peers && p_peers && m && v && lr_dev && t_dev, "adamw_peer_step: null argument");
+  CAPDEC_REQUIRE(g_slices && p_peers && m && v && lr_dev && t_dev, "adamw_peer_step: null argument");
   CAPDEC_REQUIRE(world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world, "adamw_peer_step: world=%d rank=%d (2..%d ranks)",
                  world, rank, kMaxPeers);
   CAPDEC_REQUIRE(lo >= 0 && n > 0 && lo % 4 == 0 && n % 4 == 0, "adamw_peer_step: lo and n must be multiples of 4");
   PeerSet ps;
   for (int r = 0; r < kMaxPeers; ++r) {
     const int s = r < world ? r : 0;
-    CAPDEC_REQUIRE(g_peers[s] && p_peers[s], "adamw_peer_step: null peer pointer for rank %d", s);
-    CAPDEC_REQUIRE(((uintptr_t)g_peers[s] & 15u) == 0 && ((uintptr_t)p_peers[s] & 15u) == 0, "adamw_peer_step: peer buffers must be 16-byte aligned");
-    ps.g[r] = static_cast<const float4*>(g_peers[s]);
+    CAPDEC_REQUIRE(g_slices[s] && p_peers[s], "adamw_peer_step: null peer pointer for rank %d", s);
+    CAPDEC_REQUIRE(((uintptr_t)g_slices[s] & 15u) == 0 && ((uintptr_t)p_peers[s] & 15u) == 0, "adamw_peer_step: peer buffers must be 16-byte aligned");
+    ps.g[r] = static_cast<const float4*>(g_slices[s]);
     ps.p[r] = static_cast<float4*>(p_peers[s]);
   }
   const int64_t n4 = n / 4;

@@ -382,13 +382,20 @@ def peer_close(ptr: int, offset: int) -> None:
     _lib.check(_lib.load().capdec_peer_close(ptr, int(offset)), "peer_close")
 
 
-def adamw_peer_step(g_ptrs, p_ptrs, rank, lo, n, m, v, lr_dev, t_dev, beta1=0.9, beta2=0.999, eps=1e-6,
+def copy_async(dst_ptr: int, src_ptr: int, nbytes: int) -> None:
+    """cudaMemcpyAsync between two device addresses (peer addresses included) on the current stream; a copy-engine
+    memcpy node when the stream is being captured."""
+    _lib.check(_lib.load().capdec_copy_async(dst_ptr, src_ptr, int(nbytes), _stream()), "copy_async")
+
+
+def adamw_peer_step(g_slices, p_ptrs, rank, lo, n, m, v, lr_dev, t_dev, beta1=0.9, beta2=0.999, eps=1e-6,
                     weight_decay=0.0, grad_denom=None):
-    """Fused reduce-scatter + HF-AdamW + all-gather over peer memory: `g_ptrs` / `p_ptrs` = device addresses of every
-    rank's gradient / parameter buffer (ints, rank order); this rank updates elements [lo, lo + n)."""
-    world = len(g_ptrs)
+    """Fused reduce-scatter + HF-AdamW + all-gather: `g_slices[r]` = device address of this rank's slice [lo, lo + n) of
+    the gradients rank r computed (a peer buffer or local staging), `p_ptrs[r]` = device address of rank r's parameter
+    buffer (ints, rank order)."""
+    world = len(g_slices)
     arr = ctypes.c_void_p * world
-    rc = _lib.load().capdec_adamw_peer_step(arr(*g_ptrs), arr(*p_ptrs), world, rank, int(lo), int(n), m.data_ptr(),
+    rc = _lib.load().capdec_adamw_peer_step(arr(*g_slices), arr(*p_ptrs), world, rank, int(lo), int(n), m.data_ptr(),
                                             v.data_ptr(), lr_dev.data_ptr(), t_dev.data_ptr(), beta1, beta2, eps,
                                             weight_decay, _ptr(grad_denom), _stream())
     _lib.check(rc, "adamw_peer_step")

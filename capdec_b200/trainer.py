@@ -19,6 +19,23 @@ from . import ops
 from ._lib import CapdecError
 
 
+def push_plan(span, world: int, rank: int, shard: int):
+    """Where rank `rank` sends the gradients [span[0], span[1]) (trainable-parameter coordinates) of a finished bucket:
+    one entry per OTHER rank r whose slice [r * shard, (r + 1) * shard) the span touches -
+    (r, first element, number of elements, element offset inside rank r's staging area).  A rank's staging area holds
+    world - 1 slots of `shard` floats, one per source rank in rank order with the owner itself left out."""
+    out = []
+    lo, hi = span
+    for r in range(world):
+        if r == rank:
+            continue
+        a, b = max(lo, r * shard), min(hi, (r + 1) * shard)
+        if b > a:
+            slot = rank if rank < r else rank - 1
+            out.append((r, a, b - a, slot * shard + (a - r * shard)))
+    return out
+
+
 class Trainer:
     def __init__(self, model, batch_size: int, seq_len: int = 40, lr: float = 2e-5, warmup_steps: int = 5000,
                  total_steps: int = 100000, noise_variance: float = 0.0, uniform_noise: bool = False,
@@ -119,9 +136,17 @@ class Trainer:
         # ... and by default the three steps are ONE kernel over NVLink peer memory (csrc/peer.cu): the owner of a slice
         # loads that slice of every rank's gradient buffer, updates, and stores the new parameters into every rank's
         # parameter buffer.  CAPDEC_DP_PEER=0 (or peers that cannot map each other's memory) keeps the NCCL sequence.
-        self.peer = False
+        # ... and the gradients reach their owner while the backward pass is still running: as soon as a GPT-2 block's
+        # gradients are final, every rank's COPY ENGINES push its share of that bucket into the owners' staging areas
+        # (memcpy nodes inside the step's CUDA graph).  No SM is involved - unlike an NCCL kernel, the transfer takes
+        # nothing from the persistent GEMM CTAs - and the update kernel then reads all N contributions from local HBM:
+        # the only exposed NVLink traffic of a step is the parameter all-gather.  CAPDEC_DP_PUSH=0: the update kernel
+        # loads the gradients over NVLink itself (measured 365 GB/s per direction at N = 2: loads are latency-bound).
+        self.peer = self.push = False
         if self.sharded and os.environ.get("CAPDEC_DP_PEER", "1") != "0" and self.world <= 8:
-            self.peer = self._peer_setup()
+            want_push = (os.environ.get("CAPDEC_DP_PUSH", "1") != "0" and self.train_gpt
+                         and self.n_train == fl.grads.numel() - fl.tail)
+            self.peer = self._peer_setup(want_push)
         self.use_graph = use_cuda_graph
         self._g_fb = self._g_opt = self._g_eval = None
         self._warm = 0
@@ -140,12 +165,17 @@ class Trainer:
         else:
             pfx = self.prefix_d                                 # train.py:28-29: variance 0 -> untouched
         hook = self._reduce_layer if (self.overlap or self.segmented) else (self._opt_layer if self.opt_overlap else None)
+        if self.push:
+            hook = self._push_layer
         if layer_hook is not None:       # segmented capture: the hook cuts the graph instead of launching a collective
             hook = layer_hook
         self._stats_taken = False
         eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False, on_layer_done=hook)
         if layer_hook is not None:
             return
+        if self.push:          # [mapper | wte | wpe] became final last; then the step (graph) ends with every push issued
+            self._push_span(self.head_span)
+            torch.cuda.current_stream().wait_stream(self.push_stream)
         if self.opt_overlap:
             self._take_stats()
             self._adamw_span(*self.head_span)
@@ -201,29 +231,38 @@ class Trainer:
         if hi < self.n_train:
             ops.zero_fill(self.g_flat[hi:])
 
-    def _peer_setup(self) -> bool:
-        """Exchange CUDA-IPC handles of the flat gradient / parameter buffers and map every peer's (one process per GPU,
-        one node).  Collective: every rank learns whether ALL ranks succeeded, so that all take the same path."""
+    def _peer_setup(self, want_push: bool) -> bool:
+        """Exchange CUDA-IPC handles of the flat gradient / parameter buffers (and of the gradient staging area) and map
+        every peer's (one process per GPU, one node).  Collective: every rank learns whether ALL ranks succeeded, so that
+        all take the same path."""
         dist = torch.distributed
         rank = dist.get_rank(self.pg)
+        sh = self.shard[1] - self.shard[0]
+        staging = torch.empty((self.world - 1) * sh, device=self.dev) if want_push else None
         try:
-            mine = (ops.peer_export(self.g_flat), ops.peer_export(self.p_flat))
+            mine = (ops.peer_export(self.g_flat), ops.peer_export(self.p_flat),
+                    ops.peer_export(staging) if want_push else None)
         except CapdecError as e:
             mine = str(e)
         table = [None] * self.world
         dist.all_gather_object(table, mine, group=self.pg)
-        g_ptrs, p_ptrs, opened, err = [], [], [], None
+        g_ptrs, p_ptrs, s_ptrs, opened, err = [], [], [], [], None
         if any(isinstance(x, str) for x in table):
             err = next(x for x in table if isinstance(x, str))
         else:
             try:
-                for r, ((gh, goff), (ph, poff)) in enumerate(table):
+                for r, (gx, px, sx) in enumerate(table):
                     if r == rank:
                         g_ptrs.append(self.g_flat.data_ptr()); p_ptrs.append(self.p_flat.data_ptr())
+                        s_ptrs.append(staging.data_ptr() if want_push else 0)
                         continue
-                    gp = ops.peer_open(gh, goff); opened.append((gp, goff))
-                    pp = ops.peer_open(ph, poff); opened.append((pp, poff))
-                    g_ptrs.append(gp); p_ptrs.append(pp)
+                    for exp, dst in ((gx, g_ptrs), (px, p_ptrs), (sx, s_ptrs)):
+                        if exp is None:
+                            dst.append(0)
+                            continue
+                        ptr = ops.peer_open(*exp)
+                        opened.append((ptr, exp[1]))
+                        dst.append(ptr)
             except CapdecError as e:
                 err = str(e)
         oks = [None] * self.world
@@ -238,7 +277,34 @@ class Trainer:
             return False
         self.g_ptrs, self.p_ptrs, self._peer_opened, self.rank = g_ptrs, p_ptrs, opened, rank
         self.fence = torch.zeros(4, device=self.dev)
+        lo = self.shard[0]
+        if want_push:
+            self.push = True
+            self.staging, self.staging_ptrs = staging, s_ptrs
+            self.push_stream = torch.cuda.Stream(device=self.dev)
+            # the update kernel reads rank r's contribution to this rank's slice from its local staging slot (own: in place)
+            self.g_slices = [self.g_flat.data_ptr() + 4 * lo if r == rank else
+                             staging.data_ptr() + 4 * sh * (r if r < rank else r - 1) for r in range(self.world)]
+        else:
+            self.g_slices = [ptr + 4 * lo for ptr in g_ptrs]      # straight from the peers' gradient buffers (NVLink loads)
         return True
+
+    def _push_span(self, span):
+        """Copy-engine pushes of this rank's gradients [span) into the staging areas of the ranks that own them, on the
+        side stream, ordered after everything the main stream has issued so far (memcpy nodes under graph capture)."""
+        plan = push_plan(span, self.world, self.rank, self.shard[1] - self.shard[0])
+        if not plan:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.push_stream.wait_event(ev)
+        base = self.g_flat.data_ptr()
+        with torch.cuda.stream(self.push_stream):
+            for r, first, count, dst_off in plan:
+                ops.copy_async(self.staging_ptrs[r] + 4 * dst_off, base + 4 * first, 4 * count)
+
+    def _push_layer(self, l: int):
+        self._push_span(self.layer_spans[l])
 
     def _peer_opt(self):
         """Sharded update in one kernel over peer memory.  The all-reduce of the global counts completes on a rank only
@@ -248,7 +314,7 @@ class Trainer:
         lo, hi = self.shard
         self.stats.copy_(self.tail)
         torch.distributed.all_reduce(self.stats, group=self.pg)
-        ops.adamw_peer_step(self.g_ptrs, self.p_ptrs, self.rank, lo, hi - lo, self.m_flat, self.v_flat, self.lr_dev,
+        ops.adamw_peer_step(self.g_slices, self.p_ptrs, self.rank, lo, hi - lo, self.m_flat, self.v_flat, self.lr_dev,
                             self.t_dev, self.betas[0], self.betas[1], self.eps, self.wd, grad_denom=self.stats[0:1])
         torch.distributed.all_reduce(self.fence, group=self.pg)
         ops.zero_fill(self.g_flat)

@@ -300,17 +300,22 @@ int capdec_adamw_step(float* p, float* g, float* m, float* v, int64_t n, const f
  * One process per GPU.  capdec_peer_export: CUDA-IPC handle (64 bytes) of the device allocation that contains `ptr` and
  * the byte offset of `ptr` inside it; capdec_peer_open (in ANOTHER process of the same node): maps that allocation with
  * peer access and returns the address that corresponds to `ptr`; capdec_peer_close unmaps it.
- * capdec_adamw_peer_step: g_peers / p_peers are HOST arrays of `world` device pointers (entry r = the gradient /
- * parameter buffer of rank r, element 0 = the first trainable parameter; entry `rank` is this process's own buffer).
- * This rank owns elements [lo, lo + n): g = sum over r of g_peers[r][lo + i] (rank order), the HF-AdamW update of
- * capdec_adamw_step with this rank's moments m, v ([n] each), and the new value stored to p_peers[r][lo + i] for EVERY r
- * - reduce-scatter + update + all-gather in one kernel, no staging.  The caller orders it across ranks: every rank's
- * gradients are final before any rank launches, and no rank reads its parameters / clears its gradients before every
- * rank's launch has finished (capdec_b200/trainer.py brackets it with two 16-byte all-reduces). */
+ * capdec_adamw_peer_step: g_slices / p_peers are HOST arrays of `world` device pointers.  This rank owns elements
+ * [lo, lo + n) of the flat parameter buffer.  g_slices[r] = where the gradients of that slice, as computed by rank r, can
+ * be read ([n] floats: a peer's gradient buffer + lo, or a local staging area peers pushed into with capdec_copy_async);
+ * p_peers[r] = the parameter buffer of rank r (element 0 = the first trainable parameter; entry `rank` is this process's
+ * own).  g = sum over r of g_slices[r][i] (rank order), the HF-AdamW update of capdec_adamw_step with this rank's moments
+ * m, v ([n] each), and the new value stored to p_peers[r][lo + i] for EVERY r - reduce-scatter + update + all-gather in
+ * one kernel.  The caller orders it across ranks: every rank's gradients are final (and pushed) before any rank launches,
+ * and no rank reads its parameters / clears its gradients before every rank's launch has finished
+ * (capdec_b200/trainer.py brackets it with two 16-byte all-reduces).
+ * capdec_copy_async: cudaMemcpyAsync(dst, src, bytes, default kind) on `stream` - device / peer pointers; a memcpy node
+ * under CUDA-graph capture, executed by the copy engines. */
 int capdec_peer_export(const void* ptr, void* handle64, int64_t* offset_out);
 int capdec_peer_open(const void* handle64, int64_t offset, void** ptr_out);
 int capdec_peer_close(void* ptr, int64_t offset);
-int capdec_adamw_peer_step(void* const* g_peers, void* const* p_peers, int world, int rank, int64_t lo, int64_t n,
+int capdec_copy_async(void* dst, const void* src, int64_t bytes, capdec_stream_t stream);
+int capdec_adamw_peer_step(void* const* g_slices, void* const* p_peers, int world, int rank, int64_t lo, int64_t n,
                            float* m, float* v, const float* lr_dev, const float* t_dev, float beta1, float beta2,
                            float eps, float weight_decay, const float* grad_denom_dev, capdec_stream_t stream);
 

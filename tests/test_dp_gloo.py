@@ -72,3 +72,35 @@ def test_two_rank_sum_reduce_equals_global_mean(tmp_path):
     # averaging per-rank MEANS instead would be wrong here (unequal token counts) — guard the design choice
     n0, n1 = (tokens[:2] != 0).sum().item(), (tokens[2:] != 0).sum().item()
     assert n0 != n1
+
+
+def test_push_plan_covers_every_gradient_exactly_once():
+    """Host logic of the copy-engine gradient pushes (capdec_b200.trainer.push_plan): over all buckets of a step, every
+    rank sends every element that another rank owns exactly once, into its own slot of the owner's staging area, and the
+    slots of the world - 1 sources tile that area without overlap."""
+    from capdec_b200.trainer import push_plan
+    for world in (2, 3, 8):
+        shard = 4 * 37
+        n = world * shard
+        spans = [(n - 50 - 40 * i, n - 50 - 40 * (i - 1)) for i in range(1, 6)]        # "layers", back to front
+        spans = [(max(0, a), b) for a, b in spans] + [(0, max(0, n - 50 - 200))] + [(n - 50, n)]
+        assert sorted(x for a, b in spans for x in range(a, b)) == list(range(n))
+        for owner in range(world):
+            filled = {}
+            for rank in range(world):
+                if rank == owner:
+                    assert all(r != rank for sp in spans for (r, _, _, _) in push_plan(sp, world, rank, shard))
+                    continue
+                for sp in spans:
+                    for r, first, count, off in push_plan(sp, world, rank, shard):
+                        if r != owner:
+                            continue
+                        assert owner * shard <= first and first + count <= (owner + 1) * shard
+                        for i in range(count):
+                            key = off + i
+                            assert key not in filled, "two pushes land on the same staging element"
+                            filled[key] = (rank, first + i)
+            assert sorted(filled) == list(range((world - 1) * shard))
+            for key, (rank, elem) in filled.items():       # slot = source rank with the owner left out, element order kept
+                slot = rank if rank < owner else rank - 1
+                assert key == slot * shard + (elem - owner * shard)

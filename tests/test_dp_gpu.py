@@ -45,12 +45,12 @@ def _worker(rank, world, port, out_dir):
     dist.all_gather(gathered, flat)
     if rank == 0:
         torch.save({"losses": losses, "identical": all(torch.equal(gathered[0], g) for g in gathered[1:]),
-                    "params": flat.cpu(), "peer": tr.peer, "sharded": tr.sharded}, os.path.join(out_dir, "dp.pt"))
+                    "params": flat.cpu(), "peer": tr.peer, "push": tr.push, "sharded": tr.sharded}, os.path.join(out_dir, "dp.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def _check_against_single_gpu(tmp_path, expect_peer=None):
+def _check_against_single_gpu(tmp_path, expect_peer=None, expect_push=None):
     import torch.multiprocessing as mp
     import capdec_b200 as cb
     from oracle import capdec_oracle as O
@@ -59,6 +59,8 @@ def _check_against_single_gpu(tmp_path, expect_peer=None):
     assert got["identical"], "ranks diverged"
     if expect_peer is not None:
         assert got["peer"] == expect_peer, "the data-parallel update did not take the expected path"
+    if expect_push is not None:
+        assert got["push"] == expect_push, "the gradients did not travel the expected way"
     sd = O.make_state_dict(seed=1)
     tokens, prefix, _ = O.make_batch(seed=2, B=8)
     tokens[0, 10:] = 0
@@ -76,8 +78,16 @@ def _check_against_single_gpu(tmp_path, expect_peer=None):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_two_gpu_data_parallel_matches_single_gpu(tmp_path):
-    """Default path: the sharded update as ONE kernel over NVLink peer memory (csrc/peer.cu)."""
-    _check_against_single_gpu(tmp_path, expect_peer=True)
+    """Default path: copy-engine pushes of every finished gradient bucket into the owners' staging areas during the
+    backward pass, then the sharded update as ONE kernel that all-gathers over NVLink peer memory (csrc/peer.cu)."""
+    _check_against_single_gpu(tmp_path, expect_peer=True, expect_push=True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_two_gpu_peer_update_with_nvlink_gradient_loads_matches_single_gpu(tmp_path, monkeypatch):
+    """CAPDEC_DP_PUSH=0: the update kernel loads the peers' gradients over NVLink itself (no staging)."""
+    monkeypatch.setenv("CAPDEC_DP_PUSH", "0")
+    _check_against_single_gpu(tmp_path, expect_peer=True, expect_push=False)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")

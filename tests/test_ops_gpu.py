@@ -468,7 +468,7 @@ def test_adamw_peer_step_is_reduce_scatter_update_all_gather(ops, world):
     for owner in range(world):
         lo = owner * sh
         m, v = m0[lo:lo + sh].clone(), v0[lo:lo + sh].clone()
-        ops.adamw_peer_step([g.data_ptr() for g in gs], [q.data_ptr() for q in ps], owner, lo, sh, m, v, lr_dev, t_dev,
+        ops.adamw_peer_step([g[lo:].data_ptr() for g in gs], [q.data_ptr() for q in ps], owner, lo, sh, m, v, lr_dev, t_dev,
                             b1, b2, eps, wd, grad_denom=denom)
         # same arithmetic as adamw_kernel up to the compiler's FMA contraction of the two kernels (1 ulp)
         assert torch.allclose(m, mr[lo:lo + sh], rtol=2e-6, atol=2e-7) and torch.allclose(v, vr[lo:lo + sh], rtol=2e-6, atol=2e-7)
