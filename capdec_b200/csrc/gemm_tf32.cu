@@ -1273,7 +1273,7 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   const int bn_local = (mode == 0) ? bn : bn / 2;
   const int b_bytes = bn_local * kBlockK * 4;
   const int per_stage = (kABytes + b_bytes) * (split3 ? 2 : 1);   // 3xTF32 keeps a lo tile beside every operand tile
-  // Shared-memory split between pipeline stages and epilogue staging.  Measured (profiles/r2_gemm_epilogue.md): four
+  // Shared-memory split between pipeline stages and epilogue staging.  Measured (profiles/r2_gemm_timeline.md): four
   // stages feed the tensor core as well as six, while the epilogue - whose TMA stores queue behind the mainloop's loads in
   // the SM's one TMA engine - needs more than two staging boxes per warp to keep storing.  So: the deepest staging (<= 4
   // boxes per warp and output) that still leaves four stages.
