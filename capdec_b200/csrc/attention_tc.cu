@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(128) attention_tc_fwd_kernel(const float* __re
                                                                int64_t o_ts, float scale, int causal,
                                                                const int32_t* __restrict__ key_len, float p_drop,
                                                                const uint64_t* seed_dev, uint32_t stream_id, const int32_t* __restrict__ cu_rows) {
+  pdl_trigger();   // lets a programmatically launched successor (the GEMMs) set itself up while this grid drains
   const uint64_t seed = seed_dev ? *seed_dev : 0ull;
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
   // dense: sequence b owns rows [b*T, (b+1)*T).  packed (cu_rows != NULL): rows [cu_rows[b], cu_rows[b+1]) — only the
@@ -517,6 +518,7 @@ __global__ void __launch_bounds__(256, X3 ? 1 : 2) attention_tc_bwd8_kernel(
     float* __restrict__ dv, float* __restrict__ dbias_qkv, int H, int T_arg, int S_arg, int64_t q_bs, int64_t q_ts, int64_t kv_bs,
     int64_t kv_ts, int64_t o_bs, int64_t o_ts, float scale, int causal, const int32_t* __restrict__ key_len, float p_drop,
     const uint64_t* seed_dev, uint32_t stream_id, const int32_t* __restrict__ cu_rows) {
+  pdl_trigger();   // lets a programmatically launched successor (the GEMMs) set itself up while this grid drains
   const uint64_t seed = seed_dev ? *seed_dev : 0ull;
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
   int T = T_arg, S = S_arg;

@@ -42,6 +42,13 @@ extern std::atomic<int64_t> g_launches;  // kernels launched by this library (be
 // ----------------------------------------------------------------------------------------------
 // small device utilities
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident while its predecessor in the stream is still draining (once every CTA of the predecessor has executed
+// pdl_trigger or exited); it must call pdl_wait before touching anything the predecessor produced - the wait returns when
+// the predecessor grid has completed and its memory is visible.  Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(1024) compact_targets_kernel(const int64_t* __
 __global__ void __launch_bounds__(256) rows_gather_idx_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
                                                               const int32_t* __restrict__ row_src,
                                                               const int32_t* __restrict__ counts, int d4, int max_rows) {
+  pdl_trigger();   // lets a programmatically launched successor (the GEMMs) set itself up while this grid drains
   const int nv = counts[0], nvp = min(counts[1], max_rows);
   const int64_t total = (int64_t)nvp * d4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(256) rows_gather_idx_kernel(const float4* __re
 // dst[row] = (dst_of[row] >= 0) ? src[dst_of[row]] : 0 for every hidden row
 __global__ void __launch_bounds__(256) rows_scatter_idx_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
                                                                const int32_t* __restrict__ dst_of, int rows, int d4) {
+  pdl_trigger();   // lets a programmatically launched successor (the GEMMs) set itself up while this grid drains
   const int64_t total = (int64_t)rows * d4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / d4), c = (int)(i % d4);
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(kCeThreads) ce_kernel(float* __restrict__ logi
                                                         const float* __restrict__ n_valid, float grad_scale,
                                                         float* __restrict__ loss_sum, int write_grad,
                                                         const int32_t* __restrict__ row_limit) {
+  pdl_trigger();   // lets a programmatically launched successor (the GEMMs) set itself up while this grid drains
   __shared__ float s_m[kCeThreads / 32], s_s[kCeThreads / 32];
   __shared__ float s_bm, s_bs;
   const int row = blockIdx.x;

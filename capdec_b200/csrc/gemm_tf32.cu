@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
   constexpr int kPairsPerCluster = kQuad ? 2 : 1;
   constexpr int kCtasPerCluster = kCtasPerPair * kPairsPerCluster;
 
+  pdl_trigger();   // the next kernel of the stream may take this SM as soon as this CTA has left it
   if (threadIdx.x == 0) CAPDEC_TRACE(0, 0);
   if (threadIdx.x == 32) CAPDEC_TRACE(0, 6);   // a second warp's entry
   if (warp == 0 && lane == 0) {
@@ -330,6 +331,10 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_tf32_kernel(const __gri
   // and their latency - like the reciprocals and tile counts derived from them - now overlaps the barrier initialisation and
   // the TMEM allocation of warps 1 and 2 instead of following them)
 
+  // Everything above touched only this CTA's shared / tensor memory and the kernel parameters, so under programmatic
+  // dependent launch it ran while the previous kernel of the stream was still draining its last wave; from here on the
+  // kernel reads what its predecessors wrote.
+  pdl_wait();
   // data-dependent extents (LM head over the non-ignored caption tokens only): every role skips the same tiles
   const int m_lim = p.m_limit ? __ldg(p.m_limit) : p.M;
   const int kb_lim = p.k_limit ? min(p.kb_total, (__ldg(p.k_limit) + kBlockK - 1) / kBlockK) : p.kb_total;
@@ -1050,6 +1055,12 @@ static void choose_tiling(int M, int N, int kb_total, int accumulate, int units,
   splits = best_s > 0 ? best_s : 1;
 }
 
+// programmatic dependent launch of the GEMM kernels (CAPDEC_GEMM_PDL=0 turns it off: bring-up / A-B switch)
+static bool gemm_pdl() {
+  static const char* env = getenv("CAPDEC_GEMM_PDL");
+  return !(env && env[0] == '0');
+}
+
 template <int kMode, bool kSplit, int kEpi>
 static int max_clusters(int cluster_size, int smem_bytes) {
   static std::atomic<int> cached_dev[kMaxDevices];   // per instantiation and per device
@@ -1086,13 +1097,15 @@ static int launch_clustered(const GemmDev& p, int cluster_size, int total_tiles,
   cfg.blockDim = dim3(kSplit ? kSplitThreads : kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = cluster_size;
-  attr.val.clusterDim.y = 1;
-  attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = gemm_pdl() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<kMode, kSplit, kEpi>, p);
   if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm_tf32_kernel)");
   return CAPDEC_OK;
@@ -1360,7 +1373,18 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
     else if (!split3 && a.act == 4 && a.aux && !a.mul_act && !a.colsum) epi = 2;
     else if (!split3 && a.mul_act == 4 && a.act == 0 && !a.aux) epi = 3;
   }
-#define CAPDEC_GEMM_LAUNCH0(SPLIT, EPI, THREADS) gemm_tf32_kernel<0, SPLIT, EPI><<<grid, THREADS, smem_bytes, stream>>>(p)
+#define CAPDEC_GEMM_LAUNCH0(SPLIT, EPI, THREADS)                                                        \
+  do {                                                                                                  \
+    cudaLaunchConfig_t cfg0;                                                                            \
+    memset(&cfg0, 0, sizeof(cfg0));                                                                     \
+    cfg0.gridDim = dim3(grid); cfg0.blockDim = dim3(THREADS); cfg0.dynamicSmemBytes = smem_bytes; cfg0.stream = stream; \
+    cudaLaunchAttribute at0;                                                                            \
+    at0.id = cudaLaunchAttributeProgrammaticStreamSerialization;                                        \
+    at0.val.programmaticStreamSerializationAllowed = 1;                                                 \
+    cfg0.attrs = &at0; cfg0.numAttrs = gemm_pdl() ? 1 : 0;                                              \
+    cudaError_t e0 = cudaLaunchKernelEx(&cfg0, gemm_tf32_kernel<0, SPLIT, EPI>, p);                     \
+    if (e0 != cudaSuccess) return check_cuda(e0, "cudaLaunchKernelEx(gemm_tf32_kernel)");               \
+  } while (0)
 #define CAPDEC_GEMM_BY_EPI(MODE, CS)                                                                   \
   (epi == 1 ? launch_clustered<MODE, false, 1>(p, CS, total_tiles, smem_bytes, stream)                 \
    : epi == 2 ? launch_clustered<MODE, false, 2>(p, CS, total_tiles, smem_bytes, stream)               \

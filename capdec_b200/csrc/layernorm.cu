@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ beta, int rows, int d, float eps,
                                                          float p_drop, const uint64_t* seed_dev, uint32_t stream_id,
                                                          const int32_t* __restrict__ rows_dev) {
+  pdl_trigger();   // lets a programmatically launched successor (the GEMMs) set itself up while this grid drains
   const uint64_t seed = seed_dev ? *seed_dev : 0ull;  // device-resident: fresh masks under CUDA-graph replay
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(256, 2) add_ln_bwd_pipe_kernel(
     const float* __restrict__ gamma, const float* dh_res, float* dh_out, float* __restrict__ dy,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias_branch, int rows, int d,
     int rows_per_cta, float p_drop, const uint64_t* seed_dev, uint32_t stream_id, const int32_t* __restrict__ rows_dev) {
+  pdl_trigger();   // lets a programmatically launched successor (the GEMMs) set itself up while this grid drains
   extern __shared__ __align__(128) uint8_t ln_smem[];
   __shared__ __align__(16) float s_part[2][8][2 * kR];   // [batch parity][warp][c1_0..c1_{R-1}, c2_0..c2_{R-1}]
   __shared__ __align__(8) uint64_t full_bar[kLnStages];
