@@ -655,10 +655,12 @@ class Engine:
         self._mapper_bwd(a.prefix, a.dpp)
 
     def loss_and_grads(self, tokens, prefix, train_gpt: Optional[bool] = None, mean_reduce: bool = False,
-                       on_layer_done=None):
+                       on_layer_done=None, before_backward=None):
         """One forward+backward of train.py:348-351.  Gradients are ACCUMULATED into the flat gradient buffer,
         sum-reduced over tokens unless `mean_reduce` (then divided by the local count of non-ignored targets).
-        tail[0] <- number of non-ignored targets, tail[1] <- sum of token losses.  Returns the tail view."""
+        tail[0] <- number of non-ignored targets, tail[1] <- sum of token losses.  Returns the tail view.
+        `before_backward()` is called right before the first launch that writes a parameter gradient (the data-parallel
+        trainer clears the gradient buffer on a side stream during the forward pass and joins it there)."""
         if train_gpt is None:
             train_gpt = self.m.gpt_trainable()
         fl = self.flat
@@ -684,6 +686,8 @@ class Engine:
             ops.rows_gather_idx(a.xf, a.xsel, a.row_src, a.counts)
             ops.gemm(a.xsel, 0, wte, 0, logits, B * L, self.V, d, m_limit=nv)                       # tied lm_head
             ops.ce_fwd_bwd(logits, a.targets_c, self.V, loss_sum, n_valid=n_valid if mean_reduce else None, row_limit=nv)
+            if before_backward is not None:
+                before_backward()
             if train_gpt:
                 ops.gemm(logits, 1, a.xsel, 1, g["gpt.transformer.wte.weight"], self.V, d, B * L, accumulate=True,
                          k_limit=nv)
@@ -701,6 +705,8 @@ class Engine:
             ops.rows_gather(a.xf, a.xsel, B, T, L, P - 1)                      # hidden states of logits[:, P-1:-1]
             ops.linear_fwd(a.xsel, wte, "linear", None, logits)               # tied lm_head
             ops.ce_fwd_bwd(logits, targets, self.V, loss_sum, n_valid=n_valid if mean_reduce else None)
+            if before_backward is not None:
+                before_backward()
             if train_gpt:
                 ops.linear_wgrad(a.xsel, logits, g["gpt.transformer.wte.weight"], "linear")
             ops.linear_dgrad(logits, wte, "linear", a.dxsel)

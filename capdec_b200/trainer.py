@@ -170,7 +170,20 @@ class Trainer:
         if layer_hook is not None:       # segmented capture: the hook cuts the graph instead of launching a collective
             hook = layer_hook
         self._stats_taken = False
-        eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False, on_layer_done=hook)
+        before_bwd = None
+        if self.peer and layer_hook is None:
+            # the gradient buffer is cleared on a side stream WHILE the forward pass runs (a memset node of the step graph)
+            # instead of after the update: nobody reads it between the closing fence of the previous step and this point
+            ev = torch.cuda.Event()
+            ev.record()
+            self.zero_stream.wait_event(ev)
+            with torch.cuda.stream(self.zero_stream):
+                ops.zero_fill(self.g_flat)
+                zeroed = torch.cuda.Event()
+                zeroed.record()
+            before_bwd = lambda: torch.cuda.current_stream().wait_event(zeroed)
+        eng.loss_and_grads(self.tokens_d, pfx, train_gpt=self.train_gpt, mean_reduce=False, on_layer_done=hook,
+                           before_backward=before_bwd)
         if layer_hook is not None:
             return
         if self.push:          # [mapper | wte | wpe] became final last; then the step (graph) ends with every push issued
@@ -277,6 +290,7 @@ class Trainer:
             return False
         self.g_ptrs, self.p_ptrs, self._peer_opened, self.rank = g_ptrs, p_ptrs, opened, rank
         self.fence = torch.zeros(4, device=self.dev)
+        self.zero_stream = torch.cuda.Stream(device=self.dev)
         lo = self.shard[0]
         if want_push:
             self.push = True
@@ -316,8 +330,7 @@ class Trainer:
         torch.distributed.all_reduce(self.stats, group=self.pg)
         ops.adamw_peer_step(self.g_slices, self.p_ptrs, self.rank, lo, hi - lo, self.m_flat, self.v_flat, self.lr_dev,
                             self.t_dev, self.betas[0], self.betas[1], self.eps, self.wd, grad_denom=self.stats[0:1])
-        torch.distributed.all_reduce(self.fence, group=self.pg)
-        ops.zero_fill(self.g_flat)
+        torch.distributed.all_reduce(self.fence, group=self.pg)      # (the next step clears the gradients during its forward)
 
     def _opt(self):
         if self.opt_overlap:           # the update already ran inside _fwd_bwd

@@ -102,6 +102,7 @@ def test_segment_capture_and_replay_order(monkeypatch):
     tr.noise_variance = 0.0
     tr.prefix_d = tr.tokens_d = None
     tr.train_gpt, tr.overlap, tr.segmented, tr.opt_overlap, tr.pg = True, False, True, False, None
+    tr.peer = tr.push = False
     tr.buckets = [torch.tensor([float(l)]) for l in range(12)]      # bucket tag = layer index
     tr.head_bucket = torch.tensor([99.0])
     tr.layer_spans = [(100 + l, 101 + l) for l in range(12)]        # parameter span tag = 100 + layer index
