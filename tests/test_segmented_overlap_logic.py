@@ -72,7 +72,7 @@ def fake_stream_ctx(s):
 class FakeEngine:
     nl = 12
 
-    def loss_and_grads(self, tokens, prefix, train_gpt=True, mean_reduce=False, on_layer_done=None):
+    def loss_and_grads(self, tokens, prefix, train_gpt=True, mean_reduce=False, on_layer_done=None, before_backward=None):
         LOG.append(("kernels", "forward+head"))
         for l in reversed(range(self.nl)):
             LOG.append(("kernels", f"block{l}"))
