@@ -146,7 +146,8 @@ class Trainer:
         if self.sharded and os.environ.get("CAPDEC_DP_PEER", "1") != "0" and self.world <= 8:
             want_push = (os.environ.get("CAPDEC_DP_PUSH", "1") != "0" and self.train_gpt
                          and self.n_train == fl.grads.numel() - fl.tail)
-            self.peer = self._peer_setup(want_push)
+            with torch.cuda.device(self.dev):      # the handle exchange is a collective on THIS rank's device
+                self.peer = self._peer_setup(want_push)
         self.use_graph = use_cuda_graph
         self._g_fb = self._g_opt = self._g_eval = None
         self._warm = 0
