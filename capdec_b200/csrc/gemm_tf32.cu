@@ -1032,7 +1032,9 @@ static void choose_tiling(int M, int N, int kb_total, int accumulate, int units,
     const long waves = (tiles + units - 1) / units;
     const double kb = (double)((kb_total + s - 1) / s);
     // per-tile time ~ k-blocks x (operand bytes per k-block, the L2 feed is the limiter) + epilogue
-    const double per_kb = (bn >= 256) ? 1.0 : (bn == 192 ? 0.82 : (bn == 128 ? 0.62 : 0.40));
+    // (measured with the CTA timeline, profiles/r2_gemm_timeline.md: a 192-wide tile issues its k-blocks in 13.8 k clk against
+    // 14.0 k for a 256-wide one - the tensor pipe does not get proportionally faster below N = 256)
+    const double per_kb = (bn >= 256) ? 1.0 : (bn == 192 ? 0.95 : (bn == 128 ? 0.62 : 0.40));
     const double epi = (bn / 256.0) * 5.0;
     return waves * (kb * per_kb + epi + 1.5);
   };
