@@ -1262,8 +1262,13 @@ static int launch_plan(const GemmArgs& a, const GemmPlan& pl, cudaStream_t strea
   static const char* env_lsu = getenv("CAPDEC_GEMM_LSU_STORE");
   p.c_ptr = a.C; p.aux_ptr = a.aux; p.ldc = (long long)a.ldc;
   p.lsu_store = (!a.accumulate && (N % 4) == 0 && env_lsu && env_lsu[0] == '1') ? 1 : 0;
-  static const char* env_raster = getenv("CAPDEC_GEMM_RASTER");   // bring-up / A-B switch: tile order inside a wave
-  p.raster = env_raster ? atoi(env_raster) : 0;
+  // Tile order inside a wave.  n-fastest (0) lets the clusters of a wave share A rows and read every B panel once per row
+  // of tiles: right while B (a trunk weight, <= 9.4 MB) lives in L2.  The tied LM head's B is wte, 154 MB > L2: walking n
+  // first re-streams it from HBM for each of the 24-40 row tiles (3.7 GB per launch - the GEMM was HBM-bound at 560 TF/s);
+  // m-fastest (1) keeps three B panels hot per wave and reads wte once.  CAPDEC_GEMM_RASTER forces either (A-B switch).
+  static const char* env_raster = getenv("CAPDEC_GEMM_RASTER");
+  const double b_bytes_all = (double)N * (double)K * 4.0, a_bytes_all = (double)((a.m_limit && t_m_hint > 0 && t_m_hint < M) ? t_m_hint : M) * (double)K * 4.0;
+  p.raster = env_raster ? atoi(env_raster) : ((b_bytes_all > 48e6 && b_bytes_all > a_bytes_all) ? 1 : 0);
   static const char* env_dbg = getenv("CAPDEC_GEMM_DBG");
   p.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
   static const char* env_sched = getenv("CAPDEC_GEMM_SCHED");   // "dynamic" / "static": overrides capdec_gemm_set_schedule
