@@ -57,6 +57,31 @@ def main():
         step()
     e1.record(); torch.cuda.synchronize()
     s_ms = e0.elapsed_time(e1) / reps
+    # the default (push) variant's kernel: all N gradient contributions are local (staging), only the parameter stores cross NVLink
+    staging = torch.randn((world - 1) * sh, device="cuda") * 1e-3
+    gl_slices = [g.data_ptr() + 4 * rank * sh if r == rank else staging.data_ptr() + 4 * sh * (r if r < rank else r - 1)
+                 for r in range(world)]
+    for _ in range(2):
+        ops.adamw_peer_step(gl_slices, pp, rank, rank * sh, sh, m, v, lr, t, grad_denom=den)
+    dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        ops.adamw_peer_step(gl_slices, pp, rank, rank * sh, sh, m, v, lr, t, grad_denom=den)
+    e1.record(); torch.cuda.synchronize()
+    p_ms = e0.elapsed_time(e1) / reps
+    # the copy-engine push of one rank's gradients to its peers (what runs during the backward pass)
+    sp = [None] * world
+    dist.all_gather_object(sp, ops.peer_export(staging))
+    s_ptrs = [staging.data_ptr() if r == rank else ops.peer_open(*sp[r]) for r in range(world)]
+    dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        for r in range(world):
+            if r != rank:
+                slot = rank if rank < r else rank - 1
+                ops.copy_async(s_ptrs[r] + 4 * slot * sh, g.data_ptr() + 4 * r * sh, 4 * sh)
+    e1.record(); torch.cuda.synchronize()
+    c_ms = e0.elapsed_time(e1) / reps
     # plain local AdamW on the slice for comparison
     pl, gl = p[rank * sh:(rank + 1) * sh], g[rank * sh:(rank + 1) * sh]
     e0.record()
@@ -68,6 +93,8 @@ def main():
     if rank == 0:
         print(f"N={world}: peer kernel {k_ms:.3f} ms ({remote / k_ms * 1e3:.0f} GB/s in + the same out per rank over NVLink), "
               f"with its two 16-byte all-reduces {s_ms:.3f} ms, local AdamW on the 1/N slice {l_ms:.3f} ms", flush=True)
+        print(f"N={world}: push-variant kernel (gradients local, parameter stores over NVLink) {p_ms:.3f} ms = {remote / p_ms * 1e3:.0f} GB/s out per rank; "
+              f"copy-engine push of the gradients ({remote * 1e3:.0f} MB per rank, all ranks at once) {c_ms:.3f} ms = {remote / c_ms * 1e3:.0f} GB/s", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
