@@ -1190,9 +1190,12 @@ static GemmPlan heuristic_plan(const GemmArgs& a, int block_n, int split_k, int 
       // Measured on B200 (profiles/r1_gemm_modes.md): stacking the two pairs in M and multicasting B (mode 3) wins
       // 10-16 % at the dense C2 extent (M = 12800) when B is MN-major; sharing A (mode 2) loses to wave quantisation on
       // every shape of this model, and few-row problems (wgrad, M = 768) stay on plain pairs.
+      // Round 2, after the pipeline work (profiles/r2_gemm_timeline.md): at dense extents plain pairs are at least as fast
+      // on every shape (roofline anchor 72.6 us = 0.759 of peak on pairs, 74.3 us = 0.742 on quads, 148 vs 132 SMs), so the
+      // quad is proposed for row-limited launches only (packed qkv: 56 vs 61 us) - where the Trainer measures the plan anyway.
       const int mt = (m_live + 255) / 256;
       const double waste_b = (double)(((mt + 1) / 2) * 2) / mt;
-      if (mt >= 8 && waste_b <= 1.15 && a.b_major && block_n != 192) mode = 3;
+      if (a.m_limit && mt >= 8 && waste_b <= 1.15 && a.b_major && block_n != 192) mode = 3;
     } else if (forced == 2 || forced == 3) {
       mode = forced;
     }
