@@ -138,6 +138,11 @@ def test_gemm_planner_returns_legal_plans_on_cpu():
                     assert not (bn == 192 and mode == 3 and b_major), (M, N, K)
                     assert splits == 1 or (acc and (K + 31) // 32 // splits >= 4), (M, N, K, splits)
     assert {0, 1, 3} <= seen_modes
+    # engine heuristic (profiles/r2_gemm_timeline.md): CTA pairs at dense extents, the B-sharing quad for row-limited launches
+    assert lib.capdec_gemm_plan_query(12800, 2304, 768, 1, 0, 0, 0, 0) & 0xFF == 1
+    lib.capdec_gemm_set_row_hint(8820)
+    assert lib.capdec_gemm_plan_query(12800, 2304, 768, 1, 0, 0, 0, 1) & 0xFF == 3
+    lib.capdec_gemm_set_row_hint(0)
     # explicit requests are honoured
     code = lib.capdec_gemm_plan_query(12800, 768, 3072, 0, 1, 192, 3, 0)
     assert (code >> 8) & 0xFFF == 192 and code >> 20 == 3
